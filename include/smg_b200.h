@@ -1,0 +1,168 @@
+/*
+ * smg_b200.h - C ABI of libsmg_b200.so, the B200 (sm_100a) implementation of the
+ * SMG-multimodal-grasping grasp-affordance hot path.
+ *
+ * The reference (fukangl/SMG-multimodal-grasping) is pure Python and has no FFI or
+ * plugin interface; its boundary for this path is the Python surface of
+ * code/models.py, code/trainer.py, code/utils.py and code/NMS.py (SURVEY.md
+ * section 8(b)).  The entry points below are what a ctypes binding of that surface
+ * calls; each one cites the reference code it replaces.  INTEGRATION.md shows the
+ * binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative smg_status otherwise;
+ *     smg_last_error() returns a thread-local message.  No exceptions cross the ABI.
+ *   - all `dev_*` pointers are DEVICE pointers owned by the caller (torch tensors'
+ *     data_ptr()); `host_*` pointers are host memory.  `stream` is a cudaStream_t
+ *     (NULL = default stream).  Work is enqueued asynchronously on `stream` unless
+ *     the function is documented as synchronous.
+ *   - a handle is bound to one GPU; it owns only workspace and re-packed weights.
+ *     Not thread-safe per handle.  One handle per GPU per process.
+ *   - "sample" = one H x H network input (a rotated scene or an object-masked
+ *     scene); BatchNorm statistics are always per sample (reference: batch 1,
+ *     train mode, code/trainer.py:95).
+ */
+#ifndef SMG_B200_H
+#define SMG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smg_handle smg_handle;
+
+typedef enum smg_status {
+    SMG_OK = 0,
+    SMG_ERR_INVALID = -1, /* bad argument */
+    SMG_ERR_CUDA = -2,    /* CUDA runtime error (message in smg_last_error) */
+    SMG_ERR_STATE = -3,   /* weights not set, workspace too small, ... */
+    SMG_ERR_UNSUPPORTED = -4
+} smg_status;
+
+/* arithmetic mode of the trunk / head convolutions */
+typedef enum smg_precision {
+    SMG_PREC_FP32 = 0, /* CUDA-core FFMA, fp32 operands: parity <= 1e-4 vs the fp32 reference */
+    SMG_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
+    SMG_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
+} smg_precision;
+
+/* which DenseNet-121 trunk / which head (code/models.py:308-310, :316-343) */
+enum { SMG_TRUNK_SUCTION = 0, SMG_TRUNK_GRASP = 1, SMG_TRUNK_GS = 2, SMG_NUM_TRUNKS = 3 };
+enum { SMG_HEAD_SUCTION = 0, SMG_HEAD_GRASP = 1, SMG_HEAD_GS = 2, SMG_NUM_HEADS = 3 };
+
+#define SMG_TRUNK_NUM_PARAMS 362 /* conv/BN affine tensors of densenet121().features, state_dict order */
+#define SMG_HEAD_NUM_PARAMS 6    /* norm0.w, norm0.b, conv0.w, norm1.w, norm1.b, conv1.w */
+#define SMG_TRUNK_BN_CHANNELS 41824 /* sum of num_features over the 121 BatchNorm2d of one trunk */
+
+int smg_version(void);
+const char* smg_last_error(void);
+
+/* ---- lifetime ------------------------------------------------------------------ */
+/* Allocate workspace for up to `max_samples` samples of H x H input (H multiple of 32;
+ * the heads need H = 640, code/models.py:322).  `train_samples` > 0 additionally
+ * reserves the saved activations needed by smg_qbackward for that many samples.   */
+int smg_create(int device, int max_samples, int H, smg_handle** out);
+int smg_destroy(smg_handle* h);
+int smg_set_precision(smg_handle* h, int precision);
+int smg_get_precision(smg_handle* h);
+/* bytes of device workspace held by the handle */
+int64_t smg_workspace_bytes(smg_handle* h);
+
+/* ---- weights --------------------------------------------------------------------
+ * Re-pack fp32 parameters (device pointers, contiguous, torch layouts) into the
+ * kernel layouts.  Replaces what `model.cuda()` / `load_state_dict` do for the
+ * reference (code/trainer.py:85-92); call again after every optimizer step.
+ * Trunk parameter order (n = SMG_TRUNK_NUM_PARAMS): conv0.weight, norm0.weight,
+ * norm0.bias, then per dense layer norm1.w, norm1.b, conv1.w, norm2.w, norm2.b,
+ * conv2.w, per transition norm.w, norm.b, conv.w (in state_dict order), norm5.w, norm5.b. */
+int smg_set_trunk_weights(smg_handle* h, int trunk_id, const float* const* dev_params, int n, void* stream);
+/* Head parameter order (SMG_HEAD_NUM_PARAMS): norm0.w[2048], norm0.b, conv0.w[64,2048,1,1],
+ * norm1.w[64], norm1.b, conv1.w[n_out,64,20,20]; n_out = 1 (reinforcement) or 3 (reactive). */
+int smg_set_head_weights(smg_handle* h, int head_id, const float* const* dev_params, int n_out, void* stream);
+
+/* ---- K1: input stage ------------------------------------------------------------
+ * smg_prep: code/trainer.py:165-191.  224x224 float64 heightmaps -> float32 [n,3,H,H]
+ * (nearest zoom x2, zero pad to H, (x-mean)/std, 3 identical channels).             */
+int smg_prep(smg_handle* h, const double* dev_heightmaps, int n, int hm_size, double mean, double stddev,
+             float* dev_out, void* stream);
+/* smg_rotate: code/models.py:371-382.  F.affine_grid(align_corners=True) +
+ * F.grid_sample(mode='nearest', zero padding) of one [3,H,H] image for each listed
+ * rotation index (angle = idx * 360/num_rotations degrees) -> [n_rot,3,H,H].        */
+int smg_rotate(smg_handle* h, const float* dev_in, const int* host_rot_idx, int n_rot, int num_rotations,
+               float* dev_out, void* stream);
+/* same index arithmetic, returned as source linear indices (-1 = outside): test hook  */
+int smg_rotate_index_map(smg_handle* h, int rot_idx, int num_rotations, int32_t* dev_out, void* stream);
+
+/* ---- trunk / head ---------------------------------------------------------------
+ * smg_trunk_forward: `trunk.features(x)` (code/models.py:384-385) for n samples
+ * [n,3,H,H] -> dev_feat [n,1024,H/32,H/32] (NCHW float32, after norm5).  If
+ * dev_bn_mean/dev_bn_var are non-NULL they receive the per-sample batch statistics
+ * of all 121 BatchNorm layers, [n, SMG_TRUNK_BN_CHANNELS] each, in module order
+ * (biased variance), from which the caller applies the running-stat EMA.            */
+int smg_trunk_forward(smg_handle* h, int trunk_id, const float* dev_in, int n, float* dev_feat,
+                      float* dev_bn_mean, float* dev_bn_var, void* stream);
+
+/* smg_qforward: the fused, de-duplicated Q pass.  One scene image and n_masks masked
+ * images ([3,H,H] each); evaluates head(cat(trunk(rotate(scene, r)), trunk(mask_k))) for
+ * every listed rotation r and every mask k (code/models.py:371-389; the reference
+ * recomputes the mask pass per rotation and the scene passes per object).
+ * dev_q receives [n_masks, n_rot, n_out] float32.  Optional dev_bn_mean/var:
+ * [n_rot + n_masks, SMG_TRUNK_BN_CHANNELS] (rotations first, then masks).            */
+int smg_qforward(smg_handle* h, int trunk_id, int head_id, const float* dev_scene, const float* dev_masks,
+                 int n_masks, const int* host_rot_idx, int n_rot, int num_rotations, float* dev_q,
+                 float* dev_bn_mean, float* dev_bn_var, void* stream);
+/* same, starting from 224x224 float64 heightmaps (fuses smg_prep): Trainer.forward,
+ * code/trainer.py:162-207.                                                          */
+int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm,
+                      const double* dev_mask_hms, int n_masks, int hm_size, double mean, double stddev,
+                      const int* host_rot_idx, int n_rot, int num_rotations, float* dev_q, void* stream);
+
+/* ---- training (code/trainer.py:278-384) -----------------------------------------
+ * smg_qforward with n_masks = n_rot = 1 and save_for_backward; then smg_qbackward
+ * with dq = dLoss/dQ [n_out] produces gradients for every trunk / head parameter in
+ * the smg_set_*_weights order (device pointers to caller-owned float32 buffers of
+ * the parameter shapes; gradients are WRITTEN, not accumulated).                     */
+int smg_qforward_train(smg_handle* h, int trunk_id, int head_id, const float* dev_scene, const float* dev_mask,
+                       int rot_idx, int num_rotations, float* dev_q, float* dev_bn_mean, float* dev_bn_var,
+                       void* stream);
+int smg_qbackward(smg_handle* h, const float* dev_dq, float* const* dev_trunk_grads, float* const* dev_head_grads,
+                  void* stream);
+/* fused Adam over a flat list of tensors (torch.optim.Adam, code/trainer.py:99,383) */
+int smg_adam_step(smg_handle* h, float* const* dev_params, const float* const* dev_grads, float* const* dev_m,
+                  float* const* dev_v, const int64_t* host_numel, int n_tensors, int step, float lr, float beta1,
+                  float beta2, float eps, void* stream);
+
+/* ---- K9: action argmax (code/main.py:167-173,194-195) ----------------------------
+ * dev_q [n] float32 -> dev_out[0] = max value, dev_out_idx[0] = first index of the max
+ * (np.argmax first-max-wins).                                                       */
+int smg_argmax(smg_handle* h, const float* dev_q, int n, float* dev_out, int32_t* dev_out_idx, void* stream);
+
+/* ---- K11: heightmap (code/utils.py:12-68, depth path) -----------------------------
+ * depth [480,640] float64 (metres), K 3x3 and pose 4x4 float64 row-major on the HOST;
+ * writes depth_heightmap [224,224] and depth_mask [448,448] float64, bit-exact with
+ * the reference's numpy + cv2.warpPerspective result; host_A_htor (optional, 9 doubles)
+ * receives cv2.getPerspectiveTransform(dst_heightmap, src).                          */
+int smg_heightmap(smg_handle* h, const double* dev_depth, const double* host_K, const double* host_pose,
+                  double* dev_out224, double* dev_out448, double* host_A_htor, void* stream);
+
+/* ---- K12: box NMS (code/NMS.py:8-59) ---------------------------------------------
+ * boxes [n,2,2] float32 ((x1,y1),(x2,y2)); keeps index-order greedy survivors.
+ * dev_keep [n] int32 receives kept indices, dev_n_keep[0] their count.  n <= 1024.   */
+int smg_nms(smg_handle* h, const float* dev_boxes, int n, float co_thresh, float min_area, float max_area,
+            int32_t* dev_keep, int32_t* dev_n_keep, void* stream);
+
+/* ---- introspection --------------------------------------------------------------- */
+/* number of kernels this library has launched on behalf of the handle since creation */
+int64_t smg_launch_count(smg_handle* h);
+/* copy an internal activation for tests: what = "conv0", "pool0", "block1".."block4",
+ * "trans1".."trans3" (NHWC float32 of the last forward, sample `sample`) -> NCHW.     */
+int smg_debug_read(smg_handle* h, const char* what, int sample, float* dev_out_nchw, int64_t capacity_floats,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMG_B200_H */

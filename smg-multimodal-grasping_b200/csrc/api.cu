@@ -1,0 +1,553 @@
+// api.cu - C ABI entry points, workspace management and the trunk / Q-pass schedule.
+//
+// The schedule of one trunk pass over n samples (torchvision densenet121().features as called at
+// /root/reference/code/models.py:384-385) is a fixed kernel sequence on one stream:
+//   conv0+stats -> norm0/relu/maxpool+stats -> for each dense layer {1x1 conv (BN-ReLU prologue,
+//   stats epilogue) -> 3x3 conv (same), written into the block buffer slice} -> per transition
+//   {BN-ReLU + 2x2 avg-pool prologue, 1x1 conv, stats} ...  norm5 is folded into the head prologue.
+// All n samples run through every kernel together (M = n * H*W rows), with BatchNorm statistics
+// kept per sample, exactly like the reference's batch-1 calls.
+#include "smg_internal.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace smg {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int launch_bn_export_region(smg_handle* h, int n, const double* stats, int stats_stride, int c_count, double cnt,
+                            float* mean, float* var, int out_stride, int out_off, cudaStream_t st);
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
+    if (h->precision == SMG_PREC_FP32) return launch_conv_ffma(h, a, st);
+    return launch_conv_umma(h, a, h->precision, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// trunk forward over `n` samples already resident in h->input
+// ---------------------------------------------------------------------------------------
+static int trunk_forward(smg_handle* h, int trunk_id, int n, cudaStream_t st) {
+    TrunkW& T = h->trunks[trunk_id];
+    SMG_CHECK(T.set, SMG_ERR_STATE, "trunk %d: weights not set (call smg_set_trunk_weights)", trunk_id);
+    SMG_CHECK(n >= 1 && n <= h->max_samples, SMG_ERR_INVALID, "trunk_forward: n=%d outside [1,%d]", n, h->max_samples);
+    const int S = h->max_samples;
+    (void)S;
+    SMG_CUDA(cudaMemsetAsync(h->stats, 0, h->stats_bytes, st));
+    SMG_TRY(launch_conv0(h, h->input, n, T.conv0, h->conv0, stats_ptr(h, h->st_conv0), st));
+    SMG_TRY(launch_pool0(h, n, h->conv0, stats_ptr(h, h->st_conv0), T.norm0.gamma, T.norm0.beta, h->block[0],
+                         h->geom[0].c_tot, stats_ptr(h, h->st_block[0]), st));
+    int layer_index = 0;
+    for (int b = 0; b < kNumBlocks; ++b) {
+        const BlockGeom& g = h->geom[b];
+        double* st_blk = stats_ptr(h, h->st_block[b]);
+        for (int l = 0; l < kBlockLayers[b]; ++l, ++layer_index) {
+            const DenseLayerW& L = T.layers[b][l];
+            const int cin = g.c_in + l * kGrowth;
+            double* st_bott = stats_ptr(h, h->st_bott + (size_t)layer_index * kBottleneck);
+            ConvArgs a1;
+            a1.in = h->block[b]; a1.in_cstride = g.c_tot; a1.cin = cin; a1.hin = g.hw;
+            a1.in_stats = st_blk; a1.in_stats_stride = g.c_tot;
+            a1.gamma = L.norm1.gamma; a1.beta = L.norm1.beta;
+            a1.taps = 1; a1.w = &L.conv1;
+            a1.out = h->bott; a1.out_cstride = kBottleneck; a1.out_coff = 0; a1.cout = kBottleneck;
+            a1.out_stats = st_bott; a1.out_stats_stride = kBottleneck;
+            a1.n = n;
+            SMG_TRY(conv_dispatch(h, a1, st));
+            ConvArgs a2;
+            a2.in = h->bott; a2.in_cstride = kBottleneck; a2.cin = kBottleneck; a2.hin = g.hw;
+            a2.in_stats = st_bott; a2.in_stats_stride = kBottleneck;
+            a2.gamma = L.norm2.gamma; a2.beta = L.norm2.beta;
+            a2.taps = 9; a2.w = &L.conv2;
+            a2.out = h->block[b]; a2.out_cstride = g.c_tot; a2.out_coff = cin; a2.cout = kGrowth;
+            a2.out_stats = st_blk; a2.out_stats_stride = g.c_tot;
+            a2.n = n;
+            SMG_TRY(conv_dispatch(h, a2, st));
+        }
+        if (b < kNumBlocks - 1) {
+            const TransitionW& R = T.trans[b];
+            const BlockGeom& gn = h->geom[b + 1];
+            ConvArgs at;
+            at.in = h->block[b]; at.in_cstride = g.c_tot; at.cin = g.c_tot; at.hin = g.hw;
+            at.in_stats = st_blk; at.in_stats_stride = g.c_tot;
+            at.gamma = R.norm.gamma; at.beta = R.norm.beta;
+            at.pool = 1; at.taps = 1; at.w = &R.conv;
+            at.out = h->block[b + 1]; at.out_cstride = gn.c_tot; at.out_coff = 0; at.cout = g.c_tot / 2;
+            at.out_stats = stats_ptr(h, h->st_block[b + 1]); at.out_stats_stride = gn.c_tot;
+            at.n = n;
+            SMG_TRY(conv_dispatch(h, at, st));
+        }
+    }
+    h->last_n = n;
+    return SMG_OK;
+}
+
+// per-sample BN statistics of all 121 BatchNorm layers in module order
+static int export_bn_stats(smg_handle* h, int n, float* mean, float* var, cudaStream_t st) {
+    int off = 0;
+    const int total = SMG_TRUNK_BN_CHANNELS;
+    const double cnt0 = (double)(h->H / 2) * (h->H / 2);
+    SMG_TRY(launch_bn_export_region(h, n, stats_ptr(h, h->st_conv0), 64, 64, cnt0, mean, var, total, off, st));
+    off += 64;
+    int layer_index = 0;
+    for (int b = 0; b < kNumBlocks; ++b) {
+        const BlockGeom& g = h->geom[b];
+        const double cnt = (double)g.hw * g.hw;
+        for (int l = 0; l < kBlockLayers[b]; ++l, ++layer_index) {
+            const int cin = g.c_in + l * kGrowth;
+            SMG_TRY(launch_bn_export_region(h, n, stats_ptr(h, h->st_block[b]), g.c_tot, cin, cnt, mean, var, total, off, st));
+            off += cin;
+            SMG_TRY(launch_bn_export_region(h, n, stats_ptr(h, h->st_bott + (size_t)layer_index * kBottleneck), kBottleneck,
+                                            kBottleneck, cnt, mean, var, total, off, st));
+            off += kBottleneck;
+        }
+        // transition norm (b<3) or norm5 (b==3): statistics of the whole block buffer
+        SMG_TRY(launch_bn_export_region(h, n, stats_ptr(h, h->st_block[b]), g.c_tot, g.c_tot, cnt, mean, var, total, off, st));
+        off += g.c_tot;
+    }
+    SMG_CHECK(off == total, SMG_ERR_STATE, "bn export: %d channels, expected %d", off, total);
+    return SMG_OK;
+}
+
+// heads for all (mask, rotation) pairs; samples [0,n_rot) are scenes, [n_rot, n_rot+n_masks) masks
+static int heads_forward(smg_handle* h, int trunk_id, int head_id, int n_rot, int n_masks, float* dev_q,
+                         cudaStream_t st) {
+    TrunkW& T = h->trunks[trunk_id];
+    HeadW& Hd = h->heads[head_id];
+    SMG_CHECK(Hd.set, SMG_ERR_STATE, "head %d: weights not set (call smg_set_head_weights)", head_id);
+    const BlockGeom& g = h->geom[3];
+    SMG_CHECK(g.hw == kHeadK, SMG_ERR_INVALID, "heads need H=640 (block-4 spatial %d != %d)", g.hw, kHeadK);
+    const int n = n_rot + n_masks;
+    const double* st4 = stats_ptr(h, h->st_block[3]);
+    for (int half = 0; half < 2; ++half) {
+        const int s0 = half == 0 ? 0 : n_rot;
+        const int cnt = half == 0 ? n_rot : n_masks;
+        SMG_TRY(launch_head_prepare(h, cnt, st4 + 2 * (size_t)s0 * g.c_tot, g.c_tot, T.norm5, Hd.norm0, half,
+                                    h->head_scale + (size_t)s0 * kFeatC, h->head_shift + (size_t)s0 * kFeatC, st));
+        ConvArgs a;
+        a.in = h->block[3] + (size_t)s0 * g.hw * g.hw * g.c_tot; a.in_cstride = g.c_tot; a.cin = kFeatC; a.hin = g.hw;
+        a.prologue_mode = 1;
+        a.scale = h->head_scale + (size_t)s0 * kFeatC; a.shift = h->head_shift + (size_t)s0 * kFeatC;
+        a.taps = 1; a.w = &Hd.conv0[half];
+        a.out = h->head_p + (size_t)s0 * g.hw * g.hw * kHeadMid; a.out_cstride = kHeadMid; a.out_coff = 0; a.cout = kHeadMid;
+        a.out_stats = nullptr;
+        a.n = cnt;
+        SMG_TRY(conv_dispatch(h, a, st));
+    }
+    (void)n;
+    return launch_head_tail(h, h->head_p, n_rot, n_masks, Hd, dev_q, st);
+}
+
+__global__ void pack_head_conv1_kernel(const float* __restrict__ w, float* __restrict__ out, int n_out, int npix) {
+    // torch [n_out][64][npix] -> [n_out][npix][64]
+    const int total = n_out * 64 * npix;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i % 64, p = (i / 64) % npix, o = i / (64 * npix);
+        out[i] = w[((size_t)o * 64 + c) * npix + p];
+    }
+}
+
+__global__ void pack_conv0_kernel(const float* __restrict__ w, float* __restrict__ out) {
+    // torch [64][3][7][7] -> [147][64]
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 147 * 64) {
+        const int co = i % 64, k = i / 64;
+        out[i] = w[co * 147 + k];
+    }
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct ArenaPlanner {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        const size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    }
+};
+
+static void plan_conv(ArenaPlanner& p, ConvW& cw, int cin, int cout, int taps, uint8_t* base) {
+    cw.cin = cin; cw.cout = cout; cw.taps = taps;
+    const size_t o1 = p.take(conv_packed_bytes_ffma(cin, cout, taps));
+    const size_t o2 = p.take(conv_packed_bytes_umma(cin, cout, taps, 4));
+    const size_t o3 = p.take(conv_packed_bytes_umma(cin, cout, taps, 2));
+    if (base) {
+        cw.w_ffma = reinterpret_cast<float*>(base + o1);
+        cw.w_tf32 = base + o2;
+        cw.w_bf16 = base + o3;
+    }
+}
+static void plan_bn(ArenaPlanner& p, BnP& b, int c, uint8_t* base) {
+    b.c = c;
+    const size_t o1 = p.take((size_t)c * 4), o2 = p.take((size_t)c * 4);
+    if (base) {
+        b.gamma = reinterpret_cast<float*>(base + o1);
+        b.beta = reinterpret_cast<float*>(base + o2);
+    }
+}
+
+static size_t plan_trunk(smg_handle* h, TrunkW& T, uint8_t* base) {
+    ArenaPlanner p;
+    const size_t o = p.take(147 * 64 * 4);
+    if (base) T.conv0 = reinterpret_cast<float*>(base + o);
+    plan_bn(p, T.norm0, 64, base);
+    for (int b = 0; b < kNumBlocks; ++b) {
+        T.layers[b].resize(kBlockLayers[b]);
+        for (int l = 0; l < kBlockLayers[b]; ++l) {
+            DenseLayerW& L = T.layers[b][l];
+            const int cin = h->geom[b].c_in + l * kGrowth;
+            plan_bn(p, L.norm1, cin, base);
+            plan_conv(p, L.conv1, cin, kBottleneck, 1, base);
+            plan_bn(p, L.norm2, kBottleneck, base);
+            plan_conv(p, L.conv2, kBottleneck, kGrowth, 9, base);
+        }
+        if (b < kNumBlocks - 1) {
+            plan_bn(p, T.trans[b].norm, h->geom[b].c_tot, base);
+            plan_conv(p, T.trans[b].conv, h->geom[b].c_tot, h->geom[b].c_tot / 2, 1, base);
+        }
+    }
+    plan_bn(p, T.norm5, kFeatC, base);
+    return p.off;
+}
+
+}  // namespace smg
+
+using namespace smg;
+
+extern "C" {
+
+int smg_version(void) { return 100; }
+const char* smg_last_error(void) { return smg::get_error(); }
+
+int smg_create(int device, int max_samples, int H, smg_handle** out) {
+    SMG_CHECK(out != nullptr, SMG_ERR_INVALID, "smg_create: out is NULL");
+    SMG_CHECK(max_samples >= 1 && max_samples <= 4096, SMG_ERR_INVALID, "smg_create: max_samples %d", max_samples);
+    SMG_CHECK(H >= 64 && H % 32 == 0 && H <= 1024, SMG_ERR_INVALID, "smg_create: H=%d must be a multiple of 32 in [64,1024]", H);
+    int ndev = 0;
+    SMG_CUDA(cudaGetDeviceCount(&ndev));
+    SMG_CHECK(device >= 0 && device < ndev, SMG_ERR_INVALID, "smg_create: device %d of %d", device, ndev);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    SMG_CUDA(cudaGetDeviceProperties(&prop, device));
+    SMG_CHECK(prop.major == 10, SMG_ERR_UNSUPPORTED,
+              "smg_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    smg_handle* h = new smg_handle();
+    h->device = device;
+    h->max_samples = max_samples;
+    h->H = H;
+    h->num_sms = prop.multiProcessorCount;
+    int c = kInitFeatures, hw = H / 4;
+    for (int b = 0; b < kNumBlocks; ++b) {
+        h->geom[b].hw = hw;
+        h->geom[b].c_in = c;
+        h->geom[b].c_tot = c + kBlockLayers[b] * kGrowth;
+        c = h->geom[b].c_tot / 2;
+        hw /= 2;
+    }
+    const size_t S = max_samples;
+    // stats arena layout (double2 per sample)
+    size_t off = 0;
+    h->st_conv0 = off; off += 64;
+    for (int b = 0; b < kNumBlocks; ++b) { h->st_block[b] = off; off += h->geom[b].c_tot; }
+    h->st_bott = off; off += (size_t)58 * kBottleneck;
+    h->stats_doubles_per_sample = 2 * off;
+    h->stats_bytes = S * 2 * off * sizeof(double);
+
+    ArenaPlanner p;
+    const size_t o_in = p.take(S * 3 * H * H * 4);
+    const size_t o_c0 = p.take(S * (size_t)(H / 2) * (H / 2) * 64 * 4);
+    size_t o_blk[kNumBlocks];
+    for (int b = 0; b < kNumBlocks; ++b) o_blk[b] = p.take(S * (size_t)h->geom[b].hw * h->geom[b].hw * h->geom[b].c_tot * 4);
+    const size_t o_bott = p.take(S * (size_t)(H / 4) * (H / 4) * kBottleneck * 4);
+    const size_t o_stats = p.take(h->stats_bytes);
+    const size_t o_hs = p.take(S * kFeatC * 4), o_hh = p.take(S * kFeatC * 4);
+    const size_t o_hp = p.take(S * (size_t)h->geom[3].hw * h->geom[3].hw * kHeadMid * 4);
+    const size_t o_tmp = p.take((size_t)3 * H * H * 4);
+    uint8_t* base = nullptr;
+    cudaError_t e = cudaMalloc(&base, p.off);
+    if (e != cudaSuccess) {
+        set_error("smg_create: cudaMalloc(%zu bytes) failed: %s", p.off, cudaGetErrorString(e));
+        delete h;
+        return SMG_ERR_CUDA;
+    }
+    h->workspace_bytes = (int64_t)p.off;
+    h->input = reinterpret_cast<float*>(base + o_in);
+    h->conv0 = reinterpret_cast<float*>(base + o_c0);
+    for (int b = 0; b < kNumBlocks; ++b) h->block[b] = reinterpret_cast<float*>(base + o_blk[b]);
+    h->bott = reinterpret_cast<float*>(base + o_bott);
+    h->stats = reinterpret_cast<double*>(base + o_stats);
+    h->head_scale = reinterpret_cast<float*>(base + o_hs);
+    h->head_shift = reinterpret_cast<float*>(base + o_hh);
+    h->head_p = reinterpret_cast<float*>(base + o_hp);
+    h->scene_tmp = reinterpret_cast<float*>(base + o_tmp);
+    *out = h;
+    return SMG_OK;
+}
+
+int smg_destroy(smg_handle* h) {
+    if (!h) return SMG_OK;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    if (h->input) cudaFree(h->input);  // base of the workspace arena
+    for (int t = 0; t < SMG_NUM_TRUNKS; ++t)
+        if (h->trunks[t].arena) cudaFree(h->trunks[t].arena);
+    for (int t = 0; t < SMG_NUM_HEADS; ++t)
+        if (h->heads[t].arena) cudaFree(h->heads[t].arena);
+    delete h;
+    return SMG_OK;
+}
+
+int smg_set_precision(smg_handle* h, int precision) {
+    SMG_CHECK(h != nullptr, SMG_ERR_INVALID, "NULL handle");
+    SMG_CHECK(precision >= SMG_PREC_FP32 && precision <= SMG_PREC_BF16, SMG_ERR_INVALID, "precision %d", precision);
+    h->precision = precision;
+    return SMG_OK;
+}
+int smg_get_precision(smg_handle* h) { return h ? h->precision : SMG_ERR_INVALID; }
+int64_t smg_workspace_bytes(smg_handle* h) { return h ? h->workspace_bytes : 0; }
+int64_t smg_launch_count(smg_handle* h) { return h ? h->launches : 0; }
+
+int smg_set_trunk_weights(smg_handle* h, int trunk_id, const float* const* dev_params, int n, void* stream) {
+    SMG_CHECK(h != nullptr && dev_params != nullptr, SMG_ERR_INVALID, "NULL argument");
+    SMG_CHECK(trunk_id >= 0 && trunk_id < SMG_NUM_TRUNKS, SMG_ERR_INVALID, "trunk_id %d", trunk_id);
+    SMG_CHECK(n == SMG_TRUNK_NUM_PARAMS, SMG_ERR_INVALID, "expected %d trunk tensors, got %d", SMG_TRUNK_NUM_PARAMS, n);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    TrunkW& T = h->trunks[trunk_id];
+    if (!T.arena) {
+        T.arena_bytes = plan_trunk(h, T, nullptr);
+        SMG_CUDA(cudaMalloc(&T.arena, T.arena_bytes));
+        plan_trunk(h, T, reinterpret_cast<uint8_t*>(T.arena));
+    }
+    int i = 0;
+    auto copy_bn = [&](BnP& b) -> int {
+        SMG_CUDA(cudaMemcpyAsync(b.gamma, dev_params[i++], (size_t)b.c * 4, cudaMemcpyDeviceToDevice, st));
+        SMG_CUDA(cudaMemcpyAsync(b.beta, dev_params[i++], (size_t)b.c * 4, cudaMemcpyDeviceToDevice, st));
+        return SMG_OK;
+    };
+    pack_conv0_kernel<<<(147 * 64 + 255) / 256, 256, 0, st>>>(dev_params[i++], T.conv0);
+    h->launches++;
+    SMG_TRY(copy_bn(T.norm0));
+    for (int b = 0; b < kNumBlocks; ++b) {
+        for (int l = 0; l < kBlockLayers[b]; ++l) {
+            DenseLayerW& L = T.layers[b][l];
+            SMG_TRY(copy_bn(L.norm1));
+            SMG_TRY(pack_conv_weights(h, dev_params[i++], L.conv1, 0, L.conv1.cin, st));
+            SMG_TRY(copy_bn(L.norm2));
+            SMG_TRY(pack_conv_weights(h, dev_params[i++], L.conv2, 0, L.conv2.cin, st));
+        }
+        if (b < kNumBlocks - 1) {
+            SMG_TRY(copy_bn(T.trans[b].norm));
+            SMG_TRY(pack_conv_weights(h, dev_params[i++], T.trans[b].conv, 0, T.trans[b].conv.cin, st));
+        }
+    }
+    SMG_TRY(copy_bn(T.norm5));
+    SMG_CHECK(i == SMG_TRUNK_NUM_PARAMS, SMG_ERR_STATE, "consumed %d trunk tensors", i);
+    SMG_CUDA(cudaGetLastError());
+    T.set = true;
+    return SMG_OK;
+}
+
+int smg_set_head_weights(smg_handle* h, int head_id, const float* const* dev_params, int n_out, void* stream) {
+    SMG_CHECK(h != nullptr && dev_params != nullptr, SMG_ERR_INVALID, "NULL argument");
+    SMG_CHECK(head_id >= 0 && head_id < SMG_NUM_HEADS, SMG_ERR_INVALID, "head_id %d", head_id);
+    SMG_CHECK(n_out >= 1 && n_out <= 4, SMG_ERR_INVALID, "n_out %d", n_out);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    HeadW& Hd = h->heads[head_id];
+    const int npix = kHeadK * kHeadK;
+    if (!Hd.arena || Hd.n_out != n_out) {
+        if (Hd.arena) { cudaFree(Hd.arena); Hd.arena = nullptr; }
+        for (int pass = 0; pass < 2; ++pass) {
+            ArenaPlanner p;
+            uint8_t* base = reinterpret_cast<uint8_t*>(Hd.arena);
+            plan_bn(p, Hd.norm0, 2 * kFeatC, base);
+            plan_conv(p, Hd.conv0[0], kFeatC, kHeadMid, 1, base);
+            plan_conv(p, Hd.conv0[1], kFeatC, kHeadMid, 1, base);
+            plan_bn(p, Hd.norm1, kHeadMid, base);
+            const size_t o = p.take((size_t)n_out * npix * kHeadMid * 4);
+            if (base) Hd.conv1 = reinterpret_cast<float*>(base + o);
+            if (pass == 0) {
+                Hd.arena_bytes = p.off;
+                SMG_CUDA(cudaMalloc(&Hd.arena, Hd.arena_bytes));
+            }
+        }
+        Hd.n_out = n_out;
+    }
+    SMG_CUDA(cudaMemcpyAsync(Hd.norm0.gamma, dev_params[0], 2 * kFeatC * 4, cudaMemcpyDeviceToDevice, st));
+    SMG_CUDA(cudaMemcpyAsync(Hd.norm0.beta, dev_params[1], 2 * kFeatC * 4, cudaMemcpyDeviceToDevice, st));
+    SMG_TRY(pack_conv_weights(h, dev_params[2], Hd.conv0[0], 0, 2 * kFeatC, st));
+    SMG_TRY(pack_conv_weights(h, dev_params[2], Hd.conv0[1], kFeatC, 2 * kFeatC, st));
+    SMG_CUDA(cudaMemcpyAsync(Hd.norm1.gamma, dev_params[3], kHeadMid * 4, cudaMemcpyDeviceToDevice, st));
+    SMG_CUDA(cudaMemcpyAsync(Hd.norm1.beta, dev_params[4], kHeadMid * 4, cudaMemcpyDeviceToDevice, st));
+    pack_head_conv1_kernel<<<64, 256, 0, st>>>(dev_params[5], Hd.conv1, n_out, npix);
+    h->launches++;
+    SMG_CUDA(cudaGetLastError());
+    Hd.set = true;
+    return SMG_OK;
+}
+
+int smg_prep(smg_handle* h, const double* dev_heightmaps, int n, int hm_size, double mean, double stddev,
+             float* dev_out, void* stream) {
+    SMG_CHECK(h && dev_heightmaps && dev_out && n >= 1, SMG_ERR_INVALID, "smg_prep: bad argument");
+    SMG_CHECK(stddev != 0.0, SMG_ERR_INVALID, "smg_prep: stddev is 0 (the reference's published literal gives NaN)");
+    DeviceGuard guard(h->device);
+    return launch_prep(h, dev_heightmaps, n, hm_size, mean, stddev, dev_out, (cudaStream_t)stream);
+}
+
+int smg_rotate(smg_handle* h, const float* dev_in, const int* host_rot_idx, int n_rot, int num_rotations,
+               float* dev_out, void* stream) {
+    SMG_CHECK(h && dev_in && dev_out && host_rot_idx && n_rot >= 1 && num_rotations >= 1, SMG_ERR_INVALID,
+              "smg_rotate: bad argument");
+    DeviceGuard guard(h->device);
+    return launch_rotate(h, dev_in, host_rot_idx, n_rot, num_rotations, dev_out, (cudaStream_t)stream);
+}
+
+int smg_rotate_index_map(smg_handle* h, int rot_idx, int num_rotations, int32_t* dev_out, void* stream) {
+    SMG_CHECK(h && dev_out && num_rotations >= 1, SMG_ERR_INVALID, "smg_rotate_index_map: bad argument");
+    DeviceGuard guard(h->device);
+    return launch_rotate_index_map(h, rot_idx, num_rotations, dev_out, (cudaStream_t)stream);
+}
+
+int smg_trunk_forward(smg_handle* h, int trunk_id, const float* dev_in, int n, float* dev_feat, float* dev_bn_mean,
+                      float* dev_bn_var, void* stream) {
+    SMG_CHECK(h && dev_in, SMG_ERR_INVALID, "smg_trunk_forward: bad argument");
+    SMG_CHECK(trunk_id >= 0 && trunk_id < SMG_NUM_TRUNKS, SMG_ERR_INVALID, "trunk_id %d", trunk_id);
+    SMG_CHECK(n >= 1 && n <= h->max_samples, SMG_ERR_INVALID, "n=%d outside [1,%d]", n, h->max_samples);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    SMG_CUDA(cudaMemcpyAsync(h->input, dev_in, (size_t)n * 3 * h->H * h->H * 4, cudaMemcpyDeviceToDevice, st));
+    SMG_TRY(trunk_forward(h, trunk_id, n, st));
+    if (dev_feat)
+        SMG_TRY(launch_norm5_export(h, n, h->block[3], stats_ptr(h, h->st_block[3]), h->geom[3].c_tot,
+                                    h->trunks[trunk_id].norm5, dev_feat, st));
+    if (dev_bn_mean && dev_bn_var) SMG_TRY(export_bn_stats(h, n, dev_bn_mean, dev_bn_var, st));
+    return SMG_OK;
+}
+
+static int qforward_common(smg_handle* h, int trunk_id, int head_id, int n_masks, int n_rot, float* dev_q,
+                           float* dev_bn_mean, float* dev_bn_var, cudaStream_t st) {
+    SMG_TRY(trunk_forward(h, trunk_id, n_rot + n_masks, st));
+    SMG_TRY(heads_forward(h, trunk_id, head_id, n_rot, n_masks, dev_q, st));
+    if (dev_bn_mean && dev_bn_var) SMG_TRY(export_bn_stats(h, n_rot + n_masks, dev_bn_mean, dev_bn_var, st));
+    return SMG_OK;
+}
+
+int smg_qforward(smg_handle* h, int trunk_id, int head_id, const float* dev_scene, const float* dev_masks,
+                 int n_masks, const int* host_rot_idx, int n_rot, int num_rotations, float* dev_q, float* dev_bn_mean,
+                 float* dev_bn_var, void* stream) {
+    SMG_CHECK(h && dev_scene && dev_masks && host_rot_idx && dev_q, SMG_ERR_INVALID, "smg_qforward: NULL argument");
+    SMG_CHECK(trunk_id >= 0 && trunk_id < SMG_NUM_TRUNKS && head_id >= 0 && head_id < SMG_NUM_HEADS, SMG_ERR_INVALID,
+              "smg_qforward: trunk %d / head %d", trunk_id, head_id);
+    SMG_CHECK(n_masks >= 1 && n_rot >= 1 && n_masks + n_rot <= h->max_samples, SMG_ERR_INVALID,
+              "smg_qforward: %d rotations + %d masks exceed max_samples %d", n_rot, n_masks, h->max_samples);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t img = (size_t)3 * h->H * h->H;
+    SMG_TRY(launch_rotate(h, dev_scene, host_rot_idx, n_rot, num_rotations, h->input, st));
+    SMG_CUDA(cudaMemcpyAsync(h->input + (size_t)n_rot * img, dev_masks, (size_t)n_masks * img * 4, cudaMemcpyDeviceToDevice, st));
+    return qforward_common(h, trunk_id, head_id, n_masks, n_rot, dev_q, dev_bn_mean, dev_bn_var, st);
+}
+
+int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm, const double* dev_mask_hms,
+                      int n_masks, int hm_size, double mean, double stddev, const int* host_rot_idx, int n_rot,
+                      int num_rotations, float* dev_q, void* stream) {
+    SMG_CHECK(h && dev_scene_hm && dev_mask_hms && host_rot_idx && dev_q, SMG_ERR_INVALID, "smg_qforward_maps: NULL argument");
+    SMG_CHECK(trunk_id >= 0 && trunk_id < SMG_NUM_TRUNKS && head_id >= 0 && head_id < SMG_NUM_HEADS, SMG_ERR_INVALID,
+              "smg_qforward_maps: trunk %d / head %d", trunk_id, head_id);
+    SMG_CHECK(n_masks >= 1 && n_rot >= 1 && n_masks + n_rot <= h->max_samples, SMG_ERR_INVALID,
+              "smg_qforward_maps: %d rotations + %d masks exceed max_samples %d", n_rot, n_masks, h->max_samples);
+    SMG_CHECK(stddev != 0.0, SMG_ERR_INVALID, "smg_qforward_maps: stddev is 0");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t img = (size_t)3 * h->H * h->H;
+    SMG_TRY(launch_prep(h, dev_scene_hm, 1, hm_size, mean, stddev, h->scene_tmp, st));
+    SMG_TRY(launch_rotate(h, h->scene_tmp, host_rot_idx, n_rot, num_rotations, h->input, st));
+    SMG_TRY(launch_prep(h, dev_mask_hms, n_masks, hm_size, mean, stddev, h->input + (size_t)n_rot * img, st));
+    return qforward_common(h, trunk_id, head_id, n_masks, n_rot, dev_q, nullptr, nullptr, st);
+}
+
+int smg_qforward_train(smg_handle*, int, int, const float*, const float*, int, int, float*, float*, float*, void*) {
+    set_error("smg_qforward_train: the backward path is not built yet");
+    return SMG_ERR_UNSUPPORTED;
+}
+int smg_qbackward(smg_handle*, const float*, float* const*, float* const*, void*) {
+    set_error("smg_qbackward: the backward path is not built yet");
+    return SMG_ERR_UNSUPPORTED;
+}
+int smg_adam_step(smg_handle*, float* const*, const float* const*, float* const*, float* const*, const int64_t*, int,
+                  int, float, float, float, float, void*) {
+    set_error("smg_adam_step: not built yet");
+    return SMG_ERR_UNSUPPORTED;
+}
+
+int smg_argmax(smg_handle* h, const float* dev_q, int n, float* dev_out, int32_t* dev_out_idx, void* stream) {
+    SMG_CHECK(h && dev_q && dev_out && dev_out_idx, SMG_ERR_INVALID, "smg_argmax: NULL argument");
+    DeviceGuard guard(h->device);
+    return launch_argmax(h, dev_q, n, dev_out, dev_out_idx, (cudaStream_t)stream);
+}
+
+int smg_heightmap(smg_handle* h, const double* dev_depth, const double* host_K, const double* host_pose,
+                  double* dev_out224, double* dev_out448, double* host_A_htor, void* stream) {
+    SMG_CHECK(h && dev_depth && host_K && host_pose && dev_out224 && dev_out448, SMG_ERR_INVALID, "smg_heightmap: NULL argument");
+    DeviceGuard guard(h->device);
+    return launch_heightmap(h, dev_depth, host_K, host_pose, dev_out224, dev_out448, host_A_htor, (cudaStream_t)stream);
+}
+
+int smg_nms(smg_handle* h, const float* dev_boxes, int n, float co_thresh, float min_area, float max_area,
+            int32_t* dev_keep, int32_t* dev_n_keep, void* stream) {
+    SMG_CHECK(h && dev_keep && dev_n_keep && (dev_boxes || n == 0), SMG_ERR_INVALID, "smg_nms: NULL argument");
+    DeviceGuard guard(h->device);
+    return launch_nms(h, dev_boxes, n, co_thresh, min_area, max_area, dev_keep, dev_n_keep, (cudaStream_t)stream);
+}
+
+int smg_debug_read(smg_handle* h, const char* what, int sample, float* dev_out_nchw, int64_t capacity_floats,
+                   void* stream) {
+    SMG_CHECK(h && what && dev_out_nchw, SMG_ERR_INVALID, "smg_debug_read: NULL argument");
+    SMG_CHECK(sample >= 0 && sample < h->last_n, SMG_ERR_INVALID, "smg_debug_read: sample %d of %d", sample, h->last_n);
+    DeviceGuard guard(h->device);
+    const float* src = nullptr;
+    int hw = 0, c = 0, cstride = 0;
+    if (!strcmp(what, "conv0")) {
+        hw = h->H / 2; c = 64; cstride = 64; src = h->conv0;
+    } else if (!strcmp(what, "pool0")) {
+        hw = h->geom[0].hw; c = 64; cstride = h->geom[0].c_tot; src = h->block[0];
+    } else if (!strncmp(what, "block", 5) && what[5] >= '1' && what[5] <= '4') {
+        const int b = what[5] - '1';
+        hw = h->geom[b].hw; c = h->geom[b].c_tot; cstride = c; src = h->block[b];
+    } else if (!strncmp(what, "trans", 5) && what[5] >= '1' && what[5] <= '3') {
+        const int b = what[5] - '1' + 1;
+        hw = h->geom[b].hw; c = h->geom[b].c_in; cstride = h->geom[b].c_tot; src = h->block[b];
+    } else if (!strcmp(what, "bott")) {
+        hw = h->geom[3].hw; c = kBottleneck; cstride = kBottleneck; src = h->bott;
+    } else {
+        set_error("smg_debug_read: unknown activation '%s'", what);
+        return SMG_ERR_INVALID;
+    }
+    SMG_CHECK((int64_t)hw * hw * c <= capacity_floats, SMG_ERR_INVALID, "smg_debug_read: need %lld floats",
+              (long long)hw * hw * c);
+    src += (size_t)sample * hw * hw * cstride;
+    return launch_nhwc_to_nchw(h, src, hw, c, cstride, dev_out_nchw, (cudaStream_t)stream);
+}
+
+}  // extern "C"

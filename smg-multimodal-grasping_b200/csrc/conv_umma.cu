@@ -1,0 +1,598 @@
+// conv_umma.cu - tensor-core implicit-GEMM convolution for sm_100a (tcgen05 + TMEM + bulk TMA).
+//
+// Same contract as conv_ffma.cu (BN-ReLU prologue, optional 2x2 avg-pool prologue, 1x1 or
+// 3x3 taps, raw output + (sum,sumsq) epilogue) with operands rounded to tf32 or bf16 and
+// fp32 accumulation in tensor memory.  Serves torchvision densenet `_DenseLayer.conv1/conv2`,
+// `_Transition.conv` and the head's 1x1 conv (/root/reference/code/models.py:319,384-387).
+//
+// CTA = one 128-pixel output tile x BN output channels, 10 warps:
+//   warps 0-3  A producers: global (NHWC fp32, pre-BN) -> registers -> relu(x*scale+shift) ->
+//              tf32/bf16 -> shared memory in the UMMA no-swizzle K-major layout
+//              [16-byte K chunk][row][16 B]  (core matrix = 8 rows x 16 B contiguous, SBO = 128 B,
+//              LBO = padded row count x 16 B).  A row shift of s pixels is a start-address
+//              offset of 16*s bytes, which is what makes the 3x3 taps free: the activation patch
+//              (tile + halo) is transformed ONCE and the 9 taps are 9 shifted descriptors.
+//   warps 4-7  epilogue: tcgen05.ld accumulator -> shared staging -> coalesced NHWC stores into the
+//              layer's channel slice + per-channel (sum, sumsq) -> double atomics.
+//   warp 8     MMA issuer (one lane): tcgen05.mma kind::tf32 / kind::f16, M=128, N=BN, D in TMEM;
+//              tcgen05.commit releases shared-memory stages and finally signals the epilogue.
+//   warp 9     weight loader (one lane): cp.async.bulk (TMA bulk copy, mbarrier complete_tx) of
+//              pre-packed weight stage images (pack.cu writes them in the exact smem layout).
+#include "smg_internal.cuh"
+
+namespace smg {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+template <int ELT>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    if (ELT == 4) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    }
+}
+// 32 lanes x 32 columns of 32-bit accumulators -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, no swizzle, K-major: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+struct UmmaDev {
+    const float* in;
+    int in_cstride, cin, hin;
+    int prologue_mode;
+    const double* in_stats;
+    int in_stats_stride;
+    const float* gamma;
+    const float* beta;
+    const float* scale;
+    const float* shift;
+    int relu;
+    const uint8_t* w;  // packed stage images
+    float* out;
+    int out_cstride, out_coff, cout;
+    double* out_stats;
+    int out_stats_stride;
+    int hout;
+    // 3x3 patch tiling
+    int wp, ht, tiles_x;
+};
+
+constexpr int UM = 128;         // rows per tile (UMMA M)
+constexpr int KC = 32;          // channels per K group
+constexpr int NA = 3;           // A stages (1x1)
+constexpr int NB1 = 3;          // B stages (1x1)
+constexpr int NB9 = 6;          // B stages (3x3)
+constexpr int MAX_WP = 42;
+constexpr int PATCH_ROWS = UM + 2 * MAX_WP + 2;  // 214
+
+template <int ELT> struct EltCfg;
+template <> struct EltCfg<4> {
+    static constexpr int CH = 8;          // 16-byte chunks per 32-channel group
+    static constexpr int EPC = 4;         // elements per chunk
+    static constexpr int A_ROWS = 129;    // padded rows: (rows mod 8) == 1 -> conflict-free 16 B stores
+    static constexpr int P_ROWS = 215;
+    static constexpr uint32_t FMT = 2;    // TF32
+};
+template <> struct EltCfg<2> {
+    static constexpr int CH = 4;
+    static constexpr int EPC = 8;
+    static constexpr int A_ROWS = 130;    // (rows mod 8) == 2
+    static constexpr int P_ROWS = 218;
+    static constexpr uint32_t FMT = 1;    // BF16
+};
+
+template <int ELT, int BN, int TAPS>
+struct SmemPlan {
+    using E = EltCfg<ELT>;
+    static constexpr int A_LBO = (TAPS == 9 ? E::P_ROWS : E::A_ROWS) * 16;
+    static constexpr int A_SLOT = E::CH * A_LBO;                      // one 32-channel group
+    static constexpr int A_SLOTS = TAPS == 9 ? 4 : NA;
+    static constexpr int B_STAGE = E::CH * BN * 16;
+    static constexpr int B_SLOTS = TAPS == 9 ? NB9 : NB1;
+    static constexpr int OFF_BAR = 0;
+    static constexpr int OFF_SC = 256;
+    static constexpr int OFF_A = OFF_SC + 2 * 1024 * 4;
+    static constexpr int OFF_B = OFF_A + A_SLOTS * A_SLOT;
+    static constexpr int STAGING = UM * (BN + 1) * 4;
+    static constexpr int END_AB = OFF_B + B_SLOTS * B_STAGE;
+    static constexpr int TOTAL = (OFF_A + STAGING > END_AB ? OFF_A + STAGING : END_AB);
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int ELT, int BN, int TAPS, int POOL>
+__global__ void __launch_bounds__(320, 1)
+conv_umma_kernel(UmmaDev a) {
+    using E = EltCfg<ELT>;
+    using P = SmemPlan<ELT, BN, TAPS>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
+    uint64_t* a_full = bars;            // [4]
+    uint64_t* a_empty = bars + 4;       // [4]
+    uint64_t* b_full = bars + 8;        // [8]
+    uint64_t* b_empty = bars + 16;      // [8]
+    uint64_t* tmem_full = bars + 24;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 25);
+    float* s_sc = reinterpret_cast<float*>(smem + P::OFF_SC);
+    float* s_sh = s_sc + 1024;
+    uint8_t* sA = smem + P::OFF_A;
+    uint8_t* sB = smem + P::OFF_B;
+    float* s_out = reinterpret_cast<float*>(smem + P::OFF_A);  // staging aliases the operand stages
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int s = blockIdx.z;
+    const int ntile = blockIdx.y;
+    const int hout = a.hout, hin = a.hin;
+    const int hw_out = hout * hout;
+    const int KG = a.cin / KC;
+
+    // tile origin
+    int m0 = 0, h0 = 0, w0 = 0;
+    if (TAPS == 9) {
+        const int ty = blockIdx.x / a.tiles_x, tx = blockIdx.x - ty * a.tiles_x;
+        h0 = ty * a.ht;
+        w0 = tx * (a.wp - 2);
+    } else {
+        m0 = blockIdx.x * UM;
+    }
+
+    // ---- one-time setup
+    if (warp == 8 && lane == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_ptr, BN);
+    // BN prologue parameters of this sample
+    if (a.prologue_mode == 0) {
+        const double cnt = (double)hin * hin;
+        for (int c = tid; c < a.cin; c += 320) {
+            const double* st = a.in_stats + 2 * ((size_t)s * a.in_stats_stride + c);
+            const double m = st[0] / cnt;
+            double var = st[1] / cnt - m * m;
+            if (var < 0) var = 0;
+            const float sc = a.gamma[c] * (float)(1.0 / sqrt(var + (double)kBnEps));
+            s_sc[c] = sc;
+            s_sh[c] = a.beta[c] - (float)m * sc;
+        }
+    } else {
+        for (int c = tid; c < a.cin; c += 320) {
+            s_sc[c] = a.scale[(size_t)s * a.cin + c];
+            s_sh[c] = a.shift[(size_t)s * a.cin + c];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const float* inp = a.in + (size_t)s * hin * hin * a.in_cstride;
+
+    if (warp < 4) {
+        // =============================== A producers ===============================
+        const int c = tid % E::CH;            // chunk within the 32-channel group
+        const int r0 = tid / E::CH;           // first row handled by this thread
+        constexpr int RSTEP = 128 / E::CH;    // row stride between iterations
+        if (TAPS == 1) {
+            constexpr int RI = UM / RSTEP;    // rows per thread per stage
+            // per-row input offsets (in floats, relative to inp), -1 = row beyond the sample
+            int roff[RI];
+#pragma unroll
+            for (int i = 0; i < RI; ++i) {
+                const int m = m0 + r0 + i * RSTEP;
+                if (m < hw_out) {
+                    if (POOL) {
+                        const int oy = m / hout, ox = m - oy * hout;
+                        roff[i] = ((2 * oy) * hin + 2 * ox) * a.in_cstride;
+                    } else {
+                        roff[i] = m * a.in_cstride;
+                    }
+                } else {
+                    roff[i] = -1;
+                }
+            }
+            for (int kg = 0; kg < KG; ++kg) {
+                const int slot = kg % NA;
+                const uint32_t ph = (kg / NA) & 1;
+                mbar_wait(&a_empty[slot], ph ^ 1);
+                const int ch0 = kg * KC + c * E::EPC;
+                float sc[E::EPC], sh[E::EPC];
+#pragma unroll
+                for (int e = 0; e < E::EPC; ++e) { sc[e] = s_sc[ch0 + e]; sh[e] = s_sh[ch0 + e]; }
+                uint8_t* dst = sA + slot * P::A_SLOT + c * P::A_LBO;
+                float v[RI][E::EPC];
+#pragma unroll
+                for (int i = 0; i < RI; ++i) {
+                    if (roff[i] >= 0) {
+                        const float* src = inp + roff[i] + ch0;
+                        if (POOL) {
+#pragma unroll
+                            for (int e = 0; e < E::EPC; ++e) v[i][e] = 0.f;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float* sq = src + ((q >> 1) * hin + (q & 1)) * a.in_cstride;
+#pragma unroll
+                                for (int e4 = 0; e4 < E::EPC / 4; ++e4) {
+                                    const float4 x = __ldg(reinterpret_cast<const float4*>(sq) + e4);
+                                    float t0 = fmaf(x.x, sc[4 * e4 + 0], sh[4 * e4 + 0]);
+                                    float t1 = fmaf(x.y, sc[4 * e4 + 1], sh[4 * e4 + 1]);
+                                    float t2 = fmaf(x.z, sc[4 * e4 + 2], sh[4 * e4 + 2]);
+                                    float t3 = fmaf(x.w, sc[4 * e4 + 3], sh[4 * e4 + 3]);
+                                    if (a.relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); t2 = fmaxf(t2, 0.f); t3 = fmaxf(t3, 0.f); }
+                                    v[i][4 * e4 + 0] += t0; v[i][4 * e4 + 1] += t1;
+                                    v[i][4 * e4 + 2] += t2; v[i][4 * e4 + 3] += t3;
+                                }
+                            }
+#pragma unroll
+                            for (int e = 0; e < E::EPC; ++e) v[i][e] *= 0.25f;
+                        } else {
+#pragma unroll
+                            for (int e4 = 0; e4 < E::EPC / 4; ++e4) {
+                                const float4 x = __ldg(reinterpret_cast<const float4*>(src) + e4);
+                                v[i][4 * e4 + 0] = x.x; v[i][4 * e4 + 1] = x.y;
+                                v[i][4 * e4 + 2] = x.z; v[i][4 * e4 + 3] = x.w;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < E::EPC; ++e) v[i][e] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < RI; ++i) {
+                    if (!POOL && roff[i] >= 0) {
+#pragma unroll
+                        for (int e = 0; e < E::EPC; ++e) {
+                            float t = fmaf(v[i][e], sc[e], sh[e]);
+                            v[i][e] = a.relu ? fmaxf(t, 0.f) : t;
+                        }
+                    }
+                    uint4 pk;
+                    if (ELT == 4) {
+                        pk = make_uint4(__float_as_uint(v[i][0]), __float_as_uint(v[i][1]), __float_as_uint(v[i][2]),
+                                        __float_as_uint(v[i][3]));
+                    } else {
+                        pk = make_uint4(pack_bf16x2(v[i][0], v[i][1]), pack_bf16x2(v[i][2], v[i][3]),
+                                        pack_bf16x2(v[i][4 % E::EPC], v[i][5 % E::EPC]),
+                                        pack_bf16x2(v[i][6 % E::EPC], v[i][7 % E::EPC]));
+                    }
+                    *reinterpret_cast<uint4*>(dst + (r0 + i * RSTEP) * 16) = pk;
+                }
+                fence_proxy_async();
+                mbar_arrive(&a_full[slot]);
+            }
+        } else {
+            // 3x3: fill the (ht+2) x wp activation patch once per 32-channel group
+            const int wp = a.wp;
+            const int pfill = (a.ht + 2) * wp;
+            for (int g = 0; g < 4; ++g) {
+                const int ch0 = g * KC + c * E::EPC;
+                float sc[E::EPC], sh[E::EPC];
+#pragma unroll
+                for (int e = 0; e < E::EPC; ++e) { sc[e] = s_sc[ch0 + e]; sh[e] = s_sh[ch0 + e]; }
+                uint8_t* dst = sA + g * P::A_SLOT + c * P::A_LBO;
+#pragma unroll 4
+                for (int q = r0; q < pfill; q += RSTEP) {
+                    const int py = q / wp, px = q - py * wp;
+                    const int y = h0 - 1 + py, x = w0 - 1 + px;
+                    float v[E::EPC];
+                    if (y >= 0 && y < hin && x >= 0 && x < hin) {
+                        const float* src = inp + ((size_t)y * hin + x) * a.in_cstride + ch0;
+#pragma unroll
+                        for (int e4 = 0; e4 < E::EPC / 4; ++e4) {
+                            const float4 xv = __ldg(reinterpret_cast<const float4*>(src) + e4);
+                            v[4 * e4 + 0] = xv.x; v[4 * e4 + 1] = xv.y; v[4 * e4 + 2] = xv.z; v[4 * e4 + 3] = xv.w;
+                        }
+#pragma unroll
+                        for (int e = 0; e < E::EPC; ++e) {
+                            float t = fmaf(v[e], sc[e], sh[e]);
+                            v[e] = a.relu ? fmaxf(t, 0.f) : t;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < E::EPC; ++e) v[e] = 0.f;  // conv zero padding (post-activation)
+                    }
+                    uint4 pk;
+                    if (ELT == 4) {
+                        pk = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                                        __float_as_uint(v[3]));
+                    } else {
+                        pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                        pack_bf16x2(v[4 % E::EPC], v[5 % E::EPC]), pack_bf16x2(v[6 % E::EPC], v[7 % E::EPC]));
+                    }
+                    *reinterpret_cast<uint4*>(dst + q * 16) = pk;
+                }
+                fence_proxy_async();
+                mbar_arrive(&a_full[g]);
+            }
+        }
+    } else if (warp == 9) {
+        // =============================== weight loader ===============================
+        if (lane == 0) {
+            const int nstages = TAPS == 9 ? 36 : KG;
+            const uint8_t* wsrc = a.w + (size_t)ntile * nstages * P::B_STAGE;
+            for (int j = 0; j < nstages; ++j) {
+                const int slot = j % P::B_SLOTS;
+                const uint32_t ph = (j / P::B_SLOTS) & 1;
+                mbar_wait(&b_empty[slot], ph ^ 1);
+                mbar_arrive_expect_tx(&b_full[slot], P::B_STAGE);
+                tma_bulk_load(sB + slot * P::B_STAGE, wsrc + (size_t)j * P::B_STAGE, P::B_STAGE, &b_full[slot]);
+            }
+        }
+    } else if (warp == 8) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (E::FMT << 7) | (E::FMT << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                       ((uint32_t)(UM >> 4) << 24);
+            constexpr int MMAS = E::CH / 2;  // instructions per 32-channel group (2 chunks = 32 B of K each)
+            const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+            uint32_t accum = 0;
+            if (TAPS == 1) {
+                for (int kg = 0; kg < KG; ++kg) {
+                    const int sa = kg % NA, sb = kg % NB1;
+                    mbar_wait(&a_full[sa], (kg / NA) & 1);
+                    mbar_wait(&b_full[sb], (kg / NB1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < MMAS; ++k) {
+                        const uint64_t ad = make_desc(sA_u + sa * P::A_SLOT + 2 * k * P::A_LBO, P::A_LBO, 128);
+                        const uint64_t bd = make_desc(sB_u + sb * P::B_STAGE + 2 * k * BN * 16, BN * 16, 128);
+                        umma<ELT>(tmem_base, ad, bd, idesc, accum);
+                        accum = 1;
+                    }
+                    umma_commit(&a_empty[sa]);
+                    umma_commit(&b_empty[sb]);
+                }
+            } else {
+                for (int g = 0; g < 4; ++g) {
+                    mbar_wait(&a_full[g], 0);
+                    for (int t = 0; t < 9; ++t) {
+                        const int j = g * 9 + t;
+                        const int sb = j % NB9;
+                        mbar_wait(&b_full[sb], (j / NB9) & 1);
+                        tc_fence_after();
+                        const int shift = (t / 3) * a.wp + (t % 3);
+#pragma unroll
+                        for (int k = 0; k < MMAS; ++k) {
+                            const uint64_t ad =
+                                make_desc(sA_u + g * P::A_SLOT + 2 * k * P::A_LBO + shift * 16, P::A_LBO, 128);
+                            const uint64_t bd = make_desc(sB_u + sb * P::B_STAGE + 2 * k * BN * 16, BN * 16, 128);
+                            umma<ELT>(tmem_base, ad, bd, idesc, accum);
+                            accum = 1;
+                        }
+                        umma_commit(&b_empty[sb]);
+                    }
+                }
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        // =============================== epilogue (warps 4-7) ===============================
+        const int e = warp - 4;              // TMEM lane partition of this warp
+        const int row = e * 32 + lane;       // accumulator row == tile row
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        bool valid;
+        if (TAPS == 9) {
+            const int i = row / a.wp, j = row - i * a.wp;
+            valid = i < a.ht && j < a.wp - 2 && h0 + i < hout && w0 + j < hout;
+        } else {
+            valid = m0 + row < hw_out;
+        }
+#pragma unroll
+        for (int cb = 0; cb < BN; cb += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + cb, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s_out[row * (BN + 1) + cb + i] = valid ? v[i] : 0.f;
+        }
+        tc_fence_before();
+        // sync the 4 epilogue warps only
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // coalesced stores: warp e handles rows e, e+4, ...
+        for (int r = e; r < UM; r += 4) {
+            int pix;
+            bool ok;
+            if (TAPS == 9) {
+                const int i = r / a.wp, j = r - i * a.wp;
+                ok = i < a.ht && j < a.wp - 2 && h0 + i < hout && w0 + j < hout;
+                pix = (h0 + i) * hout + w0 + j;
+            } else {
+                ok = m0 + r < hw_out;
+                pix = m0 + r;
+            }
+            if (!ok) continue;
+            float* o = a.out + ((size_t)s * hw_out + pix) * a.out_cstride + a.out_coff + ntile * BN;
+#pragma unroll
+            for (int cb = 0; cb < BN; cb += 32) o[cb + lane] = s_out[r * (BN + 1) + cb + lane];
+        }
+        // per-channel statistics of this tile (invalid rows were staged as zeros)
+        if (a.out_stats != nullptr) {
+            const int t = tid - 128;
+            constexpr int GROUPS = 128 / BN;       // row groups
+            constexpr int RPG = UM / GROUPS;       // rows per group
+            const int cidx = t % BN, g = t / BN;
+            float su = 0.f, sq = 0.f;
+            for (int r = g * RPG; r < (g + 1) * RPG; ++r) {
+                const float x = s_out[r * (BN + 1) + cidx];
+                su += x;
+                sq = fmaf(x, x, sq);
+            }
+            double* st = a.out_stats + 2 * ((size_t)s * a.out_stats_stride + a.out_coff + ntile * BN + cidx);
+            atomicAdd(st, (double)su);
+            atomicAdd(st + 1, (double)sq);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+void umma_patch_geometry(int hw, int* wp, int* ht) {
+    // patch width wp = tile width + 2 halo columns; ht*wp <= 128 output rows per MMA tile
+    if (hw + 2 <= MAX_WP) {
+        *wp = hw + 2;
+    } else {
+        // split the row into equal column tiles of at most MAX_WP-2 pixels
+        const int nt = (hw + (MAX_WP - 2) - 1) / (MAX_WP - 2);
+        const int wt = (hw + nt - 1) / nt;
+        *wp = wt + 2;
+    }
+    *ht = UM / *wp;
+    if (*ht > hw) *ht = hw;
+}
+
+template <int ELT, int BN, int TAPS, int POOL>
+static int launch_umma(smg_handle* h, const UmmaDev& d, int n, cudaStream_t st) {
+    using P = SmemPlan<ELT, BN, TAPS>;
+    static bool attr = false;
+    if (!attr) {
+        SMG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<ELT, BN, TAPS, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      P::TOTAL));
+        attr = true;
+    }
+    dim3 grid;
+    if (TAPS == 9) {
+        const int wt = d.wp - 2;
+        const int tx = (d.hout + wt - 1) / wt, ty = (d.hout + d.ht - 1) / d.ht;
+        grid = dim3(tx * ty, 1, n);
+    } else {
+        grid = dim3((d.hout * d.hout + UM - 1) / UM, d.cout / BN, n);
+    }
+    conv_umma_kernel<ELT, BN, TAPS, POOL><<<grid, 320, P::TOTAL, st>>>(d);
+    h->launches++;
+    SMG_CUDA(cudaGetLastError());
+    return SMG_OK;
+}
+
+template <int ELT>
+static int dispatch(smg_handle* h, const ConvArgs& a, UmmaDev& d, cudaStream_t st) {
+    d.w = ELT == 4 ? a.w->w_tf32 : a.w->w_bf16;
+    SMG_CHECK(d.w != nullptr, SMG_ERR_STATE, "conv_umma: weights not packed");
+    if (a.taps == 9) {
+        SMG_CHECK(a.cin == 128 && a.cout == 32 && !a.pool, SMG_ERR_UNSUPPORTED, "conv_umma: 3x3 expects 128->32");
+        umma_patch_geometry(d.hout, &d.wp, &d.ht);
+        const int wt = d.wp - 2;
+        d.tiles_x = (d.hout + wt - 1) / wt;
+        return launch_umma<ELT, 32, 9, 0>(h, d, a.n, st);
+    }
+    SMG_CHECK(a.cin % KC == 0 && a.cin <= 1024, SMG_ERR_UNSUPPORTED, "conv_umma: cin %d unsupported", a.cin);
+    if (a.cout == 64) {
+        SMG_CHECK(!a.pool, SMG_ERR_UNSUPPORTED, "conv_umma: pooled N=64 not built");
+        return launch_umma<ELT, 64, 1, 0>(h, d, a.n, st);
+    }
+    SMG_CHECK(a.cout % 128 == 0, SMG_ERR_UNSUPPORTED, "conv_umma: cout %d unsupported", a.cout);
+    if (a.pool) return launch_umma<ELT, 128, 1, 1>(h, d, a.n, st);
+    return launch_umma<ELT, 128, 1, 0>(h, d, a.n, st);
+}
+
+int launch_conv_umma(smg_handle* h, const ConvArgs& a, int precision, cudaStream_t st) {
+    SMG_CHECK(a.w != nullptr, SMG_ERR_STATE, "conv_umma: no weights");
+    UmmaDev d;
+    d.in = a.in; d.in_cstride = a.in_cstride; d.cin = a.cin; d.hin = a.hin;
+    d.prologue_mode = a.prologue_mode; d.in_stats = a.in_stats; d.in_stats_stride = a.in_stats_stride;
+    d.gamma = a.gamma; d.beta = a.beta; d.scale = a.scale; d.shift = a.shift; d.relu = a.relu;
+    d.out = a.out; d.out_cstride = a.out_cstride; d.out_coff = a.out_coff; d.cout = a.cout;
+    d.out_stats = a.out_stats; d.out_stats_stride = a.out_stats_stride;
+    d.hout = a.pool ? a.hin / 2 : a.hin;
+    d.wp = d.ht = d.tiles_x = 0;
+    if (precision == SMG_PREC_TF32) return dispatch<4>(h, a, d, st);
+    if (precision == SMG_PREC_BF16) return dispatch<2>(h, a, d, st);
+    set_error("conv_umma: precision %d is not a tensor-core mode", precision);
+    return SMG_ERR_INVALID;
+}
+
+}  // namespace smg

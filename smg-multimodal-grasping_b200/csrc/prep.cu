@@ -1,0 +1,140 @@
+// prep.cu - K1: the input stage of the Q pass.  HBM-bound, one pass, fully coalesced writes.
+//
+//   smg_prep    code/trainer.py:165-191   nearest zoom x2 + zero pad + (x-mean)/std + 3 channels
+//   smg_rotate  code/models.py:371-382    F.affine_grid(align_corners=True) + F.grid_sample(nearest)
+//
+// The rotation index arithmetic replicates torch's float32 evaluation order exactly
+// (probe-verified against torch 2.11 CPU, see oracle/qnet.py::rotate_index_map):
+//   base   = linspace(-1,1,H):  fma(step,i,-1) for i < H/2, fma(-step,H-1-i,1) otherwise
+//   grid   = fma(1,t2, fma(by,t1, bx*t0))      (bmm K=3 accumulation order)
+//   index  = nearbyint((grid+1) * ((H-1)/2))   (ties to even), zero outside [0,H)
+#include "smg_internal.cuh"
+
+#include <math.h>
+
+namespace smg {
+
+__global__ void prep_kernel(const double* __restrict__ hm, int n, int hs, double mean, double stddev,
+                            float* __restrict__ out, int H) {
+    const int pad = (H - 2 * hs) / 2;
+    const size_t plane = (size_t)H * H;
+    const size_t total = (size_t)n * plane;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int s = (int)(i / plane);
+        const int rem = (int)(i - (size_t)s * plane);
+        const int y = rem / H, x = rem - y * H;
+        const int yy = y - pad, xx = x - pad;
+        double v = 0.0;
+        if (yy >= 0 && yy < 2 * hs && xx >= 0 && xx < 2 * hs) v = hm[((size_t)s * hs + (yy >> 1)) * hs + (xx >> 1)];
+        const float f = (float)((v - mean) / stddev);
+        float* o = out + (size_t)s * 3 * plane + rem;
+        o[0] = f;
+        o[plane] = f;
+        o[2 * plane] = f;
+    }
+}
+
+__device__ __forceinline__ float base_coord(int i, int H, float step) {
+    return (i < H / 2) ? __fmaf_rn(step, (float)i, -1.0f) : __fmaf_rn(-step, (float)(H - 1 - i), 1.0f);
+}
+
+__device__ __forceinline__ int rotate_src_index(int x, int y, int H, const float* t) {
+    const float step = __fdiv_rn(2.0f, (float)(H - 1));
+    const float half = __fdiv_rn((float)(H - 1), 2.0f);
+    const float bx = base_coord(x, H, step);
+    const float by = base_coord(y, H, step);
+    const float gx = __fmaf_rn(1.0f, t[2], __fmaf_rn(by, t[1], __fmul_rn(bx, t[0])));
+    const float gy = __fmaf_rn(1.0f, t[5], __fmaf_rn(by, t[4], __fmul_rn(bx, t[3])));
+    const float ix = rintf(__fmul_rn(__fadd_rn(gx, 1.0f), half));
+    const float iy = rintf(__fmul_rn(__fadd_rn(gy, 1.0f), half));
+    if (ix >= 0.0f && ix < (float)H && iy >= 0.0f && iy < (float)H) return (int)iy * H + (int)ix;
+    return -1;
+}
+
+struct RotTheta {
+    float t[32][6];
+};
+
+__global__ void rotate_kernel(const float* __restrict__ in, int n_rot, RotTheta th, float* __restrict__ out, int H) {
+    const size_t plane = (size_t)H * H;
+    const size_t total = (size_t)n_rot * plane;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / plane);
+        const int rem = (int)(i - (size_t)r * plane);
+        const int y = rem / H, x = rem - y * H;
+        const int src = rotate_src_index(x, y, H, th.t[r]);
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        if (src >= 0) {
+            v0 = __ldg(in + src);
+            v1 = __ldg(in + plane + src);
+            v2 = __ldg(in + 2 * plane + src);
+        }
+        float* o = out + (size_t)r * 3 * plane + rem;
+        o[0] = v0;
+        o[plane] = v1;
+        o[2 * plane] = v2;
+    }
+}
+
+__global__ void rotate_index_kernel(RotTheta th, int32_t* __restrict__ out, int H) {
+    const int total = H * H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int y = i / H, x = i - y * H;
+        out[i] = rotate_src_index(x, y, H, th.t[0]);
+    }
+}
+
+// code/models.py:372-376: float64 angle -> 2x3 affine matrix -> float32
+void rotation_theta(int rot_idx, int num_rot, float* t6) {
+    const double deg = (double)rot_idx * (360.0 / (double)num_rot);
+    const double th = deg * (M_PI / 180.0);  // np.radians
+    const double c = cos(-th), s = sin(-th);
+    t6[0] = (float)c;
+    t6[1] = (float)s;
+    t6[2] = 0.0f;
+    t6[3] = (float)(-s);
+    t6[4] = (float)c;
+    t6[5] = 0.0f;
+}
+
+int launch_prep(smg_handle* h, const double* hm, int n, int hm_size, double mean, double stddev, float* out,
+                cudaStream_t st) {
+    SMG_CHECK(2 * hm_size <= h->H, SMG_ERR_INVALID, "smg_prep: 2*hm_size %d exceeds H %d", 2 * hm_size, h->H);
+    const size_t total = (size_t)n * h->H * h->H;
+    const int threads = 256;
+    const int blocks = (int)((total + threads - 1) / threads);
+    prep_kernel<<<blocks < h->num_sms * 16 ? blocks : h->num_sms * 16, threads, 0, st>>>(hm, n, hm_size, mean, stddev,
+                                                                                         out, h->H);
+    h->launches++;
+    SMG_CUDA(cudaGetLastError());
+    return SMG_OK;
+}
+
+int launch_rotate(smg_handle* h, const float* in, const int* host_rot, int n_rot, int num_rot, float* out,
+                  cudaStream_t st) {
+    for (int base = 0; base < n_rot; base += 32) {
+        const int cnt = n_rot - base < 32 ? n_rot - base : 32;
+        RotTheta th;
+        for (int i = 0; i < cnt; ++i) rotation_theta(host_rot[base + i], num_rot, th.t[i]);
+        const size_t total = (size_t)cnt * h->H * h->H;
+        const int threads = 256;
+        const int blocks = (int)((total + threads - 1) / threads);
+        rotate_kernel<<<blocks < h->num_sms * 16 ? blocks : h->num_sms * 16, threads, 0, st>>>(
+            in, cnt, th, out + (size_t)base * 3 * h->H * h->H, h->H);
+        h->launches++;
+        SMG_CUDA(cudaGetLastError());
+    }
+    return SMG_OK;
+}
+
+int launch_rotate_index_map(smg_handle* h, int rot, int num_rot, int32_t* out, cudaStream_t st) {
+    RotTheta th;
+    rotation_theta(rot, num_rot, th.t[0]);
+    const int total = h->H * h->H;
+    rotate_index_kernel<<<(total + 255) / 256, 256, 0, st>>>(th, out, h->H);
+    h->launches++;
+    SMG_CUDA(cudaGetLastError());
+    return SMG_OK;
+}
+
+}  // namespace smg

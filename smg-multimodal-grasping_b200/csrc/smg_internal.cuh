@@ -1,0 +1,228 @@
+// smg_internal.cuh - shared declarations of libsmg_b200.so (not part of the public ABI).
+//
+// Data layout in HBM (per handle, sized for max_samples S and input size H):
+//   input      [S,3,H,H]            fp32 planar (what the reference feeds the net)
+//   conv0 raw  [S,H/2,H/2,64]       fp32 NHWC, pre-BN
+//   block b    [S,Hb,Hb,Ctot_b]     fp32 NHWC, pre-BN ("dense block buffer": every dense layer
+//                                   writes its 32 new channels into its slice, so torch.cat
+//                                   (densenet `bn_function`) never copies)
+//   bottleneck [S,Hb,Hb,128]        fp32 NHWC scratch (conv1 output of the layer in flight)
+//   stats      double2 per (sample, channel): (sum x, sum x^2) over H*W, accumulated by the
+//              kernel that PRODUCES the channel; every consumer BN derives mean/var from it.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/smg_b200.h"
+
+namespace smg {
+
+constexpr int kNumBlocks = 4;
+constexpr int kBlockLayers[kNumBlocks] = {6, 12, 24, 16};
+constexpr int kGrowth = 32;
+constexpr int kBottleneck = 128;
+constexpr int kInitFeatures = 64;
+constexpr float kBnEps = 1e-5f;
+constexpr int kHeadMid = 64;
+constexpr int kHeadK = 20;  // 20x20 valid conv (code/models.py:322)
+constexpr int kFeatC = 1024;
+
+// thread-local error string
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define SMG_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            smg::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return SMG_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define SMG_CHECK(cond, code, ...)          \
+    do {                                    \
+        if (!(cond)) {                      \
+            smg::set_error(__VA_ARGS__);    \
+            return (code);                  \
+        }                                   \
+    } while (0)
+
+#define SMG_TRY(expr)            \
+    do {                         \
+        int _s = (expr);         \
+        if (_s != SMG_OK) return _s; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// one convolution of the trunk as the implicit-GEMM kernels see it
+// ---------------------------------------------------------------------------------------
+struct ConvW {
+    // fp32 CUDA-core layout: [taps][Cin][Cout]
+    float* w_ffma = nullptr;
+    // tcgen05 layouts: a sequence of ready-to-copy shared-memory stage images
+    // (no-swizzle K-major core matrices, see conv_umma.cu), tf32 (4-byte) and bf16
+    uint8_t* w_tf32 = nullptr;
+    uint8_t* w_bf16 = nullptr;
+    int cin = 0, cout = 0, taps = 1;
+};
+
+struct BnP {
+    float* gamma = nullptr;
+    float* beta = nullptr;
+    int c = 0;
+};
+
+struct DenseLayerW {
+    BnP norm1;
+    ConvW conv1;  // 1x1 Cin -> 128
+    BnP norm2;
+    ConvW conv2;  // 3x3 128 -> 32
+};
+
+struct TransitionW {
+    BnP norm;
+    ConvW conv;  // 1x1 C -> C/2 (applied after the 2x2 average pool, which commutes with it)
+};
+
+struct TrunkW {
+    bool set = false;
+    float* conv0 = nullptr;  // [147][64], k = (c*7+kh)*7+kw
+    BnP norm0;
+    std::vector<DenseLayerW> layers[kNumBlocks];
+    TransitionW trans[kNumBlocks - 1];
+    BnP norm5;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+};
+
+struct HeadW {
+    bool set = false;
+    int n_out = 0;
+    BnP norm0;        // 2048
+    ConvW conv0[2];   // 1x1 2048 -> 64 split into the scene half [0] and the mask half [1] (K = 1024 each)
+    BnP norm1;        // 64
+    float* conv1 = nullptr;  // [n_out][400][64]  (pixel-major, channel fastest)
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+};
+
+// geometry of one dense block
+struct BlockGeom {
+    int hw;     // spatial size (square)
+    int c_in;   // channels entering the block
+    int c_tot;  // channels at the end of the block
+};
+
+}  // namespace smg
+
+// the public opaque handle
+struct smg_handle {
+    int device = 0;
+    int max_samples = 0;
+    int H = 0;
+    int precision = SMG_PREC_FP32;
+    int num_sms = 148;
+    int64_t launches = 0;
+    int64_t workspace_bytes = 0;
+
+    smg::BlockGeom geom[smg::kNumBlocks];
+    smg::TrunkW trunks[SMG_NUM_TRUNKS];
+    smg::HeadW heads[SMG_NUM_HEADS];
+
+    // workspace
+    float* input = nullptr;       // [S,3,H,H]
+    float* conv0 = nullptr;       // [S,H/2,H/2,64]
+    float* block[smg::kNumBlocks] = {nullptr, nullptr, nullptr, nullptr};
+    float* bott = nullptr;        // [S,H/4,H/4,128]
+    double* stats = nullptr;      // stats arena (zeroed once per forward)
+    size_t stats_doubles_per_sample = 0;
+    size_t stats_bytes = 0;
+    // offsets (in double2 units, per sample) into the stats arena
+    size_t st_conv0 = 0;
+    size_t st_block[smg::kNumBlocks] = {0, 0, 0, 0};
+    size_t st_bott = 0;  // + layer_index*128, layer_index over all 58 dense layers
+    // head workspace
+    float* head_scale = nullptr;  // [S,1024]
+    float* head_shift = nullptr;  // [S,1024]
+    float* head_p = nullptr;      // [S,400,64]
+    float* scene_tmp = nullptr;   // [3,H,H] staging for smg_qforward_maps
+    float* mask_tmp = nullptr;    // unused placeholder
+    int last_n = 0;               // samples of the last trunk forward (for smg_debug_read)
+};
+
+namespace smg {
+
+inline double* stats_ptr(const smg_handle* h, size_t off_double2) {
+    return h->stats + 2 * off_double2 * (size_t)h->max_samples;
+}
+// stats layout: for a region with C channels: [S][C] double2, region base = off * S
+
+// ---- kernels (defined in the .cu files) ---------------------------------------------
+// K1
+int launch_prep(smg_handle* h, const double* hm, int n, int hm_size, double mean, double stddev, float* out,
+                cudaStream_t st);
+int launch_rotate(smg_handle* h, const float* in, const int* host_rot, int n_rot, int num_rot, float* out,
+                  cudaStream_t st);
+int launch_rotate_index_map(smg_handle* h, int rot, int num_rot, int32_t* out, cudaStream_t st);
+// stem
+int launch_conv0(smg_handle* h, const float* in, int n, const float* w, float* out, double* stats, cudaStream_t st);
+int launch_pool0(smg_handle* h, int n, const float* conv0, const double* stats_in, const float* gamma,
+                 const float* beta, float* out, int out_cstride, double* stats_out, cudaStream_t st);
+
+// generic convolution (1x1 / 3x3 / pooled 1x1) with BN-ReLU prologue and stats epilogue
+struct ConvArgs {
+    const float* in = nullptr;  // NHWC, pre-BN
+    int in_cstride = 0;         // floats per pixel
+    int cin = 0;
+    int hin = 0;                // input spatial size (square)
+    // prologue: mode 0 = derive scale/shift from (stats, gamma, beta); mode 1 = read scale/shift [S][cin]
+    int prologue_mode = 0;
+    const double* in_stats = nullptr;  // [S][in_stats_stride] double2
+    int in_stats_stride = 0;
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    const float* scale = nullptr;
+    const float* shift = nullptr;
+    int relu = 1;
+    int pool = 0;  // 1: average the 2x2 window of prologue outputs (transition); output spatial = hin/2
+    int taps = 1;  // 1 or 9 (3x3, pad 1)
+    const ConvW* w = nullptr;
+    float* out = nullptr;
+    int out_cstride = 0;
+    int out_coff = 0;
+    int cout = 0;
+    double* out_stats = nullptr;  // [S][out_stats_stride] double2, at channel out_coff; may be null
+    int out_stats_stride = 0;
+    int n = 0;  // samples
+};
+int launch_conv_ffma(smg_handle* h, const ConvArgs& a, cudaStream_t st);
+int launch_conv_umma(smg_handle* h, const ConvArgs& a, int precision, cudaStream_t st);
+
+// head
+int launch_head_prepare(smg_handle* h, int n, const double* stats4, int stats_stride, const BnP& norm5,
+                        const BnP& hnorm0, int half, float* scale, float* shift, cudaStream_t st);
+int launch_norm5_export(smg_handle* h, int n, const float* block4, const double* stats4, int stats_stride,
+                        const BnP& norm5, float* out_nchw, cudaStream_t st);
+int launch_head_tail(smg_handle* h, const float* p, int n_rot, int n_masks, const HeadW& hw, float* q,
+                     cudaStream_t st);
+int launch_bn_export(smg_handle* h, int trunk_id, int n, float* mean, float* var, cudaStream_t st);
+int launch_argmax(smg_handle* h, const float* q, int n, float* out, int32_t* out_idx, cudaStream_t st);
+int launch_nhwc_to_nchw(smg_handle* h, const float* in, int hw, int c, int cstride, float* out, cudaStream_t st);
+
+// K11 / K12
+int launch_heightmap(smg_handle* h, const double* depth, const double* K, const double* pose, double* out224,
+                     double* out448, double* host_A_htor, cudaStream_t st);
+int launch_nms(smg_handle* h, const float* boxes, int n, float thr, float amin, float amax, int32_t* keep,
+               int32_t* n_keep, cudaStream_t st);
+
+// weight packing
+int pack_conv_weights(smg_handle* h, const float* w_oihw, ConvW& cw, int k_offset, int k_total, cudaStream_t st);
+size_t conv_packed_bytes_ffma(int cin, int cout, int taps);
+size_t conv_packed_bytes_umma(int cin, int cout, int taps, int elt_bytes);
+
+}  // namespace smg

@@ -1,0 +1,200 @@
+// stem.cu - K2/K4: densenet `features.conv0` (7x7 stride 2 pad 3, 3->64) and
+// `norm0 + relu0 + pool0` (train-mode BN, ReLU, 3x3 stride-2 max pool), torchvision
+// densenet.py as called at /root/reference/code/models.py:384-385.
+//
+// conv0 is a K=147 direct convolution on the CUDA cores (4% of the trunk's MACs, Cin=3
+// does not tile onto the tensor cores); it writes the raw output NHWC and accumulates
+// the per-(sample,channel) sum / sum-of-squares that norm0 needs.  pool0 applies
+// norm0+ReLU on the fly, max-pools, writes channels [0,64) of the dense-block-1 buffer
+// and accumulates THEIR statistics (needed by every norm1 of block 1).
+#include "smg_internal.cuh"
+
+namespace smg {
+
+constexpr int C0_TILE = 16;                       // 16x16 output pixels per CTA
+constexpr int C0_PATCH = 2 * C0_TILE + 5;         // 37 input rows/cols
+constexpr int C0_K = 147;
+constexpr int C0_STAGE_LD = 65;                   // padded row of the output staging tile
+
+__global__ void __launch_bounds__(256, 1)
+conv0_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
+             double* __restrict__ stats, int H, int stats_stride) {
+    extern __shared__ float sm[];
+    float* s_w = sm;                                   // [147][64]
+    float* s_in = s_w + C0_K * 64;                     // [3][37][37] (+pad)
+    float* s_out = s_in + 3 * C0_PATCH * C0_PATCH + 1; // [256][65]
+    const int Ho = H / 2;
+    const int tiles = Ho / C0_TILE;
+    const int s = blockIdx.y;
+    const int ty = blockIdx.x / tiles, tx = blockIdx.x % tiles;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < C0_K * 64; i += 256) s_w[i] = w[i];
+    const int iy0 = ty * C0_TILE * 2 - 3, ix0 = tx * C0_TILE * 2 - 3;
+    const float* inp = in + (size_t)s * 3 * H * H;
+    for (int i = tid; i < 3 * C0_PATCH * C0_PATCH; i += 256) {
+        const int c = i / (C0_PATCH * C0_PATCH);
+        const int r = i - c * C0_PATCH * C0_PATCH;
+        const int py = r / C0_PATCH, px = r - py * C0_PATCH;
+        const int y = iy0 + py, x = ix0 + px;
+        float v = 0.f;
+        if (y >= 0 && y < H && x >= 0 && x < H) v = inp[((size_t)c * H + y) * H + x];
+        s_in[i] = v;
+    }
+    __syncthreads();
+
+    const int oy = tid / C0_TILE, ox = tid % C0_TILE;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    for (int c = 0; c < 3; ++c) {
+        for (int kh = 0; kh < 7; ++kh) {
+            const float* irow = s_in + (c * C0_PATCH + (2 * oy + kh)) * C0_PATCH + 2 * ox;
+            const float* wrow = s_w + ((c * 7 + kh) * 7) * 64;
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw) {
+                const float v = irow[kw];
+                const float4* w4 = reinterpret_cast<const float4*>(wrow + kw * 64);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float4 ww = w4[j];
+                    acc[4 * j + 0] = fmaf(v, ww.x, acc[4 * j + 0]);
+                    acc[4 * j + 1] = fmaf(v, ww.y, acc[4 * j + 1]);
+                    acc[4 * j + 2] = fmaf(v, ww.z, acc[4 * j + 2]);
+                    acc[4 * j + 3] = fmaf(v, ww.w, acc[4 * j + 3]);
+                }
+            }
+        }
+    }
+    // stage the [256 pixel][64 channel] tile for coalesced stores + column statistics
+#pragma unroll
+    for (int i = 0; i < 64; ++i) s_out[tid * C0_STAGE_LD + i] = acc[i];
+    __syncthreads();
+    float* outp = out + (size_t)s * Ho * Ho * 64;
+    for (int i = tid; i < 256 * 64; i += 256) {
+        const int p = i >> 6, c = i & 63;
+        const int py = p / C0_TILE, px = p - py * C0_TILE;
+        outp[((size_t)(ty * C0_TILE + py) * Ho + tx * C0_TILE + px) * 64 + c] = s_out[p * C0_STAGE_LD + c];
+    }
+    // column sums: thread = (channel c, row group g of 64 pixels)
+    {
+        const int c = tid & 63, g = tid >> 6;
+        float su = 0.f, sq = 0.f;
+        for (int p = g * 64; p < g * 64 + 64; ++p) {
+            const float v = s_out[p * C0_STAGE_LD + c];
+            su += v;
+            sq = fmaf(v, v, sq);
+        }
+        __syncthreads();
+        float* red = s_in;  // reuse
+        red[tid] = su;
+        red[256 + tid] = sq;
+        __syncthreads();
+        if (tid < 64) {
+            const double a = (double)red[tid] + (double)red[64 + tid] + (double)red[128 + tid] + (double)red[192 + tid];
+            const double b = (double)red[256 + tid] + (double)red[320 + tid] + (double)red[384 + tid] +
+                             (double)red[448 + tid];
+            double* st = stats + 2 * ((size_t)s * stats_stride + tid);
+            atomicAdd(st, a);
+            atomicAdd(st + 1, b);
+        }
+    }
+}
+
+// norm0 + ReLU + maxpool 3x3/2 pad 1.  thread = (pixel, 4-channel group); CTA = 16 pixel lanes x 16 groups.
+__global__ void __launch_bounds__(256)
+pool0_kernel(const float* __restrict__ conv0, const double* __restrict__ stats_in, int stats_in_stride,
+             const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
+             int out_cstride, double* __restrict__ stats_out, int stats_out_stride, int Hc, int pix_per_cta) {
+    __shared__ float s_sc[64], s_sh[64];
+    __shared__ float s_sum[16][64], s_sq[16][64];
+    const int s = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int Hp = Hc / 2;
+    if (tid < 64) {
+        const double* st = stats_in + 2 * ((size_t)s * stats_in_stride + tid);
+        const double cnt = (double)Hc * Hc;
+        const double m = st[0] / cnt;
+        double var = st[1] / cnt - m * m;
+        if (var < 0) var = 0;
+        const float sc = gamma[tid] * (float)(1.0 / sqrt(var + (double)kBnEps));
+        s_sc[tid] = sc;
+        s_sh[tid] = beta[tid] - (float)m * sc;
+    }
+    __syncthreads();
+    const int cg = tid & 15, pl = tid >> 4;
+    const float4 sc = *reinterpret_cast<const float4*>(&s_sc[cg * 4]);
+    const float4 sh = *reinterpret_cast<const float4*>(&s_sh[cg * 4]);
+    const float* cin = conv0 + (size_t)s * Hc * Hc * 64;
+    float* o = out + (size_t)s * Hp * Hp * out_cstride;
+    float4 su = make_float4(0, 0, 0, 0), sq = make_float4(0, 0, 0, 0);
+    const int p0 = blockIdx.x * pix_per_cta;
+    const int p1 = min(p0 + pix_per_cta, Hp * Hp);
+    for (int p = p0 + pl; p < p1; p += 16) {
+        const int py = p / Hp, px = p - py * Hp;
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int y = 2 * py - 1 + dy;
+            if (y < 0 || y >= Hc) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int x = 2 * px - 1 + dx;
+                if (x < 0 || x >= Hc) continue;
+                const float4 v = *reinterpret_cast<const float4*>(cin + ((size_t)y * Hc + x) * 64 + cg * 4);
+                m.x = fmaxf(m.x, fmaxf(fmaf(v.x, sc.x, sh.x), 0.f));
+                m.y = fmaxf(m.y, fmaxf(fmaf(v.y, sc.y, sh.y), 0.f));
+                m.z = fmaxf(m.z, fmaxf(fmaf(v.z, sc.z, sh.z), 0.f));
+                m.w = fmaxf(m.w, fmaxf(fmaf(v.w, sc.w, sh.w), 0.f));
+            }
+        }
+        *reinterpret_cast<float4*>(o + (size_t)p * out_cstride + cg * 4) = m;
+        su.x += m.x; su.y += m.y; su.z += m.z; su.w += m.w;
+        sq.x = fmaf(m.x, m.x, sq.x); sq.y = fmaf(m.y, m.y, sq.y);
+        sq.z = fmaf(m.z, m.z, sq.z); sq.w = fmaf(m.w, m.w, sq.w);
+    }
+    s_sum[pl][cg * 4 + 0] = su.x; s_sum[pl][cg * 4 + 1] = su.y; s_sum[pl][cg * 4 + 2] = su.z; s_sum[pl][cg * 4 + 3] = su.w;
+    s_sq[pl][cg * 4 + 0] = sq.x; s_sq[pl][cg * 4 + 1] = sq.y; s_sq[pl][cg * 4 + 2] = sq.z; s_sq[pl][cg * 4 + 3] = sq.w;
+    __syncthreads();
+    if (tid < 64) {
+        double a = 0, b = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            a += (double)s_sum[i][tid];
+            b += (double)s_sq[i][tid];
+        }
+        double* st = stats_out + 2 * ((size_t)s * stats_out_stride + tid);
+        atomicAdd(st, a);
+        atomicAdd(st + 1, b);
+    }
+}
+
+int launch_conv0(smg_handle* h, const float* in, int n, const float* w, float* out, double* stats, cudaStream_t st) {
+    const int Ho = h->H / 2;
+    SMG_CHECK(Ho % C0_TILE == 0, SMG_ERR_INVALID, "conv0: H/2 must be a multiple of %d", C0_TILE);
+    const size_t smem = (size_t)(C0_K * 64 + 3 * C0_PATCH * C0_PATCH + 1 + 256 * C0_STAGE_LD) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        SMG_CUDA(cudaFuncSetAttribute(conv0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid((Ho / C0_TILE) * (Ho / C0_TILE), n);
+    conv0_kernel<<<grid, 256, smem, st>>>(in, w, out, stats, h->H, 64);
+    h->launches++;
+    SMG_CUDA(cudaGetLastError());
+    return SMG_OK;
+}
+
+int launch_pool0(smg_handle* h, int n, const float* conv0, const double* stats_in, const float* gamma,
+                 const float* beta, float* out, int out_cstride, double* stats_out, cudaStream_t st) {
+    const int Hc = h->H / 2, Hp = Hc / 2;
+    const int pix_per_cta = 256;
+    dim3 grid((Hp * Hp + pix_per_cta - 1) / pix_per_cta, n);
+    pool0_kernel<<<grid, 256, 0, st>>>(conv0, stats_in, 64, gamma, beta, out, out_cstride, stats_out, out_cstride, Hc,
+                                       pix_per_cta);
+    h->launches++;
+    SMG_CUDA(cudaGetLastError());
+    return SMG_OK;
+}
+
+}  // namespace smg

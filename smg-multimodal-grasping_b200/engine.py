@@ -1,0 +1,233 @@
+"""Host-side owner of one `smg_handle` (one per GPU): weight re-packing and raw calls.
+
+PyTorch is used for device memory, streams and tensors only; every kernel that runs
+comes from csrc/libsmg_b200.so through the C ABI in include/smg_b200.h.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+TRUNK_ATTRS = ("suction_depth_trunk", "grasp_depth_trunk", "gs_depth_trunk")  # == SMG_TRUNK_* ids
+HEAD_ATTRS = ("suctionnet_val", "graspnet_val", "gsnet_val")                  # == SMG_HEAD_* ids
+# style -> (trunk id, head id); style 2 feeds the gs trunk to the SUCTION head (code/models.py:434,507,582)
+STYLE_ROUTE = {0: (1, 1), 1: (0, 0), 2: (2, 0)}
+PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
+TRUNK_BN_CHANNELS = 41824
+
+_engines = {}
+
+
+def trunk_param_list(trunk):
+    """The 362 conv / BN-affine tensors of `densenet121().features` in state_dict order."""
+    out = []
+    for name, p in trunk.features.named_parameters():
+        out.append(p)
+    return out
+
+
+def head_param_list(head):
+    """norm0.w, norm0.b, conv0.w, norm1.w, norm1.b, conv1.w of a head Sequential (code/models.py:316-323)."""
+    mods = list(head.children())
+    norm0, conv0, norm1, conv1 = mods[0], mods[2], mods[3], mods[5]
+    return [norm0.weight, norm0.bias, conv0.weight, norm1.weight, norm1.bias, conv1.weight]
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+class Engine:
+    """One handle bound to one CUDA device."""
+
+    def __init__(self, device=0, max_samples=32, H=640, precision="fp32"):
+        if not torch.cuda.is_available():
+            raise _lib.SmgError("smg_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.max_samples = int(max_samples)
+        self.H = int(H)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.smg_create(self.device.index, self.max_samples, self.H, ctypes.byref(h)))
+        self.h = h
+        self.set_precision(precision)
+        self._sig = {}
+        self._staged = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) is not None and self.h:
+                self.lib.smg_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ misc
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_precision(self, precision):
+        self.precision = precision
+        _lib.check(self.lib.smg_set_precision(self.h, PRECISIONS[precision]))
+
+    def launch_count(self):
+        return int(self.lib.smg_launch_count(self.h))
+
+    def workspace_bytes(self):
+        return int(self.lib.smg_workspace_bytes(self.h))
+
+    # ------------------------------------------------------------------ weights
+    def _device_params(self, key, params):
+        """fp32 contiguous tensors on this device (parameters living on the CPU are staged)."""
+        out = []
+        for i, p in enumerate(params):
+            t = p.detach()
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(self.device, torch.float32).contiguous()
+            out.append(t)
+        self._staged[key] = out  # keep staged copies alive until the packing kernels ran
+        return out
+
+    def sync_weights(self, model, force=False):
+        """Re-pack the model's parameters if they changed (load_state_dict, optimizer step, .cuda())."""
+        n_out = 3 if model.__class__.__name__ == "reactive_net" else 1
+        for tid, attr in enumerate(TRUNK_ATTRS):
+            params = trunk_param_list(getattr(model, attr))
+            sig = (id(model), tuple((p.data_ptr(), p._version) for p in params))
+            if force or self._sig.get(("t", tid)) != sig:
+                dev = self._device_params(("t", tid), params)
+                _lib.check(self.lib.smg_set_trunk_weights(self.h, tid, _ptr_array(dev), len(dev), self._stream()))
+                self._sig[("t", tid)] = sig
+        for hid, attr in enumerate(HEAD_ATTRS):
+            params = head_param_list(getattr(model, attr))
+            sig = (id(model), tuple((p.data_ptr(), p._version) for p in params))
+            if force or self._sig.get(("h", hid)) != sig:
+                dev = self._device_params(("h", hid), params)
+                _lib.check(self.lib.smg_set_head_weights(self.h, hid, _ptr_array(dev), n_out, self._stream()))
+                self._sig[("h", hid)] = sig
+        self.n_out = n_out
+
+    # ------------------------------------------------------------------ K1
+    def prep(self, heightmaps, mean, std):
+        """[n,hs,hs] float64 (cuda) -> [n,3,H,H] float32: code/trainer.py:165-191."""
+        hm = heightmaps.to(self.device, torch.float64).contiguous()
+        n, hs = hm.shape[0], hm.shape[-1]
+        out = torch.empty((n, 3, self.H, self.H), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.smg_prep(self.h, hm.data_ptr(), n, hs, float(mean), float(std), out.data_ptr(), self._stream()))
+        return out
+
+    def rotate(self, image, rot_idx, num_rotations):
+        """[3,H,H] float32 -> [len(rot_idx),3,H,H]: code/models.py:371-382."""
+        img = image.to(self.device, torch.float32).contiguous().view(3, self.H, self.H)
+        rot = (ctypes.c_int * len(rot_idx))(*[int(r) for r in rot_idx])
+        out = torch.empty((len(rot_idx), 3, self.H, self.H), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.smg_rotate(self.h, img.data_ptr(), rot, len(rot_idx), int(num_rotations), out.data_ptr(),
+                                       self._stream()))
+        return out
+
+    def rotate_index_map(self, rot_idx, num_rotations):
+        out = torch.empty((self.H, self.H), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.smg_rotate_index_map(self.h, int(rot_idx), int(num_rotations), out.data_ptr(), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ trunk / Q
+    def trunk_forward(self, trunk_id, x, want_bn_stats=False):
+        """`trunk.features(x)` for x [n,3,H,H] -> [n,1024,H/32,H/32] (+ optional per-sample BN stats)."""
+        x = x.to(self.device, torch.float32).contiguous()
+        n = x.shape[0]
+        feat = torch.empty((n, 1024, self.H // 32, self.H // 32), dtype=torch.float32, device=self.device)
+        mean = var = None
+        pm = pv = None
+        if want_bn_stats:
+            mean = torch.empty((n, TRUNK_BN_CHANNELS), dtype=torch.float32, device=self.device)
+            var = torch.empty_like(mean)
+            pm, pv = mean.data_ptr(), var.data_ptr()
+        _lib.check(self.lib.smg_trunk_forward(self.h, int(trunk_id), x.data_ptr(), n, feat.data_ptr(), pm, pv, self._stream()))
+        return (feat, mean, var) if want_bn_stats else feat
+
+    def qforward(self, style, scene, masks, rot_idx, num_rotations, want_bn_stats=False):
+        """Q for every (mask, rotation): [n_masks, n_rot, n_out].  scene [3,H,H], masks [n,3,H,H] float32."""
+        tid, hid = STYLE_ROUTE[int(style)]
+        scene = scene.to(self.device, torch.float32).contiguous()
+        masks = masks.to(self.device, torch.float32).contiguous().view(-1, 3, self.H, self.H)
+        n_masks, n_rot = masks.shape[0], len(rot_idx)
+        rot = (ctypes.c_int * n_rot)(*[int(r) for r in rot_idx])
+        q = torch.empty((n_masks, n_rot, self.n_out), dtype=torch.float32, device=self.device)
+        mean = var = None
+        pm = pv = None
+        if want_bn_stats:
+            mean = torch.empty((n_rot + n_masks, TRUNK_BN_CHANNELS), dtype=torch.float32, device=self.device)
+            var = torch.empty_like(mean)
+            pm, pv = mean.data_ptr(), var.data_ptr()
+        _lib.check(self.lib.smg_qforward(self.h, tid, hid, scene.data_ptr(), masks.data_ptr(), n_masks, rot, n_rot,
+                                         int(num_rotations), q.data_ptr(), pm, pv, self._stream()))
+        return (q, mean, var) if want_bn_stats else q
+
+    def qforward_maps(self, style, scene_hm, mask_hms, mean, std, rot_idx, num_rotations):
+        """Same from 224x224 float64 heightmaps already on the device (fuses code/trainer.py:165-191)."""
+        tid, hid = STYLE_ROUTE[int(style)]
+        n_masks, hs = mask_hms.shape[0], mask_hms.shape[-1]
+        n_rot = len(rot_idx)
+        rot = (ctypes.c_int * n_rot)(*[int(r) for r in rot_idx])
+        q = torch.empty((n_masks, n_rot, self.n_out), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.smg_qforward_maps(self.h, tid, hid, scene_hm.data_ptr(), mask_hms.data_ptr(), n_masks, hs,
+                                              float(mean), float(std), rot, n_rot, int(num_rotations), q.data_ptr(),
+                                              self._stream()))
+        return q
+
+    def debug_read(self, what, sample, shape):
+        out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.smg_debug_read(self.h, what.encode(), int(sample), out.data_ptr(), out.numel(), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ K9 / K11 / K12
+    def argmax(self, q):
+        q = q.to(self.device, torch.float32).contiguous().view(-1)
+        val = torch.empty(1, dtype=torch.float32, device=self.device)
+        idx = torch.empty(1, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.smg_argmax(self.h, q.data_ptr(), q.numel(), val.data_ptr(), idx.data_ptr(), self._stream()))
+        return val, idx
+
+    def heightmap(self, depth, intrinsics, pose):
+        """depth [480,640] float64 -> (depth_heightmap [224,224], depth_mask [448,448], A_htor [3,3])."""
+        d = depth.to(self.device, torch.float64).contiguous()
+        K = np.ascontiguousarray(intrinsics, dtype=np.float64)
+        P = np.ascontiguousarray(pose, dtype=np.float64)
+        A = np.empty(9, dtype=np.float64)
+        o224 = torch.empty((224, 224), dtype=torch.float64, device=self.device)
+        o448 = torch.empty((448, 448), dtype=torch.float64, device=self.device)
+        dp = ctypes.POINTER(ctypes.c_double)
+        _lib.check(self.lib.smg_heightmap(self.h, d.data_ptr(), K.ctypes.data_as(dp), P.ctypes.data_as(dp), o224.data_ptr(),
+                                          o448.data_ptr(), A.ctypes.data_as(dp), self._stream()))
+        return o224, o448, A.reshape(3, 3)
+
+    def nms(self, boxes, co_thresh, min_area, max_area):
+        b = boxes.to(self.device, torch.float32).contiguous().view(-1, 4)
+        n = b.shape[0]
+        keep = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.smg_nms(self.h, b.data_ptr() if n else None, n, float(co_thresh), float(min_area),
+                                    float(max_area), keep.data_ptr(), cnt.data_ptr(), self._stream()))
+        return keep, cnt
+
+
+def get_engine(device=0, max_samples=32, H=640, precision=None):
+    """Process-wide engine for a device (one handle per GPU); grows the workspace on demand."""
+    if isinstance(device, torch.device):
+        device = device.index or 0
+    key = (int(device), int(H))
+    eng = _engines.get(key)
+    if eng is None or eng.max_samples < max_samples:
+        prec = precision or (eng.precision if eng is not None else "fp32")
+        if eng is not None:
+            eng.__del__()
+        eng = Engine(device, max_samples, H, prec)
+        _engines[key] = eng
+    elif precision is not None and eng.precision != precision:
+        eng.set_precision(precision)
+    return eng

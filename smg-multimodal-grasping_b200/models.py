@@ -1,0 +1,165 @@
+"""Drop-in `reinforcement_net` / `reactive_net` whose forward runs on libsmg_b200.so.
+
+Boundary kept from the reference:
+  * class names, constructor `(use_cuda)`, attribute names (`suction_depth_trunk`,
+    `grasp_depth_trunk`, `gs_depth_trunk`, `suctionnet_val`, `graspnet_val`, `gsnet_val`,
+    `gnum_rotations`, `snum_rotations`, `gra_prob`, `suc_prob`, `gs_prob`) and the 2217
+    state_dict keys (code/models.py:15-69, :301-358), so reference snapshots load unchanged;
+  * `forward(input_depth_data, m_input_depth_data, style=0, is_volatile=False,
+    specific_rotation=-1)` with the reference's three branches and return types
+    (code/models.py:361-586, :72-296).
+The parameter containers are ordinary torch modules (torchvision's DenseNet-121 tree is
+used for storage and key names only; its forward is never called).  The arithmetic is
+done by the CUDA library; without it (or without a GPU) forward raises - no fallback.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torchvision
+
+from . import engine as _engine
+
+# running-stat momentum of nn.BatchNorm2d (torch default), used for the EMA side effect
+_BN_MOMENTUM = 0.1
+
+
+def _make_head(prefix, n_out):
+    return nn.Sequential(OrderedDict([
+        (prefix + '-norm0', nn.BatchNorm2d(2048)),
+        (prefix + '-relu0', nn.ReLU(inplace=True)),
+        (prefix + '-conv0', nn.Conv2d(2048, 64, kernel_size=1, stride=1, bias=False)),
+        (prefix + '-norm1', nn.BatchNorm2d(64)),
+        (prefix + '-relu1', nn.ReLU(inplace=True)),
+        (prefix + '-conv1', nn.Conv2d(64, n_out, kernel_size=20, stride=1, bias=False)),
+    ]))
+
+
+class _SmgNet(nn.Module):
+    """Shared implementation; `N_OUT` = 1 (Q value) or 3 (class logits)."""
+
+    N_OUT = 1
+    precision = "fp32"          # "fp32" | "tf32" | "bf16": arithmetic mode of the convolutions
+    update_running_stats = True  # reproduce BatchNorm's running_mean/var side effect
+
+    def __init__(self, use_cuda):
+        super().__init__()
+        self.use_cuda = use_cuda
+        # same construction order as the reference so that a given torch seed yields the same
+        # random-init weights (code/models.py:308-353); no network here, so no ImageNet weights
+        self.suction_depth_trunk = torchvision.models.densenet.densenet121(weights=None)
+        self.grasp_depth_trunk = torchvision.models.densenet.densenet121(weights=None)
+        self.gs_depth_trunk = torchvision.models.densenet.densenet121(weights=None)
+        self.gnum_rotations = 1
+        self.snum_rotations = 1
+        self.suctionnet_val = _make_head('suction-val', self.N_OUT)
+        self.graspnet_val = _make_head('grasp-val', self.N_OUT)
+        # the reference re-uses the 'grasp-val-*' names for the ES head (code/models.py:336-343)
+        self.gsnet_val = _make_head('grasp-val', self.N_OUT)
+        for name, m in self.named_modules():
+            if 'suction-' in name or 'grasp-' in name or 'gs-' in name:
+                if isinstance(m, nn.Conv2d):
+                    nn.init.kaiming_normal_(m.weight.data)
+                elif isinstance(m, nn.BatchNorm2d):
+                    m.weight.data.fill_(1)
+                    m.bias.data.zero_()
+        self.gra_prob = []
+        self.suc_prob = []
+        self.gs_prob = []
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _device_index(self):
+        p = next(self.parameters())
+        if p.is_cuda:
+            return p.device.index
+        return torch.cuda.current_device()
+
+    def _engine(self, n_samples):
+        eng = _engine.get_engine(self._device_index(), max(n_samples, 18), 640, self.precision)
+        eng.sync_weights(self)
+        return eng
+
+    def _bn_modules(self, trunk):
+        return [m for m in trunk.features.modules() if isinstance(m, nn.BatchNorm2d)]
+
+    @torch.no_grad()
+    def _apply_running_stats(self, trunk, mean, var, order):
+        """BatchNorm2d train-mode side effect: running = (1-m)*running + m*batch for each trunk call in
+        `order` (sample indices; the reference calls trunk(scene_r) then trunk(mask) per rotation)."""
+        k = len(order)
+        w = torch.zeros(mean.shape[0], dtype=torch.float64, device=mean.device)
+        for i, s in enumerate(order):
+            w[s] += _BN_MOMENTUM * (1 - _BN_MOMENTUM) ** (k - 1 - i)
+        decay = (1 - _BN_MOMENTUM) ** k
+        bm = (w[:, None] * mean.double()).sum(0)
+        off = 0
+        for m in self._bn_modules(trunk):
+            c = m.num_features
+            m.running_mean.mul_(decay).add_(bm[off:off + c].to(m.running_mean))
+            off += c
+        # unbiased variance: n/(n-1) with n = H*W of that layer; recover n from the layer geometry
+        off = 0
+        H = 640
+        counts = _bn_counts(H)
+        bv = (w[:, None] * var.double()).sum(0)
+        for m, n in zip(self._bn_modules(trunk), counts):
+            c = m.num_features
+            m.running_var.mul_(decay).add_((bv[off:off + c] * (n / (n - 1.0))).to(m.running_var))
+            m.num_batches_tracked += k
+            off += c
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, input_depth_data, m_input_depth_data, style=0, is_volatile=False, specific_rotation=-1):
+        if not is_volatile:
+            from .autograd import q_forward_with_grad
+            return q_forward_with_grad(self, input_depth_data, m_input_depth_data, style, specific_rotation)
+        if specific_rotation == -1:
+            if style == 0:
+                rots, nrot = list(range(self.gnum_rotations)), self.gnum_rotations
+            elif style == 1:
+                rots, nrot = list(range(self.snum_rotations)), self.snum_rotations
+            else:
+                rots, nrot = [0], self.gnum_rotations          # code/models.py:418
+        else:
+            # the reference derives the angle from gnum_rotations for every style and pins the ES
+            # primitive to rotation 0 (code/models.py:469,491,545)
+            rots, nrot = [0 if style == 2 else int(specific_rotation)], self.gnum_rotations
+        q = self._q(input_depth_data, m_input_depth_data, style, rots, nrot)  # [n_rot, C]
+        outs = [q[i].view(1, self.N_OUT, 1, 1) for i in range(len(rots))]
+        return outs if specific_rotation == -1 else outs[0]
+
+    @torch.no_grad()
+    def _q(self, scene, mask, style, rots, nrot):
+        eng = self._engine(len(rots) + 1)
+        scene = scene.reshape(3, 640, 640)
+        mask = mask.reshape(1, 3, 640, 640)
+        if self.update_running_stats:
+            q, mean, var = eng.qforward(style, scene, mask, rots, nrot, want_bn_stats=True)
+            trunk = getattr(self, _engine.TRUNK_ATTRS[_engine.STYLE_ROUTE[style][0]])
+            order = []
+            for i in range(len(rots)):
+                order += [i, len(rots)]
+            self._apply_running_stats(trunk, mean, var, order)
+        else:
+            q = eng.qforward(style, scene, mask, rots, nrot)
+        return q[0]
+
+
+def _bn_counts(H):
+    """H*W seen by each of the 121 trunk BatchNorm layers, in module order."""
+    counts = [(H // 2) ** 2]
+    hw = H // 4
+    for b, nl in enumerate((6, 12, 24, 16)):
+        counts += [hw * hw] * (2 * nl + 1)  # norm1/norm2 per layer + transition norm / norm5
+        hw //= 2
+    return counts
+
+
+class reactive_net(_SmgNet):
+    """Reactive policy: 3-class logits per (scene, mask, rotation) (code/models.py:15-296)."""
+    N_OUT = 3
+
+
+class reinforcement_net(_SmgNet):
+    """DRL policy: scalar Q per (scene, mask, rotation) (code/models.py:301-586)."""
+    N_OUT = 1
