@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py - 16-rotation Q inferences/s of the SMG grasp-affordance hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision tf32|bf16|fp32]
+
+Unit of work U: one (scene, object mask, primitive) evaluated at R = 16
+rotations -> 16 Q scalars == one `Trainer.forward(..., is_volatile=True)` call of the reference with
+gnum_rotations = 16: 17 distinct 640x640 DenseNet-121 trunk passes (16 rotated scenes + 1 masked
+scene) + 16 heads = 788.0 GFLOP.  One "step" = one U per GPU on seeded synthetic 224x224 heightmaps
+with random-init weights (no datasets / checkpoints offline).
+
+  value   U/s with the heightmaps already resident in HBM (CUDA events around K steps)
+  e2e     U/s through the reference-facing call Trainer.forward: float64 heightmaps in pinned host
+          memory, H2D copy and D2H read of the 16 Q values inside the timed region
+  roofline      dominant kernel class timed with CUDA events inside the library (smg_profile_*)
+  cpu_baseline  the oracle port of the reference path (recomputing the mask pass per rotation, as the
+                reference does) timed on this box's host cores on a bounded sample
+
+`--impl reference` times that CPU path alone (the reference is CUDA-only as written and cannot be
+imported on the GPU box; the oracle is its pinned restatement).  N > 1 (torchrun): every rank
+evaluates its own units (weak scaling over independent scenes - the rotations / replay samples shard
+without a data-path collective); the per-rank best (Q, rotation) tuples are exchanged with one tiny
+NCCL all_gather per step, which is the path's only real exchange (code/main.py:170-173).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+R = 16
+MEAN, STD = 0.01, 0.03
+GFLOP_PER_PASS = 46.255
+GFLOP_PER_HEAD = 0.105
+GFLOP_PER_UNIT = 17 * GFLOP_PER_PASS + 16 * GFLOP_PER_HEAD  # 788.0
+METRIC = "16-rot Q-map inferences/s"
+UNIT = "inferences/s"
+WORKLOAD = ("reinforcement_net (E+S+ES heads) forward, primitive E (style 0), R=16 rotations, one synthetic "
+            "224x224 heightmap + one object mask -> 16 Q; 17 distinct 640x640 DenseNet-121 passes per unit")
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            c = [v.strip() for v in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_units(n_units, seed0):
+    import numpy as np
+    import smg_b200.synth as synth
+    scenes, masks = [], []
+    for i in range(n_units):
+        sc = synth.make_scene(seed0 + i, num_objects=4, cluttered=False)
+        scenes.append(sc["scene"])
+        masks.append(synth.masked_scene(sc["scene"], sc["masks"], [0]))
+    return np.stack(scenes), np.stack(masks)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, on the host cores
+# ------------------------------------------------------------------------------------------------
+_CPU_CACHE = {}
+
+
+def cpu_reference_time(rotations_per_sample, repeats=1):
+    """Seconds for `rotations_per_sample` rotations of one unit executed the way the reference does:
+    per rotation: rotate, trunk(scene), trunk(mask), cat, head (code/models.py:371-389)."""
+    import torch
+    from oracle import qnet
+    import smg_b200.models as models
+    torch.set_num_threads(os.cpu_count())
+    if "sd" not in _CPU_CACHE:
+        torch.manual_seed(0)
+        _CPU_CACHE["sd"] = models.reinforcement_net(True).state_dict()
+        scenes, masks = make_units(1, 100)
+        _CPU_CACHE["x"] = qnet.preprocess(scenes[0], MEAN, STD)
+        _CPU_CACHE["m"] = qnet.preprocess(masks[0], MEAN, STD)
+    sd, x, m = _CPU_CACHE["sd"], _CPU_CACHE["x"], _CPU_CACHE["m"]
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            for r in range(rotations_per_sample):
+                qnet.q_forward(sd, x, m, 0, [r], R)  # one rotation per call -> mask pass recomputed each time
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return best
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    cores = os.cpu_count()
+    t_rot = cpu_reference_time(1)  # also the warm-up of the thread pool
+    budget = 150.0
+    rps = int(max(1, min(R, budget / max(1e-9, (args.steps + args.warmup) * t_rot))))
+    for _ in range(args.warmup):
+        cpu_reference_time(rps)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_time(rps)
+    dt = time.perf_counter() - t0
+    units = args.steps * rps / float(R)
+    value = units / dt
+    sample = ("%d of %d rotations per step (each: rotate + trunk(scene) + trunk(mask) + head, fp32, torch %s CPU), "
+              "scaled by 16/%d" % (rps, R, torch.__version__, rps))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    from smg_b200.trainer import Trainer
+
+    torch.manual_seed(0)
+    tr = Trainer("reinforcement", 0.5, False, None, False, precision=args.precision)
+    tr.model.gnum_rotations = tr.model.snum_rotations = R
+    tr.model.update_running_stats = False  # snapshot-only side effect; not part of the Q result
+    eng = tr.model._engine(R + 1)
+
+    # precision guard: the timed mode must agree with the fp32 mode on the bench input (tolerance 1e-2)
+    scenes, masks = make_units(max(2, args.steps + args.warmup), 100 + 1000 * rank)
+    q_fast = tr.forward(scenes[0], masks[0], 0, True, False)
+    precision = args.precision
+    note = None
+    if precision != "fp32":
+        tr.model.precision = "fp32"
+        q_ref = tr.forward(scenes[0], masks[0], 0, True, False)
+        err = float(np.abs(q_fast - q_ref).max() / np.abs(q_ref).max())
+        if not np.isfinite(err) or err > (1e-2 if precision == "tf32" else 1e-1):
+            note = "%s mode disagreed with fp32 mode (err %.3g); benchmarking fp32 mode instead" % (precision, err)
+            precision = "fp32"
+        else:
+            note = "%s vs fp32 mode on the bench input: max|dQ|/max|Q| = %.2e" % (precision, err)
+        tr.model.precision = precision
+        eng = tr.model._engine(R + 1)
+
+    rots = list(range(R))
+    scenes_d = torch.from_numpy(scenes).to(dev)
+    masks_d = torch.from_numpy(masks).to(dev)
+    nu = scenes.shape[0]
+    best = torch.zeros(2, device=dev)
+    gathered = [torch.zeros(2, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step_resident(i):
+        q = eng.qforward_maps(0, scenes_d[i % nu], masks_d[i % nu:i % nu + 1], MEAN, STD, rots, R)
+        val, idx = eng.argmax(q)
+        if world > 1:  # per-GPU best (Q, rotation) tuples: the path's only exchange
+            best[0] = val[0]
+            best[1] = idx[0].float()
+            dist.all_gather(gathered, best)
+        return q
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_resident(args.warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * args.steps / (ms_max / 1e3)
+
+    # ---- e2e: Trainer.forward with host heightmaps (pinned), H2D + D2H inside the timed region
+    pin_s = [torch.from_numpy(scenes[i]).pin_memory() for i in range(nu)]
+    pin_m = [torch.from_numpy(masks[i]).pin_memory() for i in range(nu)]
+    for i in range(args.warmup):
+        tr.forward(pin_s[i % nu].numpy(), pin_m[i % nu].numpy(), 0, True, False)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        qh = tr.forward(pin_s[(args.warmup + i) % nu].numpy(), pin_m[(args.warmup + i) % nu].numpy(), 0, True, False)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / (float(t.item()) / 1e3)
+    h2d = int(scenes[0].nbytes + masks[0].nbytes)
+    d2h = int(qh.size * 4)
+
+    # ---- roofline of the dominant kernel class (rank 0, separate short pass with event pairs per launch)
+    line_extra = {}
+    if rank == 0:
+        peaks = measured_peaks()
+        eng.profile_enable(True)
+        nprof = min(3, args.steps)
+        for i in range(nprof):
+            step_resident(i)
+        prof = eng.profile_read()
+        eng.profile_enable(False)
+        total_ms = sum(v["ms"] for v in prof.values())
+        dom = max(("conv1x1", "conv3x3", "stem"), key=lambda k: prof[k]["ms"])
+        d = prof[dom]
+        per_launch_ms = d["ms"] / max(1, d["launches"])
+        if dom == "stem":
+            achieved = d["bytes"] / 1e9 / (d["ms"] / 1e3)
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": None}
+        else:
+            achieved = d["flops"] / 1e12 / (d["ms"] / 1e3)
+            roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None}
+        roof.update({"kernel": dom, "avg_launch_ms": per_launch_ms, "launches_per_step": d["launches"] // nprof,
+                     "share_of_step": d["ms"] / total_ms if total_ms else None, "peak_source": peaks["source"],
+                     "note": "peak = dense bf16 cuBLAS sustained; tf32 operands run at half the bf16 tensor rate" if precision == "tf32" else None,
+                     "classes": {k: {"ms_per_step": v["ms"] / nprof, "launches_per_step": v["launches"] // nprof,
+                                     "tflops": (v["flops"] / 1e12 / (v["ms"] / 1e3)) if v["ms"] else None,
+                                     "algo_gbs": (v["bytes"] / 1e9 / (v["ms"] / 1e3)) if v["ms"] else None}
+                                 for k, v in prof.items()}})
+        line_extra["roofline"] = roof
+        line_extra["whole_step_tflops"] = GFLOP_PER_UNIT * value / 1e3
+
+        # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
+        if world == 1 and not args.no_cpu_baseline:
+            rps = 2
+            dt = cpu_reference_time(rps)
+            line_extra["cpu_baseline"] = {
+                "value": (rps / float(R)) / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                "sample": "%d of %d rotations of one unit (each: rotate + trunk(scene) + trunk(mask) + head, fp32 torch CPU, "
+                          "all host threads), scaled by 16/%d; %.1f s of CPU work" % (rps, R, rps, dt)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[precision],
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "units_per_step_per_gpu": 1, "rotations": R, "precision": precision,
+                           "precision_note": note, "image_mean": MEAN, "image_std": STD,
+                           "l2": "working set per step (17 samples x 87 MB of fp32 activations) exceeds the 126 MB L2",
+                           "parallelism": "dp%d over independent units; all_gather of per-GPU best (Q, rot)" % world},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "clocks": clocks, "gflop_per_unit": GFLOP_PER_UNIT}
+        line.update(line_extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

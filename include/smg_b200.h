@@ -118,7 +118,8 @@ int smg_qforward(smg_handle* h, int trunk_id, int head_id, const float* dev_scen
  * code/trainer.py:162-207.                                                          */
 int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm,
                       const double* dev_mask_hms, int n_masks, int hm_size, double mean, double stddev,
-                      const int* host_rot_idx, int n_rot, int num_rotations, float* dev_q, void* stream);
+                      const int* host_rot_idx, int n_rot, int num_rotations, float* dev_q, float* dev_bn_mean,
+                      float* dev_bn_var, void* stream);
 
 /* ---- training (code/trainer.py:278-384) -----------------------------------------
  * smg_qforward with n_masks = n_rot = 1 and save_for_backward; then smg_qbackward
@@ -161,6 +162,26 @@ int64_t smg_launch_count(smg_handle* h);
  * "trans1".."trans3" (NHWC float32 of the last forward, sample `sample`) -> NCHW.     */
 int smg_debug_read(smg_handle* h, const char* what, int sample, float* dev_out_nchw, int64_t capacity_floats,
                    void* stream);
+
+/* Per-kernel-class device timing for roofline reporting.  While enabled, every launch of a class is
+ * bracketed by CUDA events on the launching stream.  Classes: 0 stem (conv0, norm0+pool0), 1 conv 1x1
+ * (dense-layer bottlenecks, transitions, head), 2 conv 3x3, 3 everything else.  smg_profile_read
+ * synchronises, then returns per class the summed milliseconds, launch count, algorithmic FLOPs and
+ * algorithmic bytes since smg_profile_enable(h, 1), and clears the records.                          */
+#define SMG_PROFILE_CLASSES 4
+int smg_profile_enable(smg_handle* h, int enable);
+int smg_profile_read(smg_handle* h, double* host_ms, int64_t* host_launches, double* host_flops, double* host_bytes);
+
+/* run ONE convolution of the generic conv kernel on caller tensors (unit-test hook for conv_ffma.cu /
+ * conv_umma.cu): in NHWC [n,hin,hin,in_cstride] (channels [0,cin) used), prologue a = relu?(x*scale+shift)
+ * with scale/shift [n,cin], optional 2x2 average pool of the prologue output, taps 1 (1x1) or 9 (3x3 pad 1),
+ * torch OIHW weights [cout,cin,k,k]; writes channels [out_coff,out_coff+cout) of out NHWC
+ * [n,hout,hout,out_cstride] and, if non-NULL, ACCUMULATES (sum, sumsq) into dev_out_stats [n,out_cstride,2].
+ * Synchronous.                                                                                          */
+int smg_debug_conv(smg_handle* h, int precision, const float* dev_in, int n, int hin, int cin, int in_cstride,
+                   const float* dev_scale, const float* dev_shift, int relu, int pool, int taps,
+                   const float* dev_w_oihw, int cout, float* dev_out, int out_cstride, int out_coff,
+                   double* dev_out_stats, void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,7 @@ PROTOTYPES = {
     "smg_rotate_index_map": (I, [VP, I, I, VP, VP]),
     "smg_trunk_forward": (I, [VP, I, VP, I, VP, VP, VP, VP]),
     "smg_qforward": (I, [VP, I, I, VP, VP, I, c_int_p, I, I, VP, VP, VP, VP]),
-    "smg_qforward_maps": (I, [VP, I, I, VP, VP, I, I, ctypes.c_double, ctypes.c_double, c_int_p, I, I, VP, VP]),
+    "smg_qforward_maps": (I, [VP, I, I, VP, VP, I, I, ctypes.c_double, ctypes.c_double, c_int_p, I, I, VP, VP, VP, VP]),
     "smg_qforward_train": (I, [VP, I, I, VP, VP, I, I, VP, VP, VP, VP]),
     "smg_qbackward": (I, [VP, VP, c_void_pp, c_void_pp, VP]),
     "smg_adam_step": (I, [VP, c_void_pp, c_void_pp, c_void_pp, c_void_pp, c_int64_p, I, I,
@@ -40,6 +40,9 @@ PROTOTYPES = {
     "smg_nms": (I, [VP, VP, I, ctypes.c_float, ctypes.c_float, ctypes.c_float, VP, VP, VP]),
     "smg_launch_count": (ctypes.c_int64, [VP]),
     "smg_debug_read": (I, [VP, ctypes.c_char_p, I, VP, ctypes.c_int64, VP]),
+    "smg_profile_enable": (I, [VP, I]),
+    "smg_profile_read": (I, [VP, c_double_p, c_int64_p, c_double_p, c_double_p]),
+    "smg_debug_conv": (I, [VP, I, VP, I, I, I, I, VP, VP, I, I, I, VP, I, VP, I, I, VP, VP]),
 }
 
 _lib = None

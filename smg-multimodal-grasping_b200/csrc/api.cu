@@ -38,7 +38,32 @@ struct DeviceGuard {
     }
 };
 
+// brackets the launches issued inside its lifetime with CUDA events when profiling is enabled
+struct ProfScope {
+    smg_handle* h;
+    cudaStream_t st;
+    size_t idx = (size_t)-1;
+    ProfScope(smg_handle* h_, cudaStream_t st_, int cls, double flops, double bytes) : h(h_), st(st_) {
+        if (!h->profile) return;
+        smg_handle::ProfRec r;
+        r.cls = cls; r.flops = flops; r.bytes = bytes;
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, st);
+        idx = h->prof.size();
+        h->prof.push_back(r);
+    }
+    ~ProfScope() {
+        if (idx != (size_t)-1) cudaEventRecord(h->prof[idx].e1, st);
+    }
+};
+
 static int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
+    const int hout = a.pool ? a.hin / 2 : a.hin;
+    const double px = (double)a.n * hout * hout;
+    // algorithmic traffic: every input element of the layer read once, every output written once (fp32)
+    const double bytes = 4.0 * ((double)a.n * a.hin * a.hin * a.cin + px * a.cout);
+    ProfScope ps(h, st, a.taps == 9 ? 2 : 1, 2.0 * px * a.cout * a.cin * a.taps, bytes);
     if (h->precision == SMG_PREC_FP32) return launch_conv_ffma(h, a, st);
     return launch_conv_umma(h, a, h->precision, st);
 }
@@ -53,9 +78,14 @@ static int trunk_forward(smg_handle* h, int trunk_id, int n, cudaStream_t st) {
     const int S = h->max_samples;
     (void)S;
     SMG_CUDA(cudaMemsetAsync(h->stats, 0, h->stats_bytes, st));
-    SMG_TRY(launch_conv0(h, h->input, n, T.conv0, h->conv0, stats_ptr(h, h->st_conv0), st));
-    SMG_TRY(launch_pool0(h, n, h->conv0, stats_ptr(h, h->st_conv0), T.norm0.gamma, T.norm0.beta, h->block[0],
-                         h->geom[0].c_tot, stats_ptr(h, h->st_block[0]), st));
+    {
+        const double hc = (double)(h->H / 2) * (h->H / 2);
+        // stem traffic: input read + conv0 written, conv0 read + pooled output written
+        ProfScope ps(h, st, 0, 2.0 * n * hc * 64 * 147, 4.0 * n * (3.0 * h->H * h->H + 2 * hc * 64 + hc / 4 * 64));
+        SMG_TRY(launch_conv0(h, h->input, n, T.conv0, h->conv0, stats_ptr(h, h->st_conv0), st));
+        SMG_TRY(launch_pool0(h, n, h->conv0, stats_ptr(h, h->st_conv0), T.norm0.gamma, T.norm0.beta, h->block[0],
+                             h->geom[0].c_tot, stats_ptr(h, h->st_block[0]), st));
+    }
     int layer_index = 0;
     for (int b = 0; b < kNumBlocks; ++b) {
         const BlockGeom& g = h->geom[b];
@@ -471,7 +501,7 @@ int smg_qforward(smg_handle* h, int trunk_id, int head_id, const float* dev_scen
 
 int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm, const double* dev_mask_hms,
                       int n_masks, int hm_size, double mean, double stddev, const int* host_rot_idx, int n_rot,
-                      int num_rotations, float* dev_q, void* stream) {
+                      int num_rotations, float* dev_q, float* dev_bn_mean, float* dev_bn_var, void* stream) {
     SMG_CHECK(h && dev_scene_hm && dev_mask_hms && host_rot_idx && dev_q, SMG_ERR_INVALID, "smg_qforward_maps: NULL argument");
     SMG_CHECK(trunk_id >= 0 && trunk_id < SMG_NUM_TRUNKS && head_id >= 0 && head_id < SMG_NUM_HEADS, SMG_ERR_INVALID,
               "smg_qforward_maps: trunk %d / head %d", trunk_id, head_id);
@@ -484,7 +514,7 @@ int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* de
     SMG_TRY(launch_prep(h, dev_scene_hm, 1, hm_size, mean, stddev, h->scene_tmp, st));
     SMG_TRY(launch_rotate(h, h->scene_tmp, host_rot_idx, n_rot, num_rotations, h->input, st));
     SMG_TRY(launch_prep(h, dev_mask_hms, n_masks, hm_size, mean, stddev, h->input + (size_t)n_rot * img, st));
-    return qforward_common(h, trunk_id, head_id, n_masks, n_rot, dev_q, nullptr, nullptr, st);
+    return qforward_common(h, trunk_id, head_id, n_masks, n_rot, dev_q, dev_bn_mean, dev_bn_var, st);
 }
 
 int smg_qforward_train(smg_handle*, int, int, const float*, const float*, int, int, float*, float*, float*, void*) {
@@ -548,6 +578,69 @@ int smg_debug_read(smg_handle* h, const char* what, int sample, float* dev_out_n
               (long long)hw * hw * c);
     src += (size_t)sample * hw * hw * cstride;
     return launch_nhwc_to_nchw(h, src, hw, c, cstride, dev_out_nchw, (cudaStream_t)stream);
+}
+
+int smg_profile_enable(smg_handle* h, int enable) {
+    SMG_CHECK(h != nullptr, SMG_ERR_INVALID, "NULL handle");
+    DeviceGuard guard(h->device);
+    for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    h->prof.clear();
+    h->profile = enable != 0;
+    return SMG_OK;
+}
+
+int smg_profile_read(smg_handle* h, double* host_ms, int64_t* host_launches, double* host_flops, double* host_bytes) {
+    SMG_CHECK(h && host_ms && host_launches && host_flops && host_bytes, SMG_ERR_INVALID, "smg_profile_read: NULL argument");
+    DeviceGuard guard(h->device);
+    SMG_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < SMG_PROFILE_CLASSES; ++i) { host_ms[i] = 0; host_launches[i] = 0; host_flops[i] = 0; host_bytes[i] = 0; }
+    for (auto& r : h->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        host_ms[r.cls] += ms;
+        host_launches[r.cls] += 1;
+        host_flops[r.cls] += r.flops;
+        host_bytes[r.cls] += r.bytes;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    h->prof.clear();
+    return SMG_OK;
+}
+
+int smg_debug_conv(smg_handle* h, int precision, const float* dev_in, int n, int hin, int cin, int in_cstride,
+                   const float* dev_scale, const float* dev_shift, int relu, int pool, int taps,
+                   const float* dev_w_oihw, int cout, float* dev_out, int out_cstride, int out_coff,
+                   double* dev_out_stats, void* stream) {
+    SMG_CHECK(h && dev_in && dev_scale && dev_shift && dev_w_oihw && dev_out, SMG_ERR_INVALID, "smg_debug_conv: NULL argument");
+    SMG_CHECK(taps == 1 || taps == 9, SMG_ERR_INVALID, "smg_debug_conv: taps %d", taps);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ConvW cw;
+    ArenaPlanner p;
+    plan_conv(p, cw, cin, cout, taps, nullptr);
+    uint8_t* base = nullptr;
+    SMG_CUDA(cudaMalloc(&base, p.off));
+    ArenaPlanner p2;
+    plan_conv(p2, cw, cin, cout, taps, base);
+    int status = pack_conv_weights(h, dev_w_oihw, cw, 0, cin, st);
+    if (status == SMG_OK) {
+        ConvArgs a;
+        a.in = dev_in; a.in_cstride = in_cstride; a.cin = cin; a.hin = hin;
+        a.prologue_mode = 1; a.scale = dev_scale; a.shift = dev_shift; a.relu = relu;
+        a.pool = pool; a.taps = taps; a.w = &cw;
+        a.out = dev_out; a.out_cstride = out_cstride; a.out_coff = out_coff; a.cout = cout;
+        a.out_stats = dev_out_stats; a.out_stats_stride = out_cstride;
+        a.n = n;
+        status = precision == SMG_PREC_FP32 ? launch_conv_ffma(h, a, st) : launch_conv_umma(h, a, precision, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(base);
+    if (status == SMG_OK && e != cudaSuccess) {
+        set_error("smg_debug_conv: %s", cudaGetErrorString(e));
+        return SMG_ERR_CUDA;
+    }
+    return status;
 }
 
 }  // extern "C"

@@ -153,6 +153,15 @@ struct smg_handle {
     float* scene_tmp = nullptr;   // [3,H,H] staging for smg_qforward_maps
     float* mask_tmp = nullptr;    // unused placeholder
     int last_n = 0;               // samples of the last trunk forward (for smg_debug_read)
+
+    // optional per-kernel-class timing (bench.py roofline): CUDA events around every launch of a class
+    bool profile = false;
+    struct ProfRec {
+        int cls;
+        cudaEvent_t e0, e1;
+        double flops, bytes;
+    };
+    std::vector<ProfRec> prof;
 };
 
 namespace smg {

@@ -168,22 +168,57 @@ class Engine:
                                          int(num_rotations), q.data_ptr(), pm, pv, self._stream()))
         return (q, mean, var) if want_bn_stats else q
 
-    def qforward_maps(self, style, scene_hm, mask_hms, mean, std, rot_idx, num_rotations):
+    def qforward_maps(self, style, scene_hm, mask_hms, mean, std, rot_idx, num_rotations, want_bn_stats=False):
         """Same from 224x224 float64 heightmaps already on the device (fuses code/trainer.py:165-191)."""
         tid, hid = STYLE_ROUTE[int(style)]
         n_masks, hs = mask_hms.shape[0], mask_hms.shape[-1]
         n_rot = len(rot_idx)
         rot = (ctypes.c_int * n_rot)(*[int(r) for r in rot_idx])
         q = torch.empty((n_masks, n_rot, self.n_out), dtype=torch.float32, device=self.device)
+        mean_t = var_t = None
+        pm = pv = None
+        if want_bn_stats:
+            mean_t = torch.empty((n_rot + n_masks, TRUNK_BN_CHANNELS), dtype=torch.float32, device=self.device)
+            var_t = torch.empty_like(mean_t)
+            pm, pv = mean_t.data_ptr(), var_t.data_ptr()
         _lib.check(self.lib.smg_qforward_maps(self.h, tid, hid, scene_hm.data_ptr(), mask_hms.data_ptr(), n_masks, hs,
                                               float(mean), float(std), rot, n_rot, int(num_rotations), q.data_ptr(),
-                                              self._stream()))
-        return q
+                                              pm, pv, self._stream()))
+        return (q, mean_t, var_t) if want_bn_stats else q
 
     def debug_read(self, what, sample, shape):
         out = torch.empty(shape, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.smg_debug_read(self.h, what.encode(), int(sample), out.data_ptr(), out.numel(), self._stream()))
         return out
+
+    def profile_enable(self, enable=True):
+        _lib.check(self.lib.smg_profile_enable(self.h, int(bool(enable))))
+
+    def profile_read(self):
+        """Per kernel class (stem, conv1x1, conv3x3, other): dict(ms, launches, flops, bytes) since profile_enable."""
+        ms = (ctypes.c_double * 4)()
+        ln = (ctypes.c_int64 * 4)()
+        fl = (ctypes.c_double * 4)()
+        by = (ctypes.c_double * 4)()
+        _lib.check(self.lib.smg_profile_read(self.h, ms, ln, fl, by))
+        names = ("stem", "conv1x1", "conv3x3", "other")
+        return {names[i]: {"ms": ms[i], "launches": int(ln[i]), "flops": fl[i], "bytes": by[i]} for i in range(4)}
+
+    def debug_conv(self, precision, x_nhwc, cin, scale, shift, relu, pool, w_oihw, out_cstride=None, out_coff=0,
+                   want_stats=True):
+        """One generic-conv launch on caller tensors (unit-test hook).  Returns (out NHWC, stats [n,C,2] f64)."""
+        n, hin, _, cstride = x_nhwc.shape
+        cout, taps = w_oihw.shape[0], w_oihw.shape[2] * w_oihw.shape[3]
+        hout = hin // 2 if pool else hin
+        out_cstride = out_cstride or cout
+        out = torch.zeros((n, hout, hout, out_cstride), dtype=torch.float32, device=self.device)
+        stats = torch.zeros((n, out_cstride, 2), dtype=torch.float64, device=self.device) if want_stats else None
+        _lib.check(self.lib.smg_debug_conv(
+            self.h, PRECISIONS[precision], x_nhwc.contiguous().data_ptr(), n, hin, cin, cstride,
+            scale.contiguous().data_ptr(), shift.contiguous().data_ptr(), int(relu), int(pool), taps,
+            w_oihw.contiguous().data_ptr(), cout, out.data_ptr(), out_cstride, out_coff,
+            stats.data_ptr() if want_stats else None, self._stream()))
+        return out, stats
 
     # ------------------------------------------------------------------ K9 / K11 / K12
     def argmax(self, q):
@@ -216,11 +251,18 @@ class Engine:
         return keep, cnt
 
 
-def get_engine(device=0, max_samples=32, H=640, precision=None):
-    """Process-wide engine for a device (one handle per GPU); grows the workspace on demand."""
+def drop_engine(owner):
+    """Release the engines of a model that is going away."""
+    for key in [k for k in _engines if k[2] == owner]:
+        _engines.pop(key).__del__()
+
+
+def get_engine(device=0, max_samples=32, H=640, precision=None, owner=None):
+    """Engine for (device, owner); `owner` separates models with different weights (model vs model_target).
+    The workspace grows on demand."""
     if isinstance(device, torch.device):
         device = device.index or 0
-    key = (int(device), int(H))
+    key = (int(device), int(H), owner)
     eng = _engines.get(key)
     if eng is None or eng.max_samples < max_samples:
         prec = precision or (eng.precision if eng is not None else "fp32")

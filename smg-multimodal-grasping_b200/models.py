@@ -12,6 +12,7 @@ The parameter containers are ordinary torch modules (torchvision's DenseNet-121 
 used for storage and key names only; its forward is never called).  The arithmetic is
 done by the CUDA library; without it (or without a GPU) forward raises - no fallback.
 """
+import weakref
 from collections import OrderedDict
 
 import torch
@@ -75,7 +76,10 @@ class _SmgNet(nn.Module):
         return torch.cuda.current_device()
 
     def _engine(self, n_samples):
-        eng = _engine.get_engine(self._device_index(), max(n_samples, 18), 640, self.precision)
+        if getattr(self, "_finalizer_owner", None) != id(self):  # also true for a deepcopy of a live model
+            object.__setattr__(self, "_finalizer_owner", id(self))
+            weakref.finalize(self, _engine.drop_engine, id(self))
+        eng = _engine.get_engine(self._device_index(), max(n_samples, 18), 640, self.precision, owner=id(self))
         eng.sync_weights(self)
         return eng
 

@@ -1,0 +1,202 @@
+"""Drop-in `Trainer` (reference: code/trainer.py:17-384) over the CUDA library.
+
+Kept from the reference: constructor arguments, `forward(depth_heightmap, m_depth_heightmap, style,
+is_volatile, is_target, specific_rotation)` -> numpy array of Q / P(class 0), `get_label_value`,
+`backprop` (Huber / weighted CE + Adam lr 1e-4), `model` / `model_target` / `optimizer` attributes.
+
+Differences, all deliberate:
+  * `image_mean` / `image_std` are instance attributes defaulting to 0.01 / 0.03.  The reference's
+    published literals are 0 / 0, which makes every prediction NaN.
+  * pre-processing (zoom x2, pad, normalise, 3 channels) runs on the GPU fused with the rotation
+    stage; only the 224x224 float64 heightmaps cross PCIe.
+  * `forward_all` evaluates all objects x rotations of one primitive in ONE de-duplicated pass
+    (the reference's step loop recomputes identical trunk passes, code/main.py:158-192).
+  * a CUDA device is required; `force_cpu=True` raises instead of silently running elsewhere.
+"""
+import copy
+
+import numpy as np
+import torch
+
+from . import engine as _engine
+from .models import reactive_net, reinforcement_net
+from .utils import CrossEntropyLoss2d
+
+
+class Trainer(object):
+    def __init__(self, method, future_reward_discount, load_snapshot, snapshot_file, force_cpu,
+                 precision="fp32", device=None):
+        self.method = method
+        if force_cpu or not torch.cuda.is_available():
+            raise RuntimeError("smg_b200.Trainer needs a CUDA device (B200); there is no CPU path")
+        self.use_cuda = True
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.image_mean = 0.01
+        self.image_std = 0.03
+
+        if self.method == 'reactive':
+            self.model = reactive_net(self.use_cuda)
+            w = torch.ones(3)
+            w[2] = 0  # class 2 = "no loss" (code/trainer.py:38-45)
+            self.suction_criterion = CrossEntropyLoss2d(w.to(self.device))
+            self.grasp_criterion = CrossEntropyLoss2d(w.to(self.device))
+            self.gs_criterion = CrossEntropyLoss2d(w.to(self.device))
+            if load_snapshot:
+                self.model.load_state_dict(torch.load(snapshot_file))
+            self.model = self.model.to(self.device)
+        elif self.method == 'reinforcement':
+            self.model = reinforcement_net(self.use_cuda)
+            self.model_target = copy.deepcopy(self.model)
+            self.model_target.load_state_dict(self.model.state_dict())
+            self.future_reward_discount = future_reward_discount
+            if load_snapshot:
+                self.model.load_state_dict(torch.load(snapshot_file))
+            self.model = self.model.to(self.device)
+            self.model_target = self.model_target.to(self.device)
+        else:
+            raise ValueError("method must be 'reactive' or 'reinforcement'")
+        self.model.precision = precision
+        if self.method == 'reinforcement':
+            self.model_target.precision = precision
+        self.model.train()
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0)
+        self.iteration = 0
+        self.executed_action_log = []
+        self.label_value_log = []
+        self.reward_value_log = []
+        self.predicted_value_log = []
+        self.use_heuristic_log = []
+        self.is_exploit_log = []
+        self.clearance_log = []
+        self.grasping_type_log = []
+        self.episode_success_log = []
+        self.training_loss_log = []
+
+    def preload(self, transitions_directory):
+        import os
+        self.executed_action_log = np.loadtxt(os.path.join(transitions_directory, 'executed-action.log.txt'), delimiter=' ')
+        self.iteration = self.executed_action_log.shape[0] - 2
+
+    # ------------------------------------------------------------------ forward
+    def _rotations(self, model, style, specific_rotation):
+        """Rotation indices / divisor exactly as the nets' forward picks them (code/models.py:361-510)."""
+        if specific_rotation == -1:
+            if style == 0:
+                return list(range(model.gnum_rotations)), model.gnum_rotations
+            if style == 1:
+                return list(range(model.snum_rotations)), model.snum_rotations
+            return [0], model.gnum_rotations
+        return [0 if style == 2 else int(specific_rotation)], model.gnum_rotations
+
+    def forward_all(self, depth_heightmap, m_depth_heightmaps, style=0, is_target=False, specific_rotation=-1):
+        """Q table [n_masks, n_rot(, 3)] for one scene and MANY masked heightmaps in one de-duplicated pass."""
+        model = self.model_target if (is_target and self.method == 'reinforcement') else self.model
+        rots, nrot = self._rotations(model, style, specific_rotation)
+        masks = np.ascontiguousarray(np.asarray(m_depth_heightmaps, dtype=np.float64))
+        if masks.ndim == 2:
+            masks = masks[None]
+        eng = model._engine(len(rots) + masks.shape[0])
+        scene = torch.from_numpy(np.ascontiguousarray(depth_heightmap, dtype=np.float64)).to(eng.device, non_blocking=True)
+        masks_t = torch.from_numpy(masks).to(eng.device, non_blocking=True)
+        if model.update_running_stats:
+            q, mean, var = eng.qforward_maps(style, scene, masks_t, self.image_mean, self.image_std, rots, nrot,
+                                             want_bn_stats=True)
+            trunk = getattr(model, _engine.TRUNK_ATTRS[_engine.STYLE_ROUTE[style][0]])
+            order = []
+            for k in range(masks.shape[0]):          # the reference loops objects, then rotations
+                for i in range(len(rots)):
+                    order += [i, len(rots) + k]
+            model._apply_running_stats(trunk, mean, var, order)
+        else:
+            q = eng.qforward_maps(style, scene, masks_t, self.image_mean, self.image_std, rots, nrot)
+        return q  # cuda tensor [n_masks, n_rot, n_out]
+
+    def forward(self, depth_heightmap, m_depth_heightmap, style=0, is_volatile=False, is_target=False, specific_rotation=-1):
+        if not is_volatile:
+            return self._forward_grad(depth_heightmap, m_depth_heightmap, style, specific_rotation)
+        q = self.forward_all(depth_heightmap, m_depth_heightmap, style, is_target, specific_rotation)[0]
+        if self.method == 'reactive':
+            # the reference only looks at rotation 0 and returns softmax P(class 0) (code/trainer.py:195-199)
+            return torch.softmax(q[0], dim=0)[0:1].cpu().numpy()
+        return q[:, 0].double().cpu().numpy()
+
+    def _forward_grad(self, depth_heightmap, m_depth_heightmap, style, specific_rotation):
+        eng = self.model._engine(2)
+        hm = torch.from_numpy(np.stack([np.asarray(depth_heightmap, np.float64), np.asarray(m_depth_heightmap, np.float64)]))
+        x = eng.prep(hm.to(eng.device), self.image_mean, self.image_std)
+        out = self.model.forward(x[0:1], x[1:2], style, False, specific_rotation)
+        if self.method == 'reactive':
+            return torch.softmax(out.detach().view(-1), dim=0)[0:1].cpu().numpy()
+        return out.detach().view(-1).double().cpu().numpy()
+
+    # ------------------------------------------------------------------ labels (code/trainer.py:212-274)
+    def get_label_value(self, primitive_action, objects_number, suction_success, grasp_success, gs_success,
+                        depth_heightmap, mask_depth, objects_mask, bestg_id, bests_id, bestgs_g_id, bestgs_s_id,
+                        exploit_action, bestg_conf, bests_conf, bestgs_conf):
+        if self.method == 'reactive':
+            label_value = 0
+            if primitive_action == 'suction':
+                success_value = suction_success
+                label_value = 0 if suction_success else 1
+            elif primitive_action == 'grasp':
+                success_value = grasp_success
+                label_value = 0 if grasp_success else 1
+            elif primitive_action == 'grasp_then_suction':
+                success_value = gs_success
+                label_value = 0 if gs_success == 2.5 else 1
+            return label_value, success_value
+        current_reward = 0
+        if primitive_action == 'suction':
+            current_reward = suction_success
+        elif primitive_action == 'grasp':
+            current_reward = grasp_success
+        elif primitive_action == 'grasp_then_suction':
+            current_reward = gs_success
+        if suction_success == 0 and grasp_success == 0 and gs_success == 0:
+            future_reward = 0
+        elif (objects_number == 1 and suction_success == 1) or (objects_number == 1 and grasp_success == 1) or \
+                (objects_number == 2 and gs_success == 2.5):
+            future_reward = 0
+        else:
+            # Q_target(s', argmax_a Q(s', a)) at the best rotation (code/trainer.py:259-270)
+            if exploit_action == 'grasp':
+                m = depth_heightmap * mask_depth[bestg_id[0]]
+                future_reward = self.forward(depth_heightmap, m, 0, True, True, bestg_id[1])[0]
+            elif exploit_action == 'suction':
+                m = depth_heightmap * mask_depth[bests_id[0]]
+                future_reward = self.forward(depth_heightmap, m, 1, True, True, bests_id[1])[0]
+            else:
+                m = depth_heightmap * (mask_depth[bestgs_g_id[0]] + mask_depth[bestgs_s_id[0]])
+                future_reward = self.forward(depth_heightmap, m, 2, True, True, bestgs_g_id[1])[0]
+        expected_reward = current_reward + self.future_reward_discount * future_reward
+        return expected_reward, current_reward
+
+    # ------------------------------------------------------------------ backprop (code/trainer.py:278-384)
+    def backprop(self, depth_heightmap, primitive_action, bestg_id, bests_id, bestgs_g_id, bestgs_s_id,
+                 label_value, objects_mask, sro_best, gro_best, bestgs_num):
+        mask_depth = np.asarray(objects_mask).reshape(objects_mask.shape[0], objects_mask.shape[1], objects_mask.shape[2])
+        self.optimizer.zero_grad()
+        if primitive_action == 'grasp':
+            style, m, rot, attr = 0, depth_heightmap * mask_depth[bestg_id[0]], bestg_id[1], 'gra_prob'
+        elif primitive_action == 'suction':
+            style, m, rot, attr = 1, depth_heightmap * mask_depth[bests_id[0]], bests_id[1], 'suc_prob'
+        elif primitive_action == 'grasp_then_suction':
+            style = 2
+            m = depth_heightmap * (mask_depth[bestgs_g_id[0]] + mask_depth[bestgs_s_id[0]])
+            rot, attr = bestgs_g_id[1], 'gs_prob'
+        else:
+            raise ValueError(primitive_action)
+        self.forward(depth_heightmap, m, style=style, is_volatile=False, is_target=False, specific_rotation=rot)
+        out = getattr(self.model, attr)
+        if self.method == 'reactive':
+            label = torch.full((1, 1, 1), int(label_value), dtype=torch.long, device=out.device)
+            crit = {0: self.grasp_criterion, 1: self.suction_criterion, 2: self.gs_criterion}[style]
+            loss = crit(out[0].view([1, 3, 1, 1]), label)
+        else:
+            d = out[0, 0, 0, 0] - label_value
+            loss = 0.5 * (d ** 2) if abs(float(d)) < 1 else abs(d) - 0.5  # hand-written Huber (code/trainer.py:345-348)
+        loss = loss.sum()
+        loss.backward()
+        loss_value = loss.detach().cpu().numpy()
+        self.optimizer.step()
+        return loss_value

@@ -1,0 +1,84 @@
+"""Unit tests of the generic convolution kernels (conv_ffma.cu fp32, conv_umma.cu tcgen05 tf32/bf16)
+through smg_debug_conv, against torch fp32 convolutions (TF32 disabled) on the same GPU.
+
+Covers every shape class of the trunk: 1x1 with K = 64..1024 (K not a multiple of 64), partial last
+M tile (HW % 128 != 0), the pooled transition, N = 64/128/256, 3x3 at every block's spatial size
+(patch tiling with and without column splits), channel-slice output and the statistics epilogue."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 2e-5, "tf32": 3e-3, "bf16": 2e-2}
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from smg_b200 import engine
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return engine.get_engine(0, 18, 640, "fp32", owner="conv")
+
+
+def reference(x_nhwc, cin, scale, shift, relu, pool, w):
+    x = x_nhwc[..., :cin].permute(0, 3, 1, 2).double()
+    a = x * scale.double()[:, :, None, None] + shift.double()[:, :, None, None]
+    if relu:
+        a = a.clamp_min(0)
+    if pool:
+        a = F.avg_pool2d(a, 2, 2)
+    y = F.conv2d(a, w.double(), padding=w.shape[-1] // 2)
+    return y.permute(0, 2, 3, 1).float()
+
+
+CASES = [
+    # (n, hin, cin, in_cstride, cout, k, pool)
+    (2, 16, 64, 256, 128, 1, 0),
+    (1, 40, 96, 256, 128, 1, 0),      # HW=1600: partial last tile; K=96 (not a multiple of 64)
+    (2, 20, 1024, 1024, 128, 1, 0),   # HW=400, largest K
+    (1, 20, 1024, 1024, 64, 1, 0),    # head shape N=64
+    (1, 32, 256, 256, 128, 1, 1),     # transition: pooled
+    (1, 16, 512, 512, 256, 1, 1),     # transition with two N tiles
+    (1, 160, 128, 128, 32, 3, 0),     # 3x3 block-1 size (4 column tiles)
+    (2, 80, 128, 128, 32, 3, 0),
+    (1, 40, 128, 128, 32, 3, 0),
+    (3, 20, 128, 128, 32, 3, 0),
+    (1, 8, 128, 128, 32, 3, 0),
+]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "n%d_h%d_cin%d_cs%d_cout%d_k%d_pool%d" % c)
+def test_conv_matches_torch(eng, precision, case):
+    n, hin, cin, cstride, cout, k, pool = case
+    g = torch.Generator(device="cuda").manual_seed(hash(case) % 1000)
+    x = torch.randn((n, hin, hin, cstride), generator=g, device="cuda")
+    scale = torch.rand((n, cin), generator=g, device="cuda") + 0.5
+    shift = torch.randn((n, cin), generator=g, device="cuda") * 0.3
+    w = torch.randn((cout, cin, k, k), generator=g, device="cuda") / (cin * k * k) ** 0.5
+    out_cstride, out_coff = cout + 64, 32
+    out, stats = eng.debug_conv(precision, x, cin, scale, shift, True, pool, w, out_cstride, out_coff)
+    ref = reference(x, cin, scale, shift, True, pool, w)
+    got = out[..., out_coff:out_coff + cout]
+    err = float((got - ref).abs().max() / ref.abs().max())
+    print("%s %s: rel-max err %.2e" % (precision, case, err))
+    assert err <= TOL[precision]
+    assert float(out[..., :out_coff].abs().max()) == 0 and float(out[..., out_coff + cout:].abs().max()) == 0, \
+        "wrote outside the channel slice"
+    # statistics epilogue: (sum, sumsq) per (sample, channel) of what was written
+    s_ref = got.double().sum((1, 2))
+    q_ref = (got.double() ** 2).sum((1, 2))
+    s_got, q_got = stats[:, out_coff:out_coff + cout, 0], stats[:, out_coff:out_coff + cout, 1]
+    assert float((s_got - s_ref).abs().max() / s_ref.abs().max()) <= 1e-4
+    assert float((q_got - q_ref).abs().max() / q_ref.abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_conv_no_relu_identity_prologue(eng, precision):
+    x = torch.randn((1, 20, 20, 128), device="cuda")
+    w = torch.randn((128, 128, 1, 1), device="cuda") / 11.3
+    one, zero = torch.ones((1, 128), device="cuda"), torch.zeros((1, 128), device="cuda")
+    out, _ = eng.debug_conv(precision, x, 128, one, zero, False, 0, w, want_stats=False)
+    ref = reference(x, 128, one, zero, False, 0, w)
+    assert float((out - ref).abs().max() / ref.abs().max()) <= TOL[precision]

@@ -1,0 +1,117 @@
+"""GPU parity of the self-contained kernels (K1 prep/rotate, K9 argmax, K11 heightmap, K12 NMS)
+through the C ABI, against the CPU oracle and the golden fixtures.  Integer / index / float64
+work is required to be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, MEAN, STD
+from oracle import heightmap as ohm
+from oracle import nms as onms
+from oracle import qnet
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from smg_b200 import engine
+    return engine.get_engine(0, 18, 640, "fp32", owner="kernels")
+
+
+def test_library_loaded_is_in_tree():
+    from smg_b200 import _lib
+    lib = _lib.load()
+    assert lib.smg_version() >= 100
+    assert os.path.samefile(os.path.dirname(_lib.LIB_PATH), os.path.join(os.path.dirname(GOLDEN_DIR), "..", "smg-multimodal-grasping_b200", "csrc"))
+
+
+def test_prep_matches_oracle(eng, scene_inputs):
+    scene, mask, pair, _ = scene_inputs
+    hm = torch.from_numpy(np.stack([scene, mask, pair])).cuda()
+    out = eng.prep(hm, MEAN, STD).cpu()
+    for i, v in enumerate((scene, mask, pair)):
+        assert torch.equal(out[i:i + 1], qnet.preprocess(v, MEAN, STD)), "prep differs for map %d" % i
+
+
+def test_prep_empty_map(eng):
+    out = eng.prep(torch.zeros(1, 224, 224, dtype=torch.float64, device="cuda"), MEAN, STD).cpu()
+    assert torch.equal(out, qnet.preprocess(np.zeros((224, 224)), MEAN, STD))
+
+
+@pytest.mark.parametrize("R", [1, 4, 16])
+def test_rotate_index_exact(eng, R):
+    H = 640
+    bad = 0
+    for r in range(R):
+        got = eng.rotate_index_map(r, R).cpu().numpy()
+        ref = qnet.rotate_index_map(H, r, R)
+        bad += int((got != ref).sum())
+    assert bad == 0, "rotation index mismatches vs torch-CPU arithmetic: %d pixels" % bad
+
+
+def test_rotate_values_match_torch(eng, scene_inputs):
+    x = qnet.preprocess(scene_inputs[0], MEAN, STD)
+    rots = list(range(16))
+    got = eng.rotate(x[0].cuda(), rots, 16).cpu()
+    mism_cpu = 0
+    for r in rots:
+        ref = qnet.rotate_nearest(x, r, 16)
+        mism_cpu += int((got[r:r + 1] != ref).sum())
+    assert mism_cpu == 0, "rotated images differ from torch CPU grid_sample in %d values" % mism_cpu
+    # informational: torch CUDA (cuBLAS bmm) may break .5 ties differently from torch CPU
+    xc = x.cuda()
+    mism_gpu = sum(int((got[r:r + 1].cuda() != qnet.rotate_nearest(xc, r, 16)).sum()) for r in rots)
+    print("rotate: values differing from torch CUDA grid_sample over 16 rotations: %d" % mism_gpu)
+
+
+def test_argmax_first_max_wins(eng):
+    rs = np.random.RandomState(0)
+    for n in (1, 7, 160, 1000):
+        q = rs.randn(n).astype(np.float32)
+        q[rs.randint(0, n)] = q.max()  # plant a tie
+        val, idx = eng.argmax(torch.from_numpy(q))
+        assert int(idx.item()) == int(np.argmax(q)) and float(val.item()) == float(q.max())
+
+
+def test_heightmap_bit_exact(eng, golden):
+    import smg_b200.synth as synth
+    cam = synth.make_camera(golden["heightmap"]["camera_seed"])
+    o224, o448, A = eng.heightmap(torch.from_numpy(cam["depth"]), cam["intrinsics"], cam["pose"])
+    z = np.load(os.path.join(GOLDEN_DIR, "heightmap_seed3.npz"))
+    d224, d448 = o224.cpu().numpy(), o448.cpu().numpy()
+    assert np.array_equal(d224, z["depth224"]), "224 map: %d of 50176 values differ" % int((d224 != z["depth224"]).sum())
+    assert np.array_equal(d448[::7], z["depth448_rows"])
+    assert np.array_equal(A, z["A_htor"])
+    # a second, different camera against the oracle
+    cam = synth.make_camera(11, num_objects=4, cluttered=False)
+    o224, o448, A = eng.heightmap(torch.from_numpy(cam["depth"]), cam["intrinsics"], cam["pose"])
+    r224, r448, rA = ohm.get_heightmap_depth(cam["depth"], cam["intrinsics"], cam["pose"])
+    assert np.array_equal(o224.cpu().numpy(), r224) and np.array_equal(o448.cpu().numpy(), r448) and np.array_equal(A, rA)
+
+
+def test_heightmap_dropin_signature(golden):
+    import smg_b200.synth as synth
+    from smg_b200 import utils
+    cam = synth.make_camera(golden["heightmap"]["camera_seed"])
+    out = utils.get_heightmap(cam["color"], cam["depth"], cam["intrinsics"], cam["pose"], synth.WORKSPACE_LIMITS, 0.002)
+    assert len(out) == 5 and out[1].shape == (224, 224) and out[3].shape == (448, 448) and out[1].dtype == np.float64
+
+
+def test_nms_matches_reference_lists(eng, golden):
+    import smg_b200.synth as synth
+    from smg_b200 import NMS
+    known = np.array([[[10, 10], [60, 60]], [[12, 12], [62, 62]], [[100, 100], [160, 150]], [[0, 0], [5, 5]],
+                      [[0, 0], [200, 200]]], np.float32)
+    for case in golden["nms"]:
+        if case["kind"] == "known5":
+            boxes, scores = known, np.ones(5)
+        else:
+            n = case["n"]
+            boxes, scores = synth.make_boxes(case["seed"], n) if n else (np.zeros((0, 2, 2), np.float32), np.zeros(0))
+        keep = NMS.py_cpu_nms(boxes, scores, 0.40, 224 * 224 / 60, 224 * 224 / 5)
+        assert keep == case["keep"], case
+    boxes, scores = synth.make_boxes(7, 1000)  # maximum supported size, against the oracle
+    assert NMS.py_cpu_nms(boxes, scores, 0.40, 224 * 224 / 60, 224 * 224 / 5) == onms.nms(boxes, scores, 0.40, 224 * 224 / 60, 224 * 224 / 5)
