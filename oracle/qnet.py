@@ -70,7 +70,7 @@ def rotation_theta(rotate_idx, num_rotations):
 
 def rotate_nearest(x, rotate_idx, num_rotations):
     """F.affine_grid(align_corners=True) + F.grid_sample(mode='nearest', zero padding)."""
-    theta = torch.from_numpy(rotation_theta(rotate_idx, num_rotations))[None].to(x.dtype)
+    theta = torch.from_numpy(rotation_theta(rotate_idx, num_rotations))[None].to(device=x.device, dtype=x.dtype)
     grid = F.affine_grid(theta, list(x.shape), align_corners=True)
     return F.grid_sample(x, grid, mode="nearest", align_corners=True)
 

@@ -1,0 +1,46 @@
+"""One warmed-up unit of work (R=16 Q pass) inside a cudaProfilerStart/Stop range, for ncu:
+
+  ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+      --log-file gpurun_out/launches.csv python profiles/profile_step.py --precision tf32
+  ncu --profile-from-start off --set full --clock-control none --import-source on \
+      -k regex:conv_umma -c 6 -o gpurun_out/prof_conv python profiles/profile_step.py --precision tf32
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from smg_b200.trainer import Trainer  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--precision", default="tf32")
+    ap.add_argument("--steps", type=int, default=1)
+    args = ap.parse_args()
+    torch.manual_seed(0)
+    tr = Trainer("reinforcement", 0.5, False, None, False, precision=args.precision)
+    tr.model.gnum_rotations = tr.model.snum_rotations = bench.R
+    tr.model.update_running_stats = False
+    eng = tr.model._engine(bench.R + 1)
+    scenes, masks = bench.make_units(2, 100)
+    sd, md = torch.from_numpy(scenes).cuda(), torch.from_numpy(masks).cuda()
+    rots = list(range(bench.R))
+    for i in range(3):
+        eng.qforward_maps(0, sd[i % 2], md[i % 2:i % 2 + 1], bench.MEAN, bench.STD, rots, bench.R)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    for i in range(args.steps):
+        q = eng.qforward_maps(0, sd[i % 2], md[i % 2:i % 2 + 1], bench.MEAN, bench.STD, rots, bench.R)
+        eng.argmax(q)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+
+
+if __name__ == "__main__":
+    main()

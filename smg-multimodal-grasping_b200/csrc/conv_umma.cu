@@ -168,7 +168,7 @@ struct SmemPlan {
     using E = EltCfg<ELT>;
     static constexpr int A_LBO = (TAPS == 9 ? E::P_ROWS : E::A_ROWS) * 16;
     static constexpr int A_SLOT = E::CH * A_LBO;                      // one 32-channel group
-    static constexpr int A_SLOTS = TAPS == 9 ? 4 : NA;
+    static constexpr int A_SLOTS = TAPS == 9 ? 2 : NA;
     static constexpr int B_STAGE = E::CH * BN * 16;
     static constexpr int B_SLOTS = TAPS == 9 ? NB9 : NB1;
     static constexpr int OFF_BAR = 0;
@@ -186,7 +186,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 
 template <int ELT, int BN, int TAPS, int POOL>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(320, 2)
 conv_umma_kernel(UmmaDev a) {
     using E = EltCfg<ELT>;
     using P = SmemPlan<ELT, BN, TAPS>;
@@ -349,48 +349,76 @@ conv_umma_kernel(UmmaDev a) {
                 mbar_arrive(&a_full[slot]);
             }
         } else {
-            // 3x3: fill the (ht+2) x wp activation patch once per 32-channel group
+            // 3x3: transform the (ht+2) x wp activation patch once per 32-channel group; the 9 taps are
+            // 9 shifted descriptors over it.  Two patch slots: group g+2 re-uses the slot of group g
+            // once the MMAs of group g have completed (a_empty).  All global loads of a group are
+            // issued before the first use so that 14 x 16 B per thread are in flight.
             const int wp = a.wp;
             const int pfill = (a.ht + 2) * wp;
+            constexpr int NI = (5 * MAX_WP + RSTEP - 1) / RSTEP;  // max rows per thread: (ht+2)*wp <= 5*42
+            int poff[NI];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int q = r0 + i * RSTEP;
+                const int py = q / wp, px = q - py * wp;
+                const int y = h0 - 1 + py, x = w0 - 1 + px;
+                poff[i] = (q < pfill && y >= 0 && y < hin && x >= 0 && x < hin) ? (y * hin + x) * a.in_cstride : -1;
+            }
             for (int g = 0; g < 4; ++g) {
+                const int slot = g & 1;
+                if (g >= 2) mbar_wait(&a_empty[slot], 0);
                 const int ch0 = g * KC + c * E::EPC;
                 float sc[E::EPC], sh[E::EPC];
 #pragma unroll
                 for (int e = 0; e < E::EPC; ++e) { sc[e] = s_sc[ch0 + e]; sh[e] = s_sh[ch0 + e]; }
-                uint8_t* dst = sA + g * P::A_SLOT + c * P::A_LBO;
-#pragma unroll 4
-                for (int q = r0; q < pfill; q += RSTEP) {
-                    const int py = q / wp, px = q - py * wp;
-                    const int y = h0 - 1 + py, x = w0 - 1 + px;
-                    float v[E::EPC];
-                    if (y >= 0 && y < hin && x >= 0 && x < hin) {
-                        const float* src = inp + ((size_t)y * hin + x) * a.in_cstride + ch0;
+                uint8_t* dst = sA + slot * P::A_SLOT + c * P::A_LBO;
+                constexpr int NH = (NI + 1) / 2;  // two batches keep the kernel at <= 96 registers (2 CTAs / SM)
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    float4 v[NH][E::EPC / 4];
+#pragma unroll
+                    for (int ii = 0; ii < NH; ++ii) {
+                        const int i = hb * NH + ii;
 #pragma unroll
                         for (int e4 = 0; e4 < E::EPC / 4; ++e4) {
-                            const float4 xv = __ldg(reinterpret_cast<const float4*>(src) + e4);
-                            v[4 * e4 + 0] = xv.x; v[4 * e4 + 1] = xv.y; v[4 * e4 + 2] = xv.z; v[4 * e4 + 3] = xv.w;
+                            v[ii][e4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (i < NI && poff[i < NI ? i : 0] >= 0)
+                                v[ii][e4] = __ldg(reinterpret_cast<const float4*>(inp + poff[i < NI ? i : 0] + ch0) + e4);
                         }
+                    }
 #pragma unroll
-                        for (int e = 0; e < E::EPC; ++e) {
-                            float t = fmaf(v[e], sc[e], sh[e]);
-                            v[e] = a.relu ? fmaxf(t, 0.f) : t;
+                    for (int ii = 0; ii < NH; ++ii) {
+                        const int i = hb * NH + ii;
+                        const int q = r0 + i * RSTEP;
+                        if (i < NI && q < pfill) {
+                            float t[E::EPC];
+#pragma unroll
+                            for (int e4 = 0; e4 < E::EPC / 4; ++e4) {
+                                t[4 * e4 + 0] = v[ii][e4].x; t[4 * e4 + 1] = v[ii][e4].y;
+                                t[4 * e4 + 2] = v[ii][e4].z; t[4 * e4 + 3] = v[ii][e4].w;
+                            }
+                            if (poff[i < NI ? i : 0] >= 0) {
+#pragma unroll
+                                for (int e = 0; e < E::EPC; ++e) {
+                                    const float u = fmaf(t[e], sc[e], sh[e]);
+                                    t[e] = a.relu ? fmaxf(u, 0.f) : u;
+                                }
+                            }  // else: conv zero padding (post-activation zeros)
+                            uint4 pk;
+                            if (ELT == 4) {
+                                pk = make_uint4(__float_as_uint(t[0]), __float_as_uint(t[1]), __float_as_uint(t[2]),
+                                                __float_as_uint(t[3]));
+                            } else {
+                                pk = make_uint4(pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]),
+                                                pack_bf16x2(t[4 % E::EPC], t[5 % E::EPC]),
+                                                pack_bf16x2(t[6 % E::EPC], t[7 % E::EPC]));
+                            }
+                            *reinterpret_cast<uint4*>(dst + q * 16) = pk;
                         }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < E::EPC; ++e) v[e] = 0.f;  // conv zero padding (post-activation)
                     }
-                    uint4 pk;
-                    if (ELT == 4) {
-                        pk = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
-                                        __float_as_uint(v[3]));
-                    } else {
-                        pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                        pack_bf16x2(v[4 % E::EPC], v[5 % E::EPC]), pack_bf16x2(v[6 % E::EPC], v[7 % E::EPC]));
-                    }
-                    *reinterpret_cast<uint4*>(dst + q * 16) = pk;
                 }
                 fence_proxy_async();
-                mbar_arrive(&a_full[g]);
+                mbar_arrive(&a_full[slot]);
             }
         }
     } else if (warp == 9) {
@@ -432,7 +460,8 @@ conv_umma_kernel(UmmaDev a) {
                 }
             } else {
                 for (int g = 0; g < 4; ++g) {
-                    mbar_wait(&a_full[g], 0);
+                    const int sa = g & 1;
+                    mbar_wait(&a_full[sa], (g >> 1) & 1);
                     for (int t = 0; t < 9; ++t) {
                         const int j = g * 9 + t;
                         const int sb = j % NB9;
@@ -442,13 +471,14 @@ conv_umma_kernel(UmmaDev a) {
 #pragma unroll
                         for (int k = 0; k < MMAS; ++k) {
                             const uint64_t ad =
-                                make_desc(sA_u + g * P::A_SLOT + 2 * k * P::A_LBO + shift * 16, P::A_LBO, 128);
+                                make_desc(sA_u + sa * P::A_SLOT + 2 * k * P::A_LBO + shift * 16, P::A_LBO, 128);
                             const uint64_t bd = make_desc(sB_u + sb * P::B_STAGE + 2 * k * BN * 16, BN * 16, 128);
                             umma<ELT>(tmem_base, ad, bd, idesc, accum);
                             accum = 1;
                         }
                         umma_commit(&b_empty[sb]);
                     }
+                    umma_commit(&a_empty[sa]);
                 }
             }
             umma_commit(tmem_full);
@@ -565,6 +595,8 @@ static int dispatch(smg_handle* h, const ConvArgs& a, UmmaDev& d, cudaStream_t s
     if (a.taps == 9) {
         SMG_CHECK(a.cin == 128 && a.cout == 32 && !a.pool, SMG_ERR_UNSUPPORTED, "conv_umma: 3x3 expects 128->32");
         umma_patch_geometry(d.hout, &d.wp, &d.ht);
+        SMG_CHECK((d.ht + 2) * d.wp <= 5 * MAX_WP && d.ht * d.wp <= UM, SMG_ERR_STATE, "conv_umma: patch %dx%d too large",
+                  d.ht, d.wp);
         const int wt = d.wp - 2;
         d.tiles_x = (d.hout + wt - 1) / wt;
         return launch_umma<ELT, 32, 9, 0>(h, d, a.n, st);
