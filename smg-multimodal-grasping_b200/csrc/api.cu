@@ -71,7 +71,7 @@ static int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------
 // trunk forward over `n` samples already resident in h->input
 // ---------------------------------------------------------------------------------------
-static int trunk_forward(smg_handle* h, int trunk_id, int n, cudaStream_t st) {
+static int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cudaStream_t st) {
     TrunkW& T = h->trunks[trunk_id];
     SMG_CHECK(T.set, SMG_ERR_STATE, "trunk %d: weights not set (call smg_set_trunk_weights)", trunk_id);
     SMG_CHECK(n >= 1 && n <= h->max_samples, SMG_ERR_INVALID, "trunk_forward: n=%d outside [1,%d]", n, h->max_samples);
@@ -81,8 +81,10 @@ static int trunk_forward(smg_handle* h, int trunk_id, int n, cudaStream_t st) {
     {
         const double hc = (double)(h->H / 2) * (h->H / 2);
         // stem traffic: input read + conv0 written, conv0 read + pooled output written
-        ProfScope ps(h, st, 0, 2.0 * n * hc * 64 * 147, 4.0 * n * (3.0 * h->H * h->H + 2 * hc * 64 + hc / 4 * 64));
-        SMG_TRY(launch_conv0(h, h->input, n, T.conv0, h->conv0, stats_ptr(h, h->st_conv0), st));
+        ProfScope ps(h, st, 0, 2.0 * n * hc * 64 * 49 * in_channels,
+                     4.0 * n * ((double)in_channels * h->H * h->H + 2 * hc * 64 + hc / 4 * 64));
+        SMG_TRY(launch_conv0(h, h->input, in_channels, n, in_channels == 1 ? T.conv0_folded : T.conv0, h->conv0,
+                             stats_ptr(h, h->st_conv0), st));
         SMG_TRY(launch_pool0(h, n, h->conv0, stats_ptr(h, h->st_conv0), T.norm0.gamma, T.norm0.beta, h->block[0],
                              h->geom[0].c_tot, stats_ptr(h, h->st_block[0]), st));
     }
@@ -196,12 +198,13 @@ __global__ void pack_head_conv1_kernel(const float* __restrict__ w, float* __res
     }
 }
 
-__global__ void pack_conv0_kernel(const float* __restrict__ w, float* __restrict__ out) {
-    // torch [64][3][7][7] -> [147][64]
+__global__ void pack_conv0_kernel(const float* __restrict__ w, float* __restrict__ out, float* __restrict__ folded) {
+    // torch [64][3][7][7] -> [147][64], and the channel-folded [49][64] (sum over the 3 input channels)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 147 * 64) {
         const int co = i % 64, k = i / 64;
         out[i] = w[co * 147 + k];
+        if (k < 49) folded[i] = (w[co * 147 + k] + w[co * 147 + 49 + k]) + w[co * 147 + 98 + k];
     }
 }
 
@@ -239,7 +242,11 @@ static void plan_bn(ArenaPlanner& p, BnP& b, int c, uint8_t* base) {
 static size_t plan_trunk(smg_handle* h, TrunkW& T, uint8_t* base) {
     ArenaPlanner p;
     const size_t o = p.take(147 * 64 * 4);
-    if (base) T.conv0 = reinterpret_cast<float*>(base + o);
+    const size_t of = p.take(49 * 64 * 4);
+    if (base) {
+        T.conv0 = reinterpret_cast<float*>(base + o);
+        T.conv0_folded = reinterpret_cast<float*>(base + of);
+    }
     plan_bn(p, T.norm0, 64, base);
     for (int b = 0; b < kNumBlocks; ++b) {
         T.layers[b].resize(kBlockLayers[b]);
@@ -375,7 +382,7 @@ int smg_set_trunk_weights(smg_handle* h, int trunk_id, const float* const* dev_p
         SMG_CUDA(cudaMemcpyAsync(b.beta, dev_params[i++], (size_t)b.c * 4, cudaMemcpyDeviceToDevice, st));
         return SMG_OK;
     };
-    pack_conv0_kernel<<<(147 * 64 + 255) / 256, 256, 0, st>>>(dev_params[i++], T.conv0);
+    pack_conv0_kernel<<<(147 * 64 + 255) / 256, 256, 0, st>>>(dev_params[i++], T.conv0, T.conv0_folded);
     h->launches++;
     SMG_TRY(copy_bn(T.norm0));
     for (int b = 0; b < kNumBlocks; ++b) {
@@ -442,7 +449,7 @@ int smg_prep(smg_handle* h, const double* dev_heightmaps, int n, int hm_size, do
     SMG_CHECK(h && dev_heightmaps && dev_out && n >= 1, SMG_ERR_INVALID, "smg_prep: bad argument");
     SMG_CHECK(stddev != 0.0, SMG_ERR_INVALID, "smg_prep: stddev is 0 (the reference's published literal gives NaN)");
     DeviceGuard guard(h->device);
-    return launch_prep(h, dev_heightmaps, n, hm_size, mean, stddev, dev_out, (cudaStream_t)stream);
+    return launch_prep(h, dev_heightmaps, n, hm_size, mean, stddev, dev_out, 3, (cudaStream_t)stream);
 }
 
 int smg_rotate(smg_handle* h, const float* dev_in, const int* host_rot_idx, int n_rot, int num_rotations,
@@ -450,7 +457,7 @@ int smg_rotate(smg_handle* h, const float* dev_in, const int* host_rot_idx, int 
     SMG_CHECK(h && dev_in && dev_out && host_rot_idx && n_rot >= 1 && num_rotations >= 1, SMG_ERR_INVALID,
               "smg_rotate: bad argument");
     DeviceGuard guard(h->device);
-    return launch_rotate(h, dev_in, host_rot_idx, n_rot, num_rotations, dev_out, (cudaStream_t)stream);
+    return launch_rotate(h, dev_in, host_rot_idx, n_rot, num_rotations, dev_out, 3, (cudaStream_t)stream);
 }
 
 int smg_rotate_index_map(smg_handle* h, int rot_idx, int num_rotations, int32_t* dev_out, void* stream) {
@@ -467,7 +474,7 @@ int smg_trunk_forward(smg_handle* h, int trunk_id, const float* dev_in, int n, f
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     SMG_CUDA(cudaMemcpyAsync(h->input, dev_in, (size_t)n * 3 * h->H * h->H * 4, cudaMemcpyDeviceToDevice, st));
-    SMG_TRY(trunk_forward(h, trunk_id, n, st));
+    SMG_TRY(trunk_forward(h, trunk_id, n, 3, st));
     if (dev_feat)
         SMG_TRY(launch_norm5_export(h, n, h->block[3], stats_ptr(h, h->st_block[3]), h->geom[3].c_tot,
                                     h->trunks[trunk_id].norm5, dev_feat, st));
@@ -475,9 +482,9 @@ int smg_trunk_forward(smg_handle* h, int trunk_id, const float* dev_in, int n, f
     return SMG_OK;
 }
 
-static int qforward_common(smg_handle* h, int trunk_id, int head_id, int n_masks, int n_rot, float* dev_q,
-                           float* dev_bn_mean, float* dev_bn_var, cudaStream_t st) {
-    SMG_TRY(trunk_forward(h, trunk_id, n_rot + n_masks, st));
+static int qforward_common(smg_handle* h, int trunk_id, int head_id, int n_masks, int n_rot, int in_channels,
+                           float* dev_q, float* dev_bn_mean, float* dev_bn_var, cudaStream_t st) {
+    SMG_TRY(trunk_forward(h, trunk_id, n_rot + n_masks, in_channels, st));
     SMG_TRY(heads_forward(h, trunk_id, head_id, n_rot, n_masks, dev_q, st));
     if (dev_bn_mean && dev_bn_var) SMG_TRY(export_bn_stats(h, n_rot + n_masks, dev_bn_mean, dev_bn_var, st));
     return SMG_OK;
@@ -494,9 +501,9 @@ int smg_qforward(smg_handle* h, int trunk_id, int head_id, const float* dev_scen
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t img = (size_t)3 * h->H * h->H;
-    SMG_TRY(launch_rotate(h, dev_scene, host_rot_idx, n_rot, num_rotations, h->input, st));
+    SMG_TRY(launch_rotate(h, dev_scene, host_rot_idx, n_rot, num_rotations, h->input, 3, st));
     SMG_CUDA(cudaMemcpyAsync(h->input + (size_t)n_rot * img, dev_masks, (size_t)n_masks * img * 4, cudaMemcpyDeviceToDevice, st));
-    return qforward_common(h, trunk_id, head_id, n_masks, n_rot, dev_q, dev_bn_mean, dev_bn_var, st);
+    return qforward_common(h, trunk_id, head_id, n_masks, n_rot, 3, dev_q, dev_bn_mean, dev_bn_var, st);
 }
 
 int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm, const double* dev_mask_hms,
@@ -510,11 +517,13 @@ int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* de
     SMG_CHECK(stddev != 0.0, SMG_ERR_INVALID, "smg_qforward_maps: stddev is 0");
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t img = (size_t)3 * h->H * h->H;
-    SMG_TRY(launch_prep(h, dev_scene_hm, 1, hm_size, mean, stddev, h->scene_tmp, st));
-    SMG_TRY(launch_rotate(h, h->scene_tmp, host_rot_idx, n_rot, num_rotations, h->input, st));
-    SMG_TRY(launch_prep(h, dev_mask_hms, n_masks, hm_size, mean, stddev, h->input + (size_t)n_rot * img, st));
-    return qforward_common(h, trunk_id, head_id, n_masks, n_rot, dev_q, dev_bn_mean, dev_bn_var, st);
+    // Trainer.forward feeds three identical channels (code/trainer.py:178-181): keep ONE plane per sample and use
+    // the channel-folded conv0 weights (K = 49 instead of 147)
+    const size_t img = (size_t)h->H * h->H;
+    SMG_TRY(launch_prep(h, dev_scene_hm, 1, hm_size, mean, stddev, h->scene_tmp, 1, st));
+    SMG_TRY(launch_rotate(h, h->scene_tmp, host_rot_idx, n_rot, num_rotations, h->input, 1, st));
+    SMG_TRY(launch_prep(h, dev_mask_hms, n_masks, hm_size, mean, stddev, h->input + (size_t)n_rot * img, 1, st));
+    return qforward_common(h, trunk_id, head_id, n_masks, n_rot, 1, dev_q, dev_bn_mean, dev_bn_var, st);
 }
 
 int smg_qforward_train(smg_handle*, int, int, const float*, const float*, int, int, float*, float*, float*, void*) {

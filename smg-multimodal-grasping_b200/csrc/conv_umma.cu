@@ -57,6 +57,15 @@ __device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_s
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// Ampere-style async copies (LDGSTS): raw activations land in shared memory without holding registers
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -278,6 +287,52 @@ conv_umma_kernel(UmmaDev a) {
                     roff[i] = -1;
                 }
             }
+            if (ELT == 4 && !POOL) {
+                // tf32 fast path: raw fp32 rows are cp.async'ed straight into their final UMMA slot (NA stages in
+                // flight per thread, no registers held), then normalised IN PLACE by the thread that loaded them.
+                auto issue = [&](int kg) {
+                    uint8_t* dst = sA + (kg % NA) * P::A_SLOT + c * P::A_LBO;
+                    const float* src = inp + kg * KC + c * E::EPC;
+#pragma unroll
+                    for (int i = 0; i < RI; ++i)
+                        if (roff[i] >= 0) cp_async16(dst + (r0 + i * RSTEP) * 16, src + roff[i]);
+                    cp_async_commit();
+                };
+#pragma unroll
+                for (int kg = 0; kg < NA; ++kg) {
+                    if (kg < KG) issue(kg);
+                    else cp_async_commit();
+                }
+                for (int kg = 0; kg < KG; ++kg) {
+                    const int slot = kg % NA;
+                    cp_async_wait<NA - 1>();
+                    const int ch0 = kg * KC + c * E::EPC;
+                    const float4 sc = *reinterpret_cast<const float4*>(s_sc + ch0);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_sh + ch0);
+                    uint8_t* dst = sA + slot * P::A_SLOT + c * P::A_LBO;
+#pragma unroll
+                    for (int i = 0; i < RI; ++i) {
+                        float4* p4 = reinterpret_cast<float4*>(dst + (r0 + i * RSTEP) * 16);
+                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (roff[i] >= 0) {
+                            x = *p4;
+                            x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
+                            x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+                            if (a.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                        }
+                        *p4 = x;
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(&a_full[slot]);
+                    const int next = kg + NA;
+                    if (next < KG) {
+                        mbar_wait(&a_empty[slot], ((next / NA) & 1) ^ 1);
+                        issue(next);
+                    } else {
+                        cp_async_commit();
+                    }
+                }
+            } else
             for (int kg = 0; kg < KG; ++kg) {
                 const int slot = kg % NA;
                 const uint32_t ph = (kg / NA) & 1;
@@ -364,6 +419,51 @@ conv_umma_kernel(UmmaDev a) {
                 const int y = h0 - 1 + py, x = w0 - 1 + px;
                 poff[i] = (q < pfill && y >= 0 && y < hin && x >= 0 && x < hin) ? (y * hin + x) * a.in_cstride : -1;
             }
+            if (ELT == 4) {
+                // tf32 fast path: both patch slots are filled with cp.async (raw fp32 lands in its final place,
+                // 2 x 27 KB in flight per CTA) and normalised in place by the loading thread.
+                auto issue = [&](int g) {
+                    uint8_t* dst = sA + (g & 1) * P::A_SLOT + c * P::A_LBO;
+                    const float* src = inp + g * KC + c * E::EPC;
+#pragma unroll
+                    for (int i = 0; i < NI; ++i)
+                        if (poff[i] >= 0) cp_async16(dst + (r0 + i * RSTEP) * 16, src + poff[i]);
+                    cp_async_commit();
+                };
+                issue(0);
+                issue(1);
+                for (int g = 0; g < 4; ++g) {
+                    const int slot = g & 1;
+                    cp_async_wait<1>();
+                    const int ch0 = g * KC + c * E::EPC;
+                    const float4 sc = *reinterpret_cast<const float4*>(s_sc + ch0);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_sh + ch0);
+                    uint8_t* dst = sA + slot * P::A_SLOT + c * P::A_LBO;
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        const int q = r0 + i * RSTEP;
+                        if (q < pfill) {
+                            float4* p4 = reinterpret_cast<float4*>(dst + q * 16);
+                            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);  // conv zero padding (post-activation)
+                            if (poff[i] >= 0) {
+                                x = *p4;
+                                x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
+                                x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+                                if (a.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                            }
+                            *p4 = x;
+                        }
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(&a_full[slot]);
+                    if (g + 2 < 4) {
+                        mbar_wait(&a_empty[slot], 0);
+                        issue(g + 2);
+                    } else {
+                        cp_async_commit();
+                    }
+                }
+            } else
             for (int g = 0; g < 4; ++g) {
                 const int slot = g & 1;
                 if (g >= 2) mbar_wait(&a_empty[slot], 0);

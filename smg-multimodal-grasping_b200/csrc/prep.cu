@@ -15,7 +15,7 @@
 namespace smg {
 
 __global__ void prep_kernel(const double* __restrict__ hm, int n, int hs, double mean, double stddev,
-                            float* __restrict__ out, int H) {
+                            float* __restrict__ out, int H, int channels) {
     const int pad = (H - 2 * hs) / 2;
     const size_t plane = (size_t)H * H;
     const size_t total = (size_t)n * plane;
@@ -27,10 +27,8 @@ __global__ void prep_kernel(const double* __restrict__ hm, int n, int hs, double
         double v = 0.0;
         if (yy >= 0 && yy < 2 * hs && xx >= 0 && xx < 2 * hs) v = hm[((size_t)s * hs + (yy >> 1)) * hs + (xx >> 1)];
         const float f = (float)((v - mean) / stddev);
-        float* o = out + (size_t)s * 3 * plane + rem;
-        o[0] = f;
-        o[plane] = f;
-        o[2 * plane] = f;
+        float* o = out + (size_t)s * channels * plane + rem;
+        for (int c = 0; c < channels; ++c) o[c * plane] = f;
     }
 }
 
@@ -55,7 +53,8 @@ struct RotTheta {
     float t[32][6];
 };
 
-__global__ void rotate_kernel(const float* __restrict__ in, int n_rot, RotTheta th, float* __restrict__ out, int H) {
+__global__ void rotate_kernel(const float* __restrict__ in, int n_rot, RotTheta th, float* __restrict__ out, int H,
+                              int channels) {
     const size_t plane = (size_t)H * H;
     const size_t total = (size_t)n_rot * plane;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -63,16 +62,8 @@ __global__ void rotate_kernel(const float* __restrict__ in, int n_rot, RotTheta 
         const int rem = (int)(i - (size_t)r * plane);
         const int y = rem / H, x = rem - y * H;
         const int src = rotate_src_index(x, y, H, th.t[r]);
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-        if (src >= 0) {
-            v0 = __ldg(in + src);
-            v1 = __ldg(in + plane + src);
-            v2 = __ldg(in + 2 * plane + src);
-        }
-        float* o = out + (size_t)r * 3 * plane + rem;
-        o[0] = v0;
-        o[plane] = v1;
-        o[2 * plane] = v2;
+        float* o = out + (size_t)r * channels * plane + rem;
+        for (int c = 0; c < channels; ++c) o[c * plane] = src >= 0 ? __ldg(in + c * plane + src) : 0.f;
     }
 }
 
@@ -98,20 +89,20 @@ void rotation_theta(int rot_idx, int num_rot, float* t6) {
 }
 
 int launch_prep(smg_handle* h, const double* hm, int n, int hm_size, double mean, double stddev, float* out,
-                cudaStream_t st) {
+                int channels, cudaStream_t st) {
     SMG_CHECK(2 * hm_size <= h->H, SMG_ERR_INVALID, "smg_prep: 2*hm_size %d exceeds H %d", 2 * hm_size, h->H);
     const size_t total = (size_t)n * h->H * h->H;
     const int threads = 256;
     const int blocks = (int)((total + threads - 1) / threads);
     prep_kernel<<<blocks < h->num_sms * 16 ? blocks : h->num_sms * 16, threads, 0, st>>>(hm, n, hm_size, mean, stddev,
-                                                                                         out, h->H);
+                                                                                         out, h->H, channels);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;
 }
 
 int launch_rotate(smg_handle* h, const float* in, const int* host_rot, int n_rot, int num_rot, float* out,
-                  cudaStream_t st) {
+                  int channels, cudaStream_t st) {
     for (int base = 0; base < n_rot; base += 32) {
         const int cnt = n_rot - base < 32 ? n_rot - base : 32;
         RotTheta th;
@@ -120,7 +111,7 @@ int launch_rotate(smg_handle* h, const float* in, const int* host_rot, int n_rot
         const int threads = 256;
         const int blocks = (int)((total + threads - 1) / threads);
         rotate_kernel<<<blocks < h->num_sms * 16 ? blocks : h->num_sms * 16, threads, 0, st>>>(
-            in, cnt, th, out + (size_t)base * 3 * h->H * h->H, h->H);
+            in, cnt, th, out + (size_t)base * channels * h->H * h->H, h->H, channels);
         h->launches++;
         SMG_CUDA(cudaGetLastError());
     }

@@ -92,6 +92,7 @@ struct TransitionW {
 struct TrunkW {
     bool set = false;
     float* conv0 = nullptr;  // [147][64], k = (c*7+kh)*7+kw
+    float* conv0_folded = nullptr;  // [49][64]: weights summed over the input channel (identical channels)
     BnP norm0;
     std::vector<DenseLayerW> layers[kNumBlocks];
     TransitionW trans[kNumBlocks - 1];
@@ -174,12 +175,13 @@ inline double* stats_ptr(const smg_handle* h, size_t off_double2) {
 // ---- kernels (defined in the .cu files) ---------------------------------------------
 // K1
 int launch_prep(smg_handle* h, const double* hm, int n, int hm_size, double mean, double stddev, float* out,
-                cudaStream_t st);
+                int channels, cudaStream_t st);
 int launch_rotate(smg_handle* h, const float* in, const int* host_rot, int n_rot, int num_rot, float* out,
-                  cudaStream_t st);
+                  int channels, cudaStream_t st);
 int launch_rotate_index_map(smg_handle* h, int rot, int num_rot, int32_t* out, cudaStream_t st);
 // stem
-int launch_conv0(smg_handle* h, const float* in, int n, const float* w, float* out, double* stats, cudaStream_t st);
+int launch_conv0(smg_handle* h, const float* in, int cin, int n, const float* w, float* out, double* stats,
+                 cudaStream_t st);
 int launch_pool0(smg_handle* h, int n, const float* conv0, const double* stats_in, const float* gamma,
                  const float* beta, float* out, int out_cstride, double* stats_out, cudaStream_t st);
 

@@ -2,8 +2,9 @@
 // `norm0 + relu0 + pool0` (train-mode BN, ReLU, 3x3 stride-2 max pool), torchvision
 // densenet.py as called at /root/reference/code/models.py:384-385.
 //
-// conv0 is a K=147 direct convolution on the CUDA cores (4% of the trunk's MACs, Cin=3
-// does not tile onto the tensor cores); it writes the raw output NHWC and accumulates
+// conv0 is a K=147 (K=49 when the three input channels are identical) direct convolution on the
+// CUDA cores (4% of the trunk's MACs, Cin=3 does not tile onto the tensor cores); it writes the raw
+// output NHWC and accumulates
 // the per-(sample,channel) sum / sum-of-squares that norm0 needs.  pool0 applies
 // norm0+ReLU on the fly, max-pools, writes channels [0,64) of the dense-block-1 buffer
 // and accumulates THEIR statistics (needed by every norm1 of block 1).
@@ -13,62 +14,81 @@ namespace smg {
 
 constexpr int C0_TILE = 16;                       // 16x16 output pixels per CTA
 constexpr int C0_PATCH = 2 * C0_TILE + 5;         // 37 input rows/cols
-constexpr int C0_K = 147;
+constexpr int C0_PLD = 49;                        // padded patch row (2*PLD mod 32 == 2: <= 2-way bank conflicts)
 constexpr int C0_STAGE_LD = 65;                   // padded row of the output staging tile
 
-__global__ void __launch_bounds__(256, 1)
+// CIN = 3: the general case (any [n,3,H,H] input).  CIN = 1: the three input channels are identical
+// (Trainer.forward replicates the depth map, code/trainer.py:178-181), so the 7x7 weights are summed
+// over the input channel once at pack time and K drops from 147 to 49.
+// thread = 4 consecutive output pixels x 16 output channels: per (c,kh) it loads the 13 input values its
+// 4 pixels need once and 7 x 4 broadcast LDS.128 of weights feed 7 x 64 FMAs (FMA-bound, not LDS-bound).
+template <int CIN>
+__global__ void __launch_bounds__(256, 2)
 conv0_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
              double* __restrict__ stats, int H, int stats_stride) {
+    constexpr int K = CIN * 49;
     extern __shared__ float sm[];
-    float* s_w = sm;                                   // [147][64]
-    float* s_in = s_w + C0_K * 64;                     // [3][37][37] (+pad)
-    float* s_out = s_in + 3 * C0_PATCH * C0_PATCH + 1; // [256][65]
+    float* s_w = sm;                                   // [K][64]
+    float* s_in = s_w + K * 64;                        // [CIN][37][40]
+    float* s_out = sm;                                 // [256][65] staging, aliases weights + patch after the MACs
     const int Ho = H / 2;
     const int tiles = Ho / C0_TILE;
     const int s = blockIdx.y;
     const int ty = blockIdx.x / tiles, tx = blockIdx.x % tiles;
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < C0_K * 64; i += 256) s_w[i] = w[i];
+    for (int i = tid; i < K * 64; i += 256) s_w[i] = w[i];
     const int iy0 = ty * C0_TILE * 2 - 3, ix0 = tx * C0_TILE * 2 - 3;
-    const float* inp = in + (size_t)s * 3 * H * H;
-    for (int i = tid; i < 3 * C0_PATCH * C0_PATCH; i += 256) {
-        const int c = i / (C0_PATCH * C0_PATCH);
-        const int r = i - c * C0_PATCH * C0_PATCH;
-        const int py = r / C0_PATCH, px = r - py * C0_PATCH;
+    const float* inp = in + (size_t)s * CIN * H * H;
+    for (int i = tid; i < CIN * C0_PATCH * C0_PLD; i += 256) {
+        const int c = i / (C0_PATCH * C0_PLD);
+        const int r = i - c * C0_PATCH * C0_PLD;
+        const int py = r / C0_PLD, px = r - py * C0_PLD;
         const int y = iy0 + py, x = ix0 + px;
         float v = 0.f;
-        if (y >= 0 && y < H && x >= 0 && x < H) v = inp[((size_t)c * H + y) * H + x];
+        if (px < C0_PATCH && y >= 0 && y < H && x >= 0 && x < H) v = inp[((size_t)c * H + y) * H + x];
         s_in[i] = v;
     }
     __syncthreads();
 
-    const int oy = tid / C0_TILE, ox = tid % C0_TILE;
-    float acc[64];
+    const int cg = tid >> 6;            // 16-channel group (warp-uniform)
+    const int pg = tid & 63;            // pixel group: row oy, 4 pixels starting at ox0
+    const int oy = pg >> 2, ox0 = (pg & 3) * 4;
+    float acc[4][16];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-    for (int c = 0; c < 3; ++c) {
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[p][j] = 0.f;
+    for (int c = 0; c < CIN; ++c) {
         for (int kh = 0; kh < 7; ++kh) {
-            const float* irow = s_in + (c * C0_PATCH + (2 * oy + kh)) * C0_PATCH + 2 * ox;
-            const float* wrow = s_w + ((c * 7 + kh) * 7) * 64;
+            const float* irow = s_in + (c * C0_PATCH + (2 * oy + kh)) * C0_PLD + 2 * ox0;
+            float iv[13];
+#pragma unroll
+            for (int t = 0; t < 13; ++t) iv[t] = irow[t];
+            const float* wrow = s_w + ((c * 7 + kh) * 7) * 64 + cg * 16;
 #pragma unroll
             for (int kw = 0; kw < 7; ++kw) {
-                const float v = irow[kw];
                 const float4* w4 = reinterpret_cast<const float4*>(wrow + kw * 64);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     const float4 ww = w4[j];
-                    acc[4 * j + 0] = fmaf(v, ww.x, acc[4 * j + 0]);
-                    acc[4 * j + 1] = fmaf(v, ww.y, acc[4 * j + 1]);
-                    acc[4 * j + 2] = fmaf(v, ww.z, acc[4 * j + 2]);
-                    acc[4 * j + 3] = fmaf(v, ww.w, acc[4 * j + 3]);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float v = iv[2 * p + kw];
+                        acc[p][4 * j + 0] = fmaf(v, ww.x, acc[p][4 * j + 0]);
+                        acc[p][4 * j + 1] = fmaf(v, ww.y, acc[p][4 * j + 1]);
+                        acc[p][4 * j + 2] = fmaf(v, ww.z, acc[p][4 * j + 2]);
+                        acc[p][4 * j + 3] = fmaf(v, ww.w, acc[p][4 * j + 3]);
+                    }
                 }
             }
         }
     }
-    // stage the [256 pixel][64 channel] tile for coalesced stores + column statistics
+    __syncthreads();  // all reads of s_w / s_in done: the staging tile may overwrite them
 #pragma unroll
-    for (int i = 0; i < 64; ++i) s_out[tid * C0_STAGE_LD + i] = acc[i];
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s_out[(oy * C0_TILE + ox0 + p) * C0_STAGE_LD + cg * 16 + j] = acc[p][j];
     __syncthreads();
     float* outp = out + (size_t)s * Ho * Ho * 64;
     for (int i = tid; i < 256 * 64; i += 256) {
@@ -86,7 +106,7 @@ conv0_kernel(const float* __restrict__ in, const float* __restrict__ w, float* _
             sq = fmaf(v, v, sq);
         }
         __syncthreads();
-        float* red = s_in;  // reuse
+        float* red = sm + 256 * C0_STAGE_LD;  // behind the staging tile
         red[tid] = su;
         red[256 + tid] = sq;
         __syncthreads();
@@ -169,20 +189,30 @@ pool0_kernel(const float* __restrict__ conv0, const double* __restrict__ stats_i
     }
 }
 
-int launch_conv0(smg_handle* h, const float* in, int n, const float* w, float* out, double* stats, cudaStream_t st) {
+template <int CIN>
+static int launch_conv0_t(smg_handle* h, const float* in, int n, const float* w, float* out, double* stats,
+                          cudaStream_t st) {
     const int Ho = h->H / 2;
-    SMG_CHECK(Ho % C0_TILE == 0, SMG_ERR_INVALID, "conv0: H/2 must be a multiple of %d", C0_TILE);
-    const size_t smem = (size_t)(C0_K * 64 + 3 * C0_PATCH * C0_PATCH + 1 + 256 * C0_STAGE_LD) * sizeof(float);
+    const size_t operands = (size_t)(CIN * 49 * 64 + CIN * C0_PATCH * C0_PLD);
+    const size_t staging = (size_t)256 * C0_STAGE_LD + 512;
+    const size_t smem = (operands > staging ? operands : staging) * sizeof(float);
     static bool attr = false;
     if (!attr) {
-        SMG_CUDA(cudaFuncSetAttribute(conv0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMG_CUDA(cudaFuncSetAttribute(conv0_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     dim3 grid((Ho / C0_TILE) * (Ho / C0_TILE), n);
-    conv0_kernel<<<grid, 256, smem, st>>>(in, w, out, stats, h->H, 64);
+    conv0_kernel<CIN><<<grid, 256, smem, st>>>(in, w, out, stats, h->H, 64);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;
+}
+
+int launch_conv0(smg_handle* h, const float* in, int cin, int n, const float* w, float* out, double* stats,
+                 cudaStream_t st) {
+    SMG_CHECK((h->H / 2) % C0_TILE == 0, SMG_ERR_INVALID, "conv0: H/2 must be a multiple of %d", C0_TILE);
+    if (cin == 1) return launch_conv0_t<1>(h, in, n, w, out, stats, st);
+    return launch_conv0_t<3>(h, in, n, w, out, stats, st);
 }
 
 int launch_pool0(smg_handle* h, int n, const float* conv0, const double* stats_in, const float* gamma,
