@@ -71,7 +71,7 @@ static int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------
 // trunk forward over `n` samples already resident in h->input
 // ---------------------------------------------------------------------------------------
-static int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cudaStream_t st) {
+static int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cudaStream_t st, bool save_bott = false) {
     TrunkW& T = h->trunks[trunk_id];
     SMG_CHECK(T.set, SMG_ERR_STATE, "trunk %d: weights not set (call smg_set_trunk_weights)", trunk_id);
     SMG_CHECK(n >= 1 && n <= h->max_samples, SMG_ERR_INVALID, "trunk_forward: n=%d outside [1,%d]", n, h->max_samples);
@@ -101,12 +101,13 @@ static int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cu
             a1.in_stats = st_blk; a1.in_stats_stride = g.c_tot;
             a1.gamma = L.norm1.gamma; a1.beta = L.norm1.beta;
             a1.taps = 1; a1.w = &L.conv1;
-            a1.out = h->bott; a1.out_cstride = kBottleneck; a1.out_coff = 0; a1.cout = kBottleneck;
+            float* bott = save_bott ? h->train.bott_saved[layer_index] : h->bott;
+            a1.out = bott; a1.out_cstride = kBottleneck; a1.out_coff = 0; a1.cout = kBottleneck;
             a1.out_stats = st_bott; a1.out_stats_stride = kBottleneck;
             a1.n = n;
             SMG_TRY(conv_dispatch(h, a1, st));
             ConvArgs a2;
-            a2.in = h->bott; a2.in_cstride = kBottleneck; a2.cin = kBottleneck; a2.hin = g.hw;
+            a2.in = bott; a2.in_cstride = kBottleneck; a2.cin = kBottleneck; a2.hin = g.hw;
             a2.in_stats = st_bott; a2.in_stats_stride = kBottleneck;
             a2.gamma = L.norm2.gamma; a2.beta = L.norm2.beta;
             a2.taps = 9; a2.w = &L.conv2;
@@ -224,10 +225,12 @@ static void plan_conv(ArenaPlanner& p, ConvW& cw, int cin, int cout, int taps, u
     const size_t o1 = p.take(conv_packed_bytes_ffma(cin, cout, taps));
     const size_t o2 = p.take(conv_packed_bytes_umma(cin, cout, taps, 4));
     const size_t o3 = p.take(conv_packed_bytes_umma(cin, cout, taps, 2));
+    const size_t o4 = p.take(conv_packed_bytes_ffma(cin, cout, taps));
     if (base) {
         cw.w_ffma = reinterpret_cast<float*>(base + o1);
         cw.w_tf32 = base + o2;
         cw.w_bf16 = base + o3;
+        cw.w_dgrad = reinterpret_cast<float*>(base + o4);
     }
 }
 static void plan_bn(ArenaPlanner& p, BnP& b, int c, uint8_t* base) {
@@ -526,18 +529,279 @@ int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* de
     return qforward_common(h, trunk_id, head_id, n_masks, n_rot, 1, dev_q, dev_bn_mean, dev_bn_var, st);
 }
 
-int smg_qforward_train(smg_handle*, int, int, const float*, const float*, int, int, float*, float*, float*, void*) {
-    set_error("smg_qforward_train: the backward path is not built yet");
-    return SMG_ERR_UNSUPPORTED;
+// ---------------------------------------------------------------------------------------
+// training: forward that keeps what the backward needs, backward, Adam
+// ---------------------------------------------------------------------------------------
+static int ensure_train_workspace(smg_handle* h) {
+    smg_handle::TrainWs& W = h->train;
+    if (W.arena) return SMG_OK;
+    const size_t S = 2;
+    for (int pass = 0; pass < 2; ++pass) {
+        ArenaPlanner p;
+        uint8_t* base = reinterpret_cast<uint8_t*>(W.arena);
+        int li = 0;
+        for (int b = 0; b < kNumBlocks; ++b)
+            for (int l = 0; l < kBlockLayers[b]; ++l, ++li) {
+                const size_t o = p.take(S * h->geom[b].hw * h->geom[b].hw * kBottleneck * 4);
+                if (base) W.bott_saved[li] = reinterpret_cast<float*>(base + o);
+            }
+        for (int b = 0; b < kNumBlocks; ++b) {
+            const size_t o = p.take(S * h->geom[b].hw * h->geom[b].hw * h->geom[b].c_tot * 4);
+            if (base) W.dblk[b] = reinterpret_cast<float*>(base + o);
+        }
+        const size_t hc = (size_t)(h->H / 2) * (h->H / 2), hq = (size_t)(h->H / 4) * (h->H / 4);
+        const size_t o_c0 = p.take(S * hc * 64 * 4);
+        const size_t o_a = p.take(S * hq * kBottleneck * 4), o_b = p.take(S * hq * kBottleneck * 4);
+        const size_t o_c = p.take(S * hq * h->geom[0].c_tot * 4);
+        const size_t o_p = p.take((size_t)kHeadK * kHeadK * kHeadMid * 4);
+        W.sums_bytes = S * (size_t)SMG_TRUNK_BN_CHANNELS * 2 * sizeof(double);
+        const size_t o_s = p.take(W.sums_bytes);
+        if (base) {
+            W.dconv0 = reinterpret_cast<float*>(base + o_c0);
+            W.t_a = reinterpret_cast<float*>(base + o_a);
+            W.t_b = reinterpret_cast<float*>(base + o_b);
+            W.t_c = reinterpret_cast<float*>(base + o_c);
+            W.dP = reinterpret_cast<float*>(base + o_p);
+            W.sums = reinterpret_cast<double*>(base + o_s);
+        } else {
+            W.bytes = p.off;
+            SMG_CUDA(cudaMalloc(&W.arena, W.bytes));
+            h->workspace_bytes += (int64_t)W.bytes;
+        }
+    }
+    return SMG_OK;
 }
-int smg_qbackward(smg_handle*, const float*, float* const*, float* const*, void*) {
-    set_error("smg_qbackward: the backward path is not built yet");
-    return SMG_ERR_UNSUPPORTED;
+
+}  // extern "C" (reopened below)
+
+namespace smg {
+
+// gradient pointer cursor over the smg_set_trunk_weights parameter order
+struct TrunkGradMap {
+    float* conv0;
+    float* norm0[2];
+    struct L { float* n1[2]; float* c1; float* n2[2]; float* c2; };
+    std::vector<L> layers[kNumBlocks];
+    struct T { float* n[2]; float* c; } trans[kNumBlocks - 1];
+    float* norm5[2];
+    void fill(float* const* g) {
+        int i = 0;
+        conv0 = g[i++]; norm0[0] = g[i++]; norm0[1] = g[i++];
+        for (int b = 0; b < kNumBlocks; ++b) {
+            layers[b].resize(kBlockLayers[b]);
+            for (int l = 0; l < kBlockLayers[b]; ++l) {
+                L& x = layers[b][l];
+                x.n1[0] = g[i++]; x.n1[1] = g[i++]; x.c1 = g[i++];
+                x.n2[0] = g[i++]; x.n2[1] = g[i++]; x.c2 = g[i++];
+            }
+            if (b < kNumBlocks - 1) { trans[b].n[0] = g[i++]; trans[b].n[1] = g[i++]; trans[b].c = g[i++]; }
+        }
+        norm5[0] = g[i++]; norm5[1] = g[i++];
+    }
+};
+
+// one BatchNorm(+ReLU) backward: reduce -> parameter grads -> apply
+static int bn_backward(smg_handle* h, BnBwd a, int S, double*& sums_cursor, float* dgamma, float* dbeta, cudaStream_t st) {
+    a.sums = sums_cursor;
+    sums_cursor += (size_t)2 * S * a.C;
+    SMG_TRY(launch_bn_bwd(h, a, S, false, st));
+    SMG_TRY(launch_bn_param_grad(h, a.sums, S, a.C, dgamma, dbeta, st));
+    return launch_bn_bwd(h, a, S, true, st);
 }
-int smg_adam_step(smg_handle*, float* const*, const float* const*, float* const*, float* const*, const int64_t*, int,
-                  int, float, float, float, float, void*) {
-    set_error("smg_adam_step: not built yet");
-    return SMG_ERR_UNSUPPORTED;
+
+static int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* const* hg, cudaStream_t st) {
+    smg_handle::TrainWs& W = h->train;
+    TrunkW& T = h->trunks[W.trunk_id];
+    HeadW& Hd = h->heads[W.head_id];
+    const int S = 2;
+    TrunkGradMap G;
+    G.fill(tg);
+    SMG_CUDA(cudaMemsetAsync(W.sums, 0, W.sums_bytes, st));
+    double* sums = W.sums;
+    const BlockGeom& g4 = h->geom[3];
+    const int npix4 = g4.hw * g4.hw;
+
+    // ---- head: BN(64)+ReLU+20x20 conv, then the two halves of the 1x1 conv, then norm0 o norm5
+    SMG_TRY(launch_head_tail_bwd(h, h->head_p, Hd, dq, W.dP, hg[3], hg[4], hg[5], st));
+    SMG_CUDA(cudaMemsetAsync(hg[2], 0, (size_t)kHeadMid * 2 * kFeatC * 4, st));
+    for (int half = 0; half < 2; ++half) {
+        const int s = half;  // sample 0 = rotated scene -> channels [0,1024), sample 1 = mask -> [1024,2048)
+        Wgrad wg{};
+        wg.g = W.dP; wg.g_cstride = kHeadMid; wg.g_coff = 0; wg.cout = kHeadMid;
+        wg.x = h->block[3] + (size_t)s * npix4 * g4.c_tot; wg.x_cstride = g4.c_tot; wg.cin = kFeatC; wg.hin = g4.hw; wg.hout = g4.hw;
+        wg.prologue_mode = 1; wg.scale = h->head_scale + (size_t)s * kFeatC; wg.shift = h->head_shift + (size_t)s * kFeatC;
+        wg.relu = 1; wg.dw = hg[2]; wg.k_total = 2 * kFeatC; wg.k_off = half * kFeatC;
+        SMG_TRY(launch_wgrad(h, wg, 1, 1, 0, st));
+        ConvArgs a;
+        a.in = W.dP; a.in_cstride = kHeadMid; a.cin = kHeadMid; a.hin = g4.hw; a.prologue_mode = 2; a.relu = 0;
+        a.taps = 1; a.w_raw = Hd.conv0[half].w_dgrad;
+        a.out = W.t_c + (size_t)s * npix4 * kFeatC; a.out_cstride = kFeatC; a.out_coff = 0; a.cout = kFeatC;
+        a.n = 1;
+        SMG_TRY(launch_conv_ffma(h, a, st));
+    }
+    SMG_TRY(launch_head_norm_bwd(h, W.t_c, h->block[3], stats_ptr(h, h->st_block[3]), g4.c_tot, T.norm5, Hd.norm0,
+                                 W.dblk[3], G.norm5[0], G.norm5[1], hg[0], hg[1], st));
+
+    // ---- dense blocks in reverse
+    int layer_index = 58;
+    for (int b = kNumBlocks - 1; b >= 0; --b) {
+        const BlockGeom& g = h->geom[b];
+        const int npix = g.hw * g.hw;
+        double* st_blk = stats_ptr(h, h->st_block[b]);
+        for (int l = kBlockLayers[b] - 1; l >= 0; --l) {
+            --layer_index;
+            const DenseLayerW& L = T.layers[b][l];
+            const TrunkGradMap::L& GL = G.layers[b][l];
+            const int cin = g.c_in + l * kGrowth;
+            double* st_bott = stats_ptr(h, h->st_bott + (size_t)layer_index * kBottleneck);
+            float* y1 = W.bott_saved[layer_index];
+            // (1) 3x3 dgrad: d relu(bn2(y1)) = conv3x3(dX[:, cin:cin+32], flipped W2)
+            {
+                ConvArgs a;
+                a.in = W.dblk[b] + cin; a.in_cstride = g.c_tot; a.cin = kGrowth; a.hin = g.hw; a.prologue_mode = 2; a.relu = 0;
+                a.taps = 9; a.w_raw = L.conv2.w_dgrad;
+                a.out = W.t_a; a.out_cstride = kBottleneck; a.out_coff = 0; a.cout = kBottleneck; a.n = S;
+                SMG_TRY(launch_conv_ffma(h, a, st));
+            }
+            // (2) 3x3 wgrad
+            SMG_CUDA(cudaMemsetAsync(GL.c2, 0, (size_t)kGrowth * kBottleneck * 9 * 4, st));
+            {
+                Wgrad wg{};
+                wg.g = W.dblk[b]; wg.g_cstride = g.c_tot; wg.g_coff = cin; wg.cout = kGrowth;
+                wg.x = y1; wg.x_cstride = kBottleneck; wg.cin = kBottleneck; wg.hin = g.hw; wg.hout = g.hw;
+                wg.prologue_mode = 0; wg.stats = st_bott; wg.stats_stride = kBottleneck; wg.gamma = L.norm2.gamma; wg.beta = L.norm2.beta;
+                wg.relu = 1; wg.dw = GL.c2; wg.k_total = kBottleneck; wg.k_off = 0;
+                SMG_TRY(launch_wgrad(h, wg, S, 9, 0, st));
+            }
+            // (3) BN2 + ReLU backward -> d y1 in t_b
+            {
+                BnBwd bb{};
+                bb.da = W.t_a; bb.da_cstride = kBottleneck; bb.x = y1; bb.x_cstride = kBottleneck;
+                bb.stats = st_bott; bb.stats_stride = kBottleneck; bb.gamma = L.norm2.gamma; bb.beta = L.norm2.beta;
+                bb.C = kBottleneck; bb.hw = g.hw; bb.relu = 1; bb.dst = W.t_b; bb.dst_cstride = kBottleneck; bb.accumulate = 0;
+                SMG_TRY(bn_backward(h, bb, S, sums, GL.n2[0], GL.n2[1], st));
+            }
+            // (4) 1x1 wgrad
+            SMG_CUDA(cudaMemsetAsync(GL.c1, 0, (size_t)kBottleneck * cin * 4, st));
+            {
+                Wgrad wg{};
+                wg.g = W.t_b; wg.g_cstride = kBottleneck; wg.g_coff = 0; wg.cout = kBottleneck;
+                wg.x = h->block[b]; wg.x_cstride = g.c_tot; wg.cin = cin; wg.hin = g.hw; wg.hout = g.hw;
+                wg.prologue_mode = 0; wg.stats = st_blk; wg.stats_stride = g.c_tot; wg.gamma = L.norm1.gamma; wg.beta = L.norm1.beta;
+                wg.relu = 1; wg.dw = GL.c1; wg.k_total = cin; wg.k_off = 0;
+                SMG_TRY(launch_wgrad(h, wg, S, 1, 0, st));
+            }
+            // (5) 1x1 dgrad: d relu(bn1(X[:, :cin])) = dy1 . W1
+            {
+                ConvArgs a;
+                a.in = W.t_b; a.in_cstride = kBottleneck; a.cin = kBottleneck; a.hin = g.hw; a.prologue_mode = 2; a.relu = 0;
+                a.taps = 1; a.w_raw = L.conv1.w_dgrad;
+                a.out = W.t_c; a.out_cstride = cin; a.out_coff = 0; a.cout = cin; a.n = S;
+                SMG_TRY(launch_conv_ffma(h, a, st));
+            }
+            // (6) BN1 + ReLU backward, accumulated into the block gradient
+            {
+                BnBwd bb{};
+                bb.da = W.t_c; bb.da_cstride = cin; bb.x = h->block[b]; bb.x_cstride = g.c_tot;
+                bb.stats = st_blk; bb.stats_stride = g.c_tot; bb.gamma = L.norm1.gamma; bb.beta = L.norm1.beta;
+                bb.C = cin; bb.hw = g.hw; bb.relu = 1; bb.dst = W.dblk[b]; bb.dst_cstride = g.c_tot; bb.accumulate = 1;
+                SMG_TRY(bn_backward(h, bb, S, sums, GL.n1[0], GL.n1[1], st));
+            }
+        }
+        if (b > 0) {
+            // transition b-1: X_b[:, :C/2] = conv1x1(avgpool(relu(bn(X_{b-1}))))
+            const BlockGeom& gp = h->geom[b - 1];
+            const TransitionW& R = T.trans[b - 1];
+            const int C = gp.c_tot, Co = C / 2;
+            double* st_prev = stats_ptr(h, h->st_block[b - 1]);
+            SMG_CUDA(cudaMemsetAsync(G.trans[b - 1].c, 0, (size_t)Co * C * 4, st));
+            {
+                Wgrad wg{};
+                wg.g = W.dblk[b]; wg.g_cstride = g.c_tot; wg.g_coff = 0; wg.cout = Co;
+                wg.x = h->block[b - 1]; wg.x_cstride = C; wg.cin = C; wg.hin = gp.hw; wg.hout = g.hw;
+                wg.prologue_mode = 0; wg.stats = st_prev; wg.stats_stride = C; wg.gamma = R.norm.gamma; wg.beta = R.norm.beta;
+                wg.relu = 1; wg.dw = G.trans[b - 1].c; wg.k_total = C; wg.k_off = 0;
+                SMG_TRY(launch_wgrad(h, wg, S, 1, 1, st));
+            }
+            {
+                ConvArgs a;
+                a.in = W.dblk[b]; a.in_cstride = g.c_tot; a.cin = Co; a.hin = g.hw; a.prologue_mode = 2; a.relu = 0;
+                a.taps = 1; a.w_raw = R.conv.w_dgrad;
+                a.out = W.t_c; a.out_cstride = C; a.out_coff = 0; a.cout = C; a.n = S;
+                SMG_TRY(launch_conv_ffma(h, a, st));
+            }
+            {
+                BnBwd bb{};
+                bb.da = W.t_c; bb.da_cstride = C; bb.da_pooled = 1; bb.x = h->block[b - 1]; bb.x_cstride = C;
+                bb.stats = st_prev; bb.stats_stride = C; bb.gamma = R.norm.gamma; bb.beta = R.norm.beta;
+                bb.C = C; bb.hw = gp.hw; bb.relu = 1; bb.dst = W.dblk[b - 1]; bb.dst_cstride = C; bb.accumulate = 0;
+                SMG_TRY(bn_backward(h, bb, S, sums, G.trans[b - 1].n[0], G.trans[b - 1].n[1], st));
+            }
+        }
+    }
+    // ---- stem: maxpool -> relu/bn0 -> conv0 wgrad (no data gradient is needed for the input image)
+    const int Hc = h->H / 2;
+    SMG_CUDA(cudaMemsetAsync(W.dconv0, 0, (size_t)S * Hc * Hc * 64 * 4, st));
+    SMG_TRY(launch_pool0_bwd(h, S, W.dblk[0], h->geom[0].c_tot, h->conv0, stats_ptr(h, h->st_conv0), T.norm0.gamma,
+                             T.norm0.beta, W.dconv0, st));
+    {
+        BnBwd bb{};
+        bb.da = W.dconv0; bb.da_cstride = 64; bb.x = h->conv0; bb.x_cstride = 64;
+        bb.stats = stats_ptr(h, h->st_conv0); bb.stats_stride = 64; bb.gamma = T.norm0.gamma; bb.beta = T.norm0.beta;
+        bb.C = 64; bb.hw = Hc; bb.relu = 1; bb.dst = W.dconv0; bb.dst_cstride = 64; bb.accumulate = 0;
+        SMG_TRY(bn_backward(h, bb, S, sums, G.norm0[0], G.norm0[1], st));
+    }
+    SMG_CUDA(cudaMemsetAsync(G.conv0, 0, (size_t)64 * 147 * 4, st));
+    SMG_TRY(launch_conv0_wgrad(h, S, W.dconv0, h->input, 3, G.conv0, st));
+    return SMG_OK;
+}
+
+}  // namespace smg
+
+extern "C" {
+
+int smg_qforward_train(smg_handle* h, int trunk_id, int head_id, const float* dev_scene, const float* dev_mask,
+                       int rot_idx, int num_rotations, float* dev_q, float* dev_bn_mean, float* dev_bn_var, void* stream) {
+    SMG_CHECK(h && dev_scene && dev_mask && dev_q, SMG_ERR_INVALID, "smg_qforward_train: NULL argument");
+    SMG_CHECK(trunk_id >= 0 && trunk_id < SMG_NUM_TRUNKS && head_id >= 0 && head_id < SMG_NUM_HEADS, SMG_ERR_INVALID,
+              "smg_qforward_train: trunk %d / head %d", trunk_id, head_id);
+    SMG_CHECK(h->max_samples >= 2, SMG_ERR_STATE, "smg_qforward_train needs max_samples >= 2");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    SMG_TRY(ensure_train_workspace(h));
+    h->train.valid = false;
+    const size_t img = (size_t)3 * h->H * h->H;
+    SMG_TRY(launch_rotate(h, dev_scene, &rot_idx, 1, num_rotations, h->input, 3, st));
+    SMG_CUDA(cudaMemcpyAsync(h->input + img, dev_mask, img * 4, cudaMemcpyDeviceToDevice, st));
+    SMG_TRY(trunk_forward(h, trunk_id, 2, 3, st, true));
+    SMG_TRY(heads_forward(h, trunk_id, head_id, 1, 1, dev_q, st));
+    if (dev_bn_mean && dev_bn_var) SMG_TRY(export_bn_stats(h, 2, dev_bn_mean, dev_bn_var, st));
+    h->train.trunk_id = trunk_id;
+    h->train.head_id = head_id;
+    h->train.valid = true;
+    return SMG_OK;
+}
+
+int smg_qbackward(smg_handle* h, const float* dev_dq, float* const* dev_trunk_grads, float* const* dev_head_grads,
+                  void* stream) {
+    SMG_CHECK(h && dev_dq && dev_trunk_grads && dev_head_grads, SMG_ERR_INVALID, "smg_qbackward: NULL argument");
+    SMG_CHECK(h->train.valid, SMG_ERR_STATE, "smg_qbackward: no smg_qforward_train result is pending on this handle");
+    DeviceGuard guard(h->device);
+    const int status = qbackward_impl(h, dev_dq, dev_trunk_grads, dev_head_grads, (cudaStream_t)stream);
+    h->train.valid = false;
+    return status;
+}
+
+int smg_adam_step(smg_handle* h, float* const* dev_params, const float* const* dev_grads, float* const* dev_m,
+                  float* const* dev_v, const int64_t* host_numel, int n_tensors, int step, float lr, float beta1,
+                  float beta2, float eps, void* stream) {
+    SMG_CHECK(h && dev_params && dev_grads && dev_m && dev_v && host_numel && n_tensors >= 0 && step >= 1, SMG_ERR_INVALID,
+              "smg_adam_step: bad argument");
+    DeviceGuard guard(h->device);
+    for (int i = 0; i < n_tensors; ++i)
+        SMG_TRY(launch_adam(h, dev_params[i], dev_grads[i], dev_m[i], dev_v[i], host_numel[i], step, lr, beta1, beta2, eps,
+                            (cudaStream_t)stream));
+    return SMG_OK;
 }
 
 int smg_argmax(smg_handle* h, const float* dev_q, int n, float* dev_out, int32_t* dev_out_idx, void* stream) {

@@ -67,10 +67,15 @@ conv_ffma_kernel(ConvDev a) {
             s_sc[c] = sc;
             s_sh[c] = a.beta[c] - (float)m * sc;
         }
-    } else {
+    } else if (a.prologue_mode == 1) {
         for (int c = tid; c < a.cin; c += 256) {
             s_sc[c] = a.scale[(size_t)s * a.cin + c];
             s_sh[c] = a.shift[(size_t)s * a.cin + c];
+        }
+    } else {
+        for (int c = tid; c < a.cin; c += 256) {
+            s_sc[c] = 1.f;
+            s_sh[c] = 0.f;
         }
     }
     __syncthreads();
@@ -206,20 +211,25 @@ static int launch_one(smg_handle* h, const ConvDev& d, int n, cudaStream_t st) {
 }
 
 int launch_conv_ffma(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
-    SMG_CHECK(a.w != nullptr && a.w->w_ffma != nullptr, SMG_ERR_STATE, "conv_ffma: weights not packed");
+    SMG_CHECK(a.w_raw != nullptr || (a.w != nullptr && a.w->w_ffma != nullptr), SMG_ERR_STATE,
+              "conv_ffma: weights not packed");
     SMG_CHECK(a.cin % FK == 0 && a.cin <= 2048, SMG_ERR_INVALID, "conv_ffma: cin %d unsupported", a.cin);
     ConvDev d;
     d.in = a.in; d.in_cstride = a.in_cstride; d.cin = a.cin; d.hin = a.hin;
     d.prologue_mode = a.prologue_mode; d.in_stats = a.in_stats; d.in_stats_stride = a.in_stats_stride;
     d.gamma = a.gamma; d.beta = a.beta; d.scale = a.scale; d.shift = a.shift; d.relu = a.relu;
-    d.w = a.w->w_ffma; d.out = a.out; d.out_cstride = a.out_cstride; d.out_coff = a.out_coff; d.cout = a.cout;
+    d.w = a.w_raw ? a.w_raw : a.w->w_ffma; d.out = a.out; d.out_cstride = a.out_cstride; d.out_coff = a.out_coff; d.cout = a.cout;
     d.out_stats = a.out_stats; d.out_stats_stride = a.out_stats_stride;
     d.hout = a.pool ? a.hin / 2 : a.hin;
     if (a.taps == 9) {
         SMG_CHECK(a.cout % 32 == 0 && !a.pool, SMG_ERR_INVALID, "conv_ffma: bad 3x3 config");
         return launch_one<32, 9, 0>(h, d, a.n, st);
     }
-    SMG_CHECK(a.cout % 64 == 0, SMG_ERR_INVALID, "conv_ffma: cout %d must be a multiple of 64", a.cout);
+    SMG_CHECK(a.cout % 32 == 0, SMG_ERR_INVALID, "conv_ffma: cout %d must be a multiple of 32", a.cout);
+    if (a.cout % 64 != 0) {
+        SMG_CHECK(!a.pool, SMG_ERR_INVALID, "conv_ffma: pooled conv needs cout %% 64 == 0");
+        return launch_one<32, 1, 0>(h, d, a.n, st);
+    }
     if (a.pool) return launch_one<64, 1, 1>(h, d, a.n, st);
     return launch_one<64, 1, 0>(h, d, a.n, st);
 }

@@ -5,8 +5,8 @@
 // fp32 accumulation in tensor memory.  Serves torchvision densenet `_DenseLayer.conv1/conv2`,
 // `_Transition.conv` and the head's 1x1 conv (/root/reference/code/models.py:319,384-387).
 //
-// CTA = one 128-pixel output tile x BN output channels, 10 warps:
-//   warps 0-3  A producers: global (NHWC fp32, pre-BN) -> registers -> relu(x*scale+shift) ->
+// CTA = one 128-pixel output tile x BN output channels, 14 warps:
+//   warps 0-3 and 10-13  two groups of A producers (each fills every other stage): global (NHWC fp32, pre-BN) -> registers -> relu(x*scale+shift) ->
 //              tf32/bf16 -> shared memory in the UMMA no-swizzle K-major layout
 //              [16-byte K chunk][row][16 B]  (core matrix = 8 rows x 16 B contiguous, SBO = 128 B,
 //              LBO = padded row count x 16 B).  A row shift of s pixels is a start-address
@@ -146,6 +146,9 @@ struct UmmaDev {
     int hout;
     // 3x3 patch tiling
     int wp, ht, tiles_x;
+    // 1: cp.async in-place producer (wins when the grid is small and the K loop is a latency chain);
+    // 0: register producer (wins when the launch is bandwidth-bound: one shared-memory pass instead of three)
+    int async_producer;
 };
 
 constexpr int UM = 128;         // rows per tile (UMMA M)
@@ -195,7 +198,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 
 template <int ELT, int BN, int TAPS, int POOL>
-__global__ void __launch_bounds__(320, 2)
+__global__ void __launch_bounds__(448, 2)
 conv_umma_kernel(UmmaDev a) {
     using E = EltCfg<ELT>;
     using P = SmemPlan<ELT, BN, TAPS>;
@@ -242,7 +245,7 @@ conv_umma_kernel(UmmaDev a) {
     // BN prologue parameters of this sample
     if (a.prologue_mode == 0) {
         const double cnt = (double)hin * hin;
-        for (int c = tid; c < a.cin; c += 320) {
+        for (int c = tid; c < a.cin; c += 448) {
             const double* st = a.in_stats + 2 * ((size_t)s * a.in_stats_stride + c);
             const double m = st[0] / cnt;
             double var = st[1] / cnt - m * m;
@@ -252,7 +255,7 @@ conv_umma_kernel(UmmaDev a) {
             s_sh[c] = a.beta[c] - (float)m * sc;
         }
     } else {
-        for (int c = tid; c < a.cin; c += 320) {
+        for (int c = tid; c < a.cin; c += 448) {
             s_sc[c] = a.scale[(size_t)s * a.cin + c];
             s_sh[c] = a.shift[(size_t)s * a.cin + c];
         }
@@ -264,10 +267,14 @@ conv_umma_kernel(UmmaDev a) {
 
     const float* inp = a.in + (size_t)s * hin * hin * a.in_cstride;
 
-    if (warp < 4) {
+    if (warp < 4 || warp >= 10) {
         // =============================== A producers ===============================
-        const int c = tid % E::CH;            // chunk within the 32-channel group
-        const int r0 = tid / E::CH;           // first row handled by this thread
+        // two groups of 4 warps; group g fills every other K stage (1x1) / patch slot g (3x3), so two stages
+        // worth of global loads are in flight per CTA without growing the per-thread register footprint
+        const int pgroup = warp < 4 ? 0 : 1;
+        const int ptid = tid & 127;               // thread index inside the group (warps 10-13 start at 320)
+        const int c = ptid % E::CH;               // chunk within the 32-channel group
+        const int r0 = ptid / E::CH;              // first row handled by this thread
         constexpr int RSTEP = 128 / E::CH;    // row stride between iterations
         if (TAPS == 1) {
             constexpr int RI = UM / RSTEP;    // rows per thread per stage
@@ -287,8 +294,8 @@ conv_umma_kernel(UmmaDev a) {
                     roff[i] = -1;
                 }
             }
-            if (ELT == 4 && !POOL) {
-                // tf32 fast path: raw fp32 rows are cp.async'ed straight into their final UMMA slot (NA stages in
+            if (ELT == 4 && !POOL && a.async_producer) {
+                // tf32 small-grid path: raw fp32 rows are cp.async'ed straight into their final UMMA slot (NA stages in
                 // flight per thread, no registers held), then normalised IN PLACE by the thread that loaded them.
                 auto issue = [&](int kg) {
                     uint8_t* dst = sA + (kg % NA) * P::A_SLOT + c * P::A_LBO;
@@ -298,14 +305,19 @@ conv_umma_kernel(UmmaDev a) {
                         if (roff[i] >= 0) cp_async16(dst + (r0 + i * RSTEP) * 16, src + roff[i]);
                     cp_async_commit();
                 };
-#pragma unroll
-                for (int kg = 0; kg < NA; ++kg) {
-                    if (kg < KG) issue(kg);
-                    else cp_async_commit();
-                }
-                for (int kg = 0; kg < KG; ++kg) {
+                // each producer group owns every other K stage and keeps one of its own stages prefetched
+                if (pgroup < KG) issue(pgroup);
+                else cp_async_commit();
+                for (int kg = pgroup; kg < KG; kg += 2) {
                     const int slot = kg % NA;
-                    cp_async_wait<NA - 1>();
+                    const int next = kg + 2;
+                    if (next < KG) {
+                        mbar_wait(&a_empty[next % NA], ((next / NA) & 1) ^ 1);
+                        issue(next);
+                    } else {
+                        cp_async_commit();
+                    }
+                    cp_async_wait<1>();
                     const int ch0 = kg * KC + c * E::EPC;
                     const float4 sc = *reinterpret_cast<const float4*>(s_sc + ch0);
                     const float4 sh = *reinterpret_cast<const float4*>(s_sh + ch0);
@@ -324,16 +336,9 @@ conv_umma_kernel(UmmaDev a) {
                     }
                     fence_proxy_async();
                     mbar_arrive(&a_full[slot]);
-                    const int next = kg + NA;
-                    if (next < KG) {
-                        mbar_wait(&a_empty[slot], ((next / NA) & 1) ^ 1);
-                        issue(next);
-                    } else {
-                        cp_async_commit();
-                    }
                 }
             } else
-            for (int kg = 0; kg < KG; ++kg) {
+            for (int kg = pgroup; kg < KG; kg += 2) {
                 const int slot = kg % NA;
                 const uint32_t ph = (kg / NA) & 1;
                 mbar_wait(&a_empty[slot], ph ^ 1);
@@ -419,8 +424,8 @@ conv_umma_kernel(UmmaDev a) {
                 const int y = h0 - 1 + py, x = w0 - 1 + px;
                 poff[i] = (q < pfill && y >= 0 && y < hin && x >= 0 && x < hin) ? (y * hin + x) * a.in_cstride : -1;
             }
-            if (ELT == 4) {
-                // tf32 fast path: both patch slots are filled with cp.async (raw fp32 lands in its final place,
+            if (ELT == 4 && a.async_producer) {
+                // tf32 small-grid path: both patch slots are filled with cp.async (raw fp32 lands in its final place,
                 // 2 x 27 KB in flight per CTA) and normalised in place by the loading thread.
                 auto issue = [&](int g) {
                     uint8_t* dst = sA + (g & 1) * P::A_SLOT + c * P::A_LBO;
@@ -430,11 +435,10 @@ conv_umma_kernel(UmmaDev a) {
                         if (poff[i] >= 0) cp_async16(dst + (r0 + i * RSTEP) * 16, src + poff[i]);
                     cp_async_commit();
                 };
-                issue(0);
-                issue(1);
-                for (int g = 0; g < 4; ++g) {
+                issue(pgroup);  // producer group g owns patch slot g: channel groups g and g+2
+                for (int g = pgroup; g < 4; g += 2) {
                     const int slot = g & 1;
-                    cp_async_wait<1>();
+                    cp_async_wait<0>();
                     const int ch0 = g * KC + c * E::EPC;
                     const float4 sc = *reinterpret_cast<const float4*>(s_sc + ch0);
                     const float4 sh = *reinterpret_cast<const float4*>(s_sh + ch0);
@@ -464,7 +468,7 @@ conv_umma_kernel(UmmaDev a) {
                     }
                 }
             } else
-            for (int g = 0; g < 4; ++g) {
+            for (int g = pgroup; g < 4; g += 2) {
                 const int slot = g & 1;
                 if (g >= 2) mbar_wait(&a_empty[slot], 0);
                 const int ch0 = g * KC + c * E::EPC;
@@ -472,9 +476,10 @@ conv_umma_kernel(UmmaDev a) {
 #pragma unroll
                 for (int e = 0; e < E::EPC; ++e) { sc[e] = s_sc[ch0 + e]; sh[e] = s_sh[ch0 + e]; }
                 uint8_t* dst = sA + slot * P::A_SLOT + c * P::A_LBO;
-                constexpr int NH = (NI + 1) / 2;  // two batches keep the kernel at <= 96 registers (2 CTAs / SM)
+                constexpr int NB = 4;                    // batches of loads (register budget: 72 at 2 x 448 threads / SM)
+                constexpr int NH = (NI + NB - 1) / NB;
 #pragma unroll
-                for (int hb = 0; hb < 2; ++hb) {
+                for (int hb = 0; hb < NB; ++hb) {
                     float4 v[NH][E::EPC / 4];
 #pragma unroll
                     for (int ii = 0; ii < NH; ++ii) {
@@ -682,7 +687,9 @@ static int launch_umma(smg_handle* h, const UmmaDev& d, int n, cudaStream_t st) 
     } else {
         grid = dim3((d.hout * d.hout + UM - 1) / UM, d.cout / BN, n);
     }
-    conv_umma_kernel<ELT, BN, TAPS, POOL><<<grid, 320, P::TOTAL, st>>>(d);
+    UmmaDev dd = d;
+    dd.async_producer = (int)(grid.x * grid.y * grid.z) < 2 * h->num_sms ? 1 : 0;
+    conv_umma_kernel<ELT, BN, TAPS, POOL><<<grid, 448, P::TOTAL, st>>>(dd);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;
@@ -721,6 +728,7 @@ int launch_conv_umma(smg_handle* h, const ConvArgs& a, int precision, cudaStream
     d.out_stats = a.out_stats; d.out_stats_stride = a.out_stats_stride;
     d.hout = a.pool ? a.hin / 2 : a.hin;
     d.wp = d.ht = d.tiles_x = 0;
+    d.async_producer = 0;
     if (precision == SMG_PREC_TF32) return dispatch<4>(h, a, d, st);
     if (precision == SMG_PREC_BF16) return dispatch<2>(h, a, d, st);
     set_error("conv_umma: precision %d is not a tensor-core mode", precision);

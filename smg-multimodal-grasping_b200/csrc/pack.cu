@@ -20,6 +20,18 @@ __global__ void pack_ffma_kernel(const float* __restrict__ w, float* __restrict_
     }
 }
 
+// data-gradient weights: out[tap'][co][ci] = w[co][ci][taps-1-tap']  (3x3: both kernel axes flipped)
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int taps,
+                                  int k_offset, int k_total) {
+    const int total = taps * cin * cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ci = i % cin;
+        const int co = (i / cin) % cout;
+        const int t = i / (cout * cin);
+        out[i] = w[((size_t)co * k_total + k_offset + ci) * taps + (taps - 1 - t)];
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ T cvt(float v);
 template <>
@@ -71,7 +83,8 @@ int pack_conv_weights(smg_handle* h, const float* w_oihw, ConvW& cw, int k_offse
                                                         cw.taps, k_offset, k_total, bn);
     pack_umma_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(cw.w_bf16),
                                                                 cw.cout, cw.cin, cw.taps, k_offset, k_total, bn);
-    h->launches += 3;
+    pack_dgrad_kernel<<<blocks, threads, 0, st>>>(w_oihw, cw.w_dgrad, cw.cout, cw.cin, cw.taps, k_offset, k_total);
+    h->launches += 4;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;
 }

@@ -68,6 +68,9 @@ struct ConvW {
     // (no-swizzle K-major core matrices, see conv_umma.cu), tf32 (4-byte) and bf16
     uint8_t* w_tf32 = nullptr;
     uint8_t* w_bf16 = nullptr;
+    // data-gradient weights for the fp32 kernels, in the same [taps][K][N] layout with the roles swapped:
+    // 1x1: [cout][cin] (the torch layout); 3x3: [flipped tap][cout][cin]
+    float* w_dgrad = nullptr;
     int cin = 0, cout = 0, taps = 1;
 };
 
@@ -155,6 +158,23 @@ struct smg_handle {
     float* mask_tmp = nullptr;    // unused placeholder
     int last_n = 0;               // samples of the last trunk forward (for smg_debug_read)
 
+    // training workspace (2 samples: rotated scene + masked scene), allocated by the first smg_qforward_train
+    struct TrainWs {
+        void* arena = nullptr;
+        size_t bytes = 0;
+        float* bott_saved[58] = {nullptr};   // conv1 output of every dense layer [2,Hb,Hb,128]
+        float* dblk[smg::kNumBlocks] = {nullptr, nullptr, nullptr, nullptr};  // gradient w.r.t. the raw block buffers
+        float* dconv0 = nullptr;             // [2,H/2,H/2,64]
+        float* t_a = nullptr;                // [2,H/4,H/4,128] scratch (d relu(bn2))
+        float* t_b = nullptr;                // [2,H/4,H/4,128] scratch (d conv1 output)
+        float* t_c = nullptr;                // [2,H/4,H/4,256] scratch (d relu(bn1) / transition dgrad)
+        float* dP = nullptr;                 // [400,64]
+        double* sums = nullptr;              // BN backward reductions, zeroed once per backward
+        size_t sums_bytes = 0;
+        bool valid = false;                  // a training forward is waiting for its backward
+        int trunk_id = -1, head_id = -1, in_channels = 3;
+    } train;
+
     // optional per-kernel-class timing (bench.py roofline): CUDA events around every launch of a class
     bool profile = false;
     struct ProfRec {
@@ -192,7 +212,7 @@ struct ConvArgs {
     int cin = 0;
     int hin = 0;                // input spatial size (square)
     // prologue: mode 0 = derive scale/shift from (stats, gamma, beta); mode 1 = read scale/shift [S][cin]
-    int prologue_mode = 0;
+    int prologue_mode = 0;             // 2 = identity (no scale/shift; used by the data-gradient convolutions)
     const double* in_stats = nullptr;  // [S][in_stats_stride] double2
     int in_stats_stride = 0;
     const float* gamma = nullptr;
@@ -203,6 +223,7 @@ struct ConvArgs {
     int pool = 0;  // 1: average the 2x2 window of prologue outputs (transition); output spatial = hin/2
     int taps = 1;  // 1 or 9 (3x3, pad 1)
     const ConvW* w = nullptr;
+    const float* w_raw = nullptr;  // conv_ffma only: overrides w->w_ffma ([taps][cin][cout] fp32)
     float* out = nullptr;
     int out_cstride = 0;
     int out_coff = 0;
@@ -230,6 +251,57 @@ int launch_heightmap(smg_handle* h, const double* depth, const double* K, const 
                      double* out448, double* host_A_htor, cudaStream_t st);
 int launch_nms(smg_handle* h, const float* boxes, int n, float thr, float amin, float amax, int32_t* keep,
                int32_t* n_keep, cudaStream_t st);
+
+// ---- backward (backward.cu) ------------------------------------------------------------
+struct BnBwd {
+    const float* da;       // gradient w.r.t. the BN(+ReLU) output, NHWC [S, hw_da^2, da_cstride]
+    int da_cstride;
+    int da_pooled;         // 1: da lives at half resolution and is spread over the 2x2 window (x 0.25)
+    const float* x;        // raw BN input, NHWC [S, hw^2, x_cstride]
+    int x_cstride;
+    const double* stats;   // (sum, sumsq) of x: [S, stats_stride] double2
+    int stats_stride;
+    const float* gamma;
+    const float* beta;
+    int C, hw, relu;
+    double* sums;          // [S, C] double2 (S1, S2)
+    float* dst;            // apply: gradient w.r.t. x, NHWC [S, hw^2, dst_cstride]
+    int dst_cstride;
+    int accumulate;
+    int pix_per_cta;
+};
+
+struct Wgrad {
+    const float* g;        // NHWC [S, hout^2, g_cstride], channels [g_coff, g_coff+cout)
+    int g_cstride, g_coff, cout;
+    const float* x;        // raw activation source NHWC [S, hin^2, x_cstride], channels [0, cin)
+    int x_cstride, cin, hin, hout;
+    int prologue_mode;     // 0 stats, 1 scale/shift arrays
+    const double* stats;
+    int stats_stride;
+    const float* gamma;
+    const float* beta;
+    const float* scale;
+    const float* shift;
+    int relu;
+    float* dw;             // torch OIHW [cout][k_total][taps], this conv occupies input channels [k_off, k_off+cin)
+    int k_total, k_off;
+    int pix_per_cta, chunks_per_sample;
+};
+
+int launch_bn_bwd(smg_handle* h, BnBwd a, int S, bool apply, cudaStream_t st);
+int launch_bn_param_grad(smg_handle* h, const double* sums, int S, int C, float* dgamma, float* dbeta, cudaStream_t st);
+int launch_wgrad(smg_handle* h, Wgrad a, int S, int taps, int pool, cudaStream_t st);
+int launch_pool0_bwd(smg_handle* h, int S, const float* g, int g_cstride, const float* conv0, const double* stats,
+                     const float* gamma, const float* beta, float* da0, cudaStream_t st);
+int launch_conv0_wgrad(smg_handle* h, int S, const float* d, const float* in, int cin, float* dw, cudaStream_t st);
+int launch_head_tail_bwd(smg_handle* h, const float* p, const HeadW& hw, const float* dq, float* dP, float* dg1,
+                         float* db1, float* dw1, cudaStream_t st);
+int launch_head_norm_bwd(smg_handle* h, const float* da0, const float* x4, const double* stats, int stats_stride,
+                         const BnP& norm5, const BnP& hnorm0, float* dx4, float* dg5, float* db5, float* dgh, float* dbh,
+                         cudaStream_t st);
+int launch_adam(smg_handle* h, float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float b1,
+                float b2, float eps, cudaStream_t st);
 
 // weight packing
 int pack_conv_weights(smg_handle* h, const float* w_oihw, ConvW& cw, int k_offset, int k_total, cudaStream_t st);

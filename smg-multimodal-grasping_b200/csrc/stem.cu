@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(256)
 pool0_kernel(const float* __restrict__ conv0, const double* __restrict__ stats_in, int stats_in_stride,
              const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
              int out_cstride, double* __restrict__ stats_out, int stats_out_stride, int Hc, int pix_per_cta) {
-    __shared__ float s_sc[64], s_sh[64];
+    __shared__ __align__(16) float s_sc[64];
+    __shared__ __align__(16) float s_sh[64];
     __shared__ float s_sum[16][64], s_sq[16][64];
     const int s = blockIdx.y;
     const int tid = threadIdx.x;
