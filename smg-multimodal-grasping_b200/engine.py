@@ -186,6 +186,35 @@ class Engine:
                                               pm, pv, self._stream()))
         return (q, mean_t, var_t) if want_bn_stats else q
 
+    # ------------------------------------------------------------------ training (code/trainer.py:278-384)
+    def qforward_train(self, style, scene, mask, rot, num_rotations):
+        """One grad-enabled Q evaluation (rotation `rot`); keeps what smg_qbackward needs inside the handle.
+        Returns (q [n_out], bn_mean, bn_var [2, TRUNK_BN_CHANNELS])."""
+        tid, hid = STYLE_ROUTE[int(style)]
+        scene = scene.to(self.device, torch.float32).contiguous()
+        mask = mask.to(self.device, torch.float32).contiguous()
+        q = torch.empty((self.n_out,), dtype=torch.float32, device=self.device)
+        mean = torch.empty((2, TRUNK_BN_CHANNELS), dtype=torch.float32, device=self.device)
+        var = torch.empty_like(mean)
+        _lib.check(self.lib.smg_qforward_train(self.h, tid, hid, scene.data_ptr(), mask.data_ptr(), int(rot),
+                                               int(num_rotations), q.data_ptr(), mean.data_ptr(), var.data_ptr(),
+                                               self._stream()))
+        return q, mean, var
+
+    def qbackward(self, dq, trunk_grads, head_grads):
+        """dLoss/dQ [n_out] -> gradients written into the given tensors (smg_set_*_weights order)."""
+        dq = dq.to(self.device, torch.float32).contiguous()
+        _lib.check(self.lib.smg_qbackward(self.h, dq.data_ptr(), _ptr_array(trunk_grads), _ptr_array(head_grads),
+                                          self._stream()))
+
+    def adam_step(self, params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8):
+        """Fused Adam over a list of tensors (torch.optim.Adam semantics, code/trainer.py:99)."""
+        n = len(params)
+        numel = (ctypes.c_int64 * n)(*[p.numel() for p in params])
+        _lib.check(self.lib.smg_adam_step(self.h, _ptr_array(params), _ptr_array(grads), _ptr_array(exp_avg),
+                                          _ptr_array(exp_avg_sq), numel, n, int(step), float(lr), float(beta1),
+                                          float(beta2), float(eps), self._stream()))
+
     def debug_read(self, what, sample, shape):
         out = torch.empty(shape, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.smg_debug_read(self.h, what.encode(), int(sample), out.data_ptr(), out.numel(), self._stream()))
