@@ -287,8 +287,37 @@ def run_gpu_arm(args):
     h2d = int(scenes[0].nbytes + masks[0].nbytes)
     d2h = int(qh.size * 4)
 
-    # ---- roofline of the dominant kernel class (rank 0, separate short pass with event pairs per launch)
+    # ---- backprop steps/s (second half of BASELINE.json's metric): Trainer.backprop through the public API
     line_extra = {}
+    if not args.no_backprop:
+        try:
+            tr.model.precision = "fp32"   # the backward kernels are fp32; keep forward and backward consistent
+            import smg_b200.synth as synth
+            sc = synth.make_scene(100 + 1000 * rank, num_objects=4, cluttered=False)
+            obj_masks = sc["masks"].astype(np.float64)
+            nb = max(3, min(args.steps, 10))
+            for i in range(3):
+                tr.backprop(sc["scene"], "grasp", [i % 4, i % R], [0, 0], [], [], 1.0, obj_masks.copy(), [0] * 4, [0] * 4, [])
+            barrier()
+            e0.record()
+            for i in range(nb):
+                tr.backprop(sc["scene"], "grasp", [i % 4, i % R], [0, 0], [], [], 1.0, obj_masks.copy(), [0] * 4, [0] * 4, [])
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            line_extra["backprop"] = {
+                "value": world * nb / (float(t.item()) / 1e3), "unit": "steps/s", "steps": nb,
+                "ms_per_step": float(t.item()) / nb, "gflop_per_step": 6 * GFLOP_PER_PASS, "precision": "fp32",
+                "what": "Trainer.backprop: grad-enabled forward (2 trunk passes + head) + backward + Adam + weight re-pack, "
+                        "host heightmaps in, loss out"}
+        except Exception as exc:  # the training path must never take the inference numbers down with it
+            line_extra["backprop"] = {"error": repr(exc)[:300]}
+        tr.model.precision = precision
+
+    # ---- roofline of the dominant kernel class (rank 0, separate short pass with event pairs per launch)
+    eng = tr.model._engine(R + 1)
     if rank == 0:
         peaks = measured_peaks()
         eng.profile_enable(True)
@@ -354,6 +383,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-backprop", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -183,6 +183,15 @@ int smg_debug_conv(smg_handle* h, int precision, const float* dev_in, int n, int
                    const float* dev_w_oihw, int cout, float* dev_out, int out_cstride, int out_coff,
                    double* dev_out_stats, void* stream);
 
+/* unit-test hook for the BatchNorm(+ReLU) backward kernels (backward.cu): x NHWC [S,hw,hw,x_cstride] is the raw
+ * BN input, dev_stats its (sum,sumsq) [S,stats_stride,2] doubles, da the gradient w.r.t. relu(bn(x)) (at half
+ * resolution and spread x0.25 if da_pooled).  Writes dx into dev_dst (accumulating if requested), the two
+ * reductions into dev_sums [S,C,2] doubles (must be zero on entry) and dgamma/dbeta [C].  Synchronous.        */
+int smg_debug_bn_bwd(smg_handle* h, const float* dev_da, int da_cstride, int da_pooled, const float* dev_x,
+                     int x_cstride, const double* dev_stats, int stats_stride, const float* dev_gamma,
+                     const float* dev_beta, int C, int hw, int relu, int S, double* dev_sums, float* dev_dst,
+                     int dst_cstride, int accumulate, float* dev_dgamma, float* dev_dbeta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "smg_debug_read": (I, [VP, ctypes.c_char_p, I, VP, ctypes.c_int64, VP]),
     "smg_profile_enable": (I, [VP, I]),
     "smg_profile_read": (I, [VP, c_double_p, c_int64_p, c_double_p, c_double_p]),
+    "smg_debug_bn_bwd": (I, [VP, VP, I, I, VP, I, VP, I, VP, VP, I, I, I, I, VP, VP, I, I, VP, VP, VP]),
     "smg_debug_conv": (I, [VP, I, VP, I, I, I, I, VP, VP, I, I, I, VP, I, VP, I, I, VP, VP]),
 }
 

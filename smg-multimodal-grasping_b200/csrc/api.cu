@@ -916,4 +916,24 @@ int smg_debug_conv(smg_handle* h, int precision, const float* dev_in, int n, int
     return status;
 }
 
+int smg_debug_bn_bwd(smg_handle* h, const float* dev_da, int da_cstride, int da_pooled, const float* dev_x,
+                     int x_cstride, const double* dev_stats, int stats_stride, const float* dev_gamma,
+                     const float* dev_beta, int C, int hw, int relu, int S, double* dev_sums, float* dev_dst,
+                     int dst_cstride, int accumulate, float* dev_dgamma, float* dev_dbeta, void* stream) {
+    SMG_CHECK(h && dev_da && dev_x && dev_stats && dev_gamma && dev_beta && dev_sums && dev_dst && dev_dgamma && dev_dbeta,
+              SMG_ERR_INVALID, "smg_debug_bn_bwd: NULL argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    BnBwd bb{};
+    bb.da = dev_da; bb.da_cstride = da_cstride; bb.da_pooled = da_pooled; bb.x = dev_x; bb.x_cstride = x_cstride;
+    bb.stats = dev_stats; bb.stats_stride = stats_stride; bb.gamma = dev_gamma; bb.beta = dev_beta;
+    bb.C = C; bb.hw = hw; bb.relu = relu; bb.sums = dev_sums; bb.dst = dev_dst; bb.dst_cstride = dst_cstride;
+    bb.accumulate = accumulate;
+    SMG_TRY(launch_bn_bwd(h, bb, S, false, st));
+    SMG_TRY(launch_bn_param_grad(h, dev_sums, S, C, dev_dgamma, dev_dbeta, st));
+    SMG_TRY(launch_bn_bwd(h, bb, S, true, st));
+    SMG_CUDA(cudaStreamSynchronize(st));
+    return SMG_OK;
+}
+
 }  // extern "C"
