@@ -71,64 +71,86 @@ static int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------
 // trunk forward over `n` samples already resident in h->input
 // ---------------------------------------------------------------------------------------
+// Samples are independent (per-sample BatchNorm), so each dense block is run over CHUNKS of samples sized to keep the
+// chunk's block buffer + bottleneck scratch inside the 126 MB L2: the 2 x layers re-reads of the block buffer then hit
+// L2 instead of HBM (block 1: 39 MB per sample -> 2-3 samples per chunk; blocks 3-4: all samples at once).
+static int chunk_samples(const smg_handle* h, int b, int n) {
+    const BlockGeom& g = h->geom[b];
+    double per_sample = (double)g.hw * g.hw * (g.c_tot + kBottleneck) * 4.0;
+    if (b == 0) per_sample += (double)(h->H / 2) * (h->H / 2) * 64 * 4.0;  // conv0 output is consumed by pool0 in-chunk
+    int cs = (int)(h->l2_chunk_bytes / per_sample);
+    if (cs < 1) cs = 1;
+    return cs < n ? cs : n;
+}
+
 static int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cudaStream_t st, bool save_bott = false) {
     TrunkW& T = h->trunks[trunk_id];
     SMG_CHECK(T.set, SMG_ERR_STATE, "trunk %d: weights not set (call smg_set_trunk_weights)", trunk_id);
     SMG_CHECK(n >= 1 && n <= h->max_samples, SMG_ERR_INVALID, "trunk_forward: n=%d outside [1,%d]", n, h->max_samples);
-    const int S = h->max_samples;
-    (void)S;
     SMG_CUDA(cudaMemsetAsync(h->stats, 0, h->stats_bytes, st));
-    {
-        const double hc = (double)(h->H / 2) * (h->H / 2);
-        // stem traffic: input read + conv0 written, conv0 read + pooled output written
-        ProfScope ps(h, st, 0, 2.0 * n * hc * 64 * 49 * in_channels,
-                     4.0 * n * ((double)in_channels * h->H * h->H + 2 * hc * 64 + hc / 4 * 64));
-        SMG_TRY(launch_conv0(h, h->input, in_channels, n, in_channels == 1 ? T.conv0_folded : T.conv0, h->conv0,
-                             stats_ptr(h, h->st_conv0), st));
-        SMG_TRY(launch_pool0(h, n, h->conv0, stats_ptr(h, h->st_conv0), T.norm0.gamma, T.norm0.beta, h->block[0],
-                             h->geom[0].c_tot, stats_ptr(h, h->st_block[0]), st));
-    }
-    int layer_index = 0;
+    const size_t in_img = (size_t)in_channels * h->H * h->H;
+    const size_t c0_img = (size_t)(h->H / 2) * (h->H / 2) * 64;
+    int layer_base = 0;
     for (int b = 0; b < kNumBlocks; ++b) {
         const BlockGeom& g = h->geom[b];
-        double* st_blk = stats_ptr(h, h->st_block[b]);
-        for (int l = 0; l < kBlockLayers[b]; ++l, ++layer_index) {
-            const DenseLayerW& L = T.layers[b][l];
-            const int cin = g.c_in + l * kGrowth;
-            double* st_bott = stats_ptr(h, h->st_bott + (size_t)layer_index * kBottleneck);
-            ConvArgs a1;
-            a1.in = h->block[b]; a1.in_cstride = g.c_tot; a1.cin = cin; a1.hin = g.hw;
-            a1.in_stats = st_blk; a1.in_stats_stride = g.c_tot;
-            a1.gamma = L.norm1.gamma; a1.beta = L.norm1.beta;
-            a1.taps = 1; a1.w = &L.conv1;
-            float* bott = save_bott ? h->train.bott_saved[layer_index] : h->bott;
-            a1.out = bott; a1.out_cstride = kBottleneck; a1.out_coff = 0; a1.cout = kBottleneck;
-            a1.out_stats = st_bott; a1.out_stats_stride = kBottleneck;
-            a1.n = n;
-            SMG_TRY(conv_dispatch(h, a1, st));
-            ConvArgs a2;
-            a2.in = bott; a2.in_cstride = kBottleneck; a2.cin = kBottleneck; a2.hin = g.hw;
-            a2.in_stats = st_bott; a2.in_stats_stride = kBottleneck;
-            a2.gamma = L.norm2.gamma; a2.beta = L.norm2.beta;
-            a2.taps = 9; a2.w = &L.conv2;
-            a2.out = h->block[b]; a2.out_cstride = g.c_tot; a2.out_coff = cin; a2.cout = kGrowth;
-            a2.out_stats = st_blk; a2.out_stats_stride = g.c_tot;
-            a2.n = n;
-            SMG_TRY(conv_dispatch(h, a2, st));
+        const size_t px = (size_t)g.hw * g.hw;
+        const int cs = save_bott ? n : chunk_samples(h, b, n);
+        for (int s0 = 0; s0 < n; s0 += cs) {
+            const int ns = s0 + cs <= n ? cs : n - s0;
+            double* st_blk = stats_ptr(h, h->st_block[b]) + 2 * (size_t)s0 * g.c_tot;
+            float* blk = h->block[b] + (size_t)s0 * px * g.c_tot;
+            if (b == 0) {
+                const double hc = (double)c0_img / 64;
+                // stem traffic: input read + conv0 written, conv0 read + pooled output written
+                ProfScope ps(h, st, 0, 2.0 * ns * hc * 64 * 49 * in_channels,
+                             4.0 * ns * ((double)in_channels * h->H * h->H + 2 * hc * 64 + hc / 4 * 64));
+                double* st_c0 = stats_ptr(h, h->st_conv0) + 2 * (size_t)s0 * 64;
+                SMG_TRY(launch_conv0(h, h->input + (size_t)s0 * in_img, in_channels, ns,
+                                     in_channels == 1 ? T.conv0_folded : T.conv0, h->conv0 + (size_t)s0 * c0_img, st_c0, st));
+                SMG_TRY(launch_pool0(h, ns, h->conv0 + (size_t)s0 * c0_img, st_c0, T.norm0.gamma, T.norm0.beta, blk, g.c_tot,
+                                     st_blk, st));
+            }
+            for (int l = 0; l < kBlockLayers[b]; ++l) {
+                const int layer_index = layer_base + l;
+                const DenseLayerW& L = T.layers[b][l];
+                const int cin = g.c_in + l * kGrowth;
+                double* st_bott = stats_ptr(h, h->st_bott + (size_t)layer_index * kBottleneck) + 2 * (size_t)s0 * kBottleneck;
+                float* bott = (save_bott ? h->train.bott_saved[layer_index] : h->bott) + (size_t)s0 * px * kBottleneck;
+                ConvArgs a1;
+                a1.in = blk; a1.in_cstride = g.c_tot; a1.cin = cin; a1.hin = g.hw;
+                a1.in_stats = st_blk; a1.in_stats_stride = g.c_tot;
+                a1.gamma = L.norm1.gamma; a1.beta = L.norm1.beta;
+                a1.taps = 1; a1.w = &L.conv1;
+                a1.out = bott; a1.out_cstride = kBottleneck; a1.out_coff = 0; a1.cout = kBottleneck;
+                a1.out_stats = st_bott; a1.out_stats_stride = kBottleneck;
+                a1.n = ns;
+                SMG_TRY(conv_dispatch(h, a1, st));
+                ConvArgs a2;
+                a2.in = bott; a2.in_cstride = kBottleneck; a2.cin = kBottleneck; a2.hin = g.hw;
+                a2.in_stats = st_bott; a2.in_stats_stride = kBottleneck;
+                a2.gamma = L.norm2.gamma; a2.beta = L.norm2.beta;
+                a2.taps = 9; a2.w = &L.conv2;
+                a2.out = blk; a2.out_cstride = g.c_tot; a2.out_coff = cin; a2.cout = kGrowth;
+                a2.out_stats = st_blk; a2.out_stats_stride = g.c_tot;
+                a2.n = ns;
+                SMG_TRY(conv_dispatch(h, a2, st));
+            }
+            if (b < kNumBlocks - 1) {
+                const TransitionW& R = T.trans[b];
+                const BlockGeom& gn = h->geom[b + 1];
+                ConvArgs at;
+                at.in = blk; at.in_cstride = g.c_tot; at.cin = g.c_tot; at.hin = g.hw;
+                at.in_stats = st_blk; at.in_stats_stride = g.c_tot;
+                at.gamma = R.norm.gamma; at.beta = R.norm.beta;
+                at.pool = 1; at.taps = 1; at.w = &R.conv;
+                at.out = h->block[b + 1] + (size_t)s0 * gn.hw * gn.hw * gn.c_tot; at.out_cstride = gn.c_tot; at.out_coff = 0;
+                at.cout = g.c_tot / 2;
+                at.out_stats = stats_ptr(h, h->st_block[b + 1]) + 2 * (size_t)s0 * gn.c_tot; at.out_stats_stride = gn.c_tot;
+                at.n = ns;
+                SMG_TRY(conv_dispatch(h, at, st));
+            }
         }
-        if (b < kNumBlocks - 1) {
-            const TransitionW& R = T.trans[b];
-            const BlockGeom& gn = h->geom[b + 1];
-            ConvArgs at;
-            at.in = h->block[b]; at.in_cstride = g.c_tot; at.cin = g.c_tot; at.hin = g.hw;
-            at.in_stats = st_blk; at.in_stats_stride = g.c_tot;
-            at.gamma = R.norm.gamma; at.beta = R.norm.beta;
-            at.pool = 1; at.taps = 1; at.w = &R.conv;
-            at.out = h->block[b + 1]; at.out_cstride = gn.c_tot; at.out_coff = 0; at.cout = g.c_tot / 2;
-            at.out_stats = stats_ptr(h, h->st_block[b + 1]); at.out_stats_stride = gn.c_tot;
-            at.n = n;
-            SMG_TRY(conv_dispatch(h, at, st));
-        }
+        layer_base += kBlockLayers[b];
     }
     h->last_n = n;
     return SMG_OK;
@@ -296,6 +318,10 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     h->max_samples = max_samples;
     h->H = H;
     h->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("SMG_L2_CHUNK_MB")) {  // tuning knob: 0 disables the chunked schedule
+        const double mb = atof(e);
+        h->l2_chunk_bytes = mb > 0 ? mb * 1e6 : 1e18;
+    }
     int c = kInitFeatures, hw = H / 4;
     for (int b = 0; b < kNumBlocks; ++b) {
         h->geom[b].hw = hw;

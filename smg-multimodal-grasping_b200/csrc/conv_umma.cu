@@ -608,11 +608,14 @@ conv_umma_kernel(UmmaDev a) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) s_out[row * (BN + 1) + cb + i] = valid ? v[i] : 0.f;
         }
-        tc_fence_before();
-        // sync the 4 epilogue warps only
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        // coalesced stores: warp e handles rows e, e+4, ...
-        for (int r = e; r < UM; r += 4) {
+    }
+    // the accumulator tile is staged: every warp of the CTA (producers, MMA and loader warps are idle by now) shares
+    // the coalesced stores and the per-channel statistics
+    tc_fence_before();
+    __syncthreads();
+    {
+        constexpr int NW = 14;
+        for (int r = warp; r < UM; r += NW) {
             int pix;
             bool ok;
             if (TAPS == 9) {
@@ -630,22 +633,23 @@ conv_umma_kernel(UmmaDev a) {
         }
         // per-channel statistics of this tile (invalid rows were staged as zeros)
         if (a.out_stats != nullptr) {
-            const int t = tid - 128;
-            constexpr int GROUPS = 128 / BN;       // row groups
-            constexpr int RPG = UM / GROUPS;       // rows per group
-            const int cidx = t % BN, g = t / BN;
-            float su = 0.f, sq = 0.f;
-            for (int r = g * RPG; r < (g + 1) * RPG; ++r) {
-                const float x = s_out[r * (BN + 1) + cidx];
-                su += x;
-                sq = fmaf(x, x, sq);
+            constexpr int GROUPS = 448 / BN;                        // row groups: 3 (N=128), 7 (N=64), 14 (N=32)
+            constexpr int RPG = (UM + GROUPS - 1) / GROUPS;          // rows per group
+            const int cidx = tid % BN, g = tid / BN;
+            if (g < GROUPS) {
+                float su = 0.f, sq = 0.f;
+                const int r1 = (g + 1) * RPG < UM ? (g + 1) * RPG : UM;
+                for (int r = g * RPG; r < r1; ++r) {
+                    const float x = s_out[r * (BN + 1) + cidx];
+                    su += x;
+                    sq = fmaf(x, x, sq);
+                }
+                double* st = a.out_stats + 2 * ((size_t)s * a.out_stats_stride + a.out_coff + ntile * BN + cidx);
+                atomicAdd(st, (double)su);
+                atomicAdd(st + 1, (double)sq);
             }
-            double* st = a.out_stats + 2 * ((size_t)s * a.out_stats_stride + a.out_coff + ntile * BN + cidx);
-            atomicAdd(st, (double)su);
-            atomicAdd(st + 1, (double)sq);
         }
     }
-    tc_fence_before();
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();

@@ -133,6 +133,7 @@ struct smg_handle {
     int num_sms = 148;
     int64_t launches = 0;
     int64_t workspace_bytes = 0;
+    double l2_chunk_bytes = 96e6;  // per-chunk activation footprint the trunk schedule aims to keep L2-resident
 
     smg::BlockGeom geom[smg::kNumBlocks];
     smg::TrunkW trunks[SMG_NUM_TRUNKS];
