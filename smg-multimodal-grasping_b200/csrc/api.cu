@@ -349,6 +349,8 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     const size_t o_hs = p.take(S * kFeatC * 4), o_hh = p.take(S * kFeatC * 4);
     const size_t o_hp = p.take(S * (size_t)h->geom[3].hw * h->geom[3].hw * kHeadMid * 4);
     const size_t o_tmp = p.take((size_t)3 * H * H * 4);
+    const size_t o_hm = p.take((1 + S) * (size_t)(H / 2) * (H / 2) * 8);
+    const size_t o_q = p.take(S * S * 4 * 4);
     uint8_t* base = nullptr;
     cudaError_t e = cudaMalloc(&base, p.off);
     if (e != cudaSuccess) {
@@ -366,6 +368,12 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     h->head_shift = reinterpret_cast<float*>(base + o_hh);
     h->head_p = reinterpret_cast<float*>(base + o_hp);
     h->scene_tmp = reinterpret_cast<float*>(base + o_tmp);
+    h->hm_stage = reinterpret_cast<double*>(base + o_hm);
+    h->q_stage = reinterpret_cast<float*>(base + o_q);
+    cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming);
+    if (const char* e = getenv("SMG_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
     *out = h;
     return SMG_OK;
 }
@@ -374,6 +382,11 @@ int smg_destroy(smg_handle* h) {
     if (!h) return SMG_OK;
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
+    for (auto& g : h->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (h->gstream) cudaStreamDestroy(h->gstream);
+    if (h->g_in) cudaEventDestroy(h->g_in);
+    if (h->g_out) cudaEventDestroy(h->g_out);
     if (h->input) cudaFree(h->input);  // base of the workspace arena
     for (int t = 0; t < SMG_NUM_TRUNKS; ++t)
         if (h->trunks[t].arena) cudaFree(h->trunks[t].arena);
@@ -535,6 +548,18 @@ int smg_qforward(smg_handle* h, int trunk_id, int head_id, const float* dev_scen
     return qforward_common(h, trunk_id, head_id, n_masks, n_rot, 3, dev_q, dev_bn_mean, dev_bn_var, st);
 }
 
+static int qforward_maps_body(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm, const double* dev_mask_hms,
+                              int n_masks, int hm_size, double mean, double stddev, const int* host_rot_idx, int n_rot,
+                              int num_rotations, float* dev_q, float* dev_bn_mean, float* dev_bn_var, cudaStream_t st) {
+    // Trainer.forward feeds three identical channels (code/trainer.py:178-181): keep ONE plane per sample and use
+    // the channel-folded conv0 weights (K = 49 instead of 147)
+    const size_t img = (size_t)h->H * h->H;
+    SMG_TRY(launch_prep(h, dev_scene_hm, 1, hm_size, mean, stddev, h->scene_tmp, 1, st));
+    SMG_TRY(launch_rotate(h, h->scene_tmp, host_rot_idx, n_rot, num_rotations, h->input, 1, st));
+    SMG_TRY(launch_prep(h, dev_mask_hms, n_masks, hm_size, mean, stddev, h->input + (size_t)n_rot * img, 1, st));
+    return qforward_common(h, trunk_id, head_id, n_masks, n_rot, 1, dev_q, dev_bn_mean, dev_bn_var, st);
+}
+
 int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm, const double* dev_mask_hms,
                       int n_masks, int hm_size, double mean, double stddev, const int* host_rot_idx, int n_rot,
                       int num_rotations, float* dev_q, float* dev_bn_mean, float* dev_bn_var, void* stream) {
@@ -546,13 +571,70 @@ int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* de
     SMG_CHECK(stddev != 0.0, SMG_ERR_INVALID, "smg_qforward_maps: stddev is 0");
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    // Trainer.forward feeds three identical channels (code/trainer.py:178-181): keep ONE plane per sample and use
-    // the channel-folded conv0 weights (K = 49 instead of 147)
-    const size_t img = (size_t)h->H * h->H;
-    SMG_TRY(launch_prep(h, dev_scene_hm, 1, hm_size, mean, stddev, h->scene_tmp, 1, st));
-    SMG_TRY(launch_rotate(h, h->scene_tmp, host_rot_idx, n_rot, num_rotations, h->input, 1, st));
-    SMG_TRY(launch_prep(h, dev_mask_hms, n_masks, hm_size, mean, stddev, h->input + (size_t)n_rot * img, 1, st));
-    return qforward_common(h, trunk_id, head_id, n_masks, n_rot, 1, dev_q, dev_bn_mean, dev_bn_var, st);
+    const size_t hm_elems = (size_t)hm_size * hm_size;
+    SMG_CHECK(2 * hm_size <= h->H, SMG_ERR_INVALID, "smg_qforward_maps: hm_size %d too large for H %d", hm_size, h->H);
+    const bool graphable = h->use_graphs && !h->profile && !dev_bn_mean && !dev_bn_var;
+    if (!graphable) return qforward_maps_body(h, trunk_id, head_id, dev_scene_hm, dev_mask_hms, n_masks, hm_size, mean, stddev,
+                                              host_rot_idx, n_rot, num_rotations, dev_q, dev_bn_mean, dev_bn_var, st);
+    // stage the inputs at fixed addresses
+    SMG_CUDA(cudaMemcpyAsync(h->hm_stage, dev_scene_hm, hm_elems * 8, cudaMemcpyDeviceToDevice, st));
+    SMG_CUDA(cudaMemcpyAsync(h->hm_stage + hm_elems, dev_mask_hms, (size_t)n_masks * hm_elems * 8, cudaMemcpyDeviceToDevice, st));
+    smg_handle::QGraph* G = nullptr;
+    for (auto& g : h->graphs)
+        if (g.trunk_id == trunk_id && g.head_id == head_id && g.n_masks == n_masks && g.n_rot == n_rot &&
+            g.num_rot == num_rotations && g.hm_size == hm_size && g.precision == h->precision && g.mean == mean &&
+            g.stddev == stddev && g.rots == std::vector<int>(host_rot_idx, host_rot_idx + n_rot)) {
+            G = &g;
+            break;
+        }
+    if (!G) {
+        smg_handle::QGraph g;
+        g.trunk_id = trunk_id; g.head_id = head_id; g.n_masks = n_masks; g.n_rot = n_rot; g.num_rot = num_rotations;
+        g.hm_size = hm_size; g.precision = h->precision; g.mean = mean; g.stddev = stddev;
+        g.rots.assign(host_rot_idx, host_rot_idx + n_rot);
+        h->graphs.push_back(g);
+        G = &h->graphs.back();
+    }
+    const size_t q_bytes = (size_t)n_masks * n_rot * h->heads[head_id].n_out * 4;
+    if (G->seen == 0 || h->graphs.size() > 64) {
+        // first sighting: run eagerly (also performs the one-time cudaFuncSetAttribute calls)
+        G->seen = 1;
+        SMG_TRY(qforward_maps_body(h, trunk_id, head_id, h->hm_stage, h->hm_stage + hm_elems, n_masks, hm_size, mean, stddev,
+                                   host_rot_idx, n_rot, num_rotations, h->q_stage, nullptr, nullptr, st));
+        SMG_CUDA(cudaMemcpyAsync(dev_q, h->q_stage, q_bytes, cudaMemcpyDeviceToDevice, st));
+        return SMG_OK;
+    }
+    SMG_CUDA(cudaEventRecord(h->g_in, st));
+    SMG_CUDA(cudaStreamWaitEvent(h->gstream, h->g_in, 0));
+    if (!G->exec) {
+        cudaGraph_t graph = nullptr;
+        const int64_t launches_before = h->launches;
+        SMG_CUDA(cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeRelaxed));
+        const int status = qforward_maps_body(h, trunk_id, head_id, h->hm_stage, h->hm_stage + hm_elems, n_masks, hm_size, mean,
+                                              stddev, host_rot_idx, n_rot, num_rotations, h->q_stage, nullptr, nullptr, h->gstream);
+        cudaError_t e = cudaStreamEndCapture(h->gstream, &graph);
+        const int64_t captured = h->launches - launches_before;
+        h->launches = launches_before;  // capturing enqueues nothing
+        if (status != SMG_OK || e != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            if (status == SMG_OK) set_error("smg_qforward_maps: graph capture failed: %s", cudaGetErrorString(e));
+            return status != SMG_OK ? status : SMG_ERR_CUDA;
+        }
+        e = cudaGraphInstantiate(&G->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            set_error("smg_qforward_maps: cudaGraphInstantiate: %s", cudaGetErrorString(e));
+            return SMG_ERR_CUDA;
+        }
+        G->n_launches = captured;
+        G->seen = 2;
+    }
+    SMG_CUDA(cudaGraphLaunch(G->exec, h->gstream));
+    h->launches += G->n_launches;
+    SMG_CUDA(cudaEventRecord(h->g_out, h->gstream));
+    SMG_CUDA(cudaStreamWaitEvent(st, h->g_out, 0));
+    SMG_CUDA(cudaMemcpyAsync(dev_q, h->q_stage, q_bytes, cudaMemcpyDeviceToDevice, st));
+    return SMG_OK;
 }
 
 // ---------------------------------------------------------------------------------------

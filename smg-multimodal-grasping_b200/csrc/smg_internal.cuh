@@ -156,7 +156,22 @@ struct smg_handle {
     float* head_shift = nullptr;  // [S,1024]
     float* head_p = nullptr;      // [S,400,64]
     float* scene_tmp = nullptr;   // [3,H,H] staging for smg_qforward_maps
-    float* mask_tmp = nullptr;    // unused placeholder
+    // CUDA-graph replay of smg_qforward_maps: the pass is a fixed sequence of ~250 launches on fixed workspace
+    // addresses, so it is captured once per (trunk, head, shapes, rotations, precision) and replayed
+    double* hm_stage = nullptr;   // [1 + S][(H/2)^2] heightmap staging (scene, then masks)
+    float* q_stage = nullptr;     // [S*S*4] result staging
+    cudaStream_t gstream = nullptr;
+    cudaEvent_t g_in = nullptr, g_out = nullptr;
+    bool use_graphs = true;
+    struct QGraph {
+        int trunk_id, head_id, n_masks, n_rot, num_rot, hm_size, precision;
+        double mean, stddev;
+        std::vector<int> rots;
+        int seen = 0;
+        int64_t n_launches = 0;   // kernels inside the captured graph (for smg_launch_count)
+        cudaGraphExec_t exec = nullptr;
+    };
+    std::vector<QGraph> graphs;
     int last_n = 0;               // samples of the last trunk forward (for smg_debug_read)
 
     // training workspace (2 samples: rotated scene + masked scene), allocated by the first smg_qforward_train
