@@ -192,7 +192,8 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     import __graft_entry__ as entry
     if rank == 0:
@@ -231,10 +232,10 @@ def run_gpu_arm(args):
     best = torch.zeros(2, device=dev)
     gathered = [torch.zeros(2, device=dev) for _ in range(world)] if world > 1 else None
 
-    def step_resident(i):
+    def step_resident(i, exchange=True):
         q = eng.qforward_maps(0, scenes_d[i % nu], masks_d[i % nu:i % nu + 1], MEAN, STD, rots, R)
         val, idx = eng.argmax(q)
-        if world > 1:  # per-GPU best (Q, rotation) tuples: the path's only exchange
+        if world > 1 and exchange:  # per-GPU best (Q, rotation) tuples: the path's only exchange
             best[0] = val[0]
             best[1] = idx[0].float()
             dist.all_gather(gathered, best)
@@ -323,7 +324,7 @@ def run_gpu_arm(args):
         eng.profile_enable(True)
         nprof = min(3, args.steps)
         for i in range(nprof):
-            step_resident(i)
+            step_resident(i, exchange=False)   # rank 0 only: no collective inside the profiled pass
         prof = eng.profile_read()
         eng.profile_enable(False)
         total_ms = sum(v["ms"] for v in prof.values())
