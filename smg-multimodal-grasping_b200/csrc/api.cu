@@ -78,9 +78,11 @@ static int chunk_samples(const smg_handle* h, int b, int n) {
     const BlockGeom& g = h->geom[b];
     double per_sample = (double)g.hw * g.hw * (g.c_tot + kBottleneck) * 4.0;
     if (b == 0) per_sample += (double)(h->H / 2) * (h->H / 2) * 64 * 4.0;  // conv0 output is consumed by pool0 in-chunk
-    int cs = (int)(h->l2_chunk_bytes / per_sample);
+    if (h->l2_chunk_bytes <= 0.0) return n;  // chunking disabled
+    const double q = h->l2_chunk_bytes / per_sample;
+    int cs = q >= (double)n ? n : (int)q;
     if (cs < 1) cs = 1;
-    return cs < n ? cs : n;
+    return cs;
 }
 
 static int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cudaStream_t st, bool save_bott = false) {
@@ -320,7 +322,7 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     h->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("SMG_L2_CHUNK_MB")) {  // tuning knob: 0 disables the chunked schedule
         const double mb = atof(e);
-        h->l2_chunk_bytes = mb > 0 ? mb * 1e6 : 1e18;
+        h->l2_chunk_bytes = mb > 0 ? mb * 1e6 : 0.0;
     }
     int c = kInitFeatures, hw = H / 4;
     for (int b = 0; b < kNumBlocks; ++b) {
@@ -374,6 +376,7 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming);
     if (const char* e = getenv("SMG_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
+    if (const char* e = getenv("SMG_ASYNC")) h->force_async = atoi(e);
     *out = h;
     return SMG_OK;
 }

@@ -631,10 +631,13 @@ conv_umma_kernel(UmmaDev a) {
 #pragma unroll
             for (int cb = 0; cb < BN; cb += 32) o[cb + lane] = s_out[r * (BN + 1) + cb + lane];
         }
-        // per-channel statistics of this tile (invalid rows were staged as zeros)
+        // per-channel statistics of this tile (invalid rows were staged as zeros): partial column sums by all
+        // threads, combined in shared memory (the scale/shift tables are dead by now), ONE double atomic pair per
+        // channel and tile
         if (a.out_stats != nullptr) {
             constexpr int GROUPS = 448 / BN;                        // row groups: 3 (N=128), 7 (N=64), 14 (N=32)
             constexpr int RPG = (UM + GROUPS - 1) / GROUPS;          // rows per group
+            float* red = s_sc;                                       // [2][GROUPS][BN] floats <= 3.5 KB
             const int cidx = tid % BN, g = tid / BN;
             if (g < GROUPS) {
                 float su = 0.f, sq = 0.f;
@@ -644,9 +647,20 @@ conv_umma_kernel(UmmaDev a) {
                     su += x;
                     sq = fmaf(x, x, sq);
                 }
-                double* st = a.out_stats + 2 * ((size_t)s * a.out_stats_stride + a.out_coff + ntile * BN + cidx);
-                atomicAdd(st, (double)su);
-                atomicAdd(st + 1, (double)sq);
+                red[g * BN + cidx] = su;
+                red[(GROUPS + g) * BN + cidx] = sq;
+            }
+            __syncthreads();
+            if (tid < BN) {
+                double su = 0.0, sq = 0.0;
+#pragma unroll
+                for (int g2 = 0; g2 < GROUPS; ++g2) {
+                    su += (double)red[g2 * BN + tid];
+                    sq += (double)red[(GROUPS + g2) * BN + tid];
+                }
+                double* st = a.out_stats + 2 * ((size_t)s * a.out_stats_stride + a.out_coff + ntile * BN + tid);
+                atomicAdd(st, su);
+                atomicAdd(st + 1, sq);
             }
         }
     }
@@ -692,7 +706,7 @@ static int launch_umma(smg_handle* h, const UmmaDev& d, int n, cudaStream_t st) 
         grid = dim3((d.hout * d.hout + UM - 1) / UM, d.cout / BN, n);
     }
     UmmaDev dd = d;
-    dd.async_producer = (int)(grid.x * grid.y * grid.z) < 2 * h->num_sms ? 1 : 0;
+    dd.async_producer = h->force_async >= 0 ? h->force_async : ((int)(grid.x * grid.y * grid.z) < 2 * h->num_sms ? 1 : 0);
     conv_umma_kernel<ELT, BN, TAPS, POOL><<<grid, 448, P::TOTAL, st>>>(dd);
     h->launches++;
     SMG_CUDA(cudaGetLastError());

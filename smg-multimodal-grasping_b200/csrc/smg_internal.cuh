@@ -133,7 +133,8 @@ struct smg_handle {
     int num_sms = 148;
     int64_t launches = 0;
     int64_t workspace_bytes = 0;
-    double l2_chunk_bytes = 96e6;  // per-chunk activation footprint the trunk schedule aims to keep L2-resident
+    double l2_chunk_bytes = 0.0;   // >0: run each dense block over sample chunks of about this footprint (L2 residency)
+    int force_async = 0;           // tuning: -1 auto by grid size, 0 register producers (default: measured fastest), 1 cp.async producers
 
     smg::BlockGeom geom[smg::kNumBlocks];
     smg::TrunkW trunks[SMG_NUM_TRUNKS];
