@@ -292,7 +292,7 @@ def run_gpu_arm(args):
     line_extra = {}
     if not args.no_backprop:
         try:
-            tr.model.precision = "fp32"   # the backward kernels are fp32; keep forward and backward consistent
+            # forward of the training step in the bench precision (tcgen05); the backward kernels are fp32 CUDA-core
             import smg_b200.synth as synth
             sc = synth.make_scene(100 + 1000 * rank, num_objects=4, cluttered=False)
             obj_masks = sc["masks"].astype(np.float64)
@@ -310,7 +310,7 @@ def run_gpu_arm(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             line_extra["backprop"] = {
                 "value": world * nb / (float(t.item()) / 1e3), "unit": "steps/s", "steps": nb,
-                "ms_per_step": float(t.item()) / nb, "gflop_per_step": 6 * GFLOP_PER_PASS, "precision": "fp32",
+                "ms_per_step": float(t.item()) / nb, "gflop_per_step": 6 * GFLOP_PER_PASS, "precision": "%s forward / fp32 backward" % precision,
                 "what": "Trainer.backprop: grad-enabled forward (2 trunk passes + head) + backward + Adam + weight re-pack, "
                         "host heightmaps in, loss out"}
         except Exception as exc:  # the training path must never take the inference numbers down with it

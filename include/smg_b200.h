@@ -83,6 +83,11 @@ int smg_set_trunk_weights(smg_handle* h, int trunk_id, const float* const* dev_p
  * norm1.w[64], norm1.b, conv1.w[n_out,64,20,20]; n_out = 1 (reinforcement) or 3 (reactive). */
 int smg_set_head_weights(smg_handle* h, int head_id, const float* const* dev_params, int n_out, void* stream);
 
+/* Which kernel layouts smg_set_*_weights writes (bit 0 fp32 FFMA, 1 tf32 tcgen05, 2 bf16 tcgen05, 3 data-gradient);
+ * default all.  Restricting it to the active precision (+ bit 3 when training) makes the per-step re-pack cheaper.
+ * Weights must be set again after the mask or the precision changes.                                            */
+int smg_set_pack_layouts(smg_handle* h, int mask);
+
 /* ---- K1: input stage ------------------------------------------------------------
  * smg_prep: code/trainer.py:165-191.  224x224 float64 heightmaps -> float32 [n,3,H,H]
  * (nearest zoom x2, zero pad to H, (x-mean)/std, 3 identical channels).             */

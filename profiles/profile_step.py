@@ -22,7 +22,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--precision", default="tf32")
     ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"])
     args = ap.parse_args()
+    if args.mode == "train":
+        return train(args)
     torch.manual_seed(0)
     tr = Trainer("reinforcement", 0.5, False, None, False, precision=args.precision)
     tr.model.gnum_rotations = tr.model.snum_rotations = bench.R
@@ -38,6 +41,24 @@ def main():
     for i in range(args.steps):
         q = eng.qforward_maps(0, sd[i % 2], md[i % 2:i % 2 + 1], bench.MEAN, bench.STD, rots, bench.R)
         eng.argmax(q)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+
+
+def train(args):
+    """One warmed-up Trainer.backprop step inside the profiler range."""
+    import numpy as np
+    import smg_b200.synth as synth
+    torch.manual_seed(0)
+    tr = Trainer("reinforcement", 0.5, False, None, False, precision=args.precision)
+    sc = synth.make_scene(100, num_objects=4, cluttered=False)
+    masks = sc["masks"].astype(np.float64)
+    for i in range(3):
+        tr.backprop(sc["scene"], "grasp", [i % 4, 0], [0, 0], [], [], 1.0, masks.copy(), [0] * 4, [0] * 4, [])
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    for i in range(args.steps):
+        tr.backprop(sc["scene"], "grasp", [i % 4, 0], [0, 0], [], [], 1.0, masks.copy(), [0] * 4, [0] * 4, [])
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
 

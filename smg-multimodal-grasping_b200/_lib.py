@@ -23,6 +23,7 @@ PROTOTYPES = {
     "smg_set_precision": (I, [VP, I]),
     "smg_get_precision": (I, [VP]),
     "smg_workspace_bytes": (ctypes.c_int64, [VP]),
+    "smg_set_pack_layouts": (I, [VP, I]),
     "smg_set_trunk_weights": (I, [VP, I, c_void_pp, I, VP]),
     "smg_set_head_weights": (I, [VP, I, c_void_pp, I, VP]),
     "smg_prep": (I, [VP, VP, I, I, ctypes.c_double, ctypes.c_double, VP, VP]),

@@ -89,6 +89,12 @@ static int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cu
     TrunkW& T = h->trunks[trunk_id];
     SMG_CHECK(T.set, SMG_ERR_STATE, "trunk %d: weights not set (call smg_set_trunk_weights)", trunk_id);
     SMG_CHECK(n >= 1 && n <= h->max_samples, SMG_ERR_INVALID, "trunk_forward: n=%d outside [1,%d]", n, h->max_samples);
+    {
+        const int need = h->precision == SMG_PREC_FP32 ? SMG_PACK_FFMA : (h->precision == SMG_PREC_TF32 ? SMG_PACK_TF32 : SMG_PACK_BF16);
+        SMG_CHECK(T.packed & need, SMG_ERR_STATE,
+                  "trunk %d: weights were packed with layout mask %d, precision %d needs %d (set the weights again)", trunk_id,
+                  T.packed, h->precision, need);
+    }
     SMG_CUDA(cudaMemsetAsync(h->stats, 0, h->stats_bytes, st));
     const size_t in_img = (size_t)in_channels * h->H * h->H;
     const size_t c0_img = (size_t)(h->H / 2) * (h->H / 2) * 64;
@@ -385,6 +391,7 @@ int smg_destroy(smg_handle* h) {
     if (!h) return SMG_OK;
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
+    if (h->job_buf) cudaFree(h->job_buf);
     for (auto& g : h->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->gstream) cudaStreamDestroy(h->gstream);
@@ -422,31 +429,34 @@ int smg_set_trunk_weights(smg_handle* h, int trunk_id, const float* const* dev_p
         plan_trunk(h, T, reinterpret_cast<uint8_t*>(T.arena));
     }
     int i = 0;
-    auto copy_bn = [&](BnP& b) -> int {
-        SMG_CUDA(cudaMemcpyAsync(b.gamma, dev_params[i++], (size_t)b.c * 4, cudaMemcpyDeviceToDevice, st));
-        SMG_CUDA(cudaMemcpyAsync(b.beta, dev_params[i++], (size_t)b.c * 4, cudaMemcpyDeviceToDevice, st));
-        return SMG_OK;
+    std::vector<PackJob> pj;
+    std::vector<CopyJob> cj;
+    auto copy_bn = [&](BnP& b) {
+        cj.push_back(CopyJob{dev_params[i++], b.gamma, b.c});
+        cj.push_back(CopyJob{dev_params[i++], b.beta, b.c});
     };
     pack_conv0_kernel<<<(147 * 64 + 255) / 256, 256, 0, st>>>(dev_params[i++], T.conv0, T.conv0_folded);
     h->launches++;
-    SMG_TRY(copy_bn(T.norm0));
+    copy_bn(T.norm0);
     for (int b = 0; b < kNumBlocks; ++b) {
         for (int l = 0; l < kBlockLayers[b]; ++l) {
             DenseLayerW& L = T.layers[b][l];
-            SMG_TRY(copy_bn(L.norm1));
-            SMG_TRY(pack_conv_weights(h, dev_params[i++], L.conv1, 0, L.conv1.cin, st));
-            SMG_TRY(copy_bn(L.norm2));
-            SMG_TRY(pack_conv_weights(h, dev_params[i++], L.conv2, 0, L.conv2.cin, st));
+            copy_bn(L.norm1);
+            pj.push_back(make_pack_job(dev_params[i++], L.conv1, 0, L.conv1.cin));
+            copy_bn(L.norm2);
+            pj.push_back(make_pack_job(dev_params[i++], L.conv2, 0, L.conv2.cin));
         }
         if (b < kNumBlocks - 1) {
-            SMG_TRY(copy_bn(T.trans[b].norm));
-            SMG_TRY(pack_conv_weights(h, dev_params[i++], T.trans[b].conv, 0, T.trans[b].conv.cin, st));
+            copy_bn(T.trans[b].norm);
+            pj.push_back(make_pack_job(dev_params[i++], T.trans[b].conv, 0, T.trans[b].conv.cin));
         }
     }
-    SMG_TRY(copy_bn(T.norm5));
+    copy_bn(T.norm5);
+    SMG_TRY(launch_pack_batch(h, pj, cj, st));
     SMG_CHECK(i == SMG_TRUNK_NUM_PARAMS, SMG_ERR_STATE, "consumed %d trunk tensors", i);
     SMG_CUDA(cudaGetLastError());
     T.set = true;
+    T.packed = h->pack_mask;
     return SMG_OK;
 }
 
@@ -486,6 +496,7 @@ int smg_set_head_weights(smg_handle* h, int head_id, const float* const* dev_par
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     Hd.set = true;
+    Hd.packed = SMG_PACK_ALL;  // the head's few tensors are always packed in every layout
     return SMG_OK;
 }
 
@@ -897,6 +908,8 @@ int smg_qbackward(smg_handle* h, const float* dev_dq, float* const* dev_trunk_gr
                   void* stream) {
     SMG_CHECK(h && dev_dq && dev_trunk_grads && dev_head_grads, SMG_ERR_INVALID, "smg_qbackward: NULL argument");
     SMG_CHECK(h->train.valid, SMG_ERR_STATE, "smg_qbackward: no smg_qforward_train result is pending on this handle");
+    SMG_CHECK(h->trunks[h->train.trunk_id].packed & SMG_PACK_DGRAD, SMG_ERR_STATE,
+              "smg_qbackward: the trunk weights were packed without the data-gradient layout (smg_set_pack_layouts)");
     DeviceGuard guard(h->device);
     const int status = qbackward_impl(h, dev_dq, dev_trunk_grads, dev_head_grads, (cudaStream_t)stream);
     h->train.valid = false;
@@ -962,6 +975,12 @@ int smg_debug_read(smg_handle* h, const char* what, int sample, float* dev_out_n
               (long long)hw * hw * c);
     src += (size_t)sample * hw * hw * cstride;
     return launch_nhwc_to_nchw(h, src, hw, c, cstride, dev_out_nchw, (cudaStream_t)stream);
+}
+
+int smg_set_pack_layouts(smg_handle* h, int mask) {
+    SMG_CHECK(h != nullptr && mask > 0 && mask <= SMG_PACK_ALL, SMG_ERR_INVALID, "smg_set_pack_layouts: mask %d", mask);
+    h->pack_mask = mask;
+    return SMG_OK;
 }
 
 int smg_profile_enable(smg_handle* h, int enable) {

@@ -67,6 +67,76 @@ __global__ void pack_umma_kernel(const float* __restrict__ w, T* __restrict__ ou
     }
 }
 
+// ---- batched variant: one launch packs every convolution of a trunk (blockIdx.y = job) ----
+__global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
+    const PackJob j = jobs[blockIdx.y];
+    const int total = j.taps * j.cin * j.cout;
+    const int kgs = j.cin / 32;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        if (mask & SMG_PACK_FFMA) {
+            const int co = i % j.cout, ci = (i / j.cout) % j.cin, t = i / (j.cout * j.cin);
+            j.ffma[i] = j.src[((size_t)co * j.k_total + j.k_off + ci) * j.taps + t];
+        }
+        if (mask & SMG_PACK_DGRAD) {
+            const int ci = i % j.cin, co = (i / j.cin) % j.cout, t = i / (j.cout * j.cin);
+            j.dgrad[i] = j.src[((size_t)co * j.k_total + j.k_off + ci) * j.taps + (j.taps - 1 - t)];
+        }
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            if (!(mask & (pass == 0 ? SMG_PACK_TF32 : SMG_PACK_BF16))) continue;
+            const int EPC = pass == 0 ? 4 : 8, CH = 32 / EPC;
+            int r = i;
+            const int e = r % EPC; r /= EPC;
+            const int n = r % j.bn; r /= j.bn;
+            const int c = r % CH; r /= CH;
+            int ntile, kg, tap;
+            if (j.taps == 1) { kg = r % kgs; r /= kgs; ntile = r; tap = 0; }
+            else { tap = r % j.taps; r /= j.taps; kg = r; ntile = 0; }
+            const int co = ntile * j.bn + n, ci = kg * 32 + c * EPC + e;
+            const float v = j.src[((size_t)co * j.k_total + j.k_off + ci) * j.taps + tap];
+            if (pass == 0) j.tf32[i] = v;
+            else j.bf16[i] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+__global__ void copy_batch_kernel(const CopyJob* __restrict__ jobs) {
+    const CopyJob j = jobs[blockIdx.x];
+    for (int i = threadIdx.x; i < j.n; i += blockDim.x) j.dst[i] = j.src[i];
+}
+
+PackJob make_pack_job(const float* w_oihw, const ConvW& cw, int k_offset, int k_total) {
+    PackJob j;
+    j.src = w_oihw; j.ffma = cw.w_ffma; j.tf32 = reinterpret_cast<float*>(cw.w_tf32);
+    j.bf16 = reinterpret_cast<__nv_bfloat16*>(cw.w_bf16); j.dgrad = cw.w_dgrad;
+    j.cin = cw.cin; j.cout = cw.cout; j.taps = cw.taps; j.k_off = k_offset; j.k_total = k_total;
+    j.bn = cw.taps == 9 ? 32 : (cw.cout < 128 ? cw.cout : 128);
+    return j;
+}
+
+int launch_pack_batch(smg_handle* h, const std::vector<PackJob>& pj, const std::vector<CopyJob>& cj, cudaStream_t st) {
+    const size_t need = pj.size() * sizeof(PackJob) + cj.size() * sizeof(CopyJob);
+    if (need > h->job_bytes) {
+        if (h->job_buf) cudaFree(h->job_buf);
+        h->job_bytes = need * 2;
+        SMG_CUDA(cudaMalloc(&h->job_buf, h->job_bytes));
+    }
+    uint8_t* base = reinterpret_cast<uint8_t*>(h->job_buf);
+    if (!pj.empty()) {
+        SMG_CUDA(cudaMemcpyAsync(base, pj.data(), pj.size() * sizeof(PackJob), cudaMemcpyHostToDevice, st));
+        pack_batch_kernel<<<dim3(48, (unsigned)pj.size()), 256, 0, st>>>(reinterpret_cast<const PackJob*>(base), h->pack_mask);
+        h->launches++;
+    }
+    if (!cj.empty()) {
+        uint8_t* cb = base + pj.size() * sizeof(PackJob);
+        SMG_CUDA(cudaMemcpyAsync(cb, cj.data(), cj.size() * sizeof(CopyJob), cudaMemcpyHostToDevice, st));
+        copy_batch_kernel<<<(unsigned)cj.size(), 256, 0, st>>>(reinterpret_cast<const CopyJob*>(cb));
+        h->launches++;
+    }
+    SMG_CUDA(cudaGetLastError());
+    return SMG_OK;
+}
+
 size_t conv_packed_bytes_ffma(int cin, int cout, int taps) { return (size_t)cin * cout * taps * sizeof(float); }
 size_t conv_packed_bytes_umma(int cin, int cout, int taps, int elt_bytes) {
     return (size_t)cin * cout * taps * elt_bytes;

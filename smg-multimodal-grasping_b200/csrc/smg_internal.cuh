@@ -94,6 +94,7 @@ struct TransitionW {
 
 struct TrunkW {
     bool set = false;
+    int packed = 0;  // SMG_PACK_* layouts that are current
     float* conv0 = nullptr;  // [147][64], k = (c*7+kh)*7+kw
     float* conv0_folded = nullptr;  // [49][64]: weights summed over the input channel (identical channels)
     BnP norm0;
@@ -106,6 +107,7 @@ struct TrunkW {
 
 struct HeadW {
     bool set = false;
+    int packed = 0;
     int n_out = 0;
     BnP norm0;        // 2048
     ConvW conv0[2];   // 1x1 2048 -> 64 split into the scene half [0] and the mask half [1] (K = 1024 each)
@@ -134,6 +136,9 @@ struct smg_handle {
     int64_t launches = 0;
     int64_t workspace_bytes = 0;
     double l2_chunk_bytes = 0.0;   // >0: run each dense block over sample chunks of about this footprint (L2 residency)
+    int pack_mask = 15;            // weight layouts written by smg_set_*_weights (SMG_PACK_*)
+    void* job_buf = nullptr;       // device table for the batched weight packer
+    size_t job_bytes = 0;
     int force_async = 0;           // tuning: -1 auto by grid size, 0 register producers (default: measured fastest), 1 cp.async producers
 
     smg::BlockGeom geom[smg::kNumBlocks];
@@ -321,6 +326,22 @@ int launch_adam(smg_handle* h, float* p, const float* g, float* m, float* v, int
                 float b2, float eps, cudaStream_t st);
 
 // weight packing
+enum { SMG_PACK_FFMA = 1, SMG_PACK_TF32 = 2, SMG_PACK_BF16 = 4, SMG_PACK_DGRAD = 8, SMG_PACK_ALL = 15 };
+struct PackJob {
+    const float* src;
+    float* ffma;
+    float* tf32;
+    __nv_bfloat16* bf16;
+    float* dgrad;
+    int cin, cout, taps, k_off, k_total, bn;
+};
+struct CopyJob {
+    const float* src;
+    float* dst;
+    int n;
+};
+PackJob make_pack_job(const float* w_oihw, const ConvW& cw, int k_offset, int k_total);
+int launch_pack_batch(smg_handle* h, const std::vector<PackJob>& pj, const std::vector<CopyJob>& cj, cudaStream_t st);
 int pack_conv_weights(smg_handle* h, const float* w_oihw, ConvW& cw, int k_offset, int k_total, cudaStream_t st);
 size_t conv_packed_bytes_ffma(int cin, int cout, int taps);
 size_t conv_packed_bytes_umma(int cin, int cout, int taps, int elt_bytes);

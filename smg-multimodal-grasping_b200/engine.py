@@ -55,9 +55,9 @@ class Engine:
         h = ctypes.c_void_p()
         _lib.check(self.lib.smg_create(self.device.index, self.max_samples, self.H, ctypes.byref(h)))
         self.h = h
-        self.set_precision(precision)
         self._sig = {}
         self._staged = {}
+        self.set_precision(precision)
 
     def __del__(self):
         try:
@@ -72,8 +72,12 @@ class Engine:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def set_precision(self, precision):
+        if getattr(self, "precision", None) != precision:
+            self._sig = {}  # the packed weight layouts depend on the precision: re-pack on the next sync
         self.precision = precision
         _lib.check(self.lib.smg_set_precision(self.h, PRECISIONS[precision]))
+        # pack only what this precision needs, plus the data-gradient layout used by the training step
+        _lib.check(self.lib.smg_set_pack_layouts(self.h, (1 << PRECISIONS[precision]) | 8))
 
     def launch_count(self):
         return int(self.lib.smg_launch_count(self.h))

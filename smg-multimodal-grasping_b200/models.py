@@ -91,26 +91,28 @@ class _SmgNet(nn.Module):
         """BatchNorm2d train-mode side effect: running = (1-m)*running + m*batch for each trunk call in
         `order` (sample indices; the reference calls trunk(scene_r) then trunk(mask) per rotation)."""
         k = len(order)
-        w = torch.zeros(mean.shape[0], dtype=torch.float64, device=mean.device)
+        wl = [0.0] * mean.shape[0]
         for i, s in enumerate(order):
-            w[s] += _BN_MOMENTUM * (1 - _BN_MOMENTUM) ** (k - 1 - i)
+            wl[s] += _BN_MOMENTUM * (1 - _BN_MOMENTUM) ** (k - 1 - i)
+        w = torch.tensor(wl, dtype=torch.float64, device=mean.device)
         decay = (1 - _BN_MOMENTUM) ** k
-        bm = (w[:, None] * mean.double()).sum(0)
-        off = 0
-        for m in self._bn_modules(trunk):
-            c = m.num_features
-            m.running_mean.mul_(decay).add_(bm[off:off + c].to(m.running_mean))
-            off += c
-        # unbiased variance: n/(n-1) with n = H*W of that layer; recover n from the layer geometry
-        off = 0
-        H = 640
-        counts = _bn_counts(H)
-        bv = (w[:, None] * var.double()).sum(0)
-        for m, n in zip(self._bn_modules(trunk), counts):
-            c = m.num_features
-            m.running_var.mul_(decay).add_((bv[off:off + c] * (n / (n - 1.0))).to(m.running_var))
-            m.num_batches_tracked += k
-            off += c
+        mods = self._bn_modules(trunk)
+        sizes = [m.num_features for m in mods]
+        # unbiased variance: n/(n-1) with n = H*W of that layer
+        key = (id(trunk), mean.device)
+        cache = self.__dict__.setdefault("_bn_unbias", {})
+        if key not in cache:
+            cache[key] = torch.cat([torch.full((c,), n / (n - 1.0), dtype=torch.float64)
+                                    for c, n in zip(sizes, _bn_counts(640))]).to(mean.device)
+        bm = (w[:, None] * mean.double()).sum(0).float()
+        bv = ((w[:, None] * var.double()).sum(0) * cache[key]).float()
+        rm, rv = [m.running_mean for m in mods], [m.running_var for m in mods]
+        # a handful of multi-tensor launches instead of ~500 tiny ones
+        torch._foreach_mul_(rm, decay)
+        torch._foreach_add_(rm, list(torch.split(bm, sizes)))
+        torch._foreach_mul_(rv, decay)
+        torch._foreach_add_(rv, list(torch.split(bv, sizes)))
+        torch._foreach_add_([m.num_batches_tracked for m in mods], k)
 
     # ------------------------------------------------------------------ forward
     def forward(self, input_depth_data, m_input_depth_data, style=0, is_volatile=False, specific_rotation=-1):

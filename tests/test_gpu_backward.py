@@ -105,8 +105,10 @@ def test_rl_grads_style2_rotated_vs_oracle(inputs):
     compare_all(grads, ref)
 
 
-def test_rl_grads_style1_rotation3_vs_oracle(inputs):
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_rl_grads_style1_rotation3_vs_oracle(inputs, precision):
     net, sd = make_net()
+    net.precision = precision   # tf32: tcgen05 forward, fp32 backward kernels
     net.gnum_rotations = net.snum_rotations = 16
     x, m, _ = inputs
     net.forward(x, m, 1, False, 3)
