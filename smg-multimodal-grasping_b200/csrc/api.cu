@@ -65,6 +65,20 @@ static int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     const double bytes = 4.0 * ((double)a.n * a.hin * a.hin * a.cin + px * a.cout);
     ProfScope ps(h, st, a.taps == 9 ? 2 : 1, 2.0 * px * a.cout * a.cin * a.taps, bytes);
     if (h->precision == SMG_PREC_FP32) return launch_conv_ffma(h, a, st);
+    if (!a.pool && h->tiles_per_cta != 1) {
+        // large launches: multi-tile CTAs (setup amortised, epilogue overlapped with the next tile)
+        const int tiles = a.taps == 9 ? 0 : (int)((px / a.n + 127) / 128);
+        int T = h->tiles_per_cta;
+        if (T == 0) {
+            const double per_launch = (a.taps == 9 ? px / 120.0 : (double)tiles * a.n) * (a.taps == 9 ? 1 : a.cout / 128.0);
+            T = (int)(per_launch / (3.0 * 2 * h->num_sms));
+            if (T > 4) T = 4;
+        }
+        if (T >= 2) {
+            const int status = launch_conv_umma_mt(h, a, h->precision, T, st);
+            if (status != SMG_ERR_UNSUPPORTED) return status;
+        }
+    }
     return launch_conv_umma(h, a, h->precision, st);
 }
 
@@ -383,6 +397,7 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming);
     if (const char* e = getenv("SMG_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
     if (const char* e = getenv("SMG_ASYNC")) h->force_async = atoi(e);
+    if (const char* e = getenv("SMG_TILES_PER_CTA")) h->tiles_per_cta = atoi(e);
     *out = h;
     return SMG_OK;
 }
@@ -1035,7 +1050,10 @@ int smg_debug_conv(smg_handle* h, int precision, const float* dev_in, int n, int
         a.out = dev_out; a.out_cstride = out_cstride; a.out_coff = out_coff; a.cout = cout;
         a.out_stats = dev_out_stats; a.out_stats_stride = out_cstride;
         a.n = n;
-        status = precision == SMG_PREC_FP32 ? launch_conv_ffma(h, a, st) : launch_conv_umma(h, a, precision, st);
+        const int saved = h->precision;
+        h->precision = precision;
+        status = conv_dispatch(h, a, st);  // same kernel selection (one-tile / multi-tile) as the trunk schedule
+        h->precision = saved;
     }
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(base);

@@ -74,6 +74,36 @@ def test_conv_matches_torch(eng, precision, case):
     assert float((q_got - q_ref).abs().max() / q_ref.abs().max()) <= 1e-4
 
 
+@pytest.mark.parametrize("tiles_per_cta", [2, 3])
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("case", [(2, 40, 96, 256, 128, 1, 0), (1, 80, 224, 256, 128, 1, 0), (2, 80, 128, 128, 32, 3, 0),
+                                  (1, 160, 128, 128, 32, 3, 0), (3, 20, 128, 128, 32, 3, 0), (1, 20, 512, 1024, 256, 1, 0)],
+                         ids=lambda c: "n%d_h%d_cin%d_cs%d_cout%d_k%d_pool%d" % c)
+def test_multi_tile_kernel_matches_torch(precision, case, tiles_per_cta, monkeypatch):
+    """The multi-tile tcgen05 kernel (conv_umma_mt.cu): T tiles per CTA, double-buffered TMEM accumulators."""
+    from smg_b200 import engine
+    monkeypatch.setenv("SMG_TILES_PER_CTA", str(tiles_per_cta))
+    eng = engine.Engine(0, 4, 640, "fp32")      # a private handle so the environment knob is read
+    n, hin, cin, cstride, cout, k, pool = case
+    g = torch.Generator(device="cuda").manual_seed(hash(case) % 1000 + tiles_per_cta)
+    x = torch.randn((n, hin, hin, cstride), generator=g, device="cuda")
+    scale = torch.rand((n, cin), generator=g, device="cuda") + 0.5
+    shift = torch.randn((n, cin), generator=g, device="cuda") * 0.3
+    w = torch.randn((cout, cin, k, k), generator=g, device="cuda") / (cin * k * k) ** 0.5
+    out_cstride, out_coff = cout + 64, 32
+    out, stats = eng.debug_conv(precision, x, cin, scale, shift, True, pool, w, out_cstride, out_coff)
+    ref = reference(x, cin, scale, shift, True, pool, w)
+    got = out[..., out_coff:out_coff + cout]
+    err = float((got - ref).abs().max() / ref.abs().max())
+    print("mt T=%d %s %s: rel-max err %.2e" % (tiles_per_cta, precision, case, err))
+    assert err <= TOL[precision]
+    assert float(out[..., :out_coff].abs().max()) == 0 and float(out[..., out_coff + cout:].abs().max()) == 0
+    s_ref, q_ref = got.double().sum((1, 2)), (got.double() ** 2).sum((1, 2))
+    assert float((stats[:, out_coff:out_coff + cout, 0] - s_ref).abs().max() / s_ref.abs().max()) <= 1e-4
+    assert float((stats[:, out_coff:out_coff + cout, 1] - q_ref).abs().max() / q_ref.abs().max()) <= 1e-4
+    del eng
+
+
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
 def test_conv_no_relu_identity_prologue(eng, precision):
     x = torch.randn((1, 20, 20, 128), device="cuda")
