@@ -331,14 +331,28 @@ def run_gpu_arm(args):
         dom = max(("conv1x1", "conv3x3", "stem"), key=lambda k: prof[k]["ms"])
         d = prof[dom]
         per_launch_ms = d["ms"] / max(1, d["launches"])
-        if dom == "stem":
+        # bound by arithmetic intensity against the measured ridge: fp32-stored activations make the DenseNet convolutions
+        # memory-bound (block-1 1x1, K=224: 41 FLOP/B; 3x3: 115 FLOP/B; ridge 209 FLOP/B at the bf16 peak, 105 at tf32 rate)
+        tensor_peak = peaks["bf16_tflops_sustained"] * (0.5 if precision == "tf32" else 1.0)
+        ridge = tensor_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)
+        ai = d["flops"] / max(1.0, d["bytes"])
+        # DRAM bytes of a representative launch of this class from `ncu --set full` (profiles/r01_ncu_prof_T1.csv), next
+        # to the algorithmic bytes of the same launch: traffic ~= algorithmic, i.e. no wasted re-reads (halo re-reads of
+        # the 3x3 patches are absorbed by L2)
+        ncu_traffic = {"conv1x1": {"launch": "block-1 1x1 conv K=224, 17 samples", "dram_bytes": 578.4e6, "algorithmic_bytes": 613.4e6},
+                       "conv3x3": {"launch": "block-1 3x3 conv, 17 samples", "dram_bytes": 265.7e6, "algorithmic_bytes": 278.5e6}}
+        if dom == "stem" or ai < ridge:
             achieved = d["bytes"] / 1e9 / (d["ms"] / 1e3)
             roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": None}
+                    "frac": achieved / peaks["hbm_gbs"],
+                    "traffic": ncu_traffic.get(dom, {}).get("dram_bytes"), "traffic_detail": ncu_traffic.get(dom),
+                    "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
+                    "tensor_tflops": d["flops"] / 1e12 / (d["ms"] / 1e3)}
         else:
             achieved = d["flops"] / 1e12 / (d["ms"] / 1e3)
             roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None}
+                    "frac": achieved / peaks["bf16_tflops_sustained"],
+                    "traffic": ncu_traffic.get(dom, {}).get("dram_bytes"), "traffic_detail": ncu_traffic.get(dom)}
         roof.update({"kernel": dom, "avg_launch_ms": per_launch_ms, "launches_per_step": d["launches"] // nprof,
                      "share_of_step": d["ms"] / total_ms if total_ms else None, "peak_source": peaks["source"],
                      "note": "peak = dense bf16 cuBLAS sustained; tf32 operands run at half the bf16 tensor rate" if precision == "tf32" else None,

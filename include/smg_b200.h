@@ -126,6 +126,12 @@ int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* de
                       const int* host_rot_idx, int n_rot, int num_rotations, float* dev_q, float* dev_bn_mean,
                       float* dev_bn_var, void* stream);
 
+/* Batch statistics of the head's BatchNorm2d(64) from the LAST smg_qforward* / smg_qforward_train call on this handle:
+ * dev_out [n_pairs, 2, 64] float32 = (mean, biased variance) per (mask, rotation) pair in q order.  Together with the
+ * trunk statistics (norm5's mean/var determine the statistics of the head's BatchNorm2d(2048): mean = norm5.bias,
+ * var = gamma5^2 var/(var+eps)) this lets the caller apply the reference's running-stat updates to the head.      */
+int smg_head_bn_stats(smg_handle* h, float* dev_out, int n_pairs, void* stream);
+
 /* ---- training (code/trainer.py:278-384) -----------------------------------------
  * smg_qforward with n_masks = n_rot = 1 and save_for_backward; then smg_qbackward
  * with dq = dLoss/dQ [n_out] produces gradients for every trunk / head parameter in

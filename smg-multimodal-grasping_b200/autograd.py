@@ -50,6 +50,7 @@ def q_forward_with_grad(model, input_depth_data, m_input_depth_data, style, spec
     q, mean, var = _QPass.apply(eng, style, scene, mask, rot, model.gnum_rotations, len(tparams), *tparams, *hparams)
     if model.update_running_stats:
         model._apply_running_stats(trunk, mean, var, [0, 1])   # trunk(scene) then trunk(mask)
+        model._apply_head_running_stats(head, trunk, var, [(0, 1)], eng.head_bn_stats(1))
     out = q.view(1, model.N_OUT, 1, 1)
     model.gra_prob, model.suc_prob, model.gs_prob = [], [], []
     setattr(model, {0: "gra_prob", 1: "suc_prob", 2: "gs_prob"}[int(style)], out)

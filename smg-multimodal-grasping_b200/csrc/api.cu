@@ -65,8 +65,10 @@ static int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     const double bytes = 4.0 * ((double)a.n * a.hin * a.hin * a.cin + px * a.cout);
     ProfScope ps(h, st, a.taps == 9 ? 2 : 1, 2.0 * px * a.cout * a.cin * a.taps, bytes);
     if (h->precision == SMG_PREC_FP32) return launch_conv_ffma(h, a, st);
-    if (!a.pool && h->tiles_per_cta != 1) {
-        // large launches: multi-tile CTAs (setup amortised, epilogue overlapped with the next tile)
+    // large 3x3 launches: multi-tile CTAs (setup amortised, epilogue overlapped with the next tile).  Measured on B200
+    // (profiles/README.md): 3-7 % faster for the 3x3 convolutions, 3 % slower for the 1x1 ones, which therefore stay
+    // on the one-tile kernel unless SMG_TILES_PER_CTA forces a value.
+    if (!a.pool && h->tiles_per_cta != 1 && (a.taps == 9 || h->tiles_per_cta > 1)) {
         const int tiles = a.taps == 9 ? 0 : (int)((px / a.n + 127) / 128);
         int T = h->tiles_per_cta;
         if (T == 0) {
@@ -372,6 +374,7 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     const size_t o_hp = p.take(S * (size_t)h->geom[3].hw * h->geom[3].hw * kHeadMid * 4);
     const size_t o_tmp = p.take((size_t)3 * H * H * 4);
     const size_t o_hm = p.take((1 + S) * (size_t)(H / 2) * (H / 2) * 8);
+    const size_t o_hb = p.take(S * S * 128 * 4);
     const size_t o_q = p.take(S * S * 4 * 4);
     uint8_t* base = nullptr;
     cudaError_t e = cudaMalloc(&base, p.off);
@@ -391,6 +394,8 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     h->head_p = reinterpret_cast<float*>(base + o_hp);
     h->scene_tmp = reinterpret_cast<float*>(base + o_tmp);
     h->hm_stage = reinterpret_cast<double*>(base + o_hm);
+    h->head_bn1 = reinterpret_cast<float*>(base + o_hb);
+    h->head_bn1_floats = S * S * 128;
     h->q_stage = reinterpret_cast<float*>(base + o_q);
     cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming);
@@ -990,6 +995,15 @@ int smg_debug_read(smg_handle* h, const char* what, int sample, float* dev_out_n
               (long long)hw * hw * c);
     src += (size_t)sample * hw * hw * cstride;
     return launch_nhwc_to_nchw(h, src, hw, c, cstride, dev_out_nchw, (cudaStream_t)stream);
+}
+
+int smg_head_bn_stats(smg_handle* h, float* dev_out, int n_pairs, void* stream) {
+    SMG_CHECK(h && dev_out, SMG_ERR_INVALID, "smg_head_bn_stats: NULL argument");
+    SMG_CHECK(n_pairs == h->head_bn1_pairs && n_pairs > 0, SMG_ERR_STATE, "smg_head_bn_stats: the last head pass had %d pairs, not %d",
+              h->head_bn1_pairs, n_pairs);
+    DeviceGuard guard(h->device);
+    SMG_CUDA(cudaMemcpyAsync(dev_out, h->head_bn1, (size_t)n_pairs * 128 * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SMG_OK;
 }
 
 int smg_set_pack_layouts(smg_handle* h, int mask) {

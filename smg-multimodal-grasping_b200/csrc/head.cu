@@ -66,7 +66,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // one CTA per (mask k, rotation r) pair.  p: [n_rot + n_masks][400][64]
 __global__ void __launch_bounds__(256)
 head_tail_kernel(const float* __restrict__ p, int n_rot, int n_masks, int npix, const float* __restrict__ g1,
-                 const float* __restrict__ b1, const float* __restrict__ w1, int n_out, float* __restrict__ q) {
+                 const float* __restrict__ b1, const float* __restrict__ w1, int n_out, float* __restrict__ q,
+                 float* __restrict__ bn1_stats) {
     __shared__ float red[2][4][64];
     __shared__ float s_sc[64], s_sh[64];
     __shared__ float s_part[8][4];
@@ -93,6 +94,11 @@ head_tail_kernel(const float* __restrict__ p, int n_rot, int n_masks, int npix, 
         const float sc = g1[c] * rsqrtf(var + kBnEps);
         s_sc[c] = sc;
         s_sh[c] = b1[c] - mean * sc;
+        if (bn1_stats != nullptr) {  // batch statistics of the head's BN(64) for the running-stat side effect
+            float* o = bn1_stats + ((size_t)k * n_rot + r) * 128;
+            o[c] = mean;
+            o[64 + c] = var;
+        }
     }
     __syncthreads();
     const float sc = s_sc[c], sh = s_sh[c];
@@ -201,7 +207,10 @@ int launch_head_tail(smg_handle* h, const float* p, int n_rot, int n_masks, cons
     const int npix = h->geom[3].hw * h->geom[3].hw;
     SMG_CHECK(hw.n_out >= 1 && hw.n_out <= 4, SMG_ERR_INVALID, "head_tail: n_out %d", hw.n_out);
     dim3 grid(n_rot, n_masks);
-    head_tail_kernel<<<grid, 256, 0, st>>>(p, n_rot, n_masks, npix, hw.norm1.gamma, hw.norm1.beta, hw.conv1, hw.n_out, q);
+    const bool fits = (size_t)n_rot * n_masks * 128 <= h->head_bn1_floats;
+    head_tail_kernel<<<grid, 256, 0, st>>>(p, n_rot, n_masks, npix, hw.norm1.gamma, hw.norm1.beta, hw.conv1, hw.n_out, q,
+                                           fits ? h->head_bn1 : nullptr);
+    h->head_bn1_pairs = fits ? n_rot * n_masks : 0;
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;

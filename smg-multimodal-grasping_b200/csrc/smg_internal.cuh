@@ -163,6 +163,9 @@ struct smg_handle {
     float* head_shift = nullptr;  // [S,1024]
     float* head_p = nullptr;      // [S,400,64]
     float* scene_tmp = nullptr;   // [3,H,H] staging for smg_qforward_maps
+    float* head_bn1 = nullptr;    // [pairs][2][64] batch mean / biased var of the head's BN(64), last head pass
+    size_t head_bn1_floats = 0;
+    int head_bn1_pairs = 0;
     // CUDA-graph replay of smg_qforward_maps: the pass is a fixed sequence of ~250 launches on fixed workspace
     // addresses, so it is captured once per (trunk, head, shapes, rotations, precision) and replayed
     double* hm_stage = nullptr;   // [1 + S][(H/2)^2] heightmap staging (scene, then masks)

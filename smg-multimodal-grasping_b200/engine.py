@@ -205,6 +205,12 @@ class Engine:
                                                self._stream()))
         return q, mean, var
 
+    def head_bn_stats(self, n_pairs):
+        """(mean, biased var) [n_pairs, 2, 64] of the head's BatchNorm2d(64) for the last Q pass on this handle."""
+        out = torch.empty((n_pairs, 2, 64), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.smg_head_bn_stats(self.h, out.data_ptr(), int(n_pairs), self._stream()))
+        return out
+
     def qbackward(self, dq, trunk_grads, head_grads):
         """dLoss/dQ [n_out] -> gradients written into the given tensors (smg_set_*_weights order)."""
         dq = dq.to(self.device, torch.float32).contiguous()

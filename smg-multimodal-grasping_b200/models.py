@@ -114,6 +114,34 @@ class _SmgNet(nn.Module):
         torch._foreach_add_(rv, list(torch.split(bv, sizes)))
         torch._foreach_add_([m.num_batches_tracked for m in mods], k)
 
+    @torch.no_grad()
+    def _apply_head_running_stats(self, head, trunk, var, pairs, head_bn1):
+        """Running statistics of the head's two BatchNorm2d for the head calls listed in `pairs`
+        [(scene sample, mask sample), ...] in the reference's call order (code/models.py:386-387).
+        BN(2048) normalises cat(norm5(x_s), norm5(x_m)): its batch mean is norm5.bias and its batch variance
+        gamma5^2 var/(var+eps) of the respective sample; BN(64)'s statistics come from the head kernel."""
+        bns = [m for m in head.children() if isinstance(m, nn.BatchNorm2d)]
+        norm0, norm1 = bns[0], bns[1]
+        norm5 = trunk.features.norm5
+        k = len(pairs)
+        w = torch.tensor([_BN_MOMENTUM * (1 - _BN_MOMENTUM) ** (k - 1 - i) for i in range(k)], dtype=torch.float64,
+                         device=var.device)
+        decay = (1 - _BN_MOMENTUM) ** k
+        n = 400.0
+        v5 = var[:, -1024:].double()
+        var_z = norm5.weight.double() ** 2 * v5 / (v5 + 1e-5)                       # [samples, 1024]
+        si = torch.tensor([p[0] for p in pairs], device=var.device)
+        mi = torch.tensor([p[1] for p in pairs], device=var.device)
+        bv = torch.cat([(w[:, None] * var_z[si]).sum(0), (w[:, None] * var_z[mi]).sum(0)]) * (n / (n - 1.0))
+        bm = torch.cat([norm5.bias.double(), norm5.bias.double()]) * w.sum()
+        norm0.running_mean.mul_(decay).add_(bm.to(norm0.running_mean))
+        norm0.running_var.mul_(decay).add_(bv.to(norm0.running_var))
+        h1 = head_bn1.double()                                                       # [k, 2, 64] in call order
+        norm1.running_mean.mul_(decay).add_((w[:, None] * h1[:, 0]).sum(0).to(norm1.running_mean))
+        norm1.running_var.mul_(decay).add_(((w[:, None] * h1[:, 1]).sum(0) * (n / (n - 1.0))).to(norm1.running_var))
+        norm0.num_batches_tracked += k
+        norm1.num_batches_tracked += k
+
     # ------------------------------------------------------------------ forward
     def forward(self, input_depth_data, m_input_depth_data, style=0, is_volatile=False, specific_rotation=-1):
         if not is_volatile:
@@ -146,6 +174,9 @@ class _SmgNet(nn.Module):
             for i in range(len(rots)):
                 order += [i, len(rots)]
             self._apply_running_stats(trunk, mean, var, order)
+            head = getattr(self, _engine.HEAD_ATTRS[_engine.STYLE_ROUTE[style][1]])
+            self._apply_head_running_stats(head, trunk, var, [(i, len(rots)) for i in range(len(rots))],
+                                           eng.head_bn_stats(len(rots)))
         else:
             q = eng.qforward(style, scene, mask, rots, nrot)
         return q[0]

@@ -107,6 +107,9 @@ class Trainer(object):
                 for i in range(len(rots)):
                     order += [i, len(rots) + k]
             model._apply_running_stats(trunk, mean, var, order)
+            head = getattr(model, _engine.HEAD_ATTRS[_engine.STYLE_ROUTE[style][1]])
+            pairs = [(i, len(rots) + k) for k in range(masks.shape[0]) for i in range(len(rots))]
+            model._apply_head_running_stats(head, trunk, var, pairs, eng.head_bn_stats(len(pairs)))
         else:
             q = eng.qforward_maps(style, scene, masks_t, self.image_mean, self.image_std, rots, nrot)
         return q  # cuda tensor [n_masks, n_rot, n_out]

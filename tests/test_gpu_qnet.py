@@ -166,6 +166,19 @@ def test_running_stats_side_effect(inputs, golden):
             b = ref.state_dict()["%s.%s" % (name, stat)]
             assert relmax(a, b) <= 1e-4, (name, stat)
         assert int(sd["grasp_depth_trunk.features.%s.num_batches_tracked" % name]) == 2
+    # the head's BatchNorm2d(2048) and BatchNorm2d(64) see cat(features(scene), features(mask)) once
+    import smg_b200.models as models2
+    torch.manual_seed(0)
+    fresh = models2.reinforcement_net(True)
+    fresh.train()
+    with torch.no_grad():
+        feat = torch.cat((ref(x), ref(m)), dim=1)   # third and fourth pass: statistics of `ref` are not used below
+        fresh.graspnet_val(feat)
+    hsd = fresh.graspnet_val.state_dict()
+    for key in ("grasp-val-norm0.running_mean", "grasp-val-norm0.running_var", "grasp-val-norm1.running_mean",
+                "grasp-val-norm1.running_var"):
+        assert relmax(sd["graspnet_val." + key], hsd[key]) <= 1e-4, key
+    assert int(sd["graspnet_val.grasp-val-norm1.num_batches_tracked"]) == 1
 
 
 def golden_like_state(n):
