@@ -177,7 +177,9 @@ def test_running_stats_side_effect(inputs, golden):
     hsd = fresh.graspnet_val.state_dict()
     for key in ("grasp-val-norm0.running_mean", "grasp-val-norm0.running_var", "grasp-val-norm1.running_mean",
                 "grasp-val-norm1.running_var"):
-        assert relmax(sd["graspnet_val." + key], hsd[key]) <= 1e-4, key
+        a, b = sd["graspnet_val." + key].double(), hsd[key].double()
+        # norm0's batch mean is norm5.bias (0 at init): torch accumulates ~1e-9 of rounding noise there, so absolute
+        assert float((a - b).abs().max()) <= 1e-4 * max(float(b.abs().max()), 1e-2), key
     assert int(sd["graspnet_val.grasp-val-norm1.num_batches_tracked"]) == 1
 
 
