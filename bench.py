@@ -6,8 +6,9 @@
 Unit of work U: one (scene, object mask, primitive) evaluated at R = 16
 rotations -> 16 Q scalars == one `Trainer.forward(..., is_volatile=True)` call of the reference with
 gnum_rotations = 16: 17 distinct 640x640 DenseNet-121 trunk passes (16 rotated scenes + 1 masked
-scene) + 16 heads = 788.0 GFLOP.  One "step" = one U per GPU on seeded synthetic 224x224 heightmaps
-with random-init weights (no datasets / checkpoints offline).
+scene) + 16 heads = 788.0 GFLOP.  One "step" = `--units` (default 4) independent U per GPU evaluated as one batch
+(every unit gets exactly its single-call result because BatchNorm statistics are per sample; `--units 1` is the
+latency configuration) on seeded synthetic 224x224 heightmaps with random-init weights (no datasets offline).
 
   value   U/s with the heightmaps already resident in HBM (CUDA events around K steps)
   e2e     U/s through the reference-facing call Trainer.forward: float64 heightmaps in pinned host
@@ -206,10 +207,10 @@ def run_gpu_arm(args):
     tr = Trainer("reinforcement", 0.5, False, None, False, precision=args.precision)
     tr.model.gnum_rotations = tr.model.snum_rotations = R
     tr.model.update_running_stats = False  # snapshot-only side effect; not part of the Q result
-    eng = tr.model._engine(R + 1)
+    eng = tr.model._engine(args.units * (R + 1))
 
     # precision guard: the timed mode must agree with the fp32 mode on the bench input (tolerance 1e-2)
-    scenes, masks = make_units(max(2, args.steps + args.warmup), 100 + 1000 * rank)
+    scenes, masks = make_units(max(2 * args.units, 8), 100 + 1000 * rank)
     q_fast = tr.forward(scenes[0], masks[0], 0, True, False)
     precision = args.precision
     note = None
@@ -223,7 +224,7 @@ def run_gpu_arm(args):
         else:
             note = "%s vs fp32 mode on the bench input: max|dQ|/max|Q| = %.2e" % (precision, err)
         tr.model.precision = precision
-        eng = tr.model._engine(R + 1)
+        eng = tr.model._engine(args.units * (R + 1))
 
     rots = list(range(R))
     scenes_d = torch.from_numpy(scenes).to(dev)
@@ -232,8 +233,18 @@ def run_gpu_arm(args):
     best = torch.zeros(2, device=dev)
     gathered = [torch.zeros(2, device=dev) for _ in range(world)] if world > 1 else None
 
+    U = args.units
+
+    def unit_slice(i):
+        j = (i * U) % nu
+        return slice(j, j + U) if j + U <= nu else slice(0, U)
+
     def step_resident(i, exchange=True):
-        q = eng.qforward_maps(0, scenes_d[i % nu], masks_d[i % nu:i % nu + 1], MEAN, STD, rots, R)
+        sl = unit_slice(i)
+        if U == 1:
+            q = eng.qforward_maps(0, scenes_d[sl][0], masks_d[sl], MEAN, STD, rots, R)
+        else:
+            q = eng.qforward_maps_batch(0, scenes_d[sl], masks_d[sl][:, None], MEAN, STD, rots, R)
         val, idx = eng.argmax(q)
         if world > 1 and exchange:  # per-GPU best (Q, rotation) tuples: the path's only exchange
             best[0] = val[0]
@@ -268,24 +279,31 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * args.steps / (ms_max / 1e3)
+    value = world * args.steps * U / (ms_max / 1e3)
 
     # ---- e2e: Trainer.forward with host heightmaps (pinned), H2D + D2H inside the timed region
-    pin_s = [torch.from_numpy(scenes[i]).pin_memory() for i in range(nu)]
-    pin_m = [torch.from_numpy(masks[i]).pin_memory() for i in range(nu)]
+    pin_s = torch.from_numpy(scenes).pin_memory()
+    pin_m = torch.from_numpy(masks).pin_memory()
+
+    def step_e2e(i):
+        sl = unit_slice(i)
+        if U == 1:
+            return tr.forward(pin_s[sl][0].numpy(), pin_m[sl][0].numpy(), 0, True, False)
+        return tr.forward_batch(pin_s[sl].numpy(), pin_m[sl].numpy(), 0)
+
     for i in range(args.warmup):
-        tr.forward(pin_s[i % nu].numpy(), pin_m[i % nu].numpy(), 0, True, False)
+        step_e2e(i)
     barrier()
     e0.record()
     for i in range(args.steps):
-        qh = tr.forward(pin_s[(args.warmup + i) % nu].numpy(), pin_m[(args.warmup + i) % nu].numpy(), 0, True, False)
+        qh = step_e2e(args.warmup + i)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps / (float(t.item()) / 1e3)
-    h2d = int(scenes[0].nbytes + masks[0].nbytes)
+    e2e_value = world * args.steps * U / (float(t.item()) / 1e3)
+    h2d = int(U * (scenes[0].nbytes + masks[0].nbytes))
     d2h = int(qh.size * 4)
 
     # ---- backprop steps/s (second half of BASELINE.json's metric): Trainer.backprop through the public API
@@ -363,7 +381,7 @@ def run_gpu_arm(args):
                                      "algo_gbs": (v["bytes"] / 1e9 / (v["ms"] / 1e3)) if v["ms"] else None}
                                  for k, v in prof.items()}})
         line_extra["roofline"] = roof
-        line_extra["whole_step_tflops"] = GFLOP_PER_UNIT * value / 1e3
+        line_extra["whole_step_tflops"] = GFLOP_PER_UNIT * value / 1e3 / world
 
         # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
         if world == 1 and not args.no_cpu_baseline:
@@ -379,9 +397,9 @@ def run_gpu_arm(args):
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[precision],
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "units_per_step_per_gpu": 1, "rotations": R, "precision": precision,
+                "config": {"workload": WORKLOAD, "units_per_step_per_gpu": U, "rotations": R, "precision": precision,
                            "precision_note": note, "image_mean": MEAN, "image_std": STD,
-                           "l2": "working set per step (17 samples x 87 MB of fp32 activations) exceeds the 126 MB L2",
+                           "l2": "working set per step (%d samples x 87 MB of fp32 activations) exceeds the 126 MB L2" % (U * (R + 1)),
                            "parallelism": "dp%d over independent units; all_gather of per-GPU best (Q, rot)" % world},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": clocks, "gflop_per_unit": GFLOP_PER_UNIT}
@@ -401,6 +419,8 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-backprop", action="store_true")
+    ap.add_argument("--units", type=int, default=4,
+                    help="independent (scene, mask) units evaluated per step and GPU as one batch (1 = latency mode)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

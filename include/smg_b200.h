@@ -126,6 +126,14 @@ int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* de
                       const int* host_rot_idx, int n_rot, int num_rotations, float* dev_q, float* dev_bn_mean,
                       float* dev_bn_var, void* stream);
 
+/* `groups` independent units in one batch: scene g [hm,hm] with its n_masks masked heightmaps [groups, n_masks, hm, hm];
+ * dev_q receives [groups, n_masks, n_rot, n_out].  Every unit is evaluated exactly as by smg_qforward_maps (BatchNorm
+ * statistics are per sample), the batch only gives the late, small layers more CTAs per launch.                   */
+int smg_qforward_maps_batch(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hms,
+                            const double* dev_mask_hms, int groups, int n_masks, int hm_size, double mean, double stddev,
+                            const int* host_rot_idx, int n_rot, int num_rotations, float* dev_q, float* dev_bn_mean,
+                            float* dev_bn_var, void* stream);
+
 /* Batch statistics of the head's BatchNorm2d(64) from the LAST smg_qforward* / smg_qforward_train call on this handle:
  * dev_out [n_pairs, 2, 64] float32 = (mean, biased variance) per (mask, rotation) pair in q order.  Together with the
  * trunk statistics (norm5's mean/var determine the statistics of the head's BatchNorm2d(2048): mean = norm5.bias,

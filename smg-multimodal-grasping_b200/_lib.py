@@ -32,6 +32,7 @@ PROTOTYPES = {
     "smg_trunk_forward": (I, [VP, I, VP, I, VP, VP, VP, VP]),
     "smg_qforward": (I, [VP, I, I, VP, VP, I, c_int_p, I, I, VP, VP, VP, VP]),
     "smg_qforward_maps": (I, [VP, I, I, VP, VP, I, I, ctypes.c_double, ctypes.c_double, c_int_p, I, I, VP, VP, VP, VP]),
+    "smg_qforward_maps_batch": (I, [VP, I, I, VP, VP, I, I, I, ctypes.c_double, ctypes.c_double, c_int_p, I, I, VP, VP, VP, VP]),
     "smg_head_bn_stats": (I, [VP, VP, I, VP]),
     "smg_qforward_train": (I, [VP, I, I, VP, VP, I, I, VP, VP, VP, VP]),
     "smg_qbackward": (I, [VP, VP, c_void_pp, c_void_pp, VP]),

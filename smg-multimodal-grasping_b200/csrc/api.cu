@@ -209,17 +209,17 @@ static int export_bn_stats(smg_handle* h, int n, float* mean, float* var, cudaSt
 
 // heads for all (mask, rotation) pairs; samples [0,n_rot) are scenes, [n_rot, n_rot+n_masks) masks
 static int heads_forward(smg_handle* h, int trunk_id, int head_id, int n_rot, int n_masks, float* dev_q,
-                         cudaStream_t st) {
+                         cudaStream_t st, int groups = 1) {
     TrunkW& T = h->trunks[trunk_id];
     HeadW& Hd = h->heads[head_id];
     SMG_CHECK(Hd.set, SMG_ERR_STATE, "head %d: weights not set (call smg_set_head_weights)", head_id);
     const BlockGeom& g = h->geom[3];
     SMG_CHECK(g.hw == kHeadK, SMG_ERR_INVALID, "heads need H=640 (block-4 spatial %d != %d)", g.hw, kHeadK);
-    const int n = n_rot + n_masks;
+    const int n = groups * (n_rot + n_masks);
     const double* st4 = stats_ptr(h, h->st_block[3]);
     for (int half = 0; half < 2; ++half) {
-        const int s0 = half == 0 ? 0 : n_rot;
-        const int cnt = half == 0 ? n_rot : n_masks;
+        const int s0 = half == 0 ? 0 : groups * n_rot;
+        const int cnt = groups * (half == 0 ? n_rot : n_masks);
         SMG_TRY(launch_head_prepare(h, cnt, st4 + 2 * (size_t)s0 * g.c_tot, g.c_tot, T.norm5, Hd.norm0, half,
                                     h->head_scale + (size_t)s0 * kFeatC, h->head_shift + (size_t)s0 * kFeatC, st));
         ConvArgs a;
@@ -233,7 +233,7 @@ static int heads_forward(smg_handle* h, int trunk_id, int head_id, int n_rot, in
         SMG_TRY(conv_dispatch(h, a, st));
     }
     (void)n;
-    return launch_head_tail(h, h->head_p, n_rot, n_masks, Hd, dev_q, st);
+    return launch_head_tail(h, h->head_p, n_rot, n_masks, Hd, dev_q, st, groups);
 }
 
 __global__ void pack_head_conv1_kernel(const float* __restrict__ w, float* __restrict__ out, int n_out, int npix) {
@@ -372,7 +372,7 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     const size_t o_stats = p.take(h->stats_bytes);
     const size_t o_hs = p.take(S * kFeatC * 4), o_hh = p.take(S * kFeatC * 4);
     const size_t o_hp = p.take(S * (size_t)h->geom[3].hw * h->geom[3].hw * kHeadMid * 4);
-    const size_t o_tmp = p.take((size_t)3 * H * H * 4);
+    const size_t o_tmp = p.take((S > 3 ? S : 3) * (size_t)H * H * 4);
     const size_t o_hm = p.take((1 + S) * (size_t)(H / 2) * (H / 2) * 8);
     const size_t o_hb = p.take(S * S * 128 * 4);
     const size_t o_q = p.take(S * S * 4 * 4);
@@ -559,10 +559,10 @@ int smg_trunk_forward(smg_handle* h, int trunk_id, const float* dev_in, int n, f
 }
 
 static int qforward_common(smg_handle* h, int trunk_id, int head_id, int n_masks, int n_rot, int in_channels,
-                           float* dev_q, float* dev_bn_mean, float* dev_bn_var, cudaStream_t st) {
-    SMG_TRY(trunk_forward(h, trunk_id, n_rot + n_masks, in_channels, st));
-    SMG_TRY(heads_forward(h, trunk_id, head_id, n_rot, n_masks, dev_q, st));
-    if (dev_bn_mean && dev_bn_var) SMG_TRY(export_bn_stats(h, n_rot + n_masks, dev_bn_mean, dev_bn_var, st));
+                           float* dev_q, float* dev_bn_mean, float* dev_bn_var, cudaStream_t st, int groups = 1) {
+    SMG_TRY(trunk_forward(h, trunk_id, groups * (n_rot + n_masks), in_channels, st));
+    SMG_TRY(heads_forward(h, trunk_id, head_id, n_rot, n_masks, dev_q, st, groups));
+    if (dev_bn_mean && dev_bn_var) SMG_TRY(export_bn_stats(h, groups * (n_rot + n_masks), dev_bn_mean, dev_bn_var, st));
     return SMG_OK;
 }
 
@@ -582,26 +582,39 @@ int smg_qforward(smg_handle* h, int trunk_id, int head_id, const float* dev_scen
     return qforward_common(h, trunk_id, head_id, n_masks, n_rot, 3, dev_q, dev_bn_mean, dev_bn_var, st);
 }
 
+// `groups` independent units (scene g with its n_masks masked scenes) evaluated as ONE batch: samples are laid out as
+// [groups x n_rot] rotated scenes followed by [groups x n_masks] masked scenes, so the trunk and the head GEMMs see
+// one long sample axis (more CTAs per launch for the small late layers) and only the pairing in head_tail is per group.
 static int qforward_maps_body(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm, const double* dev_mask_hms,
                               int n_masks, int hm_size, double mean, double stddev, const int* host_rot_idx, int n_rot,
-                              int num_rotations, float* dev_q, float* dev_bn_mean, float* dev_bn_var, cudaStream_t st) {
+                              int num_rotations, float* dev_q, float* dev_bn_mean, float* dev_bn_var, cudaStream_t st,
+                              int groups = 1) {
     // Trainer.forward feeds three identical channels (code/trainer.py:178-181): keep ONE plane per sample and use
     // the channel-folded conv0 weights (K = 49 instead of 147)
     const size_t img = (size_t)h->H * h->H;
-    SMG_TRY(launch_prep(h, dev_scene_hm, 1, hm_size, mean, stddev, h->scene_tmp, 1, st));
-    SMG_TRY(launch_rotate(h, h->scene_tmp, host_rot_idx, n_rot, num_rotations, h->input, 1, st));
-    SMG_TRY(launch_prep(h, dev_mask_hms, n_masks, hm_size, mean, stddev, h->input + (size_t)n_rot * img, 1, st));
-    return qforward_common(h, trunk_id, head_id, n_masks, n_rot, 1, dev_q, dev_bn_mean, dev_bn_var, st);
+    SMG_TRY(launch_prep(h, dev_scene_hm, groups, hm_size, mean, stddev, h->scene_tmp, 1, st));
+    for (int g = 0; g < groups; ++g)
+        SMG_TRY(launch_rotate(h, h->scene_tmp + (size_t)g * img, host_rot_idx, n_rot, num_rotations,
+                              h->input + (size_t)g * n_rot * img, 1, st));
+    SMG_TRY(launch_prep(h, dev_mask_hms, groups * n_masks, hm_size, mean, stddev, h->input + (size_t)groups * n_rot * img, 1, st));
+    return qforward_common(h, trunk_id, head_id, n_masks, n_rot, 1, dev_q, dev_bn_mean, dev_bn_var, st, groups);
 }
 
 int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm, const double* dev_mask_hms,
                       int n_masks, int hm_size, double mean, double stddev, const int* host_rot_idx, int n_rot,
                       int num_rotations, float* dev_q, float* dev_bn_mean, float* dev_bn_var, void* stream) {
+    return smg_qforward_maps_batch(h, trunk_id, head_id, dev_scene_hm, dev_mask_hms, 1, n_masks, hm_size, mean, stddev,
+                                   host_rot_idx, n_rot, num_rotations, dev_q, dev_bn_mean, dev_bn_var, stream);
+}
+
+int smg_qforward_maps_batch(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm, const double* dev_mask_hms,
+                            int groups, int n_masks, int hm_size, double mean, double stddev, const int* host_rot_idx,
+                            int n_rot, int num_rotations, float* dev_q, float* dev_bn_mean, float* dev_bn_var, void* stream) {
     SMG_CHECK(h && dev_scene_hm && dev_mask_hms && host_rot_idx && dev_q, SMG_ERR_INVALID, "smg_qforward_maps: NULL argument");
     SMG_CHECK(trunk_id >= 0 && trunk_id < SMG_NUM_TRUNKS && head_id >= 0 && head_id < SMG_NUM_HEADS, SMG_ERR_INVALID,
               "smg_qforward_maps: trunk %d / head %d", trunk_id, head_id);
-    SMG_CHECK(n_masks >= 1 && n_rot >= 1 && n_masks + n_rot <= h->max_samples, SMG_ERR_INVALID,
-              "smg_qforward_maps: %d rotations + %d masks exceed max_samples %d", n_rot, n_masks, h->max_samples);
+    SMG_CHECK(groups >= 1 && n_masks >= 1 && n_rot >= 1 && groups * (n_masks + n_rot) <= h->max_samples, SMG_ERR_INVALID,
+              "smg_qforward_maps: %d x (%d rotations + %d masks) exceed max_samples %d", groups, n_rot, n_masks, h->max_samples);
     SMG_CHECK(stddev != 0.0, SMG_ERR_INVALID, "smg_qforward_maps: stddev is 0");
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -609,13 +622,14 @@ int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* de
     SMG_CHECK(2 * hm_size <= h->H, SMG_ERR_INVALID, "smg_qforward_maps: hm_size %d too large for H %d", hm_size, h->H);
     const bool graphable = h->use_graphs && !h->profile && !dev_bn_mean && !dev_bn_var;
     if (!graphable) return qforward_maps_body(h, trunk_id, head_id, dev_scene_hm, dev_mask_hms, n_masks, hm_size, mean, stddev,
-                                              host_rot_idx, n_rot, num_rotations, dev_q, dev_bn_mean, dev_bn_var, st);
-    // stage the inputs at fixed addresses
-    SMG_CUDA(cudaMemcpyAsync(h->hm_stage, dev_scene_hm, hm_elems * 8, cudaMemcpyDeviceToDevice, st));
-    SMG_CUDA(cudaMemcpyAsync(h->hm_stage + hm_elems, dev_mask_hms, (size_t)n_masks * hm_elems * 8, cudaMemcpyDeviceToDevice, st));
+                                              host_rot_idx, n_rot, num_rotations, dev_q, dev_bn_mean, dev_bn_var, st, groups);
+    // stage the inputs at fixed addresses: [groups] scenes, then [groups x n_masks] masks
+    double* stage_masks = h->hm_stage + (size_t)groups * hm_elems;
+    SMG_CUDA(cudaMemcpyAsync(h->hm_stage, dev_scene_hm, (size_t)groups * hm_elems * 8, cudaMemcpyDeviceToDevice, st));
+    SMG_CUDA(cudaMemcpyAsync(stage_masks, dev_mask_hms, (size_t)groups * n_masks * hm_elems * 8, cudaMemcpyDeviceToDevice, st));
     smg_handle::QGraph* G = nullptr;
     for (auto& g : h->graphs)
-        if (g.trunk_id == trunk_id && g.head_id == head_id && g.n_masks == n_masks && g.n_rot == n_rot &&
+        if (g.trunk_id == trunk_id && g.head_id == head_id && g.n_masks == n_masks && g.n_rot == n_rot && g.groups == groups &&
             g.num_rot == num_rotations && g.hm_size == hm_size && g.precision == h->precision && g.mean == mean &&
             g.stddev == stddev && g.rots == std::vector<int>(host_rot_idx, host_rot_idx + n_rot)) {
             G = &g;
@@ -623,18 +637,18 @@ int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* de
         }
     if (!G) {
         smg_handle::QGraph g;
-        g.trunk_id = trunk_id; g.head_id = head_id; g.n_masks = n_masks; g.n_rot = n_rot; g.num_rot = num_rotations;
+        g.trunk_id = trunk_id; g.head_id = head_id; g.n_masks = n_masks; g.n_rot = n_rot; g.num_rot = num_rotations; g.groups = groups;
         g.hm_size = hm_size; g.precision = h->precision; g.mean = mean; g.stddev = stddev;
         g.rots.assign(host_rot_idx, host_rot_idx + n_rot);
         h->graphs.push_back(g);
         G = &h->graphs.back();
     }
-    const size_t q_bytes = (size_t)n_masks * n_rot * h->heads[head_id].n_out * 4;
+    const size_t q_bytes = (size_t)groups * n_masks * n_rot * h->heads[head_id].n_out * 4;
     if (G->seen == 0 || h->graphs.size() > 64) {
         // first sighting: run eagerly (also performs the one-time cudaFuncSetAttribute calls)
         G->seen = 1;
-        SMG_TRY(qforward_maps_body(h, trunk_id, head_id, h->hm_stage, h->hm_stage + hm_elems, n_masks, hm_size, mean, stddev,
-                                   host_rot_idx, n_rot, num_rotations, h->q_stage, nullptr, nullptr, st));
+        SMG_TRY(qforward_maps_body(h, trunk_id, head_id, h->hm_stage, stage_masks, n_masks, hm_size, mean, stddev,
+                                   host_rot_idx, n_rot, num_rotations, h->q_stage, nullptr, nullptr, st, groups));
         SMG_CUDA(cudaMemcpyAsync(dev_q, h->q_stage, q_bytes, cudaMemcpyDeviceToDevice, st));
         return SMG_OK;
     }
@@ -644,8 +658,9 @@ int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* de
         cudaGraph_t graph = nullptr;
         const int64_t launches_before = h->launches;
         SMG_CUDA(cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeRelaxed));
-        const int status = qforward_maps_body(h, trunk_id, head_id, h->hm_stage, h->hm_stage + hm_elems, n_masks, hm_size, mean,
-                                              stddev, host_rot_idx, n_rot, num_rotations, h->q_stage, nullptr, nullptr, h->gstream);
+        const int status = qforward_maps_body(h, trunk_id, head_id, h->hm_stage, stage_masks, n_masks, hm_size, mean,
+                                              stddev, host_rot_idx, n_rot, num_rotations, h->q_stage, nullptr, nullptr, h->gstream,
+                                              groups);
         cudaError_t e = cudaStreamEndCapture(h->gstream, &graph);
         const int64_t captured = h->launches - launches_before;
         h->launches = launches_before;  // capturing enqueues nothing

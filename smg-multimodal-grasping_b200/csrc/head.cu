@@ -71,10 +71,12 @@ head_tail_kernel(const float* __restrict__ p, int n_rot, int n_masks, int npix, 
     __shared__ float red[2][4][64];
     __shared__ float s_sc[64], s_sh[64];
     __shared__ float s_part[8][4];
-    const int r = blockIdx.x, k = blockIdx.y;
+    // samples: [groups x n_rot] rotated scenes, then [groups x n_masks] masked scenes; blockIdx.z = group (unit)
+    const int r = blockIdx.x, k0 = blockIdx.y, grp = blockIdx.z, groups = gridDim.z;
+    const int k = grp * n_masks + k0;   // mask index over all groups == row of q / bn1_stats
     const int tid = threadIdx.x, c = tid & 63, g = tid >> 6;
-    const float* ps = p + (size_t)r * npix * 64;
-    const float* pm = p + (size_t)(n_rot + k) * npix * 64;
+    const float* ps = p + (size_t)(grp * n_rot + r) * npix * 64;
+    const float* pm = p + (size_t)(groups * n_rot + k) * npix * 64;
     // pass 1: mean
     float su = 0.f;
     for (int px = g; px < npix; px += 4) su += ps[px * 64 + c] + pm[px * 64 + c];
@@ -203,14 +205,14 @@ int launch_norm5_export(smg_handle* h, int n, const float* block4, const double*
 }
 
 int launch_head_tail(smg_handle* h, const float* p, int n_rot, int n_masks, const HeadW& hw, float* q,
-                     cudaStream_t st) {
+                     cudaStream_t st, int groups) {
     const int npix = h->geom[3].hw * h->geom[3].hw;
     SMG_CHECK(hw.n_out >= 1 && hw.n_out <= 4, SMG_ERR_INVALID, "head_tail: n_out %d", hw.n_out);
-    dim3 grid(n_rot, n_masks);
-    const bool fits = (size_t)n_rot * n_masks * 128 <= h->head_bn1_floats;
+    dim3 grid(n_rot, n_masks, groups);
+    const bool fits = (size_t)groups * n_rot * n_masks * 128 <= h->head_bn1_floats;
     head_tail_kernel<<<grid, 256, 0, st>>>(p, n_rot, n_masks, npix, hw.norm1.gamma, hw.norm1.beta, hw.conv1, hw.n_out, q,
                                            fits ? h->head_bn1 : nullptr);
-    h->head_bn1_pairs = fits ? n_rot * n_masks : 0;
+    h->head_bn1_pairs = fits ? groups * n_rot * n_masks : 0;
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;

@@ -174,7 +174,7 @@ struct smg_handle {
     cudaEvent_t g_in = nullptr, g_out = nullptr;
     bool use_graphs = true;
     struct QGraph {
-        int trunk_id, head_id, n_masks, n_rot, num_rot, hm_size, precision;
+        int trunk_id, head_id, n_masks, n_rot, num_rot, hm_size, precision, groups;
         double mean, stddev;
         std::vector<int> rots;
         int seen = 0;
@@ -268,7 +268,7 @@ int launch_head_prepare(smg_handle* h, int n, const double* stats4, int stats_st
 int launch_norm5_export(smg_handle* h, int n, const float* block4, const double* stats4, int stats_stride,
                         const BnP& norm5, float* out_nchw, cudaStream_t st);
 int launch_head_tail(smg_handle* h, const float* p, int n_rot, int n_masks, const HeadW& hw, float* q,
-                     cudaStream_t st);
+                     cudaStream_t st, int groups = 1);
 int launch_bn_export(smg_handle* h, int trunk_id, int n, float* mean, float* var, cudaStream_t st);
 int launch_argmax(smg_handle* h, const float* q, int n, float* out, int32_t* out_idx, cudaStream_t st);
 int launch_nhwc_to_nchw(smg_handle* h, const float* in, int hw, int c, int cstride, float* out, cudaStream_t st);

@@ -114,6 +114,26 @@ class Trainer(object):
             q = eng.qforward_maps(style, scene, masks_t, self.image_mean, self.image_std, rots, nrot)
         return q  # cuda tensor [n_masks, n_rot, n_out]
 
+    def forward_batch(self, depth_heightmaps, m_depth_heightmaps, style=0, is_target=False, specific_rotation=-1):
+        """G independent (scene, masked scene[s]) units in ONE pass: depth_heightmaps [G,224,224], m_depth_heightmaps
+        [G,224,224] or [G,M,224,224] -> numpy Q [G, M, n_rot].  Each unit gets exactly the result `forward` would give
+        it (BatchNorm statistics are per sample); batching only makes the late layers of the trunk more efficient.
+        The BatchNorm running-statistics side effect is not reproduced on this path."""
+        model = self.model_target if (is_target and self.method == 'reinforcement') else self.model
+        rots, nrot = self._rotations(model, style, specific_rotation)
+        scenes = np.ascontiguousarray(np.asarray(depth_heightmaps, dtype=np.float64))
+        masks = np.ascontiguousarray(np.asarray(m_depth_heightmaps, dtype=np.float64))
+        if masks.ndim == 3:
+            masks = masks[:, None]
+        G, M = masks.shape[0], masks.shape[1]
+        eng = model._engine(G * (len(rots) + M))
+        s_t = torch.from_numpy(scenes).to(eng.device, non_blocking=True)
+        m_t = torch.from_numpy(masks).to(eng.device, non_blocking=True)
+        q = eng.qforward_maps_batch(style, s_t, m_t, self.image_mean, self.image_std, rots, nrot)
+        if self.method == 'reactive':
+            return torch.softmax(q[:, :, :1, :], dim=3)[..., 0].cpu().numpy()
+        return q[..., 0].double().cpu().numpy()
+
     def forward(self, depth_heightmap, m_depth_heightmap, style=0, is_volatile=False, is_target=False, specific_rotation=-1):
         if not is_volatile:
             return self._forward_grad(depth_heightmap, m_depth_heightmap, style, specific_rotation)
