@@ -65,6 +65,17 @@ static int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     const double bytes = 4.0 * ((double)a.n * a.hin * a.hin * a.cin + px * a.cout);
     ProfScope ps(h, st, a.taps == 9 ? 2 : 1, 2.0 * px * a.cout * a.cin * a.taps, bytes);
     if (h->precision == SMG_PREC_FP32) return launch_conv_ffma(h, a, st);
+    // tf32: activations fetched by tensor-map TMA (conv_umma_tma.cu; SMG_TMA bit 0 = 1x1 layers, bit 1 = 3x3 layers)
+    if (h->precision == SMG_PREC_TF32 && !a.pool) {
+        if (a.taps == 1 && (h->use_tma & 1)) {
+            const int status = launch_conv_umma_tma(h, a, st);
+            if (status != SMG_ERR_UNSUPPORTED) return status;
+        }
+        if (a.taps == 9 && (h->use_tma & 2)) {
+            const int status = launch_conv3_umma_tma(h, a, st);
+            if (status != SMG_ERR_UNSUPPORTED) return status;
+        }
+    }
     // large 3x3 launches: multi-tile CTAs (setup amortised, epilogue overlapped with the next tile).  Measured on B200
     // (profiles/README.md): 3-7 % faster for the 3x3 convolutions, 3 % slower for the 1x1 ones, which therefore stay
     // on the one-tile kernel unless SMG_TILES_PER_CTA forces a value.
@@ -403,6 +414,7 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     if (const char* e = getenv("SMG_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
     if (const char* e = getenv("SMG_ASYNC")) h->force_async = atoi(e);
     if (const char* e = getenv("SMG_TILES_PER_CTA")) h->tiles_per_cta = atoi(e);
+    if (const char* e = getenv("SMG_TMA")) h->use_tma = atoi(e);
     *out = h;
     return SMG_OK;
 }
