@@ -1,0 +1,378 @@
+// conv3_persist.cu - persistent tf32 3x3 convolution (128 -> 32 channels) with the weights resident in shared memory.
+//
+// Serves torchvision densenet `_DenseLayer.conv2` (58 of the 120 trunk convolutions; /root/reference/code/models.py:319
+// builds the trunks) with the contract of conv_umma.cu: BN-ReLU prologue, raw NHWC output slice, (sum, sumsq) epilogue.
+//
+// Why another kernel: with one tile per CTA the 3x3 layers are a latency chain (ncu, profiles/README.md): a tile waits
+// for its patch, then for 144 MMAs, then for its epilogue, and the 144 KB of packed weights are re-fetched from L2 for
+// every 128-pixel tile - as many bytes as the activations.  Here
+//   * ONE CTA per SM owns the whole shared memory: the 36 weight stage images (144 KB) are loaded ONCE per launch;
+//   * the CTA walks a contiguous range of the flattened (sample, tile) list; three patch slots are refilled by 4-D
+//     tensor-map TMA boxes (channels, x, y, sample; halo zero-filled by the copy engine, 128-byte swizzle) as soon as
+//     the MMAs that read them retire, independently of tile boundaries;
+//   * the accumulator is double buffered in TMEM; the 4 epilogue warps drain tile i (TMEM -> registers -> global, one
+//     128-byte row per thread) while the MMA warp is already working on tile i+1;
+//   * output statistics are reduced with warp shuffles into shared double accumulators and flushed to HBM once per
+//     (CTA, sample) instead of once per tile.
+// Warp roles: 0-3 and 10-13 in-place BN-ReLU transform of the landed patch, 4-7 epilogue, 8 MMA issuer, 9 TMA loader.
+#include <cuda.h>
+
+#include "umma_common.cuh"
+
+namespace smg {
+
+namespace {
+
+constexpr int P_NSLOT = 3;
+constexpr int P_SLOT = 27 * 1024;                 // >= 214 patch rows x 128 B, multiple of the 1024-byte swizzle period
+constexpr int P_WBYTES = 36 * 4096;               // 4 channel groups x 9 taps, each 8 chunks x 32 rows x 16 B
+constexpr int P_OFF_A = 0;
+constexpr int P_OFF_W = P_OFF_A + P_NSLOT * P_SLOT;
+constexpr int P_OFF_BAR = P_OFF_W + P_WBYTES;     // 16 barriers + TMEM pointer
+constexpr int P_OFF_SC = P_OFF_BAR + 160;         // scale[128], shift[128]
+constexpr int P_OFF_ACC = P_OFF_SC + 1024;        // double (sum, sumsq)[32]
+constexpr int P_TOTAL = P_OFF_ACC + 512;
+static_assert(P_TOTAL <= 232448, "shared-memory plan exceeds the 227 KB of one SM");
+
+__device__ __forceinline__ void tma_tile_4d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// lane l ends with the sum over the warp of x[l]; 31 shuffles (halving exchange)
+__device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? x[i] : x[i + half];
+            const float keep = up ? x[i + half] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return x[0];
+}
+
+struct TileCoord {
+    int s, h0, w0;
+};
+
+__global__ void __launch_bounds__(448, 1)
+conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int total_tiles) {
+    constexpr int BN = 32;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_OFF_BAR);
+    uint64_t* raw_full = bars;          // [3] patch landed (raw)
+    uint64_t* a_ready = bars + 3;       // [3] patch normalised (256 transform threads)
+    uint64_t* a_empty = bars + 6;       // [3] MMAs reading the slot retired
+    uint64_t* tmem_full = bars + 9;     // [2]
+    uint64_t* tmem_empty = bars + 11;   // [2] 128 epilogue threads
+    uint64_t* w_full = bars + 13;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+    float* s_sc = reinterpret_cast<float*>(smem + P_OFF_SC);
+    float* s_sh = s_sc + 128;
+    double* s_acc = reinterpret_cast<double*>(smem + P_OFF_ACC);   // [32][2]
+    uint8_t* sA = smem + P_OFF_A;
+    uint8_t* sW = smem + P_OFF_W;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int hout = a.hout, hin = a.hin;
+    const int hw_out = hout * hout;
+    const int wp = a.wp;
+    const int pfill = (a.ht + 2) * wp;
+    const int tps = a.tiles_per_sample;
+    // contiguous, balanced share of the flattened (sample, tile) list
+    const int tile_begin = (int)(((long long)blockIdx.x * total_tiles) / gridDim.x);
+    const int tile_end = (int)(((long long)(blockIdx.x + 1) * total_tiles) / gridDim.x);
+    const int ntiles = tile_end - tile_begin;
+    auto coord = [&](int tile) {
+        TileCoord c;
+        c.s = tile / tps;
+        const int rem = tile - c.s * tps;
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        c.h0 = ty * a.ht;
+        c.w0 = tx * (wp - 2);
+        return c;
+    };
+
+    if (warp == 8 && lane == 0) {
+        if (smem_u32(smem) & 1023u) __trap();   // the swizzled slots rely on a 1024-byte aligned window
+        for (int i = 0; i < P_NSLOT; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&a_ready[i], 256); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_ptr, 2 * BN);
+    if (tid < 64) s_acc[tid] = 0.0;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 9) {
+        // =============================== loader ===============================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_full, P_WBYTES);
+            for (int i = 0; i < 9; ++i) tma_bulk_load(sW + i * 16384, a.w + (size_t)i * 16384, 16384, w_full);
+            for (int n = 0; n < 4 * ntiles; ++n) {
+                const int slot = n % P_NSLOT;
+                const TileCoord c = coord(tile_begin + (n >> 2));
+                mbar_wait(&a_empty[slot], ((n / P_NSLOT) & 1) ^ 1);
+                mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)pfill * 128u);
+                tma_tile_4d(sA + slot * P_SLOT, &tmA, (n & 3) * KC, c.w0 - 1, c.h0 - 1, c.s, &raw_full[slot]);
+            }
+        }
+    } else if (warp < 4 || warp >= 10) {
+        // =============================== in-place transform ===============================
+        const int ptid = warp < 4 ? tid : tid - 192;          // 0..255
+        const int j = ptid & 7;                               // physical 16-byte piece of the 128-byte row
+        const int rbase = ptid >> 3;                          // patch rows rbase + 32 i
+        const int chunk = j ^ (rbase & 7);                    // logical 4-channel chunk held by that piece
+        constexpr int NI = 7;                                 // 7 x 32 = 224 >= patch rows
+        int cur_s = -1;
+        uint32_t inside = 0, filled = 0;
+        for (int n = 0; n < 4 * ntiles; ++n) {
+            const int g = n & 3;
+            const int slot = n % P_NSLOT;
+            if (g == 0) {
+                const TileCoord c = coord(tile_begin + (n >> 2));
+                if (c.s != cur_s) {
+                    // BN scale/shift of the new sample (every transform thread has left the previous tile's tables)
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    if (ptid < 128) {
+                        float sc, sh;
+                        if (a.prologue_mode == 0) {
+                            const double cnt = (double)hin * hin;
+                            const double* st = a.in_stats + 2 * ((size_t)c.s * a.in_stats_stride + ptid);
+                            const double m = st[0] / cnt;
+                            double var = st[1] / cnt - m * m;
+                            if (var < 0) var = 0;
+                            sc = a.gamma[ptid] * (float)(1.0 / sqrt(var + (double)kBnEps));
+                            sh = a.beta[ptid] - (float)m * sc;
+                        } else {
+                            sc = a.scale[(size_t)c.s * a.cin + ptid];
+                            sh = a.shift[(size_t)c.s * a.cin + ptid];
+                        }
+                        s_sc[ptid] = sc;
+                        s_sh[ptid] = sh;
+                    }
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    cur_s = c.s;
+                }
+                inside = 0;
+                filled = 0;
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    const int q = rbase + 32 * i;
+                    const int py = q / wp, px = q - py * wp;
+                    const int y = c.h0 - 1 + py, x = c.w0 - 1 + px;
+                    if (q < pfill) {
+                        filled |= 1u << i;
+                        if (y >= 0 && y < hin && x >= 0 && x < hin) inside |= 1u << i;
+                    }
+                }
+            }
+            const float4 sc = *reinterpret_cast<const float4*>(s_sc + g * KC + chunk * 4);
+            const float4 sh = *reinterpret_cast<const float4*>(s_sh + g * KC + chunk * 4);
+            mbar_wait(&raw_full[slot], (n / P_NSLOT) & 1);
+            uint8_t* base = sA + slot * P_SLOT + rbase * 128 + j * 16;
+            float4 x[NI];
+#pragma unroll
+            for (int i = 0; i < NI; ++i)
+                if (filled & (1u << i)) x[i] = *reinterpret_cast<const float4*>(base + i * 32 * 128);
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                if (!(filled & (1u << i))) continue;
+                float4 y;
+                y.x = fmaf(x[i].x, sc.x, sh.x); y.y = fmaf(x[i].y, sc.y, sh.y);
+                y.z = fmaf(x[i].z, sc.z, sh.z); y.w = fmaf(x[i].w, sc.w, sh.w);
+                if (a.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+                if (!(inside & (1u << i))) y = make_float4(0.f, 0.f, 0.f, 0.f);   // conv zero padding is post-activation
+                *reinterpret_cast<float4*>(base + i * 32 * 128) = y;
+            }
+            fence_proxy_async();
+            mbar_arrive(&a_ready[slot]);
+        }
+    } else if (warp == 8) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                       ((uint32_t)(UM >> 4) << 24);
+            const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
+            mbar_wait(w_full, 0);
+            for (int it = 0; it < ntiles; ++it) {
+                const int buf = it & 1;
+                mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                uint32_t accum = 0;
+                for (int g = 0; g < 4; ++g) {
+                    const int n = it * 4 + g;
+                    const int slot = n % P_NSLOT;
+                    mbar_wait(&a_ready[slot], (n / P_NSLOT) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        // tap (dy, dx) = a shift of dy*wp + dx patch rows = +128 B per row on the start address; the swizzle
+                        // phase follows the absolute address, so descriptor base_offset stays 0
+                        const uint32_t start = sA_u + slot * P_SLOT + ((t / 3) * wp + (t % 3)) * 128;
+                        const uint32_t wst = sW_u + (g * 9 + t) * 4096;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = make_desc_sw128(start + k * 32);
+                            const uint64_t bd = make_desc(wst + 2 * k * BN * 16, BN * 16, 128);
+                            umma<4>(d_tmem, ad, bd, idesc, accum);
+                            accum = 1;
+                        }
+                    }
+                    umma_commit(&a_empty[slot]);
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        // =============================== epilogue (warps 4-7) ===============================
+        const int e = warp - 4;              // TMEM lane partition of this warp
+        const int row = e * 32 + lane;       // accumulator row == tile row
+        const int t = tid - 128;             // 0..127 inside the epilogue group
+        const int ri = row / wp, rj = row - ri * wp;
+        int cur_s = -1;
+        auto flush = [&](int s_done) {
+            // per-(CTA, sample) statistics -> HBM
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (t < 64 && a.out_stats != nullptr) {
+                const int ch = t >> 1, which = t & 1;
+                atomicAdd(a.out_stats + 2 * ((size_t)s_done * a.out_stats_stride + a.out_coff + ch) + which, s_acc[t]);
+                s_acc[t] = 0.0;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
+        for (int it = 0; it < ntiles; ++it) {
+            const TileCoord c = coord(tile_begin + it);
+            const int buf = it & 1;
+            if (c.s != cur_s) {
+                if (cur_s >= 0) flush(cur_s);
+                cur_s = c.s;
+            }
+            const bool valid = ri < a.ht && rj < wp - 2 && c.h0 + ri < hout && c.w0 + rj < hout;
+            mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(buf * BN), v);
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[buf]);
+            if (valid) {
+                float4* o = reinterpret_cast<float4*>(a.out + ((size_t)c.s * hw_out + (c.h0 + ri) * hout + c.w0 + rj) * a.out_cstride +
+                                                      a.out_coff);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            if (a.out_stats != nullptr) {
+                float sq[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (!valid) v[i] = 0.f;
+                    sq[i] = v[i] * v[i];
+                }
+                const float su = warp_transpose_sum(v, lane);     // lane = channel
+                const float ss = warp_transpose_sum(sq, lane);
+                atomicAdd(&s_acc[2 * lane], (double)su);
+                atomicAdd(&s_acc[2 * lane + 1], (double)ss);
+            }
+        }
+        if (cur_s >= 0) flush(cur_s);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+// Returns SMG_ERR_UNSUPPORTED for shapes this kernel does not serve (the caller then uses the one-tile kernels).
+int launch_conv3_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
+    if (a.taps != 9 || a.pool || a.cin != 128 || a.cout != 32 || a.in_cstride % 4 != 0 || a.out_cstride % 4 != 0 ||
+        a.out_coff % 4 != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.out) & 15) != 0)
+        return SMG_ERR_UNSUPPORTED;
+    SMG_CHECK(a.w != nullptr && a.w->w_tf32 != nullptr, SMG_ERR_STATE, "conv3_persist: weights not packed");
+    EncodeTiledFn enc = encode_fn();
+    SMG_CHECK(enc != nullptr, SMG_ERR_CUDA, "conv3_persist: cuTensorMapEncodeTiled not available from the driver");
+    UmmaDev d;
+    d.in = a.in; d.in_cstride = a.in_cstride; d.cin = a.cin; d.hin = a.hin;
+    d.prologue_mode = a.prologue_mode; d.in_stats = a.in_stats; d.in_stats_stride = a.in_stats_stride;
+    d.gamma = a.gamma; d.beta = a.beta; d.scale = a.scale; d.shift = a.shift; d.relu = a.relu;
+    d.w = a.w->w_tf32;
+    d.out = a.out; d.out_cstride = a.out_cstride; d.out_coff = a.out_coff; d.cout = a.cout;
+    d.out_stats = a.out_stats; d.out_stats_stride = a.out_stats_stride;
+    d.hout = a.hin;
+    umma_patch_geometry(d.hout, &d.wp, &d.ht);
+    // the farthest tap reads patch rows up to 2*wp + 2 + 127
+    SMG_CHECK((2 * d.wp + 2 + UM) * 128 <= P_SLOT && (d.ht + 2) * d.wp * 128 <= P_SLOT && d.ht * d.wp <= UM, SMG_ERR_STATE,
+              "conv3_persist: patch %dx%d too large", d.ht, d.wp);
+    const int wt = d.wp - 2;
+    d.tiles_x = (d.hout + wt - 1) / wt;
+    d.tiles_per_sample = d.tiles_x * ((d.hout + d.ht - 1) / d.ht);
+    d.tiles_per_cta = 0;
+    d.async_producer = 0;
+    const int total = d.tiles_per_sample * a.n;
+
+    CUtensorMap tm;
+    const cuuint64_t dims[4] = {(cuuint64_t)a.in_cstride, (cuuint64_t)a.hin, (cuuint64_t)a.hin, (cuuint64_t)a.n};
+    const cuuint64_t strides[3] = {(cuuint64_t)a.in_cstride * 4, (cuuint64_t)a.hin * a.in_cstride * 4,
+                                   (cuuint64_t)a.hin * a.hin * a.in_cstride * 4};
+    const cuuint32_t box[4] = {KC, (cuuint32_t)d.wp, (cuuint32_t)(d.ht + 2), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.in), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SMG_CHECK(r == CUDA_SUCCESS, SMG_ERR_CUDA, "conv3_persist: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    static bool attr = false;
+    if (!attr) {
+        SMG_CUDA(cudaFuncSetAttribute(conv3_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_TOTAL));
+        attr = true;
+    }
+    const int grid = total < h->num_sms ? total : h->num_sms;
+    conv3_persist_kernel<<<grid, 448, P_TOTAL, st>>>(tm, d, total);
+    h->launches++;
+    SMG_CUDA(cudaGetLastError());
+    return SMG_OK;
+}
+
+}  // namespace smg
