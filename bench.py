@@ -356,11 +356,14 @@ def run_gpu_arm(args):
         tensor_peak = peaks["bf16_tflops_sustained"] * (0.5 if precision == "tf32" else 1.0)
         ridge = tensor_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)
         ai = d["flops"] / max(1.0, d["bytes"])
-        # DRAM bytes of a representative launch of this class from `ncu --set full` (profiles/r01_ncu_prof_T1.csv), next
-        # to the algorithmic bytes of the same launch: traffic ~= algorithmic, i.e. no wasted re-reads (halo re-reads of
-        # the 3x3 patches are absorbed by L2)
-        ncu_traffic = {"conv1x1": {"launch": "block-1 1x1 conv K=224, 17 samples", "dram_bytes": 578.4e6, "algorithmic_bytes": 613.4e6},
-                       "conv3x3": {"launch": "block-1 3x3 conv, 17 samples", "dram_bytes": 265.7e6, "algorithmic_bytes": 278.5e6}}
+        # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of a representative launch of this class from one
+        # `ncu --set full` capture of the kernels that serve the class now (profiles/r01_tma1_ncu_summary.csv,
+        # profiles/r01_persist3_ncu_summary.csv), next to the algorithmic bytes of the same launch: traffic ~= algorithmic,
+        # i.e. no wasted re-reads (halo re-reads of the 3x3 patches are absorbed by L2)
+        ncu_traffic = {"conv1x1": {"launch": "block-1 1x1 conv K=192, 17 samples (conv_umma_tma_kernel)", "dram_bytes": 517.5e6,
+                                   "algorithmic_bytes": 557.1e6},
+                       "conv3x3": {"launch": "block-1 3x3 conv, 17 samples (conv3_persist_kernel)", "dram_bytes": 307.7e6,
+                                   "algorithmic_bytes": 278.5e6}}
         if dom == "stem" or ai < ridge:
             achieved = d["bytes"] / 1e9 / (d["ms"] / 1e3)
             roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

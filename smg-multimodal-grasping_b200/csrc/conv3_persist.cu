@@ -15,9 +15,7 @@
 //   * output statistics are reduced with warp shuffles into shared double accumulators and flushed to HBM once per
 //     (CTA, sample) instead of once per tile.
 // Warp roles: 0-3 and 10-13 in-place BN-ReLU transform of the landed patch, 4-7 epilogue, 8 MMA issuer, 9 TMA loader.
-#include <cuda.h>
-
-#include "umma_common.cuh"
+#include "tma_common.cuh"
 
 namespace smg {
 
@@ -33,40 +31,6 @@ constexpr int P_OFF_SC = P_OFF_BAR + 160;         // scale[128], shift[128]
 constexpr int P_OFF_ACC = P_OFF_SC + 1024;        // double (sum, sumsq)[32]
 constexpr int P_TOTAL = P_OFF_ACC + 512;
 static_assert(P_TOTAL <= 232448, "shared-memory plan exceeds the 227 KB of one SM");
-
-__device__ __forceinline__ void tma_tile_4d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
-                                            uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
-            "r"(smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
-        : "memory");
-}
-
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-// lane l ends with the sum over the warp of x[l]; 31 shuffles (halving exchange)
-__device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
-#pragma unroll
-    for (int half = 16; half >= 1; half >>= 1) {
-        const bool up = (lane & half) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const float send = up ? x[i] : x[i + half];
-            const float keep = up ? x[i + half] : x[i];
-            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-        }
-    }
-    return x[0];
-}
 
 struct TileCoord {
     int s, h0, w0;
@@ -306,24 +270,6 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
 }  // namespace
 
 // Returns SMG_ERR_UNSUPPORTED for shapes this kernel does not serve (the caller then uses the one-tile kernels).
@@ -332,8 +278,6 @@ int launch_conv3_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
         a.out_coff % 4 != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.out) & 15) != 0)
         return SMG_ERR_UNSUPPORTED;
     SMG_CHECK(a.w != nullptr && a.w->w_tf32 != nullptr, SMG_ERR_STATE, "conv3_persist: weights not packed");
-    EncodeTiledFn enc = encode_fn();
-    SMG_CHECK(enc != nullptr, SMG_ERR_CUDA, "conv3_persist: cuTensorMapEncodeTiled not available from the driver");
     UmmaDev d;
     d.in = a.in; d.in_cstride = a.in_cstride; d.cin = a.cin; d.hin = a.hin;
     d.prologue_mode = a.prologue_mode; d.in_stats = a.in_stats; d.in_stats_stride = a.in_stats_stride;
@@ -358,11 +302,7 @@ int launch_conv3_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     const cuuint64_t strides[3] = {(cuuint64_t)a.in_cstride * 4, (cuuint64_t)a.hin * a.in_cstride * 4,
                                    (cuuint64_t)a.hin * a.hin * a.in_cstride * 4};
     const cuuint32_t box[4] = {KC, (cuuint32_t)d.wp, (cuuint32_t)(d.ht + 2), 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.in), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SMG_CHECK(r == CUDA_SUCCESS, SMG_ERR_CUDA, "conv3_persist: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    SMG_TRY(make_tensor_map_f32(&tm, a.in, 4, dims, strides, box));
     static bool attr = false;
     if (!attr) {
         SMG_CUDA(cudaFuncSetAttribute(conv3_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_TOTAL));

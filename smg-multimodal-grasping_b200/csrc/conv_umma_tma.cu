@@ -14,9 +14,7 @@
 //   warp 8 lane 0   tcgen05.mma kind::tf32, A descriptor SWIZZLE_128B (SBO = 1024 B, K step = +32 B on the start
 //                   address), B descriptor unchanged (no-swizzle stage images written by pack.cu).
 //   warps 4-7       epilogue as in conv_umma.cu; all 14 warps share the stores and statistics.
-#include <cuda.h>
-
-#include "umma_common.cuh"
+#include "tma_common.cuh"
 
 namespace smg {
 
@@ -38,34 +36,6 @@ struct TmaPlan {
     static constexpr int USED = (OFF_A + STAGING > END_AB ? OFF_A + STAGING : END_AB);
     static constexpr int TOTAL = USED + 1024;               // slack to align the dynamic window to 1024 B
 };
-
-__device__ __forceinline__ void tma_tile_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
-            "r"(smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-        : "memory");
-}
-
-__device__ __forceinline__ void tma_tile_4d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
-                                            uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
-            "r"(smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
-        : "memory");
-}
-
-// SWIZZLE_128B K-major operand: 8-row atoms of 1024 B (SBO), LBO unused (1), version 1, layout type 2
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 
 template <int BN>
 __global__ void __launch_bounds__(448, 2)
@@ -517,11 +487,9 @@ conv3_umma_tma_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a) {
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+}  // namespace
 
-EncodeTiledFn encode_fn() {
+EncodeTiledFn encode_tiled_fn() {
     static EncodeTiledFn fn = nullptr;
     static bool tried = false;
     if (!tried) {
@@ -535,7 +503,17 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-}  // namespace
+int make_tensor_map_f32(CUtensorMap* tm, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                        const cuuint32_t* box) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    SMG_CHECK(enc != nullptr, SMG_ERR_CUDA, "tensor map: cuTensorMapEncodeTiled not available from the driver");
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SMG_CHECK(r == CUDA_SUCCESS, SMG_ERR_CUDA, "tensor map: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SMG_OK;
+}
 
 // Returns SMG_ERR_UNSUPPORTED for shapes this kernel does not serve (the caller then uses conv_umma.cu).
 int launch_conv_umma_tma(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
@@ -543,18 +521,12 @@ int launch_conv_umma_tma(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
         (reinterpret_cast<uintptr_t>(a.in) & 15) != 0)
         return SMG_ERR_UNSUPPORTED;
     SMG_CHECK(a.w != nullptr && a.w->w_tf32 != nullptr, SMG_ERR_STATE, "conv_umma_tma: weights not packed");
-    EncodeTiledFn enc = encode_fn();
-    SMG_CHECK(enc != nullptr, SMG_ERR_CUDA, "conv_umma_tma: cuTensorMapEncodeTiled not available from the driver");
     const int hw = a.hin * a.hin;
     CUtensorMap tm;
     const cuuint64_t dims[3] = {(cuuint64_t)a.in_cstride, (cuuint64_t)hw, (cuuint64_t)a.n};
     const cuuint64_t strides[2] = {(cuuint64_t)a.in_cstride * 4, (cuuint64_t)hw * a.in_cstride * 4};
     const cuuint32_t box[3] = {KC, UM, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.in), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SMG_CHECK(r == CUDA_SUCCESS, SMG_ERR_CUDA, "conv_umma_tma: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    SMG_TRY(make_tensor_map_f32(&tm, a.in, 3, dims, strides, box));
 
     UmmaDev d;
     d.in = a.in; d.in_cstride = a.in_cstride; d.cin = a.cin; d.hin = a.hin;
@@ -585,8 +557,6 @@ int launch_conv3_umma_tma(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
         (reinterpret_cast<uintptr_t>(a.in) & 15) != 0)
         return SMG_ERR_UNSUPPORTED;
     SMG_CHECK(a.w != nullptr && a.w->w_tf32 != nullptr, SMG_ERR_STATE, "conv3_umma_tma: weights not packed");
-    EncodeTiledFn enc = encode_fn();
-    SMG_CHECK(enc != nullptr, SMG_ERR_CUDA, "conv3_umma_tma: cuTensorMapEncodeTiled not available from the driver");
     UmmaDev d;
     d.in = a.in; d.in_cstride = a.in_cstride; d.cin = a.cin; d.hin = a.hin;
     d.prologue_mode = a.prologue_mode; d.in_stats = a.in_stats; d.in_stats_stride = a.in_stats_stride;
@@ -609,11 +579,7 @@ int launch_conv3_umma_tma(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     const cuuint64_t strides[3] = {(cuuint64_t)a.in_cstride * 4, (cuuint64_t)a.hin * a.in_cstride * 4,
                                    (cuuint64_t)a.hin * a.hin * a.in_cstride * 4};
     const cuuint32_t box[4] = {KC, (cuuint32_t)d.wp, (cuuint32_t)(d.ht + 2), 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.in), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SMG_CHECK(r == CUDA_SUCCESS, SMG_ERR_CUDA, "conv3_umma_tma: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    SMG_TRY(make_tensor_map_f32(&tm, a.in, 4, dims, strides, box));
     static bool attr = false;
     if (!attr) {
         SMG_CUDA(cudaFuncSetAttribute(conv3_umma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Tma3Plan::TOTAL));

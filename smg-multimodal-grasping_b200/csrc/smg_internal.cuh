@@ -140,7 +140,8 @@ struct smg_handle {
     void* job_buf = nullptr;       // device table for the batched weight packer
     size_t job_bytes = 0;
     int use_tma = 7;               // tuning bit mask, tf32 layers with tensor-map TMA activations: 1 = 1x1, 2 = one-tile 3x3
-                                   // (conv_umma_tma.cu), 4 = persistent 3x3 with resident weights (conv3_persist.cu)
+                                   // (conv_umma_tma.cu), 4 = persistent 3x3 with resident weights (conv3_persist.cu),
+                                   // 8 = persistent 1x1 (conv1_persist.cu; opt-in: measured 2 % slower than the one-tile 1x1 kernel)
     int tiles_per_cta = 0;         // tuning: 0 auto, 1 one-tile kernel only, >1 fixed tiles per CTA for the multi-tile kernel
     int force_async = 0;           // tuning: -1 auto by grid size, 0 register producers (default: measured fastest), 1 cp.async producers
 
@@ -266,6 +267,7 @@ int launch_conv_umma_mt(smg_handle* h, const ConvArgs& a, int precision, int til
 int launch_conv_umma_tma(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv3_umma_tma(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv3_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st);
+int launch_conv1_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 
 // head
 int launch_head_prepare(smg_handle* h, int n, const double* stats4, int stats_stride, const BnP& norm5,

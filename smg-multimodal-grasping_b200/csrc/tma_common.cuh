@@ -1,0 +1,79 @@
+// tma_common.cuh - tensor-map TMA helpers shared by the kernels whose activation operand is fetched by
+// cp.async.bulk.tensor (conv_umma_tma.cu, conv3_persist.cu, conv1_persist.cu): tile loads, the 128-byte-swizzle UMMA
+// descriptor, the warp transpose-reduction used by the register epilogues and the driver entry point for
+// cuTensorMapEncodeTiled (resolved through the runtime, so the library does not link libcuda).
+#pragma once
+#include <cuda.h>
+
+#include "umma_common.cuh"
+
+namespace smg {
+
+__device__ __forceinline__ void tma_tile_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_tile_4d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// non-blocking probe of an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+
+// SWIZZLE_128B K-major operand: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO unused (1), version 1, layout type 2.
+// Measured on B200: the swizzle phase follows the ABSOLUTE shared-memory address, so a start address advanced by whole
+// rows (+128 B each) or by K steps (+32 B) needs no base_offset as long as the buffer itself is 1024-byte aligned.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// lane l ends with the sum over the warp's 32 lanes of x[l]; 31 shuffles (halving exchange); x is destroyed
+__device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? x[i] : x[i + half];
+            const float keep = up ? x[i + half] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return x[0];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn();   // conv_umma_tma.cu; nullptr if the driver does not export it
+
+// fp32 tensor map with 128-byte swizzle and zero fill; dims/strides innermost first (strides in bytes, rank-1 of them)
+int make_tensor_map_f32(CUtensorMap* tm, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                        const cuuint32_t* box);
+
+}  // namespace smg

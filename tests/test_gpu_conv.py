@@ -83,6 +83,7 @@ def test_multi_tile_kernel_matches_torch(precision, case, tiles_per_cta, monkeyp
     """The multi-tile tcgen05 kernel (conv_umma_mt.cu): T tiles per CTA, double-buffered TMEM accumulators."""
     from smg_b200 import engine
     monkeypatch.setenv("SMG_TILES_PER_CTA", str(tiles_per_cta))
+    monkeypatch.setenv("SMG_TMA", "0")          # otherwise the tf32 cases are served by the TMA kernels
     eng = engine.Engine(0, 4, 640, "fp32")      # a private handle so the environment knob is read
     n, hin, cin, cstride, cout, k, pool = case
     g = torch.Generator(device="cuda").manual_seed(hash(case) % 1000 + tiles_per_cta)
@@ -97,6 +98,36 @@ def test_multi_tile_kernel_matches_torch(precision, case, tiles_per_cta, monkeyp
     err = float((got - ref).abs().max() / ref.abs().max())
     print("mt T=%d %s %s: rel-max err %.2e" % (tiles_per_cta, precision, case, err))
     assert err <= TOL[precision]
+    assert float(out[..., :out_coff].abs().max()) == 0 and float(out[..., out_coff + cout:].abs().max()) == 0
+    s_ref, q_ref = got.double().sum((1, 2)), (got.double() ** 2).sum((1, 2))
+    assert float((stats[:, out_coff:out_coff + cout, 0] - s_ref).abs().max() / s_ref.abs().max()) <= 1e-4
+    assert float((stats[:, out_coff:out_coff + cout, 1] - q_ref).abs().max() / q_ref.abs().max()) <= 1e-4
+    del eng
+
+
+@pytest.mark.parametrize("tma_mask", [0, 1, 3, 7, 15])
+@pytest.mark.parametrize("case", [(5, 80, 224, 256, 128, 1, 0), (2, 40, 96, 256, 128, 1, 0), (4, 80, 128, 128, 32, 3, 0),
+                                  (1, 160, 128, 128, 32, 3, 0), (3, 20, 128, 128, 32, 3, 0), (2, 20, 1024, 1024, 128, 1, 0)],
+                         ids=lambda c: "n%d_h%d_cin%d_cs%d_cout%d_k%d_pool%d" % c)
+def test_tma_kernel_variants_match_torch(case, tma_mask, monkeypatch):
+    """Every tf32 kernel selectable through SMG_TMA: 0 register producers (conv_umma.cu / conv_umma_mt.cu), 1 one-tile 1x1
+    TMA, 2 one-tile 3x3 TMA (conv_umma_tma.cu), 4 persistent 3x3 (conv3_persist.cu), 8 persistent 1x1 (conv1_persist.cu).
+    The multi-sample cases make persistent CTAs cross sample boundaries (table re-computation, statistics flush)."""
+    from smg_b200 import engine
+    monkeypatch.setenv("SMG_TMA", str(tma_mask))
+    eng = engine.Engine(0, 5, 640, "fp32")
+    n, hin, cin, cstride, cout, k, pool = case
+    g = torch.Generator(device="cuda").manual_seed(hash(case) % 1000 + tma_mask)
+    x = torch.randn((n, hin, hin, cstride), generator=g, device="cuda")
+    scale = torch.rand((n, cin), generator=g, device="cuda") + 0.5
+    shift = torch.randn((n, cin), generator=g, device="cuda") * 0.3
+    w = torch.randn((cout, cin, k, k), generator=g, device="cuda") / (cin * k * k) ** 0.5
+    out_cstride, out_coff = cout + 64, 32
+    out, stats = eng.debug_conv("tf32", x, cin, scale, shift, True, pool, w, out_cstride, out_coff)
+    ref = reference(x, cin, scale, shift, True, pool, w)
+    got = out[..., out_coff:out_coff + cout]
+    err = float((got - ref).abs().max() / ref.abs().max())
+    assert err <= TOL["tf32"]
     assert float(out[..., :out_coff].abs().max()) == 0 and float(out[..., out_coff + cout:].abs().max()) == 0
     s_ref, q_ref = got.double().sum((1, 2)), (got.double() ** 2).sum((1, 2))
     assert float((stats[:, out_coff:out_coff + cout, 0] - s_ref).abs().max() / s_ref.abs().max()) <= 1e-4
