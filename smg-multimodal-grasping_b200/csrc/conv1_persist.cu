@@ -161,7 +161,7 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 const int slot = q % Q_NA;
                 const float4 sc = *reinterpret_cast<const float4*>(s_sc + kg * KC + chunk * 4);
                 const float4 sh = *reinterpret_cast<const float4*>(s_sh + kg * KC + chunk * 4);
-                mbar_wait(&raw_full[slot], (q / Q_NA) & 1);
+                mbar_wait_sleep(&raw_full[slot], (q / Q_NA) & 1, 64);
                 uint8_t* base = sA + slot * Q_STAGE + rbase * 128 + j * 16;
                 float4 x[16];
 #pragma unroll
@@ -241,7 +241,7 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
             const bool valid = c.m0 + row < hw_out;
             float* obase = a.out + ((size_t)c.s * hw_out + c.m0) * a.out_cstride + a.out_coff + c.nt * BN + lane;
             const int rows = min(UM, hw_out - c.m0);
-            mbar_wait(&t_full[eg], (it >> 1) & 1);
+            mbar_wait_sleep(&t_full[eg], (it >> 1) & 1, 128);
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {

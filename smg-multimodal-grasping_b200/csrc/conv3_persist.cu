@@ -10,10 +10,16 @@
 //   * the CTA walks a contiguous range of the flattened (sample, tile) list; three patch slots are refilled by 4-D
 //     tensor-map TMA boxes (channels, x, y, sample; halo zero-filled by the copy engine, 128-byte swizzle) as soon as
 //     the MMAs that read them retire, independently of tile boundaries;
-//   * the accumulator is double buffered in TMEM; the 4 epilogue warps drain tile i (TMEM -> registers -> global, one
-//     128-byte row per thread) while the MMA warp is already working on tile i+1;
-//   * output statistics are reduced with warp shuffles into shared double accumulators and flushed to HBM once per
-//     (CTA, sample) instead of once per tile.
+//   * the three dx taps of a kernel row are ONE MMA: B = [W(dy,0) | W(dy,1) | W(dy,2)] is an N = 96 operand
+//     (pack.cu: w_tf32_dx), so that E_dx[m] = sum_dy A[m + dy*wp] W(dy,dx) costs 3 shifted A reads per K step instead
+//     of 9 - measured (profiles/r01_umma_rate.csv) an M=128 MMA costs 45 cycles at N = 32 and 48 at N = 64, i.e. it is
+//     bound by the 4 KB A-operand read, not by its MACs.  out[m] = E_0[m] + E_1[m+1] + E_2[m+2] is formed by the
+//     epilogue with two warp shuffles per channel (rows 30-31 of a warp take their neighbours from the next warp
+//     through a 1 KB exchange buffer); a valid output row never needs a row beyond its own patch row;
+//   * the accumulator (96 columns) is double buffered in TMEM; the 4 epilogue warps drain tile i (TMEM -> registers ->
+//     global, one 128-byte row per thread) while the MMA warp is already working on tile i+1;
+//   * output statistics are reduced with warp shuffles into per-warp double registers and flushed to HBM once per
+//     (warp, sample) instead of once per tile.
 // Warp roles: 0-3 and 10-13 in-place BN-ReLU transform of the landed patch, 4-7 epilogue, 8 MMA issuer, 9 TMA loader.
 #include "tma_common.cuh"
 
@@ -22,15 +28,18 @@ namespace smg {
 namespace {
 
 constexpr int P_NSLOT = 3;
-constexpr int P_SLOT = 27 * 1024;                 // >= 214 patch rows x 128 B, multiple of the 1024-byte swizzle period
-constexpr int P_WBYTES = 36 * 4096;               // 4 channel groups x 9 taps, each 8 chunks x 32 rows x 16 B
+constexpr int P_SLOT = 27 * 1024;                 // slot stride: >= 212 patch rows x 128 B, multiple of the 1024-byte swizzle period
+constexpr int P_LAST = 212 * 128;                 // bytes of the last slot actually touched (rows up to 2*wp + 127)
+constexpr int P_WBYTES = 12 * 12288;              // 4 channel groups x 3 kernel rows, each 8 chunks x 96 rows x 16 B
+constexpr int P_NCOL = 96;                        // accumulator columns: dx * 32 + cout
 constexpr int P_OFF_A = 0;
-constexpr int P_OFF_W = P_OFF_A + P_NSLOT * P_SLOT;
-constexpr int P_OFF_BAR = P_OFF_W + P_WBYTES;     // 16 barriers + TMEM pointer
-constexpr int P_OFF_SC = P_OFF_BAR + 160;         // scale[128], shift[128]
-constexpr int P_OFF_ACC = P_OFF_SC + 1024;        // double (sum, sumsq)[32]
-constexpr int P_TOTAL = P_OFF_ACC + 512;
+constexpr int P_OFF_W = P_OFF_A + (P_NSLOT - 1) * P_SLOT + P_LAST;
+constexpr int P_OFF_BAR = P_OFF_W + P_WBYTES;     // 14 barriers + TMEM pointer
+constexpr int P_OFF_SC = P_OFF_BAR + 128;         // scale[128], shift[128]
+constexpr int P_OFF_XCH = P_OFF_SC + 1024;        // rows 0-1 of epilogue warps 1-3: [3][E_1 row 0 | E_2 row 0 | E_2 row 1][32]
+constexpr int P_TOTAL = P_OFF_XCH + 3 * 96 * 4;
 static_assert(P_TOTAL <= 232448, "shared-memory plan exceeds the 227 KB of one SM");
+static_assert(P_OFF_W % 128 == 0 && P_OFF_BAR % 8 == 0 && P_OFF_SC % 16 == 0, "alignment");
 
 struct TileCoord {
     int s, h0, w0;
@@ -50,7 +59,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
     float* s_sc = reinterpret_cast<float*>(smem + P_OFF_SC);
     float* s_sh = s_sc + 128;
-    double* s_acc = reinterpret_cast<double*>(smem + P_OFF_ACC);   // [32][2]
+    float* s_xch = reinterpret_cast<float*>(smem + P_OFF_XCH);
     uint8_t* sA = smem + P_OFF_A;
     uint8_t* sW = smem + P_OFF_W;
 
@@ -82,8 +91,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
         mbar_init(w_full, 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(tmem_ptr, 2 * BN);
-    if (tid < 64) s_acc[tid] = 0.0;
+    if (warp == 4) tmem_alloc(tmem_ptr, 256);   // 2 x 96 accumulator columns (power-of-two allocation)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -93,11 +101,21 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
         // =============================== loader ===============================
         if (lane == 0) {
             mbar_arrive_expect_tx(w_full, P_WBYTES);
-            for (int i = 0; i < 9; ++i) tma_bulk_load(sW + i * 16384, a.w + (size_t)i * 16384, 16384, w_full);
+            for (int i = 0; i < 12; ++i) tma_bulk_load(sW + i * 12288, a.w + (size_t)i * 12288, 12288, w_full);
+            const int pd = a.tiles_per_cta;   // L2 prefetch distance in patch loads (0 = off)
+            for (int n = 0; n < pd && n < 4 * ntiles; ++n) {
+                const TileCoord c = coord(tile_begin + (n >> 2));
+                tma_prefetch_4d(&tmA, (n & 3) * KC, c.w0 - 1, c.h0 - 1, c.s);
+            }
             for (int n = 0; n < 4 * ntiles; ++n) {
                 const int slot = n % P_NSLOT;
+                if (pd > 0 && n + pd < 4 * ntiles) {
+                    // run ahead of the three shared-memory slots: HBM -> L2 for the patch that will be loaded pd loads later
+                    const TileCoord cp = coord(tile_begin + ((n + pd) >> 2));
+                    tma_prefetch_4d(&tmA, ((n + pd) & 3) * KC, cp.w0 - 1, cp.h0 - 1, cp.s);
+                }
                 const TileCoord c = coord(tile_begin + (n >> 2));
-                mbar_wait(&a_empty[slot], ((n / P_NSLOT) & 1) ^ 1);
+                mbar_wait_sleep(&a_empty[slot], ((n / P_NSLOT) & 1) ^ 1, 64);
                 mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)pfill * 128u);
                 tma_tile_4d(sA + slot * P_SLOT, &tmA, (n & 3) * KC, c.w0 - 1, c.h0 - 1, c.s, &raw_full[slot]);
             }
@@ -154,7 +172,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
             }
             const float4 sc = *reinterpret_cast<const float4*>(s_sc + g * KC + chunk * 4);
             const float4 sh = *reinterpret_cast<const float4*>(s_sh + g * KC + chunk * 4);
-            mbar_wait(&raw_full[slot], (n / P_NSLOT) & 1);
+            mbar_wait_sleep(&raw_full[slot], (n / P_NSLOT) & 1, 64);
             uint8_t* base = sA + slot * P_SLOT + rbase * 128 + j * 16;
             float4 x[NI];
 #pragma unroll
@@ -176,7 +194,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
     } else if (warp == 8) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P_NCOL >> 3) << 17) |
                                        ((uint32_t)(UM >> 4) << 24);
             const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
             mbar_wait(w_full, 0);
@@ -184,7 +202,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 const int buf = it & 1;
                 mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
                 uint32_t accum = 0;
                 for (int g = 0; g < 4; ++g) {
                     const int n = it * 4 + g;
@@ -192,15 +210,15 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                     mbar_wait(&a_ready[slot], (n / P_NSLOT) & 1);
                     tc_fence_after();
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        // tap (dy, dx) = a shift of dy*wp + dx patch rows = +128 B per row on the start address; the swizzle
+                    for (int dy = 0; dy < 3; ++dy) {
+                        // kernel row dy = a shift of dy*wp patch rows = +128 B per row on the start address; the swizzle
                         // phase follows the absolute address, so descriptor base_offset stays 0
-                        const uint32_t start = sA_u + slot * P_SLOT + ((t / 3) * wp + (t % 3)) * 128;
-                        const uint32_t wst = sW_u + (g * 9 + t) * 4096;
+                        const uint32_t start = sA_u + slot * P_SLOT + dy * wp * 128;
+                        const uint32_t wst = sW_u + (g * 3 + dy) * 12288;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t ad = make_desc_sw128(start + k * 32);
-                            const uint64_t bd = make_desc(wst + 2 * k * BN * 16, BN * 16, 128);
+                            const uint64_t bd = make_desc(wst + 2 * k * P_NCOL * 16, P_NCOL * 16, 128);
                             umma<4>(d_tmem, ad, bd, idesc, accum);
                             accum = 1;
                         }
@@ -214,18 +232,17 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
         // =============================== epilogue (warps 4-7) ===============================
         const int e = warp - 4;              // TMEM lane partition of this warp
         const int row = e * 32 + lane;       // accumulator row == tile row
-        const int t = tid - 128;             // 0..127 inside the epilogue group
         const int ri = row / wp, rj = row - ri * wp;
+        // per-warp statistics of the rows this warp drained (lane = channel), flushed when the sample changes
+        double acc_su = 0.0, acc_ss = 0.0;
         int cur_s = -1;
         auto flush = [&](int s_done) {
-            // per-(CTA, sample) statistics -> HBM
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (t < 64 && a.out_stats != nullptr) {
-                const int ch = t >> 1, which = t & 1;
-                atomicAdd(a.out_stats + 2 * ((size_t)s_done * a.out_stats_stride + a.out_coff + ch) + which, s_acc[t]);
-                s_acc[t] = 0.0;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (a.out_stats == nullptr) return;
+            double* st = a.out_stats + 2 * ((size_t)s_done * a.out_stats_stride + a.out_coff + lane);
+            atomicAdd(st, acc_su);
+            atomicAdd(st + 1, acc_ss);
+            acc_su = 0.0;
+            acc_ss = 0.0;
         };
         for (int it = 0; it < ntiles; ++it) {
             const TileCoord c = coord(tile_begin + it);
@@ -235,12 +252,41 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 cur_s = c.s;
             }
             const bool valid = ri < a.ht && rj < wp - 2 && c.h0 + ri < hout && c.w0 + rj < hout;
-            mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+            mbar_wait_sleep(&tmem_full[buf], (it >> 1) & 1, 128);
             tc_fence_after();
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(buf * BN), v);
+            float v[32], e1[32], e2[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(buf * 128);
+            tmem_ld32(taddr, v);
+            tmem_ld32(taddr + 32, e1);
+            tmem_ld32(taddr + 64, e2);
             tc_fence_before();
             mbar_arrive(&tmem_empty[buf]);
+            // out[m] = E_0[m] + E_1[m+1] + E_2[m+2]: neighbours inside the warp by shuffle, the first two rows of the next
+            // warp through shared memory (a VALID output row m never needs a row beyond the tile: m + 2 stays in its patch row)
+            if (e > 0 && lane < 2) {
+                float* x = s_xch + (e - 1) * 96;
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) x[i] = e1[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x[32 + lane * 32 + i] = e2[i];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            {
+                // branch-free: every lane reads the exchange rows (two broadcast addresses), lanes 30/31 keep them
+                const float* x = s_xch + (e < 3 ? e : 0) * 96;   // warp 3's rows 126-127 are never valid outputs
+                const float* x2 = x + 32 + (lane & 1) * 32;      // lane 30 -> next warp's row 0, lane 31 -> its row 1
+                const bool last1 = lane == 31, last2 = lane >= 30;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float s1 = __shfl_down_sync(0xffffffffu, e1[i], 1);
+                    const float s2 = __shfl_down_sync(0xffffffffu, e2[i], 2);
+                    const float xa = x[i], xb = x2[i];
+                    v[i] = (v[i] + (last1 ? xa : s1)) + (last2 ? xb : s2);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // the exchange buffer may be rewritten for the next tile
             if (valid) {
                 float4* o = reinterpret_cast<float4*>(a.out + ((size_t)c.s * hw_out + (c.h0 + ri) * hout + c.w0 + rj) * a.out_cstride +
                                                       a.out_coff);
@@ -254,10 +300,8 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                     if (!valid) v[i] = 0.f;
                     sq[i] = v[i] * v[i];
                 }
-                const float su = warp_transpose_sum(v, lane);     // lane = channel
-                const float ss = warp_transpose_sum(sq, lane);
-                atomicAdd(&s_acc[2 * lane], (double)su);
-                atomicAdd(&s_acc[2 * lane + 1], (double)ss);
+                acc_su += (double)warp_transpose_sum(v, lane);     // lane = channel
+                acc_ss += (double)warp_transpose_sum(sq, lane);
             }
         }
         if (cur_s >= 0) flush(cur_s);
@@ -266,7 +310,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        tmem_dealloc(tmem_base, 256);
     }
 }
 
@@ -277,23 +321,23 @@ int launch_conv3_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     if (a.taps != 9 || a.pool || a.cin != 128 || a.cout != 32 || a.in_cstride % 4 != 0 || a.out_cstride % 4 != 0 ||
         a.out_coff % 4 != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.out) & 15) != 0)
         return SMG_ERR_UNSUPPORTED;
-    SMG_CHECK(a.w != nullptr && a.w->w_tf32 != nullptr, SMG_ERR_STATE, "conv3_persist: weights not packed");
+    SMG_CHECK(a.w != nullptr && a.w->w_tf32_dx != nullptr, SMG_ERR_STATE, "conv3_persist: weights not packed");
     UmmaDev d;
     d.in = a.in; d.in_cstride = a.in_cstride; d.cin = a.cin; d.hin = a.hin;
     d.prologue_mode = a.prologue_mode; d.in_stats = a.in_stats; d.in_stats_stride = a.in_stats_stride;
     d.gamma = a.gamma; d.beta = a.beta; d.scale = a.scale; d.shift = a.shift; d.relu = a.relu;
-    d.w = a.w->w_tf32;
+    d.w = a.w->w_tf32_dx;
     d.out = a.out; d.out_cstride = a.out_cstride; d.out_coff = a.out_coff; d.cout = a.cout;
     d.out_stats = a.out_stats; d.out_stats_stride = a.out_stats_stride;
     d.hout = a.hin;
     umma_patch_geometry(d.hout, &d.wp, &d.ht);
-    // the farthest tap reads patch rows up to 2*wp + 2 + 127
-    SMG_CHECK((2 * d.wp + 2 + UM) * 128 <= P_SLOT && (d.ht + 2) * d.wp * 128 <= P_SLOT && d.ht * d.wp <= UM, SMG_ERR_STATE,
+    // the last kernel row reads patch rows up to 2*wp + 127; the TMA box fills (ht+2)*wp rows
+    SMG_CHECK((2 * d.wp + UM) * 128 <= P_LAST && (d.ht + 2) * d.wp * 128 <= P_LAST && d.ht * d.wp <= UM, SMG_ERR_STATE,
               "conv3_persist: patch %dx%d too large", d.ht, d.wp);
     const int wt = d.wp - 2;
     d.tiles_x = (d.hout + wt - 1) / wt;
     d.tiles_per_sample = d.tiles_x * ((d.hout + d.ht - 1) / d.ht);
-    d.tiles_per_cta = 0;
+    d.tiles_per_cta = h->l2_prefetch;   // re-used field: L2 prefetch distance of the loader
     d.async_producer = 0;
     const int total = d.tiles_per_sample * a.n;
 

@@ -125,11 +125,11 @@ conv_umma_tma_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a) {
             for (int kg = 0; kg < KG; ++kg) {   // the MMAs of stage kg free one activation and one weight slot
                 const int ka = kg + NA_T, kb = kg + NB_T;
                 if (ka < KG) {
-                    mbar_wait(&a_empty[ka % NA_T], ((ka / NA_T) & 1) ^ 1);
+                    mbar_wait_sleep(&a_empty[ka % NA_T], ((ka / NA_T) & 1) ^ 1, 64);
                     load_a(ka);
                 }
                 if (kb < KG) {
-                    mbar_wait(&b_empty[kb % NB_T], ((kb / NB_T) & 1) ^ 1);
+                    mbar_wait_sleep(&b_empty[kb % NB_T], ((kb / NB_T) & 1) ^ 1, 64);
                     load_b(kb);
                 }
             }
@@ -145,7 +145,7 @@ conv_umma_tma_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a) {
             const int slot = kg % NA_T;
             const float4 sc = *reinterpret_cast<const float4*>(s_sc + kg * KC + chunk * 4);
             const float4 sh = *reinterpret_cast<const float4*>(s_sh + kg * KC + chunk * 4);
-            mbar_wait(&raw_full[slot], (kg / NA_T) & 1);
+            mbar_wait_sleep(&raw_full[slot], (kg / NA_T) & 1, 64);
             uint8_t* base = sA + slot * P::A_STAGE + rbase * 128 + j * 16;
             float4 x[4];
 #pragma unroll
@@ -190,7 +190,7 @@ conv_umma_tma_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a) {
         // =============================== epilogue (warps 4-7) ===============================
         const int e = warp - 4;
         const int row = e * 32 + lane;
-        mbar_wait(tmem_full, 0);
+        mbar_wait_sleep(tmem_full, 0, 128);
         tc_fence_after();
         const bool valid = m0 + row < hw_out;
 #pragma unroll
@@ -348,12 +348,12 @@ conv3_umma_tma_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a) {
             for (int j = 0; j < 36; ++j) {   // the MMAs of stage j free weight slot j % NB9; tap 8 of a group frees its patch slot
                 const int kb = j + NB9;
                 if (kb < 36) {
-                    mbar_wait(&b_empty[kb % NB9], ((kb / NB9) & 1) ^ 1);
+                    mbar_wait_sleep(&b_empty[kb % NB9], ((kb / NB9) & 1) ^ 1, 64);
                     load_b(kb);
                 }
                 const int g = j / 9;
                 if (j - g * 9 == 8 && g + 2 < 4) {
-                    mbar_wait(&a_empty[g & 1], 0);
+                    mbar_wait_sleep(&a_empty[g & 1], 0, 64);
                     load_a(g + 2);
                 }
             }
@@ -380,7 +380,7 @@ conv3_umma_tma_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a) {
             const int slot = g & 1;
             const float4 sc = *reinterpret_cast<const float4*>(s_sc + g * KC + chunk * 4);
             const float4 sh = *reinterpret_cast<const float4*>(s_sh + g * KC + chunk * 4);
-            mbar_wait(&raw_full[slot], (g >> 1) & 1);
+            mbar_wait_sleep(&raw_full[slot], (g >> 1) & 1, 64);
             uint8_t* base = sA + slot * P::A_SLOT + rbase * 128 + j * 16;
             float4 x[NI];
 #pragma unroll
@@ -433,7 +433,7 @@ conv3_umma_tma_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a) {
     } else if (warp >= 4 && warp < 8) {
         const int e = warp - 4;
         const int row = e * 32 + lane;
-        mbar_wait(tmem_full, 0);
+        mbar_wait_sleep(tmem_full, 0, 128);
         tc_fence_after();
         const int i = row / wp, jx = row - i * wp;
         const bool valid = i < a.ht && jx < wp - 2 && h0 + i < hout && w0 + jx < hout;

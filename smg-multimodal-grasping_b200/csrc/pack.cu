@@ -5,6 +5,7 @@
 //   w_tf32 / w_bf16 : stage images in the UMMA no-swizzle K-major layout (conv_umma.cu):
 //       1x1 : [ntile][kgroup(32 ch)][chunk(16 B)][n (BN rows)][elements of the chunk]
 //       3x3 : [kgroup][tap][chunk][n (32 rows)][elements of the chunk]
+//   w_tf32_dx (3x3): [kgroup][dy][chunk][dx*32 + n][4 floats]: the three dx taps as one N = 96 operand (conv3_persist.cu)
 #include "smg_internal.cuh"
 
 namespace smg {
@@ -67,6 +68,22 @@ __global__ void pack_umma_kernel(const float* __restrict__ w, T* __restrict__ ou
     }
 }
 
+// 3x3, tf32: [kg][dy][chunk][n = dx*cout + co][4] (the three dx taps side by side as one wide N operand)
+__global__ void pack_umma_dx_kernel(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int k_offset,
+                                    int k_total) {
+    const int total = 9 * cin * cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int r = i;
+        const int e = r % 4; r /= 4;
+        const int n = r % (3 * cout); r /= 3 * cout;
+        const int c = r % 8; r /= 8;
+        const int dy = r % 3; r /= 3;
+        const int kg = r;
+        const int dx = n / cout, co = n - dx * cout, ci = kg * 32 + c * 4 + e;
+        out[i] = w[((size_t)co * k_total + k_offset + ci) * 9 + dy * 3 + dx];
+    }
+}
+
 // ---- batched variant: one launch packs every convolution of a trunk (blockIdx.y = job) ----
 __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
     const PackJob j = jobs[blockIdx.y];
@@ -80,6 +97,17 @@ __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
         if (mask & SMG_PACK_DGRAD) {
             const int ci = i % j.cin, co = (i / j.cin) % j.cout, t = i / (j.cout * j.cin);
             j.dgrad[i] = j.src[((size_t)co * j.k_total + j.k_off + ci) * j.taps + (j.taps - 1 - t)];
+        }
+        if ((mask & SMG_PACK_TF32) && j.taps == 9 && j.tf32_dx != nullptr) {
+            // [kg][dy][chunk][n = dx*cout + co][e]
+            int r = i;
+            const int e = r % 4; r /= 4;
+            const int n = r % (3 * j.cout); r /= 3 * j.cout;
+            const int c = r % 8; r /= 8;
+            const int dy = r % 3; r /= 3;
+            const int kg = r;
+            const int dx = n / j.cout, co = n - dx * j.cout, ci = kg * 32 + c * 4 + e;
+            j.tf32_dx[i] = j.src[((size_t)co * j.k_total + j.k_off + ci) * 9 + dy * 3 + dx];
         }
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
@@ -108,6 +136,7 @@ __global__ void copy_batch_kernel(const CopyJob* __restrict__ jobs) {
 PackJob make_pack_job(const float* w_oihw, const ConvW& cw, int k_offset, int k_total) {
     PackJob j;
     j.src = w_oihw; j.ffma = cw.w_ffma; j.tf32 = reinterpret_cast<float*>(cw.w_tf32);
+    j.tf32_dx = reinterpret_cast<float*>(cw.w_tf32_dx);
     j.bf16 = reinterpret_cast<__nv_bfloat16*>(cw.w_bf16); j.dgrad = cw.w_dgrad;
     j.cin = cw.cin; j.cout = cw.cout; j.taps = cw.taps; j.k_off = k_offset; j.k_total = k_total;
     j.bn = cw.taps == 9 ? 32 : (cw.cout < 128 ? cw.cout : 128);
@@ -155,6 +184,11 @@ int pack_conv_weights(smg_handle* h, const float* w_oihw, ConvW& cw, int k_offse
                                                                 cw.cout, cw.cin, cw.taps, k_offset, k_total, bn);
     pack_dgrad_kernel<<<blocks, threads, 0, st>>>(w_oihw, cw.w_dgrad, cw.cout, cw.cin, cw.taps, k_offset, k_total);
     h->launches += 4;
+    if (cw.taps == 9 && cw.w_tf32_dx != nullptr) {
+        pack_umma_dx_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_tf32_dx), cw.cout, cw.cin, k_offset,
+                                                        k_total);
+        h->launches++;
+    }
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;
 }

@@ -26,6 +26,19 @@ __device__ __forceinline__ void tma_tile_4d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
+// L2 prefetch of a tensor-map box: HBM -> L2 only, no shared memory and no barrier involved.  Lets a loader run further ahead
+// than its shared-memory ring (the later cp.async.bulk.tensor of the same box then completes with L2 latency).
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 // non-blocking probe of an mbarrier phase
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     uint32_t done;
