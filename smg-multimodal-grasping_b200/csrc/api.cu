@@ -293,8 +293,10 @@ static void plan_conv(ArenaPlanner& p, ConvW& cw, int cin, int cout, int taps, u
     const size_t o3 = p.take(conv_packed_bytes_umma(cin, cout, taps, 2));
     const size_t o4 = p.take(conv_packed_bytes_ffma(cin, cout, taps));
     const size_t o5 = taps == 9 ? p.take(conv_packed_bytes_umma(cin, cout, taps, 4)) : 0;
+    const size_t o6 = taps == 9 ? p.take(conv_packed_bytes_umma(cin, cout, taps, 4)) : 0;
     if (base) {
         if (taps == 9) cw.w_tf32_dx = base + o5;
+        if (taps == 9) cw.w_tf32_dx32 = base + o6;
         cw.w_ffma = reinterpret_cast<float*>(base + o1);
         cw.w_tf32 = base + o2;
         cw.w_bf16 = base + o3;
@@ -427,6 +429,7 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     if (const char* e = getenv("SMG_TILES_PER_CTA")) h->tiles_per_cta = atoi(e);
     if (const char* e = getenv("SMG_TMA")) h->use_tma = atoi(e);
     if (const char* e = getenv("SMG_L2_PREFETCH")) h->l2_prefetch = atoi(e);
+    if (const char* e = getenv("SMG_CONV3_SLOT")) h->conv3_slot_channels = atoi(e) == 16 ? 16 : 32;
     *out = h;
     return SMG_OK;
 }

@@ -7,9 +7,11 @@
 // for its patch, then for 144 MMAs, then for its epilogue, and the 144 KB of packed weights are re-fetched from L2 for
 // every 128-pixel tile - as many bytes as the activations.  Here
 //   * ONE CTA per SM owns the whole shared memory: the 36 weight stage images (144 KB) are loaded ONCE per launch;
-//   * the CTA walks a contiguous range of the flattened (sample, tile) list; three patch slots are refilled by 4-D
-//     tensor-map TMA boxes (channels, x, y, sample; halo zero-filled by the copy engine, 128-byte swizzle) as soon as
-//     the MMAs that read them retire, independently of tile boundaries;
+//   * the CTA walks a contiguous range of the flattened (sample, tile) list; six 13.5 KB patch slots (16 channels each:
+//     rows of 64 B, 64-byte swizzle) are refilled by 4-D tensor-map TMA boxes (channels, x, y, sample; halo zero-filled
+//     by the copy engine) as soon as the MMAs that read them retire, independently of tile boundaries.  Six small slots
+//     instead of three 32-channel ones: same bytes, but a slot's load -> transform -> MMA -> refill turn-around is what
+//     bounds the kernel, and it shrinks with the slot;
 //   * the three dx taps of a kernel row are ONE MMA: B = [W(dy,0) | W(dy,1) | W(dy,2)] is an N = 96 operand
 //     (pack.cu: w_tf32_dx), so that E_dx[m] = sum_dy A[m + dy*wp] W(dy,dx) costs 3 shifted A reads per K step instead
 //     of 9 - measured (profiles/r01_umma_rate.csv) an M=128 MMA costs 45 cycles at N = 32 and 48 at N = 64, i.e. it is
@@ -27,41 +29,54 @@ namespace smg {
 
 namespace {
 
-constexpr int P_NSLOT = 3;
-constexpr int P_SLOT = 27 * 1024;                 // slot stride: >= 212 patch rows x 128 B, multiple of the 1024-byte swizzle period
-constexpr int P_LAST = 212 * 128;                 // bytes of the last slot actually touched (rows up to 2*wp + 127)
-constexpr int P_WBYTES = 12 * 12288;              // 4 channel groups x 3 kernel rows, each 8 chunks x 96 rows x 16 B
+// Two instantiations: PKC = 32 (three 27 KB patch slots, rows of 128 B, 128-byte swizzle) and PKC = 16 (six 13.5 KB slots,
+// rows of 64 B, 64-byte swizzle).  Same bytes in flight; the small-slot variant hands patches over at a finer grain.
+template <int PKC>
+struct P3 {
+    static constexpr int KCH = PKC;                       // channels per patch load
+    static constexpr int ROWB = PKC * 4;                  // bytes per patch row
+    static constexpr int NG = 128 / PKC;                  // patch loads per tile
+    static constexpr int NSLOT = PKC == 32 ? 3 : 6;
+    static constexpr int ROWS = 212;                      // patch rows touched: the TMA box fills (ht+2)*wp <= 210, the MMAs read up to 2*wp + 127
+    static constexpr int SLOT = 27 * 8 * ROWB;            // slot stride: 216 rows, a multiple of the swizzle period (8 rows)
+    static constexpr int LAST = ROWS * ROWB;              // bytes of a slot actually touched
+    static constexpr int WSTAGE = (PKC / 4) * 96 * 16;    // one (channel group, kernel row) weight image: chunks x 96 rows x 16 B
+    static constexpr int WBYTES = NG * 3 * WSTAGE;        // 144 KB
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_BAR = LAST;                  // the barriers + TMEM pointer live in the unused tail of slot 0
+    static constexpr int OFF_W = OFF_A + (NSLOT - 1) * SLOT + LAST;
+    static constexpr int OFF_SC = OFF_W + WBYTES;         // scale[128], shift[128]
+    static constexpr int OFF_XCH = OFF_SC + 1024;         // rows 0-1 of epilogue warps 1-3: [3][E_1 row 0 | E_2 row 0 | E_2 row 1][32]
+    static constexpr int TOTAL = OFF_XCH + 3 * 96 * 4;
+    static_assert(TOTAL <= 232448, "shared-memory plan exceeds the 227 KB of one SM");
+    static_assert(SLOT - LAST >= 24 * 8, "barriers do not fit the slot tail");
+    static_assert(OFF_W % 128 == 0 && OFF_BAR % 8 == 0 && OFF_SC % 16 == 0, "alignment");
+};
 constexpr int P_NCOL = 96;                        // accumulator columns: dx * 32 + cout
-constexpr int P_OFF_A = 0;
-constexpr int P_OFF_W = P_OFF_A + (P_NSLOT - 1) * P_SLOT + P_LAST;
-constexpr int P_OFF_BAR = P_OFF_W + P_WBYTES;     // 14 barriers + TMEM pointer
-constexpr int P_OFF_SC = P_OFF_BAR + 128;         // scale[128], shift[128]
-constexpr int P_OFF_XCH = P_OFF_SC + 1024;        // rows 0-1 of epilogue warps 1-3: [3][E_1 row 0 | E_2 row 0 | E_2 row 1][32]
-constexpr int P_TOTAL = P_OFF_XCH + 3 * 96 * 4;
-static_assert(P_TOTAL <= 232448, "shared-memory plan exceeds the 227 KB of one SM");
-static_assert(P_OFF_W % 128 == 0 && P_OFF_BAR % 8 == 0 && P_OFF_SC % 16 == 0, "alignment");
 
 struct TileCoord {
     int s, h0, w0;
 };
 
+template <int PKC>
 __global__ void __launch_bounds__(448, 1)
 conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int total_tiles) {
-    constexpr int BN = 32;
+    using P = P3<PKC>;
+    constexpr int NS = P::NSLOT;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_OFF_BAR);
-    uint64_t* raw_full = bars;          // [3] patch landed (raw)
-    uint64_t* a_ready = bars + 3;       // [3] patch normalised (256 transform threads)
-    uint64_t* a_empty = bars + 6;       // [3] MMAs reading the slot retired
-    uint64_t* tmem_full = bars + 9;     // [2]
-    uint64_t* tmem_empty = bars + 11;   // [2] 128 epilogue threads
-    uint64_t* w_full = bars + 13;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
-    float* s_sc = reinterpret_cast<float*>(smem + P_OFF_SC);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
+    uint64_t* raw_full = bars;          // [NS <= 6] patch landed (raw)
+    uint64_t* a_ready = bars + 6;       // [NS] patch normalised (256 transform threads)
+    uint64_t* a_empty = bars + 12;      // [NS] MMAs reading the slot retired
+    uint64_t* tmem_full = bars + 18;    // [2]
+    uint64_t* tmem_empty = bars + 20;   // [2] 128 epilogue threads
+    uint64_t* w_full = bars + 22;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 23);
+    float* s_sc = reinterpret_cast<float*>(smem + P::OFF_SC);
     float* s_sh = s_sc + 128;
-    float* s_xch = reinterpret_cast<float*>(smem + P_OFF_XCH);
-    uint8_t* sA = smem + P_OFF_A;
-    uint8_t* sW = smem + P_OFF_W;
+    float* s_xch = reinterpret_cast<float*>(smem + P::OFF_XCH);
+    uint8_t* sA = smem + P::OFF_A;
+    uint8_t* sW = smem + P::OFF_W;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -86,7 +101,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
 
     if (warp == 8 && lane == 0) {
         if (smem_u32(smem) & 1023u) __trap();   // the swizzled slots rely on a 1024-byte aligned window
-        for (int i = 0; i < P_NSLOT; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&a_ready[i], 256); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < NS; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&a_ready[i], 256); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
         mbar_init(w_full, 1);
         fence_barrier_init();
@@ -100,40 +115,43 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
     if (warp == 9) {
         // =============================== loader ===============================
         if (lane == 0) {
-            mbar_arrive_expect_tx(w_full, P_WBYTES);
-            for (int i = 0; i < 12; ++i) tma_bulk_load(sW + i * 12288, a.w + (size_t)i * 12288, 12288, w_full);
+            mbar_arrive_expect_tx(w_full, P::WBYTES);
+            for (int i = 0; i < 12; ++i) tma_bulk_load(sW + i * 12288, a.w + (size_t)i * 12288, 12288, w_full);   // 12 x 12 KB = 144 KB
             const int pd = a.tiles_per_cta;   // L2 prefetch distance in patch loads (0 = off)
-            for (int n = 0; n < pd && n < 4 * ntiles; ++n) {
-                const TileCoord c = coord(tile_begin + (n >> 2));
-                tma_prefetch_4d(&tmA, (n & 3) * KC, c.w0 - 1, c.h0 - 1, c.s);
+            for (int n = 0; n < pd && n < P::NG * ntiles; ++n) {
+                const TileCoord c = coord(tile_begin + n / P::NG);
+                tma_prefetch_4d(&tmA, (n % P::NG) * P::KCH, c.w0 - 1, c.h0 - 1, c.s);
             }
-            for (int n = 0; n < 4 * ntiles; ++n) {
-                const int slot = n % P_NSLOT;
-                if (pd > 0 && n + pd < 4 * ntiles) {
-                    // run ahead of the three shared-memory slots: HBM -> L2 for the patch that will be loaded pd loads later
-                    const TileCoord cp = coord(tile_begin + ((n + pd) >> 2));
-                    tma_prefetch_4d(&tmA, ((n + pd) & 3) * KC, cp.w0 - 1, cp.h0 - 1, cp.s);
+            for (int n = 0; n < P::NG * ntiles; ++n) {
+                const int slot = n % NS;
+                if (pd > 0 && n + pd < P::NG * ntiles) {
+                    // run ahead of the shared-memory slots: HBM -> L2 for the patch that will be loaded pd loads later
+                    const TileCoord cp = coord(tile_begin + (n + pd) / P::NG);
+                    tma_prefetch_4d(&tmA, ((n + pd) % P::NG) * P::KCH, cp.w0 - 1, cp.h0 - 1, cp.s);
                 }
-                const TileCoord c = coord(tile_begin + (n >> 2));
-                mbar_wait_sleep(&a_empty[slot], ((n / P_NSLOT) & 1) ^ 1, 64);
-                mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)pfill * 128u);
-                tma_tile_4d(sA + slot * P_SLOT, &tmA, (n & 3) * KC, c.w0 - 1, c.h0 - 1, c.s, &raw_full[slot]);
+                const TileCoord c = coord(tile_begin + n / P::NG);
+                mbar_wait_sleep(&a_empty[slot], ((n / NS) & 1) ^ 1, 64);
+                mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)(pfill * P::ROWB));
+                tma_tile_4d(sA + slot * P::SLOT, &tmA, (n % P::NG) * P::KCH, c.w0 - 1, c.h0 - 1, c.s, &raw_full[slot]);
             }
         }
     } else if (warp < 4 || warp >= 10) {
         // =============================== in-place transform ===============================
         const int ptid = warp < 4 ? tid : tid - 192;          // 0..255
-        const int j = ptid & 7;                               // physical 16-byte piece of the 128-byte row
-        const int rbase = ptid >> 3;                          // patch rows rbase + 32 i
-        const int chunk = j ^ (rbase & 7);                    // logical 4-channel chunk held by that piece
-        constexpr int NI = 7;                                 // 7 x 32 = 224 >= patch rows
+        constexpr int PPR = PKC / 4;                          // 16-byte pieces per patch row (8 or 4)
+        constexpr int RSTEP = 256 / PPR;                      // rows covered by the 256 threads per pass (32 or 64)
+        constexpr int NI = (P::ROWS + RSTEP - 1) / RSTEP;     // passes (7 or 4)
+        const int j = ptid % PPR;                             // physical 16-byte piece of the row
+        const int rbase = ptid / PPR;                         // patch rows rbase + RSTEP i
+        // logical 4-channel chunk held by that piece: 128-byte swizzle xors with (row & 7), 64-byte swizzle with (row >> 1) & 3
+        const int chunk = PKC == 32 ? (j ^ (rbase & 7)) : (j ^ ((rbase >> 1) & 3));
         int cur_s = -1;
         uint32_t inside = 0, filled = 0;
-        for (int n = 0; n < 4 * ntiles; ++n) {
-            const int g = n & 3;
-            const int slot = n % P_NSLOT;
+        for (int n = 0; n < P::NG * ntiles; ++n) {
+            const int g = n % P::NG;
+            const int slot = n % NS;
             if (g == 0) {
-                const TileCoord c = coord(tile_begin + (n >> 2));
+                const TileCoord c = coord(tile_begin + n / P::NG);
                 if (c.s != cur_s) {
                     // BN scale/shift of the new sample (every transform thread has left the previous tile's tables)
                     asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -161,7 +179,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 filled = 0;
 #pragma unroll
                 for (int i = 0; i < NI; ++i) {
-                    const int q = rbase + 32 * i;
+                    const int q = rbase + RSTEP * i;
                     const int py = q / wp, px = q - py * wp;
                     const int y = c.h0 - 1 + py, x = c.w0 - 1 + px;
                     if (q < pfill) {
@@ -170,14 +188,14 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                     }
                 }
             }
-            const float4 sc = *reinterpret_cast<const float4*>(s_sc + g * KC + chunk * 4);
-            const float4 sh = *reinterpret_cast<const float4*>(s_sh + g * KC + chunk * 4);
-            mbar_wait_sleep(&raw_full[slot], (n / P_NSLOT) & 1, 64);
-            uint8_t* base = sA + slot * P_SLOT + rbase * 128 + j * 16;
+            const float4 sc = *reinterpret_cast<const float4*>(s_sc + g * P::KCH + chunk * 4);
+            const float4 sh = *reinterpret_cast<const float4*>(s_sh + g * P::KCH + chunk * 4);
+            mbar_wait_sleep(&raw_full[slot], (n / NS) & 1, 64);
+            uint8_t* base = sA + slot * P::SLOT + rbase * P::ROWB + j * 16;
             float4 x[NI];
 #pragma unroll
             for (int i = 0; i < NI; ++i)
-                if (filled & (1u << i)) x[i] = *reinterpret_cast<const float4*>(base + i * 32 * 128);
+                if (filled & (1u << i)) x[i] = *reinterpret_cast<const float4*>(base + i * RSTEP * P::ROWB);
 #pragma unroll
             for (int i = 0; i < NI; ++i) {
                 if (!(filled & (1u << i))) continue;
@@ -186,7 +204,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 y.z = fmaf(x[i].z, sc.z, sh.z); y.w = fmaf(x[i].w, sc.w, sh.w);
                 if (a.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
                 if (!(inside & (1u << i))) y = make_float4(0.f, 0.f, 0.f, 0.f);   // conv zero padding is post-activation
-                *reinterpret_cast<float4*>(base + i * 32 * 128) = y;
+                *reinterpret_cast<float4*>(base + i * RSTEP * P::ROWB) = y;
             }
             fence_proxy_async();
             mbar_arrive(&a_ready[slot]);
@@ -204,20 +222,20 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
                 uint32_t accum = 0;
-                for (int g = 0; g < 4; ++g) {
-                    const int n = it * 4 + g;
-                    const int slot = n % P_NSLOT;
-                    mbar_wait(&a_ready[slot], (n / P_NSLOT) & 1);
+                for (int g = 0; g < P::NG; ++g) {
+                    const int n = it * P::NG + g;
+                    const int slot = n % NS;
+                    mbar_wait(&a_ready[slot], (n / NS) & 1);
                     tc_fence_after();
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
-                        // kernel row dy = a shift of dy*wp patch rows = +128 B per row on the start address; the swizzle
+                        // kernel row dy = a shift of dy*wp patch rows = +64 B per row on the start address; the swizzle
                         // phase follows the absolute address, so descriptor base_offset stays 0
-                        const uint32_t start = sA_u + slot * P_SLOT + dy * wp * 128;
-                        const uint32_t wst = sW_u + (g * 3 + dy) * 12288;
+                        const uint32_t start = sA_u + slot * P::SLOT + dy * wp * P::ROWB;
+                        const uint32_t wst = sW_u + (g * 3 + dy) * P::WSTAGE;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t ad = make_desc_sw128(start + k * 32);
+                        for (int k = 0; k < P::KCH / 8; ++k) {
+                            const uint64_t ad = PKC == 32 ? make_desc_sw128(start + k * 32) : make_desc_sw64(start + k * 32);
                             const uint64_t bd = make_desc(wst + 2 * k * P_NCOL * 16, P_NCOL * 16, 128);
                             umma<4>(d_tmem, ad, bd, idesc, accum);
                             accum = 1;
@@ -321,18 +339,18 @@ int launch_conv3_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     if (a.taps != 9 || a.pool || a.cin != 128 || a.cout != 32 || a.in_cstride % 4 != 0 || a.out_cstride % 4 != 0 ||
         a.out_coff % 4 != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.out) & 15) != 0)
         return SMG_ERR_UNSUPPORTED;
-    SMG_CHECK(a.w != nullptr && a.w->w_tf32_dx != nullptr, SMG_ERR_STATE, "conv3_persist: weights not packed");
+    SMG_CHECK(a.w != nullptr && a.w->w_tf32_dx != nullptr && a.w->w_tf32_dx32 != nullptr, SMG_ERR_STATE, "conv3_persist: weights not packed");
     UmmaDev d;
     d.in = a.in; d.in_cstride = a.in_cstride; d.cin = a.cin; d.hin = a.hin;
     d.prologue_mode = a.prologue_mode; d.in_stats = a.in_stats; d.in_stats_stride = a.in_stats_stride;
     d.gamma = a.gamma; d.beta = a.beta; d.scale = a.scale; d.shift = a.shift; d.relu = a.relu;
-    d.w = a.w->w_tf32_dx;
+    d.w = h->conv3_slot_channels == 16 ? a.w->w_tf32_dx : a.w->w_tf32_dx32;
     d.out = a.out; d.out_cstride = a.out_cstride; d.out_coff = a.out_coff; d.cout = a.cout;
     d.out_stats = a.out_stats; d.out_stats_stride = a.out_stats_stride;
     d.hout = a.hin;
     umma_patch_geometry(d.hout, &d.wp, &d.ht);
     // the last kernel row reads patch rows up to 2*wp + 127; the TMA box fills (ht+2)*wp rows
-    SMG_CHECK((2 * d.wp + UM) * 128 <= P_LAST && (d.ht + 2) * d.wp * 128 <= P_LAST && d.ht * d.wp <= UM, SMG_ERR_STATE,
+    SMG_CHECK(2 * d.wp + UM <= P3<32>::ROWS && (d.ht + 2) * d.wp <= P3<32>::ROWS && d.ht * d.wp <= UM, SMG_ERR_STATE,
               "conv3_persist: patch %dx%d too large", d.ht, d.wp);
     const int wt = d.wp - 2;
     d.tiles_x = (d.hout + wt - 1) / wt;
@@ -345,15 +363,18 @@ int launch_conv3_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     const cuuint64_t dims[4] = {(cuuint64_t)a.in_cstride, (cuuint64_t)a.hin, (cuuint64_t)a.hin, (cuuint64_t)a.n};
     const cuuint64_t strides[3] = {(cuuint64_t)a.in_cstride * 4, (cuuint64_t)a.hin * a.in_cstride * 4,
                                    (cuuint64_t)a.hin * a.hin * a.in_cstride * 4};
-    const cuuint32_t box[4] = {KC, (cuuint32_t)d.wp, (cuuint32_t)(d.ht + 2), 1};
-    SMG_TRY(make_tensor_map_f32(&tm, a.in, 4, dims, strides, box));
+    const bool small = h->conv3_slot_channels == 16;
+    const cuuint32_t box[4] = {(cuuint32_t)(small ? 16 : 32), (cuuint32_t)d.wp, (cuuint32_t)(d.ht + 2), 1};
+    SMG_TRY(make_tensor_map_f32(&tm, a.in, 4, dims, strides, box, small ? 64 : 128));
     static bool attr = false;
     if (!attr) {
-        SMG_CUDA(cudaFuncSetAttribute(conv3_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_TOTAL));
+        SMG_CUDA(cudaFuncSetAttribute(conv3_persist_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3<32>::TOTAL));
+        SMG_CUDA(cudaFuncSetAttribute(conv3_persist_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3<16>::TOTAL));
         attr = true;
     }
     const int grid = total < h->num_sms ? total : h->num_sms;
-    conv3_persist_kernel<<<grid, 448, P_TOTAL, st>>>(tm, d, total);
+    if (small) conv3_persist_kernel<16><<<grid, 448, P3<16>::TOTAL, st>>>(tm, d, total);
+    else conv3_persist_kernel<32><<<grid, 448, P3<32>::TOTAL, st>>>(tm, d, total);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;

@@ -5,7 +5,7 @@
 //   w_tf32 / w_bf16 : stage images in the UMMA no-swizzle K-major layout (conv_umma.cu):
 //       1x1 : [ntile][kgroup(32 ch)][chunk(16 B)][n (BN rows)][elements of the chunk]
 //       3x3 : [kgroup][tap][chunk][n (32 rows)][elements of the chunk]
-//   w_tf32_dx (3x3): [kgroup][dy][chunk][dx*32 + n][4 floats]: the three dx taps as one N = 96 operand (conv3_persist.cu)
+//   w_tf32_dx (3x3): [16-channel group][dy][chunk][dx*32 + n][4 floats]: the three dx taps as one N = 96 operand (conv3_persist.cu)
 #include "smg_internal.cuh"
 
 namespace smg {
@@ -68,18 +68,18 @@ __global__ void pack_umma_kernel(const float* __restrict__ w, T* __restrict__ ou
     }
 }
 
-// 3x3, tf32: [kg][dy][chunk][n = dx*cout + co][4] (the three dx taps side by side as one wide N operand)
+// 3x3, tf32: [channel group of gc][dy][chunk][n = dx*cout + co][4] ( the three dx taps side by side as one wide N operand)
 __global__ void pack_umma_dx_kernel(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int k_offset,
-                                    int k_total) {
+                                    int k_total, int gc) {
     const int total = 9 * cin * cout;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int r = i;
         const int e = r % 4; r /= 4;
         const int n = r % (3 * cout); r /= 3 * cout;
-        const int c = r % 8; r /= 8;
+        const int c = r % (gc / 4); r /= gc / 4;
         const int dy = r % 3; r /= 3;
         const int kg = r;
-        const int dx = n / cout, co = n - dx * cout, ci = kg * 32 + c * 4 + e;
+        const int dx = n / cout, co = n - dx * cout, ci = kg * gc + c * 4 + e;
         out[i] = w[((size_t)co * k_total + k_offset + ci) * 9 + dy * 3 + dx];
     }
 }
@@ -99,15 +99,21 @@ __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
             j.dgrad[i] = j.src[((size_t)co * j.k_total + j.k_off + ci) * j.taps + (j.taps - 1 - t)];
         }
         if ((mask & SMG_PACK_TF32) && j.taps == 9 && j.tf32_dx != nullptr) {
-            // [kg][dy][chunk][n = dx*cout + co][e]
-            int r = i;
-            const int e = r % 4; r /= 4;
-            const int n = r % (3 * j.cout); r /= 3 * j.cout;
-            const int c = r % 8; r /= 8;
-            const int dy = r % 3; r /= 3;
-            const int kg = r;
-            const int dx = n / j.cout, co = n - dx * j.cout, ci = kg * 32 + c * 4 + e;
-            j.tf32_dx[i] = j.src[((size_t)co * j.k_total + j.k_off + ci) * 9 + dy * 3 + dx];
+            // [channel group][dy][chunk][n = dx*cout + co][e] with 16- and 32-channel groups
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const int gc = v == 0 ? 16 : 32;
+                int r = i;
+                const int e = r % 4; r /= 4;
+                const int n = r % (3 * j.cout); r /= 3 * j.cout;
+                const int c = r % (gc / 4); r /= gc / 4;
+                const int dy = r % 3; r /= 3;
+                const int kg = r;
+                const int dx = n / j.cout, co = n - dx * j.cout, ci = kg * gc + c * 4 + e;
+                const float val = j.src[((size_t)co * j.k_total + j.k_off + ci) * 9 + dy * 3 + dx];
+                if (v == 0) j.tf32_dx[i] = val;
+                else j.tf32_dx32[i] = val;
+            }
         }
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
@@ -137,6 +143,7 @@ PackJob make_pack_job(const float* w_oihw, const ConvW& cw, int k_offset, int k_
     PackJob j;
     j.src = w_oihw; j.ffma = cw.w_ffma; j.tf32 = reinterpret_cast<float*>(cw.w_tf32);
     j.tf32_dx = reinterpret_cast<float*>(cw.w_tf32_dx);
+    j.tf32_dx32 = reinterpret_cast<float*>(cw.w_tf32_dx32);
     j.bf16 = reinterpret_cast<__nv_bfloat16*>(cw.w_bf16); j.dgrad = cw.w_dgrad;
     j.cin = cw.cin; j.cout = cw.cout; j.taps = cw.taps; j.k_off = k_offset; j.k_total = k_total;
     j.bn = cw.taps == 9 ? 32 : (cw.cout < 128 ? cw.cout : 128);
@@ -186,8 +193,10 @@ int pack_conv_weights(smg_handle* h, const float* w_oihw, ConvW& cw, int k_offse
     h->launches += 4;
     if (cw.taps == 9 && cw.w_tf32_dx != nullptr) {
         pack_umma_dx_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_tf32_dx), cw.cout, cw.cin, k_offset,
-                                                        k_total);
-        h->launches++;
+                                                        k_total, 16);
+        pack_umma_dx_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_tf32_dx32), cw.cout, cw.cin, k_offset,
+                                                        k_total, 32);
+        h->launches += 2;
     }
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;

@@ -67,9 +67,10 @@ struct ConvW {
     // tcgen05 layouts: a sequence of ready-to-copy shared-memory stage images
     // (no-swizzle K-major core matrices, see conv_umma.cu), tf32 (4-byte) and bf16
     uint8_t* w_tf32 = nullptr;
-    // 3x3 only, tf32: [kgroup][dy][chunk][dx*32 + cout][4] - the three dx taps side by side as one N = 96 operand
+    // 3x3 only, tf32: [16-channel group][dy][chunk][dx*32 + cout][4] - the three dx taps side by side as one N = 96 operand
     // (conv3_persist.cu)
     uint8_t* w_tf32_dx = nullptr;
+    uint8_t* w_tf32_dx32 = nullptr;   // same with 32-channel groups: [kgroup][dy][chunk (8)][dx*32 + cout][4]
     uint8_t* w_bf16 = nullptr;
     // data-gradient weights for the fp32 kernels, in the same [taps][K][N] layout with the roles swapped:
     // 1x1: [cout][cin] (the torch layout); 3x3: [flipped tap][cout][cin]
@@ -145,6 +146,7 @@ struct smg_handle {
     int use_tma = 7;               // tuning bit mask, tf32 layers with tensor-map TMA activations: 1 = 1x1, 2 = one-tile 3x3
                                    // (conv_umma_tma.cu), 4 = persistent 3x3 with resident weights (conv3_persist.cu),
                                    // 8 = persistent 1x1 (conv1_persist.cu; opt-in: measured 2 % slower than the one-tile 1x1 kernel)
+    int conv3_slot_channels = 32;  // tuning: channels per patch slot of conv3_persist.cu (32: 3 slots, 128-byte swizzle; 16: 6 slots, 64-byte)
     int l2_prefetch = 0;           // tuning: how many TMA boxes ahead of its shared-memory ring a persistent loader prefetches into L2
     int tiles_per_cta = 0;         // tuning: 0 auto, 1 one-tile kernel only, >1 fixed tiles per CTA for the multi-tile kernel
     int force_async = 0;           // tuning: -1 auto by grid size, 0 register producers (default: measured fastest), 1 cp.async producers
@@ -348,6 +350,7 @@ struct PackJob {
     float* ffma;
     float* tf32;
     float* tf32_dx;
+    float* tf32_dx32;
     __nv_bfloat16* bf16;
     float* dgrad;
     int cin, cout, taps, k_off, k_total, bn;

@@ -85,8 +85,19 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled_fn();   // conv_umma_tma.cu; nullptr if the driver does not export it
 
-// fp32 tensor map with 128-byte swizzle and zero fill; dims/strides innermost first (strides in bytes, rank-1 of them)
+// fp32 tensor map with 128- or 64-byte swizzle and zero fill; dims/strides innermost first (strides in bytes, rank-1 of them)
 int make_tensor_map_f32(CUtensorMap* tm, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                        const cuuint32_t* box);
+                        const cuuint32_t* box, int swizzle_bytes = 128);
+
+// SWIZZLE_64B K-major operand: rows of 64 B, 8-row atoms of 512 B (SBO), layout type 4; same absolute-address rule
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
 
 }  // namespace smg
