@@ -21,40 +21,48 @@ namespace smg {
 
 namespace {
 
-constexpr int Q_NA = 8;                            // activation stages (16 KB each)
-constexpr int Q_NB = 3;                            // weight stages (16 KB each)
 constexpr int Q_STAGE = UM * 128;                  // 128 rows x 128 B
-constexpr int Q_OFF_A = 0;
-constexpr int Q_OFF_B = Q_OFF_A + Q_NA * Q_STAGE;
-constexpr int Q_OFF_SC = Q_OFF_B + Q_NB * Q_STAGE; // scale[1024], shift[1024]
-constexpr int Q_OFF_BAR = Q_OFF_SC + 8192;
-constexpr int Q_OFF_STAGE = Q_OFF_BAR + 320;       // 2 x [128][33] floats: one 32-column accumulator chunk per epilogue group
-constexpr int Q_STAGING = UM * 33 * 4;
-constexpr int Q_TOTAL = Q_OFF_STAGE + 2 * Q_STAGING;
+constexpr int Q_RES_MAX = 7;                       // resident mode: up to 7 weight stages (K <= 224) stay in shared memory
 constexpr int Q_THREADS = 576;
-static_assert(Q_TOTAL <= 232448, "shared-memory plan exceeds the 227 KB of one SM");
+
+// RES = true: the layer's KG <= 7 weight stages are loaded once per launch (every block-1 layer and the first five of
+// block 2) - no weight re-fetch per tile, 6 activation stages; RES = false: weights stream through 3 stages, 8 activation stages.
+template <bool RES>
+struct Q1 {
+    static constexpr int NA = RES ? 6 : 8;                // even: see the transform groups
+    static constexpr int NB = RES ? Q_RES_MAX : 3;
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = OFF_A + NA * Q_STAGE;
+    static constexpr int OFF_SC = OFF_B + NB * Q_STAGE;   // scale[1024], shift[1024]
+    static constexpr int OFF_BAR = OFF_SC + 8192;
+    static constexpr int TOTAL = OFF_BAR + 320;
+    static_assert(TOTAL <= 232448, "shared-memory plan exceeds the 227 KB of one SM");
+};
 
 struct Tile1 {
     int nt, s, m0;
 };
 
+template <bool RES>
 __global__ void __launch_bounds__(Q_THREADS, 1)
 conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int total_tiles, int n_samples) {
     constexpr int BN = 128;
+    using Q = Q1<RES>;
+    constexpr int Q_NA = Q::NA, Q_NB = Q::NB;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_OFF_BAR);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q::OFF_BAR);
     uint64_t* raw_full = bars;          // [8] activations landed (raw)
-    uint64_t* a_ready = bars + 8;       // [8] normalised (the 64 transform threads that own the stage)
+    uint64_t* a_ready = bars + 8;       // [8] normalised (the 128 transform threads that own the stage)
     uint64_t* a_empty = bars + 16;      // [8] MMAs retired
     uint64_t* b_full = bars + 24;       // [4]
     uint64_t* b_empty = bars + 28;      // [4]
     uint64_t* t_full = bars + 32;       // [2] accumulator complete
     uint64_t* t_empty = bars + 34;      // [2] accumulator drained (128 epilogue threads)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 36);
-    float* s_sc = reinterpret_cast<float*>(smem + Q_OFF_SC);
+    float* s_sc = reinterpret_cast<float*>(smem + Q::OFF_SC);
     float* s_sh = s_sc + 1024;
-    uint8_t* sA = smem + Q_OFF_A;
-    uint8_t* sB = smem + Q_OFF_B;
+    uint8_t* sA = smem + Q::OFF_A;
+    uint8_t* sB = smem + Q::OFF_B;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -76,8 +84,8 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
 
     if (warp == 8 && lane == 0) {
         if (smem_u32(smem) & 1023u) __trap();   // the swizzled stages rely on a 1024-byte aligned window
-        for (int i = 0; i < Q_NA; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&a_ready[i], 64); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < Q_NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < Q_NA; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&a_ready[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }   // RES: b_full[0] = weights landed
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
         fence_barrier_init();
     }
@@ -95,6 +103,12 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
             int qa = 0, ta = 0, ka = 0;      // next activation stage: global index, tile, channel group
             int qb = 0, tb = 0, kb = 0;
             Tile1 ca = coord(tile_begin), cb = ca;
+            if (RES) {
+                // one n-tile per launch in this mode: the whole weight matrix of the layer, once
+                mbar_arrive_expect_tx(&b_full[0], (uint32_t)KG * Q_STAGE);
+                for (int kg = 0; kg < KG; ++kg) tma_bulk_load(sB + kg * Q_STAGE, a.w + (size_t)kg * Q_STAGE, Q_STAGE, &b_full[0]);
+                qb = total_stages;
+            }
             while (qa < total_stages || qb < total_stages) {
                 if (qa < total_stages && mbar_test(&a_empty[qa % Q_NA], ((qa / Q_NA) & 1) ^ 1)) {
                     const int slot = qa % Q_NA;
@@ -106,7 +120,7 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                         if (++ta < ntiles) ca = coord(tile_begin + ta);
                     }
                 }
-                if (qb < total_stages && mbar_test(&b_empty[qb % Q_NB], ((qb / Q_NB) & 1) ^ 1)) {
+                if (!RES && qb < total_stages && mbar_test(&b_empty[qb % Q_NB], ((qb / Q_NB) & 1) ^ 1)) {
                     const int slot = qb % Q_NB;
                     mbar_arrive_expect_tx(&b_full[slot], Q_STAGE);
                     tma_bulk_load(sB + slot * Q_STAGE, a.w + ((size_t)cb.nt * KG + kb) * Q_STAGE, Q_STAGE, &b_full[slot]);
@@ -120,14 +134,15 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
         }
     } else if (warp < 4 || (warp >= 10 && warp < 14)) {
         // =============================== in-place transform ===============================
-        // four groups of two warps; group g owns the stages with global index = g (mod 4), so four stages are being
-        // normalised concurrently and a stage's shared-memory round trip is hidden behind the other three
+        // two groups of four warps; group g owns the stages with global index = g (mod 2), so two stages are being
+        // normalised concurrently.  NA is even: a slot is always served by the same group, which is what keeps the
+        // one-bit barrier parity unambiguous (a group that never saw phase k of a slot must not wait for phase k+1 of it).
         const int ptid = warp < 4 ? tid : tid - 192;          // 0..255
-        const int grp = ptid >> 6;                            // 0..3
-        const int gt = ptid & 63;
+        const int grp = ptid >> 7;                            // 0..1
+        const int gt = ptid & 127;
         const int j = gt & 7;                                 // physical 16-byte piece of the 128-byte row
-        const int rbase = gt >> 3;                            // rows rbase + 8 i, i < 16
-        const int chunk = j ^ rbase;                          // logical 4-channel chunk held by that piece (row & 7 == rbase)
+        const int rbase = gt >> 3;                            // rows rbase + 16 i, i < 8
+        const int chunk = j ^ (rbase & 7);                    // logical 4-channel chunk held by that piece
         int cur_s = -1;
         int q0 = 0;                                           // global index of the tile's first stage
         for (int it = 0; it < ntiles; ++it, q0 += KG) {
@@ -155,25 +170,25 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 cur_s = c.s;
             }
-            const int nvalid = hw_out - c.m0 - rbase;         // row rbase + 8 i exists iff 8 i < nvalid
-            for (int kg = (grp - q0) & 3; kg < KG; kg += 4) {
+            const int nvalid = hw_out - c.m0 - rbase;         // row rbase + 16 i exists iff 16 i < nvalid
+            for (int kg = (grp - q0) & 1; kg < KG; kg += 2) {
                 const int q = q0 + kg;
                 const int slot = q % Q_NA;
                 const float4 sc = *reinterpret_cast<const float4*>(s_sc + kg * KC + chunk * 4);
                 const float4 sh = *reinterpret_cast<const float4*>(s_sh + kg * KC + chunk * 4);
                 mbar_wait_sleep(&raw_full[slot], (q / Q_NA) & 1, 64);
                 uint8_t* base = sA + slot * Q_STAGE + rbase * 128 + j * 16;
-                float4 x[16];
+                float4 x[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = *reinterpret_cast<const float4*>(base + i * 8 * 128);
+                for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(base + i * 16 * 128);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 8; ++i) {
                     float4 y;
                     y.x = fmaf(x[i].x, sc.x, sh.x); y.y = fmaf(x[i].y, sc.y, sh.y);
                     y.z = fmaf(x[i].z, sc.z, sh.z); y.w = fmaf(x[i].w, sc.w, sh.w);
                     if (a.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-                    if (i * 8 >= nvalid) y = make_float4(0.f, 0.f, 0.f, 0.f);   // rows beyond the sample contribute nothing
-                    *reinterpret_cast<float4*>(base + i * 8 * 128) = y;
+                    if (i * 16 >= nvalid) y = make_float4(0.f, 0.f, 0.f, 0.f);   // rows beyond the sample contribute nothing
+                    *reinterpret_cast<float4*>(base + i * 16 * 128) = y;
                 }
                 fence_proxy_async();
                 mbar_arrive(&a_ready[slot]);
@@ -186,6 +201,7 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                                        ((uint32_t)(UM >> 4) << 24);
             const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
             int q = 0;
+            if (RES) mbar_wait(&b_full[0], 0);
             for (int it = 0; it < ntiles; ++it) {
                 const int buf = it & 1;
                 mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
@@ -193,9 +209,9 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
                 uint32_t accum = 0;
                 for (int kg = 0; kg < KG; ++kg, ++q) {
-                    const int sa = q % Q_NA, sb = q % Q_NB;
+                    const int sa = q % Q_NA, sb = RES ? kg : q % Q_NB;
                     mbar_wait(&a_ready[sa], (q / Q_NA) & 1);
-                    mbar_wait(&b_full[sb], (q / Q_NB) & 1);
+                    if (!RES) mbar_wait(&b_full[sb], (q / Q_NB) & 1);
                     tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -205,7 +221,7 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                         accum = 1;
                     }
                     umma_commit(&a_empty[sa]);
-                    umma_commit(&b_empty[sb]);
+                    if (!RES) umma_commit(&b_empty[sb]);
                 }
                 umma_commit(&t_full[buf]);
             }
@@ -215,7 +231,6 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
         const int eg = warp < 8 ? 0 : 1;     // epilogue group == TMEM accumulator buffer it drains
         const int e = warp & 3;              // TMEM lane partition of this warp
         const int row = e * 32 + lane;       // accumulator row == tile row
-        float* s_stage = reinterpret_cast<float*>(smem + Q_OFF_STAGE + eg * Q_STAGING);
         // per-warp statistics of the rows this warp drained, lane = channel within a 32-column chunk; flushed to HBM when
         // the (sample, n-tile) changes
         double acc_su[4] = {0.0, 0.0, 0.0, 0.0}, acc_ss[4] = {0.0, 0.0, 0.0, 0.0};
@@ -239,8 +254,7 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 cur_nt = c.nt;
             }
             const bool valid = c.m0 + row < hw_out;
-            float* obase = a.out + ((size_t)c.s * hw_out + c.m0) * a.out_cstride + a.out_coff + c.nt * BN + lane;
-            const int rows = min(UM, hw_out - c.m0);
+            float* orow = a.out + ((size_t)c.s * hw_out + c.m0 + row) * a.out_cstride + a.out_coff + c.nt * BN;
             mbar_wait_sleep(&t_full[eg], (it >> 1) & 1, 128);
             tc_fence_after();
 #pragma unroll
@@ -251,19 +265,12 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                     tc_fence_before();
                     mbar_arrive(&t_empty[eg]);   // the accumulator is in registers: the MMA warp may overwrite it
                 }
-                // transpose through shared memory so that every store instruction writes one full 128-byte line
+                // straight from registers: each thread writes its own row (8 x 16 B = one 128-byte line per chunk); no
+                // shared-memory staging - these layers sit on the SM's shared-memory bandwidth
+                if (valid) {
+                    float4* o = reinterpret_cast<float4*>(orow + k * 32);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) s_stage[row * 33 + i] = v[i];
-                if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-                else asm volatile("bar.sync 3, 128;" ::: "memory");
-                if (rows == UM) {
-                    float w[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) w[i] = s_stage[(e + 4 * i) * 33 + lane];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) obase[(size_t)(e + 4 * i) * a.out_cstride + k * 32] = w[i];
-                } else {
-                    for (int r = e; r < rows; r += 4) obase[(size_t)r * a.out_cstride + k * 32] = s_stage[r * 33 + lane];
+                    for (int q4 = 0; q4 < 8; ++q4) o[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
                 }
                 if (a.out_stats != nullptr) {
                     float sq[32];
@@ -275,8 +282,6 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                     acc_su[k] += (double)warp_transpose_sum(v, lane);
                     acc_ss[k] += (double)warp_transpose_sum(sq, lane);
                 }
-                if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-                else asm volatile("bar.sync 3, 128;" ::: "memory");
             }
         }
         if (cur_s >= 0) flush(cur_s, cur_nt);
@@ -320,11 +325,15 @@ int launch_conv1_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     const int total = d.tiles_per_sample * a.n * (a.cout / 128);
     static bool attr = false;
     if (!attr) {
-        SMG_CUDA(cudaFuncSetAttribute(conv1_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_TOTAL));
+        SMG_CUDA(cudaFuncSetAttribute(conv1_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q1<true>::TOTAL));
+        SMG_CUDA(cudaFuncSetAttribute(conv1_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q1<false>::TOTAL));
         attr = true;
     }
     const int grid = total < h->num_sms ? total : h->num_sms;
-    conv1_persist_kernel<<<grid, Q_THREADS, Q_TOTAL, st>>>(tm, d, total, a.n);
+    if (a.cout == 128 && a.cin / KC <= Q_RES_MAX)
+        conv1_persist_kernel<true><<<grid, Q_THREADS, Q1<true>::TOTAL, st>>>(tm, d, total, a.n);
+    else
+        conv1_persist_kernel<false><<<grid, Q_THREADS, Q1<false>::TOTAL, st>>>(tm, d, total, a.n);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;

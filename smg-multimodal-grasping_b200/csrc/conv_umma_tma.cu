@@ -98,13 +98,19 @@ conv_umma_tma_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a) {
 
     // BN prologue parameters of this sample (overlaps the first TMA loads)
     if (a.prologue_mode == 0) {
-        const double cnt = (double)a.hin * a.hin;
+        // mean / variance from the double sums (the cancellation in E[x^2] - E[x]^2 needs double); the reciprocal square
+        // root itself in fp32 (rsqrtf + one Newton step, <= 1 ulp): this table is on the critical path of every CTA and
+        // the double-precision sqrt + divide sequence it replaces cost about a microsecond of it
+        const double inv = 1.0 / ((double)a.hin * a.hin);
         for (int c = tid; c < a.cin; c += 448) {
-            const double* st = a.in_stats + 2 * ((size_t)s * a.in_stats_stride + c);
-            const double m = st[0] / cnt;
-            double var = st[1] / cnt - m * m;
+            const double2 st = *reinterpret_cast<const double2*>(a.in_stats + 2 * ((size_t)s * a.in_stats_stride + c));
+            const double m = st.x * inv;
+            double var = st.y * inv - m * m;
             if (var < 0) var = 0;
-            const float sc = a.gamma[c] * (float)(1.0 / sqrt(var + (double)kBnEps));
+            const float ve = (float)(var + (double)kBnEps);
+            float r = rsqrtf(ve);
+            r = r * (1.5f - 0.5f * ve * r * r);
+            const float sc = a.gamma[c] * r;
             s_sc[c] = sc;
             s_sh[c] = a.beta[c] - (float)m * sc;
         }
@@ -205,11 +211,27 @@ conv_umma_tma_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a) {
     __syncthreads();
     {
         constexpr int NW = 14;
-        for (int r = warp; r < UM; r += NW) {
-            if (m0 + r >= hw_out) continue;
-            float* o = a.out + ((size_t)s * hw_out + m0 + r) * a.out_cstride + a.out_coff + ntile * BN;
+        // rows warp, warp + 14, ...: the loads of five rows are issued before their stores so that the shared-memory
+        // latency is paid once per group, not once per row
+        float* obase = a.out + ((size_t)s * hw_out + m0) * a.out_cstride + a.out_coff + ntile * BN + lane;
+        const int nrows = min(UM, hw_out - m0);
 #pragma unroll
-            for (int cb = 0; cb < BN; cb += 32) o[cb + lane] = s_out[r * (BN + 1) + cb + lane];
+        for (int i0 = 0; i0 < 10; i0 += 5) {
+            float x[5][BN / 32];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int r = warp + NW * (i0 + i);
+#pragma unroll
+                for (int cb = 0; cb < BN / 32; ++cb) x[i][cb] = r < UM ? s_out[r * (BN + 1) + cb * 32 + lane] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int r = warp + NW * (i0 + i);
+                if (r < nrows) {
+#pragma unroll
+                    for (int cb = 0; cb < BN / 32; ++cb) obase[(size_t)r * a.out_cstride + cb * 32] = x[i][cb];
+                }
+            }
         }
         if (a.out_stats != nullptr) {
             constexpr int GROUPS = 448 / BN;
