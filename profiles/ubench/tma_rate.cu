@@ -51,6 +51,12 @@ __global__ void __launch_bounds__(128, 1) tma_kernel(const __grid_constant__ CUt
                 mbar_expect(&bars[slot], 210 * 128);
                 asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
                              "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(&tm)), "r"(g * 32), "r"(tx * 40 - 1), "r"(ty * 3 - 1), "r"(s), "r"(smem_u32(&bars[slot])) : "memory");
+            } else if (PATTERN == 3 || PATTERN == 4) {
+                const int bw = PATTERN == 3 ? 40 : 64;
+                const int tile = i, s = tile / 800, r = tile % 800, ty = r / 20, tx = r % 20;
+                mbar_expect(&bars[slot], bw * 21 * 4);
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+                             "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(&tm)), "r"(tx * 32 - 3), "r"(ty * 16 - 3), "r"(s), "r"(smem_u32(&bars[slot])) : "memory");
             } else {
                 mbar_expect(&bars[slot], 16384);
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
@@ -92,6 +98,17 @@ int main() {
         enc(&tm4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
+    CUtensorMap tmS40, tmS64;
+    for (int v = 0; v < 2; ++v) {
+        const cuuint64_t dims[3] = {640, 640, 72};
+        const cuuint64_t str[2] = {2560, 640ull * 2560};
+        const cuuint32_t box[3] = {v == 0 ? 40u : 64u, 21, 1};
+        CUresult r = enc(v == 0 ? &tmS40 : &tmS64, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        printf("encode stem box %d: %d\n", v, (int)r);
+    }
+    cudaFuncSetAttribute(tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -99,17 +116,20 @@ int main() {
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     printf("pattern,stages_in_flight,box_bytes,total_MB,us,GB_per_s,GB_per_s_per_SM\n");
-    for (int pat = 0; pat < 3; ++pat)
+    for (int pat = 0; pat < 5; ++pat)
         for (int ns : {2, 3, 4, 6, 8, 12}) {
-            const int slot = pat == 1 ? 27 * 1024 : 16 * 1024;
+            if (pat >= 3 && ns != 4) continue;
+            const int slot = pat == 1 ? 27 * 1024 : (pat >= 3 ? 5376 : 16 * 1024);
             if ((size_t)ns * slot > 220 * 1024) continue;
-            const int total = pat == 0 ? 17 * 200 * 6 : (pat == 1 ? 17 * 216 * 4 : (int)(bytes / 16384 / 4));
-            const double box_bytes = pat == 1 ? 210 * 128 : 16384;
+            const int total = pat == 0 ? 17 * 200 * 6 : (pat == 1 ? 17 * 216 * 4 : (pat >= 3 ? 800 * 72 : (int)(bytes / 16384 / 4)));
+            const double box_bytes = pat == 1 ? 210 * 128 : (pat == 3 ? 40 * 21 * 4 : (pat == 4 ? 64 * 21 * 4 : 16384));
             float ms = 0;
             for (int rep = 0; rep < 3; ++rep) {
                 cudaEventRecord(e0);
                 if (pat == 0) tma_kernel<0><<<148, 128, ns * slot>>>(tm3, d, ns, total, slot);
                 else if (pat == 1) tma_kernel<1><<<148, 128, ns * slot>>>(tm4, d, ns, total, slot);
+                else if (pat == 3) tma_kernel<3><<<148, 128, ns * slot>>>(tmS40, d, ns, total, slot);
+                else if (pat == 4) tma_kernel<4><<<148, 128, ns * slot>>>(tmS64, d, ns, total, slot);
                 else tma_kernel<2><<<148, 128, ns * slot>>>(tm3, d, ns, total, slot);
                 cudaEventRecord(e1);
                 cudaError_t e = cudaEventSynchronize(e1);

@@ -149,8 +149,14 @@ static int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cu
                 ProfScope ps(h, st, 0, 2.0 * ns * hc * 64 * 49 * in_channels,
                              4.0 * ns * ((double)in_channels * h->H * h->H + 2 * hc * 64 + hc / 4 * 64));
                 double* st_c0 = stats_ptr(h, h->st_conv0) + 2 * (size_t)s0 * 64;
-                SMG_TRY(launch_conv0(h, h->input + (size_t)s0 * in_img, in_channels, ns,
-                                     in_channels == 1 ? T.conv0_folded : T.conv0, h->conv0 + (size_t)s0 * c0_img, st_c0, st));
+                int c0_status = SMG_ERR_UNSUPPORTED;
+                if (h->precision == SMG_PREC_TF32 && in_channels == 1 && (h->use_tma & 16))
+                    c0_status = launch_conv0_umma(h, h->input + (size_t)s0 * in_img, ns, T.conv0_umma, h->conv0 + (size_t)s0 * c0_img,
+                                                  st_c0, st);
+                if (c0_status == SMG_ERR_UNSUPPORTED)
+                    c0_status = launch_conv0(h, h->input + (size_t)s0 * in_img, in_channels, ns,
+                                             in_channels == 1 ? T.conv0_folded : T.conv0, h->conv0 + (size_t)s0 * c0_img, st_c0, st);
+                SMG_TRY(c0_status);
                 SMG_TRY(launch_pool0(h, ns, h->conv0 + (size_t)s0 * c0_img, st_c0, T.norm0.gamma, T.norm0.beta, blk, g.c_tot,
                                      st_blk, st));
             }
@@ -316,9 +322,11 @@ static size_t plan_trunk(smg_handle* h, TrunkW& T, uint8_t* base) {
     ArenaPlanner p;
     const size_t o = p.take(147 * 64 * 4);
     const size_t of = p.take(49 * 64 * 4);
+    const size_t ou = p.take(2 * 14 * 64 * 16);
     if (base) {
         T.conv0 = reinterpret_cast<float*>(base + o);
         T.conv0_folded = reinterpret_cast<float*>(base + of);
+        T.conv0_umma = reinterpret_cast<float*>(base + ou);
     }
     plan_bn(p, T.norm0, 64, base);
     for (int b = 0; b < kNumBlocks; ++b) {
@@ -483,6 +491,7 @@ int smg_set_trunk_weights(smg_handle* h, int trunk_id, const float* const* dev_p
         cj.push_back(CopyJob{dev_params[i++], b.beta, b.c});
     };
     pack_conv0_kernel<<<(147 * 64 + 255) / 256, 256, 0, st>>>(dev_params[i++], T.conv0, T.conv0_folded);
+    SMG_TRY(pack_conv0_umma(h, T.conv0_folded, T.conv0_umma, st));
     h->launches++;
     copy_bn(T.norm0);
     for (int b = 0; b < kNumBlocks; ++b) {

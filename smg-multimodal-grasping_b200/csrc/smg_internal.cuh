@@ -101,6 +101,7 @@ struct TrunkW {
     int packed = 0;  // SMG_PACK_* layouts that are current
     float* conv0 = nullptr;  // [147][64], k = (c*7+kh)*7+kw
     float* conv0_folded = nullptr;  // [49][64]: weights summed over the input channel (identical channels)
+    float* conv0_umma = nullptr;    // the folded weights as two tcgen05 B images (hi, lo) [14 chunks][64][4], k = kh*8 + kw (stem_umma.cu)
     BnP norm0;
     std::vector<DenseLayerW> layers[kNumBlocks];
     TransitionW trans[kNumBlocks - 1];
@@ -143,9 +144,10 @@ struct smg_handle {
     int pack_mask = 15;            // weight layouts written by smg_set_*_weights (SMG_PACK_*)
     void* job_buf = nullptr;       // device table for the batched weight packer
     size_t job_bytes = 0;
-    int use_tma = 7;               // tuning bit mask, tf32 layers with tensor-map TMA activations: 1 = 1x1, 2 = one-tile 3x3
+    int use_tma = 23;              // tuning bit mask, tf32 layers with tensor-map TMA activations: 1 = 1x1, 2 = one-tile 3x3
                                    // (conv_umma_tma.cu), 4 = persistent 3x3 with resident weights (conv3_persist.cu),
-                                   // 8 = persistent 1x1 (conv1_persist.cu; opt-in: measured 2 % slower than the one-tile 1x1 kernel)
+                                   // 8 = persistent 1x1 (conv1_persist.cu; opt-in: measured 2 % slower than the one-tile 1x1 kernel),
+                                   // 16 = tensor-core 7x7 stem for identical input channels (stem_umma.cu)
     int conv3_slot_channels = 32;  // tuning: channels per patch slot of conv3_persist.cu (32: 3 slots, 128-byte swizzle; 16: 6 slots, 64-byte)
     int l2_prefetch = 0;           // tuning: how many TMA boxes ahead of its shared-memory ring a persistent loader prefetches into L2
     int tiles_per_cta = 0;         // tuning: 0 auto, 1 one-tile kernel only, >1 fixed tiles per CTA for the multi-tile kernel
@@ -237,6 +239,8 @@ int launch_rotate_index_map(smg_handle* h, int rot, int num_rot, int32_t* out, c
 // stem
 int launch_conv0(smg_handle* h, const float* in, int cin, int n, const float* w, float* out, double* stats,
                  cudaStream_t st);
+int launch_conv0_umma(smg_handle* h, const float* in, int n, const float* w_umma, float* out, double* stats, cudaStream_t st);
+int pack_conv0_umma(smg_handle* h, const float* folded, float* out, cudaStream_t st);
 int launch_pool0(smg_handle* h, int n, const float* conv0, const double* stats_in, const float* gamma,
                  const float* beta, float* out, int out_cstride, double* stats_out, cudaStream_t st);
 

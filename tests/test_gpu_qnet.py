@@ -130,6 +130,30 @@ def test_dedup_table_equals_single_calls(net, scene_inputs):
             assert abs(single - table[k, r]) <= 1e-5 * max(1.0, np.abs(table).max())
 
 
+def test_maps_path_tensor_core_stem(net, scene_inputs):
+    """Heightmap entry point (one input channel): in tf32 mode conv0 runs on the tensor cores (stem_umma.cu: TMA patch ->
+    im2col operand -> tcgen05.mma); its raw output, the pooled block-1 input and Q must agree with the fp32 CUDA-core path."""
+    import smg_b200.synth as synth
+    scene, _, _, sc = scene_inputs
+    masks = np.stack([synth.masked_scene(scene, sc["masks"], [k]) for k in range(2)])
+    hm_s = torch.from_numpy(scene).cuda()
+    hm_m = torch.from_numpy(masks).cuda()
+    H = 640
+    got = {}
+    for prec in ("fp32", "tf32"):
+        net.precision = prec
+        eng = net._engine(4 + 3)
+        q = eng.qforward_maps(0, hm_s, hm_m, MEAN, STD, [0, 1, 2, 3], 16).cpu().numpy()
+        got[prec] = (q, eng.debug_read("conv0", 1, (64, H // 2, H // 2)).cpu(), eng.debug_read("pool0", 1, (64, H // 4, H // 4)).cpu())
+    c_err = float((got["tf32"][1] - got["fp32"][1]).abs().max() / got["fp32"][1].abs().max())
+    p_err = float((got["tf32"][2] - got["fp32"][2]).abs().max() / got["fp32"][2].abs().max())
+    q_err = float(np.abs(got["tf32"][0] - got["fp32"][0]).max() / np.abs(got["fp32"][0]).max())
+    print("tensor-core stem vs fp32: conv0 %.2e pool0 %.2e Q %.2e" % (c_err, p_err, q_err))
+    assert 0 < c_err <= 1e-5 and p_err <= 1e-5      # 3xTF32 split: fp32 accuracy; > 0: the tensor-core kernel really ran
+    assert q_err <= TOL["tf32"]
+    net.precision = "fp32"
+
+
 def test_batched_units_equal_single_calls(scene_inputs):
     """Trainer.forward_batch (G units in one pass) == G independent Trainer.forward calls."""
     import smg_b200.synth as synth
