@@ -215,6 +215,11 @@ conv_umma_tma_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a) {
         // latency is paid once per group, not once per row
         float* obase = a.out + ((size_t)s * hw_out + m0) * a.out_cstride + a.out_coff + ntile * BN + lane;
         const int nrows = min(UM, hw_out - m0);
+        // the statistics ride on the same pass: every lane sums the columns it stores (rows staged as zeros beyond the
+        // sample add nothing), the 14 warp partials are combined in a fixed order -> one double atomic pair per channel
+        float su[BN / 32], sq[BN / 32];
+#pragma unroll
+        for (int cb = 0; cb < BN / 32; ++cb) { su[cb] = 0.f; sq[cb] = 0.f; }
 #pragma unroll
         for (int i0 = 0; i0 < 10; i0 += 5) {
             float x[5][BN / 32];
@@ -227,6 +232,11 @@ conv_umma_tma_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a) {
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
                 const int r = warp + NW * (i0 + i);
+#pragma unroll
+                for (int cb = 0; cb < BN / 32; ++cb) {
+                    su[cb] += x[i][cb];
+                    sq[cb] = fmaf(x[i][cb], x[i][cb], sq[cb]);
+                }
                 if (r < nrows) {
 #pragma unroll
                     for (int cb = 0; cb < BN / 32; ++cb) obase[(size_t)r * a.out_cstride + cb * 32] = x[i][cb];
@@ -234,32 +244,25 @@ conv_umma_tma_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a) {
             }
         }
         if (a.out_stats != nullptr) {
-            constexpr int GROUPS = 448 / BN;
-            constexpr int RPG = (UM + GROUPS - 1) / GROUPS;
-            float* red = s_sc;
-            const int cidx = tid % BN, g = tid / BN;
-            if (g < GROUPS) {
-                float su = 0.f, sq = 0.f;
-                const int r1 = (g + 1) * RPG < UM ? (g + 1) * RPG : UM;
-                for (int r = g * RPG; r < r1; ++r) {
-                    const float x = s_out[r * (BN + 1) + cidx];
-                    su += x;
-                    sq = fmaf(x, x, sq);
-                }
-                red[g * BN + cidx] = su;
-                red[(GROUPS + g) * BN + cidx] = sq;
+            // [2][NW][BN] floats behind the staging tile (the weight stages there are dead by now)
+            float* red = reinterpret_cast<float*>(smem + P::OFF_A + ((P::STAGING + 15) & ~15));
+            static_assert(P::OFF_A + ((P::STAGING + 15) & ~15) + 2 * NW * BN * 4 <= P::USED, "no room for the warp partials");
+#pragma unroll
+            for (int cb = 0; cb < BN / 32; ++cb) {
+                red[warp * BN + cb * 32 + lane] = su[cb];
+                red[(NW + warp) * BN + cb * 32 + lane] = sq[cb];
             }
             __syncthreads();
             if (tid < BN) {
-                double su = 0.0, sq = 0.0;
+                double dsu = 0.0, dsq = 0.0;
 #pragma unroll
-                for (int g2 = 0; g2 < GROUPS; ++g2) {
-                    su += (double)red[g2 * BN + tid];
-                    sq += (double)red[(GROUPS + g2) * BN + tid];
+                for (int w2 = 0; w2 < NW; ++w2) {
+                    dsu += (double)red[w2 * BN + tid];
+                    dsq += (double)red[(NW + w2) * BN + tid];
                 }
                 double* st = a.out_stats + 2 * ((size_t)s * a.out_stats_stride + a.out_coff + ntile * BN + tid);
-                atomicAdd(st, su);
-                atomicAdd(st + 1, sq);
+                atomicAdd(st, dsu);
+                atomicAdd(st + 1, dsq);
             }
         }
     }
