@@ -168,6 +168,11 @@ int smg_argmax(smg_handle* h, const float* dev_q, int n, float* dev_out, int32_t
 int smg_heightmap(smg_handle* h, const double* dev_depth, const double* host_K, const double* host_pose,
                   double* dev_out224, double* dev_out448, double* host_A_htor, void* stream);
 
+/* Colour outputs of the same function (code/utils.py:62,64): cv2.warpPerspective of the uint8 camera image [480,640,3]
+ * with the two transforms above -> color_heightmap [224,224,3] and color_mask [448,448,3] uint8, bit-exact with cv2's
+ * 15-bit fixed-point bilinear remap (consumed by Mask R-CNN / logging, not by the Q pass).                            */
+int smg_heightmap_color(smg_handle* h, const uint8_t* dev_color, uint8_t* dev_out224, uint8_t* dev_out448, void* stream);
+
 /* ---- K12: box NMS (code/NMS.py:8-59) ---------------------------------------------
  * boxes [n,2,2] float32 ((x1,y1),(x2,y2)); keeps index-order greedy survivors.
  * dev_keep [n] int32 receives kept indices, dev_n_keep[0] their count.  n <= 1024.   */

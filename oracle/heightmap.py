@@ -148,6 +148,53 @@ def warp_perspective_f64(src, M, size):
     return out
 
 
+def warp_perspective_u8(src, M, size):
+    """cv2.warpPerspective(src uint8 [h,w,C], M, (size,size)) with INTER_LINEAR / BORDER_CONSTANT(0): same source
+    coordinates as the float path, but cv2's 8-bit remap interpolates in 15-bit fixed point (imgwarp.cpp: BilinearTab_i,
+    FixedPtCast<int, uchar, INTER_REMAP_COEF_BITS>): integer weights (32-ay)(32-ax)*32 ... that sum to 32768, result
+    (sum + 2^14) >> 15.  The entry for ax = ay = 0 would be 32768 and saturates to (32767, 0, 0, 1) in cv2's table
+    (initInterTab2D's sum correction lands on the last tap) - reproduced here although it cannot change an 8-bit result."""
+    Minv = invert3x3(np.asarray(M, dtype=np.float64))
+    h, w = src.shape[:2]
+    ys, xs = np.mgrid[0:size, 0:size].astype(np.float64)
+    X0 = Minv[0, 0] * xs + Minv[0, 1] * ys + Minv[0, 2]
+    Y0 = Minv[1, 0] * xs + Minv[1, 1] * ys + Minv[1, 2]
+    W0 = Minv[2, 0] * xs + Minv[2, 1] * ys + Minv[2, 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s = np.where(W0 != 0, INTER_TAB_SIZE / W0, 0.0)
+    X = np.rint(np.clip(X0 * s, -2147483648.0, 2147483647.0)).astype(np.int64)
+    Y = np.rint(np.clip(Y0 * s, -2147483648.0, 2147483647.0)).astype(np.int64)
+    sx, sy = X >> INTER_BITS, Y >> INTER_BITS
+    ax, ay = X & (INTER_TAB_SIZE - 1), Y & (INTER_TAB_SIZE - 1)
+    w00 = (32 - ay) * (32 - ax) * 32
+    w01 = (32 - ay) * ax * 32
+    w10 = ay * (32 - ax) * 32
+    w11 = ay * ax * 32
+    origin = (ax == 0) & (ay == 0)
+    w00 = np.where(origin, 32767, w00)
+    w11 = np.where(origin, 1, w11)
+
+    def tap(yy, xx):
+        ok = (yy >= 0) & (yy < h) & (xx >= 0) & (xx < w)
+        v = src[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)].astype(np.int64)
+        return np.where(ok[..., None], v, 0)
+
+    acc = (tap(sy, sx) * w00[..., None] + tap(sy, sx + 1) * w01[..., None] + tap(sy + 1, sx) * w10[..., None] +
+           tap(sy + 1, sx + 1) * w11[..., None])
+    return np.clip((acc + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+
+
+def get_heightmap_color(color_img):
+    """Colour outputs of utils.get_heightmap (code/utils.py:62,64): (color_heightmap 224^2, color_mask 448^2) uint8."""
+    hs, cs = HEIGHTMAP_SIZE, COLORMASK_SIZE
+    dst_h = np.array([[0, 0], [0, hs], [hs, hs], [hs, 0]], np.float32)
+    dst_m = np.array([[0, 0], [0, cs], [cs, cs], [cs, 0]], np.float32)
+    A_h = get_perspective_transform(SRC_QUAD, dst_h)
+    A_m = get_perspective_transform(SRC_QUAD, dst_m)
+    img = np.ascontiguousarray(color_img, dtype=np.uint8).reshape(480, 640, 3)
+    return warp_perspective_u8(img, A_h, hs), warp_perspective_u8(img, A_m, cs)
+
+
 def get_heightmap_depth(depth_img, cam_intrinsics, cam_pose):
     """Depth outputs of utils.get_heightmap: (depth_heightmap 224^2, depth_mask 448^2, A_htor)."""
     zw = world_z(np.asarray(depth_img, np.float64), cam_intrinsics, cam_pose).reshape(480, 640)

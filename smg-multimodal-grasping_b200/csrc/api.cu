@@ -1005,6 +1005,12 @@ int smg_argmax(smg_handle* h, const float* dev_q, int n, float* dev_out, int32_t
     return launch_argmax(h, dev_q, n, dev_out, dev_out_idx, (cudaStream_t)stream);
 }
 
+int smg_heightmap_color(smg_handle* h, const uint8_t* dev_color, uint8_t* dev_out224, uint8_t* dev_out448, void* stream) {
+    SMG_CHECK(h && dev_color && dev_out224 && dev_out448, SMG_ERR_INVALID, "smg_heightmap_color: NULL argument");
+    DeviceGuard guard(h->device);
+    return launch_heightmap_color(h, dev_color, dev_out224, dev_out448, (cudaStream_t)stream);
+}
+
 int smg_heightmap(smg_handle* h, const double* dev_depth, const double* host_K, const double* host_pose,
                   double* dev_out224, double* dev_out448, double* host_A_htor, void* stream) {
     SMG_CHECK(h && dev_depth && host_K && host_pose && dev_out224 && dev_out448, SMG_ERR_INVALID, "smg_heightmap: NULL argument");

@@ -70,6 +70,48 @@ __global__ void heightmap_kernel(const double* __restrict__ depth, HmParams p, d
     }
 }
 
+// Colour path (code/utils.py:62,64): cv2.warpPerspective of the uint8 camera image with the same two transforms.  Same
+// source coordinates as above; cv2's 8-bit remap interpolates in 15-bit fixed point (imgwarp.cpp BilinearTab_i +
+// FixedPtCast<int, uchar, 15>): integer weights (32-ay)(32-ax)*32 ... summing to 32768, result (sum + 2^14) >> 15; the
+// table entry for ax = ay = 0 saturates to (32767, 0, 0, 1).  Pinned against cv2 4.13 in tests/test_oracle_golden.py.
+__global__ void heightmap_color_kernel(const uint8_t* __restrict__ color, HmParams p, uint8_t* __restrict__ out224,
+                                       uint8_t* __restrict__ out448) {
+    const int n224 = 224 * 224, n448 = 448 * 448;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n224 + n448; i += gridDim.x * blockDim.x) {
+        const bool small = i < n224;
+        const int size = small ? 224 : 448;
+        const int j = small ? i : i - n224;
+        const double* M = small ? p.minv224 : p.minv448;
+        const int dy = j / size, dx = j - dy * size;
+        const double xs = (double)dx, ys = (double)dy;
+        const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(M[0], xs), __dmul_rn(M[1], ys)), M[2]);
+        const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M[3], xs), __dmul_rn(M[4], ys)), M[5]);
+        const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(M[6], xs), __dmul_rn(M[7], ys)), M[8]);
+        const double sc = W0 != 0.0 ? __ddiv_rn(32.0, W0) : 0.0;
+        double fX = __dmul_rn(X0, sc), fY = __dmul_rn(Y0, sc);
+        fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
+        fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
+        const long long X = __double2ll_rn(fX), Y = __double2ll_rn(fY);
+        const long long sx = X >> 5, sy = Y >> 5;
+        const int ax = (int)(X & 31), ay = (int)(Y & 31);
+        int w00 = (32 - ay) * (32 - ax) * 32, w01 = (32 - ay) * ax * 32, w10 = ay * (32 - ax) * 32, w11 = ay * ax * 32;
+        if (ax == 0 && ay == 0) { w00 = 32767; w11 = 1; }
+        const bool y0 = sy >= 0 && sy < 480, y1 = sy + 1 >= 0 && sy + 1 < 480;
+        const bool x0 = sx >= 0 && sx < 640, x1 = sx + 1 >= 0 && sx + 1 < 640;
+        uint8_t* o = (small ? out224 : out448) + (size_t)j * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int acc = 1 << 14;
+            if (y0 && x0) acc += w00 * color[((int)sy * 640 + (int)sx) * 3 + c];
+            if (y0 && x1) acc += w01 * color[((int)sy * 640 + (int)sx + 1) * 3 + c];
+            if (y1 && x0) acc += w10 * color[(((int)sy + 1) * 640 + (int)sx) * 3 + c];
+            if (y1 && x1) acc += w11 * color[(((int)sy + 1) * 640 + (int)sx + 1) * 3 + c];
+            const int v = acc >> 15;
+            o[c] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    }
+}
+
 // ---- host: cv2.getPerspectiveTransform (8x8 LU with partial pivoting) and cv2.invert (3x3) ----
 // compiled with -ffp-contract=off so the double operations round exactly like numpy / OpenCV's C++.
 static void lu_solve8(double a[8][8], double b[8]) {
@@ -155,6 +197,23 @@ int launch_heightmap(smg_handle* h, const double* depth, const double* K, const 
     if (host_A_htor) perspective_transform(d224, src, host_A_htor);  // code/utils.py:66
     const int total = 224 * 224 + 448 * 448;
     heightmap_kernel<<<(total + 255) / 256, 256, 0, st>>>(depth, p, out224, out448);
+    h->launches++;
+    SMG_CUDA(cudaGetLastError());
+    return SMG_OK;
+}
+
+int launch_heightmap_color(smg_handle* h, const uint8_t* color, uint8_t* out224, uint8_t* out448, cudaStream_t st) {
+    const float src[4][2] = {{110, 0}, {110, 400}, {510, 400}, {510, 0}};
+    const float d224[4][2] = {{0, 0}, {0, 224}, {224, 224}, {224, 0}};
+    const float d448[4][2] = {{0, 0}, {0, 448}, {448, 448}, {448, 0}};
+    double M224[9], M448[9];
+    perspective_transform(src, d224, M224);
+    perspective_transform(src, d448, M448);
+    HmParams p = {};
+    invert3x3(M224, p.minv224);
+    invert3x3(M448, p.minv448);
+    const int total = 224 * 224 + 448 * 448;
+    heightmap_color_kernel<<<(total + 255) / 256, 256, 0, st>>>(color, p, out224, out448);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;

@@ -291,6 +291,7 @@ int launch_argmax(smg_handle* h, const float* q, int n, float* out, int32_t* out
 int launch_nhwc_to_nchw(smg_handle* h, const float* in, int hw, int c, int cstride, float* out, cudaStream_t st);
 
 // K11 / K12
+int launch_heightmap_color(smg_handle* h, const uint8_t* color, uint8_t* out224, uint8_t* out448, cudaStream_t st);
 int launch_heightmap(smg_handle* h, const double* depth, const double* K, const double* pose, double* out224,
                      double* out448, double* host_A_htor, cudaStream_t st);
 int launch_nms(smg_handle* h, const float* boxes, int n, float thr, float amin, float amax, int32_t* keep,

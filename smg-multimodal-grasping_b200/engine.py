@@ -293,6 +293,16 @@ class Engine:
                                           o448.data_ptr(), A.ctypes.data_as(dp), self._stream()))
         return o224, o448, A.reshape(3, 3)
 
+    def heightmap_color(self, color):
+        """color [480,640,3] uint8 -> (color_heightmap [224,224,3], color_mask [448,448,3]) uint8 (cv2 fixed-point remap)."""
+        c = color.to(self.device, torch.uint8).contiguous()
+        if tuple(c.shape) != (480, 640, 3):
+            raise ValueError("heightmap_color expects a [480,640,3] uint8 image, got %s" % (tuple(c.shape),))
+        o224 = torch.empty((224, 224, 3), dtype=torch.uint8, device=self.device)
+        o448 = torch.empty((448, 448, 3), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.smg_heightmap_color(self.h, c.data_ptr(), o224.data_ptr(), o448.data_ptr(), self._stream()))
+        return o224, o448
+
     def nms(self, boxes, co_thresh, min_area, max_area):
         b = boxes.to(self.device, torch.float32).contiguous().view(-1, 4)
         n = b.shape[0]

@@ -17,12 +17,16 @@ def get_heightmap(color_img, depth_img, cam_intrinsics, cam_pose, workspace_limi
     `workspace_limits` / `heightmap_resolution` are accepted and ignored exactly like the reference does.
     The depth outputs (what the Q pass consumes) come from the K11 gather kernel and are bit-identical to the
     reference's numpy + cv2 result.  The two colour warps (consumed only by Mask R-CNN / logging, outside the
-    Q path) are out of scope for round 1 and returned as None.
+    Q path) reproduce cv2's 15-bit fixed-point bilinear remap bit for bit; `color_img=None` skips them (None, None).
     """
     eng = _engine.get_engine(torch.cuda.current_device() if device is None else device)
     d = torch.from_numpy(np.ascontiguousarray(depth_img, dtype=np.float64))
     o224, o448, A = eng.heightmap(d, np.asarray(cam_intrinsics, dtype=np.float64)[:3, :3], np.asarray(cam_pose, dtype=np.float64))
-    return None, o224.cpu().numpy(), None, o448.cpu().numpy(), A
+    c224 = c448 = None
+    if color_img is not None:
+        img = torch.from_numpy(np.ascontiguousarray(color_img, dtype=np.uint8).reshape(480, 640, 3))
+        c224, c448 = (t.cpu().numpy() for t in eng.heightmap_color(img))
+    return c224, o224.cpu().numpy(), c448, o448.cpu().numpy(), A
 
 
 class CrossEntropyLoss2d(nn.Module):

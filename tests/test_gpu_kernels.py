@@ -93,11 +93,21 @@ def test_heightmap_bit_exact(eng, golden):
 
 
 def test_heightmap_dropin_signature(golden):
+    import hashlib
     import smg_b200.synth as synth
     from smg_b200 import utils
     cam = synth.make_camera(golden["heightmap"]["camera_seed"])
     out = utils.get_heightmap(cam["color"], cam["depth"], cam["intrinsics"], cam["pose"], synth.WORKSPACE_LIMITS, 0.002)
     assert len(out) == 5 and out[1].shape == (224, 224) and out[3].shape == (448, 448) and out[1].dtype == np.float64
+    # colour maps: uint8, bit-identical to the reference's cv2.warpPerspective output of the same camera image
+    assert out[0].shape == (224, 224, 3) and out[2].shape == (448, 448, 3) and out[0].dtype == np.uint8
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert sha(out[0]) == golden["heightmap"]["color224_sha"] and sha(out[2]) == golden["heightmap"]["color448_sha"]
+    # and a second image against the oracle restatement, including a saturated / constant one
+    for img in (synth.make_camera(11)["color"], np.full((480, 640, 3), 255, np.uint8)):
+        got = utils.get_heightmap(img, cam["depth"], cam["intrinsics"], cam["pose"], synth.WORKSPACE_LIMITS, 0.002)
+        r224, r448 = ohm.get_heightmap_color(img)
+        assert np.array_equal(got[0], r224) and np.array_equal(got[2], r448)
 
 
 def test_nms_matches_reference_lists(eng, golden):

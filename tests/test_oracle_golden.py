@@ -149,6 +149,10 @@ def test_heightmap_bit_exact(golden):
     assert np.array_equal(A, z["A_htor"])
     assert sha(d224) == golden["heightmap"]["depth224_sha"]
     assert sha(d448) == golden["heightmap"]["depth448_sha"]
+    # colour outputs: cv2's 15-bit fixed-point 8-bit remap, pinned on the reference's own output of the same camera
+    c224, c448 = ohm.get_heightmap_color(cam["color"])
+    assert sha(c224) == golden["heightmap"]["color224_sha"]
+    assert sha(c448) == golden["heightmap"]["color448_sha"]
 
 
 def test_nms_cases(golden):
