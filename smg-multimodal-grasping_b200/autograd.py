@@ -36,7 +36,7 @@ def q_forward_with_grad(model, input_depth_data, m_input_depth_data, style, spec
     """(is_volatile=False, specific_rotation=r): returns a [1,C,1,1] tensor with grad_fn and stores it in
     model.gra_prob / suc_prob / gs_prob like the reference (code/models.py:539,561,584)."""
     rot = 0 if style == 2 else int(specific_rotation)      # ES is pinned to rotation 0 (code/models.py:567)
-    eng = model._engine(2)
+    eng = model._engine(2, style)
     tid, hid = _engine.STYLE_ROUTE[int(style)]
     trunk = getattr(model, _engine.TRUNK_ATTRS[tid])
     head = getattr(model, _engine.HEAD_ATTRS[hid])

@@ -56,6 +56,7 @@ class Engine:
         _lib.check(self.lib.smg_create(self.device.index, self.max_samples, self.H, ctypes.byref(h)))
         self.h = h
         self._sig = {}
+        self._param_lists = {}
         self._staged = {}
         self.set_precision(precision)
 
@@ -97,23 +98,38 @@ class Engine:
         self._staged[key] = out  # keep staged copies alive until the packing kernels ran
         return out
 
-    def sync_weights(self, model, force=False):
-        """Re-pack the model's parameters if they changed (load_state_dict, optimizer step, .cuda())."""
+    def sync_weights(self, model, force=False, style=None):
+        """Re-pack the model's parameters if they changed (load_state_dict, optimizer step, .cuda()).
+        `style` restricts the check to the trunk and head that style routes to (the per-call cost on the inference
+        path: 368 (data_ptr, version) pairs instead of 1104).  The Parameter lists are cached per (model, submodule):
+        torch keeps Parameter identity across .cuda() / load_state_dict / optimizer steps."""
         n_out = 3 if model.__class__.__name__ == "reactive_net" else 1
-        for tid, attr in enumerate(TRUNK_ATTRS):
-            params = trunk_param_list(getattr(model, attr))
-            sig = (id(model), tuple((p.data_ptr(), p._version) for p in params))
-            if force or self._sig.get(("t", tid)) != sig:
-                dev = self._device_params(("t", tid), params)
+        tids, hids = range(len(TRUNK_ATTRS)), range(len(HEAD_ATTRS))
+        if style is not None:
+            t_only, h_only = STYLE_ROUTE[int(style)]
+            tids, hids = (t_only,), (h_only,)
+        for tid in tids:
+            key = ("t", tid)
+            sub = getattr(model, TRUNK_ATTRS[tid])
+            params = self._param_lists.get((id(model), key, id(sub)))
+            if params is None or force:
+                params = self._param_lists[(id(model), key, id(sub))] = trunk_param_list(sub)
+            sig = (id(model), tuple([(p.data_ptr(), p._version) for p in params]))
+            if force or self._sig.get(key) != sig:
+                dev = self._device_params(key, params)
                 _lib.check(self.lib.smg_set_trunk_weights(self.h, tid, _ptr_array(dev), len(dev), self._stream()))
-                self._sig[("t", tid)] = sig
-        for hid, attr in enumerate(HEAD_ATTRS):
-            params = head_param_list(getattr(model, attr))
-            sig = (id(model), tuple((p.data_ptr(), p._version) for p in params))
-            if force or self._sig.get(("h", hid)) != sig:
-                dev = self._device_params(("h", hid), params)
+                self._sig[key] = sig
+        for hid in hids:
+            key = ("h", hid)
+            sub = getattr(model, HEAD_ATTRS[hid])
+            params = self._param_lists.get((id(model), key, id(sub)))
+            if params is None or force:
+                params = self._param_lists[(id(model), key, id(sub))] = head_param_list(sub)
+            sig = (id(model), tuple([(p.data_ptr(), p._version) for p in params]))
+            if force or self._sig.get(key) != sig:
+                dev = self._device_params(key, params)
                 _lib.check(self.lib.smg_set_head_weights(self.h, hid, _ptr_array(dev), n_out, self._stream()))
-                self._sig[("h", hid)] = sig
+                self._sig[key] = sig
         self.n_out = n_out
 
     # ------------------------------------------------------------------ K1

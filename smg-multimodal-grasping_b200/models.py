@@ -75,12 +75,12 @@ class _SmgNet(nn.Module):
             return p.device.index
         return torch.cuda.current_device()
 
-    def _engine(self, n_samples):
+    def _engine(self, n_samples, style=None):
         if getattr(self, "_finalizer_owner", None) != id(self):  # also true for a deepcopy of a live model
             object.__setattr__(self, "_finalizer_owner", id(self))
             weakref.finalize(self, _engine.drop_engine, id(self))
         eng = _engine.get_engine(self._device_index(), max(n_samples, 18), 640, self.precision, owner=id(self))
-        eng.sync_weights(self)
+        eng.sync_weights(self, style=style)
         return eng
 
     def _bn_modules(self, trunk):
@@ -164,7 +164,7 @@ class _SmgNet(nn.Module):
 
     @torch.no_grad()
     def _q(self, scene, mask, style, rots, nrot):
-        eng = self._engine(len(rots) + 1)
+        eng = self._engine(len(rots) + 1, style)
         scene = scene.reshape(3, 640, 640)
         mask = mask.reshape(1, 3, 640, 640)
         if self.update_running_stats:

@@ -95,7 +95,7 @@ class Trainer(object):
         masks = np.ascontiguousarray(np.asarray(m_depth_heightmaps, dtype=np.float64))
         if masks.ndim == 2:
             masks = masks[None]
-        eng = model._engine(len(rots) + masks.shape[0])
+        eng = model._engine(len(rots) + masks.shape[0], style)
         scene = torch.from_numpy(np.ascontiguousarray(depth_heightmap, dtype=np.float64)).to(eng.device, non_blocking=True)
         masks_t = torch.from_numpy(masks).to(eng.device, non_blocking=True)
         if model.update_running_stats:
@@ -126,7 +126,7 @@ class Trainer(object):
         if masks.ndim == 3:
             masks = masks[:, None]
         G, M = masks.shape[0], masks.shape[1]
-        eng = model._engine(G * (len(rots) + M))
+        eng = model._engine(G * (len(rots) + M), style)
         s_t = torch.from_numpy(scenes).to(eng.device, non_blocking=True)
         m_t = torch.from_numpy(masks).to(eng.device, non_blocking=True)
         q = eng.qforward_maps_batch(style, s_t, m_t, self.image_mean, self.image_std, rots, nrot)
