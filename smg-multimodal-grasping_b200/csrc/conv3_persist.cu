@@ -117,7 +117,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
         if (lane == 0) {
             mbar_arrive_expect_tx(w_full, P::WBYTES);
             for (int i = 0; i < 12; ++i) tma_bulk_load(sW + i * 12288, a.w + (size_t)i * 12288, 12288, w_full);   // 12 x 12 KB = 144 KB
-            const int pd = a.tiles_per_cta;   // L2 prefetch distance in patch loads (0 = off)
+            const int pd = a.l2_prefetch;     // L2 prefetch distance in patch loads (0 = off)
             for (int n = 0; n < pd && n < P::NG * ntiles; ++n) {
                 const TileCoord c = coord(tile_begin + n / P::NG);
                 tma_prefetch_4d(&tmA, (n % P::NG) * P::KCH, c.w0 - 1, c.h0 - 1, c.s);
@@ -355,7 +355,8 @@ int launch_conv3_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     const int wt = d.wp - 2;
     d.tiles_x = (d.hout + wt - 1) / wt;
     d.tiles_per_sample = d.tiles_x * ((d.hout + d.ht - 1) / d.ht);
-    d.tiles_per_cta = h->l2_prefetch;   // re-used field: L2 prefetch distance of the loader
+    d.tiles_per_cta = 0;
+    d.l2_prefetch = h->l2_prefetch;
     d.async_producer = 0;
     const int total = d.tiles_per_sample * a.n;
 

@@ -152,6 +152,8 @@ struct UmmaDev {
     int async_producer;
     // multi-tile kernel (conv_umma_mt.cu): tiles of one sample, tiles walked by one CTA
     int tiles_per_sample, tiles_per_cta;
+    // persistent kernels: how many TMA boxes ahead of its shared-memory ring the loader prefetches into L2 (0 = off)
+    int l2_prefetch = 0;
 };
 
 constexpr int UM = 128;         // rows per tile (UMMA M)
