@@ -4,6 +4,8 @@
 //   pattern 0: 1x1 conv operand   - tensor [17][25600][256] fp32, box 32 ch x 128 px (128 rows of 128 B, 1 KB apart), 6 K groups
 //   pattern 1: 3x3 conv patch     - tensor [17][160][160][128] fp32, box 32 ch x 42 x 5 (210 rows of 128 B, 512 B apart), 4 groups
 //   pattern 2: contiguous bulk    - cp.async.bulk of 16 KB linear chunks (upper bound of the copy engine)
+//   pattern 3/4: stem patches     - tensor [72][640][640], box 40 (64) x 21 floats, no swizzle
+//   pattern 5: pattern 0 + 96 threads per CTA writing the layer's 128-channel fp32 output (read : write = 768 : 512 B per pixel)
 #include <cstdio>
 #include <cstdint>
 #include <cuda.h>
@@ -34,6 +36,14 @@ __global__ void __launch_bounds__(128, 1) tma_kernel(const __grid_constant__ CUt
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (PATTERN == 5 && threadIdx.x >= 32) {
+        // writers: 96 threads stream the 1x1 layer's output (128 channels fp32 per pixel) of the tiles this CTA "processes"
+        const int b0 = (int)(((long long)blockIdx.x * total_boxes) / gridDim.x);
+        const int b1 = (int)(((long long)(blockIdx.x + 1) * total_boxes) / gridDim.x);
+        float4* outp = reinterpret_cast<float4*>(const_cast<float*>(base)) + (size_t)17 * 25600 * 256 / 4;   // second half of the buffer
+        for (int t = b0 / 6; t < b1 / 6; ++t)
+            for (int i = threadIdx.x - 32; i < 128 * 32; i += 96) outp[(size_t)t * 128 * 32 + i] = make_float4(1.f, 2.f, 3.f, 4.f);
+    }
     if (threadIdx.x == 0) {
         const int b0 = (int)(((long long)blockIdx.x * total_boxes) / gridDim.x);
         const int b1 = (int)(((long long)(blockIdx.x + 1) * total_boxes) / gridDim.x);
@@ -41,7 +51,7 @@ __global__ void __launch_bounds__(128, 1) tma_kernel(const __grid_constant__ CUt
             const int n = i - b0, slot = n % ns;
             if (n >= ns) mbar_wait(&bars[slot], ((n / ns) - 1) & 1);
             uint8_t* dst = smem + (size_t)slot * slot_bytes;
-            if (PATTERN == 0) {
+            if (PATTERN == 0 || PATTERN == 5) {
                 const int kg = i % 6, tile = i / 6, s = tile / 200, mt = tile % 200;
                 mbar_expect(&bars[slot], 16384);
                 asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
@@ -56,7 +66,7 @@ __global__ void __launch_bounds__(128, 1) tma_kernel(const __grid_constant__ CUt
                 const int tile = i, s = tile / 800, r = tile % 800, ty = r / 20, tx = r % 20;
                 mbar_expect(&bars[slot], bw * 21 * 4);
                 asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
-                             "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(&tm)), "r"(tx * 32 - 3), "r"(ty * 16 - 3), "r"(s), "r"(smem_u32(&bars[slot])) : "memory");
+                             "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(&tm)), "r"(tx * 32 - 4), "r"(ty * 16 - 3), "r"(s), "r"(smem_u32(&bars[slot])) : "memory");
             } else {
                 mbar_expect(&bars[slot], 16384);
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
@@ -80,7 +90,7 @@ int main() {
     EncodeTiledFn enc = (EncodeTiledFn)fp;
     const size_t bytes = (size_t)17 * 25600 * 256 * 4;
     float* d;
-    cudaMalloc(&d, bytes);
+    cudaMalloc(&d, bytes + (size_t)17 * 25600 * 128 * 4);
     cudaMemset(d, 0, bytes);
     CUtensorMap tm3, tm4;
     const cuuint32_t es[4] = {1, 1, 1, 1};
@@ -107,6 +117,7 @@ int main() {
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         printf("encode stem box %d: %d\n", v, (int)r);
     }
+    cudaFuncSetAttribute(tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -116,18 +127,19 @@ int main() {
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     printf("pattern,stages_in_flight,box_bytes,total_MB,us,GB_per_s,GB_per_s_per_SM\n");
-    for (int pat = 0; pat < 5; ++pat)
+    for (int pat = 0; pat < 6; ++pat)
         for (int ns : {2, 3, 4, 6, 8, 12}) {
-            if (pat >= 3 && ns != 4) continue;
-            const int slot = pat == 1 ? 27 * 1024 : (pat >= 3 ? 5376 : 16 * 1024);
+            if ((pat == 3 || pat == 4) && ns != 4) continue;
+            const int slot = pat == 1 ? 27 * 1024 : ((pat == 3 || pat == 4) ? 5376 : 16 * 1024);
             if ((size_t)ns * slot > 220 * 1024) continue;
-            const int total = pat == 0 ? 17 * 200 * 6 : (pat == 1 ? 17 * 216 * 4 : (pat >= 3 ? 800 * 72 : (int)(bytes / 16384 / 4)));
-            const double box_bytes = pat == 1 ? 210 * 128 : (pat == 3 ? 40 * 21 * 4 : (pat == 4 ? 64 * 21 * 4 : 16384));
+            const int total = (pat == 0 || pat == 5) ? 17 * 200 * 6 : (pat == 1 ? 17 * 216 * 4 : ((pat == 3 || pat == 4) ? 800 * 72 : (int)(bytes / 16384 / 4)));
+            const double box_bytes = pat == 5 ? 16384 + 65536.0 / 6 : pat == 1 ? 210 * 128 : (pat == 3 ? 40 * 21 * 4 : (pat == 4 ? 64 * 21 * 4 : 16384));
             float ms = 0;
             for (int rep = 0; rep < 3; ++rep) {
                 cudaEventRecord(e0);
                 if (pat == 0) tma_kernel<0><<<148, 128, ns * slot>>>(tm3, d, ns, total, slot);
                 else if (pat == 1) tma_kernel<1><<<148, 128, ns * slot>>>(tm4, d, ns, total, slot);
+                else if (pat == 5) tma_kernel<5><<<148, 128, ns * slot>>>(tm3, d, ns, total, slot);
                 else if (pat == 3) tma_kernel<3><<<148, 128, ns * slot>>>(tmS40, d, ns, total, slot);
                 else if (pat == 4) tma_kernel<4><<<148, 128, ns * slot>>>(tmS64, d, ns, total, slot);
                 else tma_kernel<2><<<148, 128, ns * slot>>>(tm3, d, ns, total, slot);

@@ -72,6 +72,10 @@ static int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
             const int status = launch_conv1_persist(h, a, st);
             if (status != SMG_ERR_UNSUPPORTED) return status;
         }
+        if (a.taps == 1 && (h->use_tma & 32)) {
+            const int status = launch_conv_umma_ts(h, a, st);
+            if (status != SMG_ERR_UNSUPPORTED) return status;
+        }
         if (a.taps == 1 && (h->use_tma & 1)) {
             const int status = launch_conv_umma_tma(h, a, st);
             if (status != SMG_ERR_UNSUPPORTED) return status;

@@ -144,10 +144,11 @@ struct smg_handle {
     int pack_mask = 15;            // weight layouts written by smg_set_*_weights (SMG_PACK_*)
     void* job_buf = nullptr;       // device table for the batched weight packer
     size_t job_bytes = 0;
-    int use_tma = 23;              // tuning bit mask, tf32 layers with tensor-map TMA activations: 1 = 1x1, 2 = one-tile 3x3
+    int use_tma = 55;              // tuning bit mask, tf32 layers with tensor-map TMA activations: 1 = 1x1, 2 = one-tile 3x3
                                    // (conv_umma_tma.cu), 4 = persistent 3x3 with resident weights (conv3_persist.cu),
                                    // 8 = persistent 1x1 (conv1_persist.cu; opt-in: measured 2 % slower than the one-tile 1x1 kernel),
-                                   // 16 = tensor-core 7x7 stem for identical input channels (stem_umma.cu)
+                                   // 16 = tensor-core 7x7 stem for identical input channels (stem_umma.cu),
+                                   // 32 = 1x1 with the activation operand in tensor memory (conv_umma_ts.cu; needs bit 0 as fallback)
     int conv3_slot_channels = 32;  // tuning: channels per patch slot of conv3_persist.cu (32: 3 slots, 128-byte swizzle; 16: 6 slots, 64-byte)
     int l2_prefetch = 0;           // tuning: how many TMA boxes ahead of its shared-memory ring a persistent loader prefetches into L2
     int tiles_per_cta = 0;         // tuning: 0 auto, 1 one-tile kernel only, >1 fixed tiles per CTA for the multi-tile kernel
@@ -276,6 +277,7 @@ int launch_conv_umma(smg_handle* h, const ConvArgs& a, int precision, cudaStream
 int launch_conv_umma_mt(smg_handle* h, const ConvArgs& a, int precision, int tiles_per_cta, cudaStream_t st);
 int launch_conv_umma_tma(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv3_umma_tma(smg_handle* h, const ConvArgs& a, cudaStream_t st);
+int launch_conv_umma_ts(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv3_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv1_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 
