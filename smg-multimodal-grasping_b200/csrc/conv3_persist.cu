@@ -60,7 +60,7 @@ struct TileCoord {
 
 template <int PKC>
 __global__ void __launch_bounds__(448, 1)
-conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int total_tiles) {
+conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int total_tiles, long long* __restrict__ trace) {
     using P = P3<PKC>;
     constexpr int NS = P::NSLOT;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -89,6 +89,10 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
     const int tile_begin = (int)(((long long)blockIdx.x * total_tiles) / gridDim.x);
     const int tile_end = (int)(((long long)(blockIdx.x + 1) * total_tiles) / gridDim.x);
     const int ntiles = tile_end - tile_begin;
+    // optional timeline of CTA 0 (SMG_CONV3_TRACE): trace[event][index], clock64 stamps of the first 64 slot uses / tiles
+    auto stamp = [&](int event, int idx) {
+        if (trace != nullptr && blockIdx.x == 0 && idx < 64) trace[event * 64 + idx] = clock64();
+    };
     auto coord = [&](int tile) {
         TileCoord c;
         c.s = tile / tps;
@@ -131,6 +135,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 }
                 const TileCoord c = coord(tile_begin + n / P::NG);
                 mbar_wait_sleep(&a_empty[slot], ((n / NS) & 1) ^ 1, 64);
+                stamp(0, n);   // slot free, load issued
                 mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)(pfill * P::ROWB));
                 tma_tile_4d(sA + slot * P::SLOT, &tmA, (n % P::NG) * P::KCH, c.w0 - 1, c.h0 - 1, c.s, &raw_full[slot]);
             }
@@ -191,6 +196,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
             const float4 sc = *reinterpret_cast<const float4*>(s_sc + g * P::KCH + chunk * 4);
             const float4 sh = *reinterpret_cast<const float4*>(s_sh + g * P::KCH + chunk * 4);
             mbar_wait_sleep(&raw_full[slot], (n / NS) & 1, 64);
+            if (ptid == 0) stamp(1, n);   // patch landed
             uint8_t* base = sA + slot * P::SLOT + rbase * P::ROWB + j * 16;
             float4 x[NI];
 #pragma unroll
@@ -208,6 +214,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
             }
             fence_proxy_async();
             mbar_arrive(&a_ready[slot]);
+            if (ptid == 0) stamp(2, n);   // this thread's part of the patch normalised
         }
     } else if (warp == 8) {
         // =============================== MMA issuer ===============================
@@ -227,6 +234,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                     const int slot = n % NS;
                     mbar_wait(&a_ready[slot], (n / NS) & 1);
                     tc_fence_after();
+                    stamp(3, n);   // MMA issue starts
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
                         // kernel row dy = a shift of dy*wp patch rows = +64 B per row on the start address; the swizzle
@@ -242,6 +250,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                         }
                     }
                     umma_commit(&a_empty[slot]);
+                    stamp(4, n);   // MMAs of the slot issued
                 }
                 umma_commit(&tmem_full[buf]);
             }
@@ -272,6 +281,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
             const bool valid = ri < a.ht && rj < wp - 2 && c.h0 + ri < hout && c.w0 + rj < hout;
             mbar_wait_sleep(&tmem_full[buf], (it >> 1) & 1, 128);
             tc_fence_after();
+            if (e == 0 && lane == 0) stamp(5, it);   // accumulator complete
             float v[32], e1[32], e2[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(buf * 128);
             tmem_ld32(taddr, v);
@@ -321,6 +331,7 @@ conv3_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 acc_su += (double)warp_transpose_sum(v, lane);     // lane = channel
                 acc_ss += (double)warp_transpose_sum(sq, lane);
             }
+            if (e == 0 && lane == 0) stamp(6, it);   // tile drained
         }
         if (cur_s >= 0) flush(cur_s);
     }
@@ -374,10 +385,28 @@ int launch_conv3_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
         attr = true;
     }
     const int grid = total < h->num_sms ? total : h->num_sms;
-    if (small) conv3_persist_kernel<16><<<grid, 448, P3<16>::TOTAL, st>>>(tm, d, total);
-    else conv3_persist_kernel<32><<<grid, 448, P3<32>::TOTAL, st>>>(tm, d, total);
+    // debugging aid: SMG_CONV3_TRACE=<file> appends the clock64 timeline of CTA 0 of every launch (synchronises!)
+    static const char* trace_path = getenv("SMG_CONV3_TRACE");
+    static long long* trace_dev = nullptr;
+    if (trace_path != nullptr && trace_dev == nullptr) SMG_CUDA(cudaMalloc(&trace_dev, 7 * 64 * sizeof(long long)));
+    if (trace_dev != nullptr) SMG_CUDA(cudaMemsetAsync(trace_dev, 0, 7 * 64 * sizeof(long long), st));
+    if (small) conv3_persist_kernel<16><<<grid, 448, P3<16>::TOTAL, st>>>(tm, d, total, trace_dev);
+    else conv3_persist_kernel<32><<<grid, 448, P3<32>::TOTAL, st>>>(tm, d, total, trace_dev);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
+    if (trace_dev != nullptr) {
+        long long host[7 * 64];
+        SMG_CUDA(cudaMemcpyAsync(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost, st));
+        SMG_CUDA(cudaStreamSynchronize(st));
+        if (FILE* f = fopen(trace_path, "a")) {
+            fprintf(f, "launch hin=%d n=%d total_tiles=%d grid=%d\n", a.hin, a.n, total, grid);
+            for (int e = 0; e < 7; ++e) {
+                for (int i = 0; i < 64; ++i) fprintf(f, "%lld ", host[e * 64 + i]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     return SMG_OK;
 }
 
