@@ -84,6 +84,23 @@ __global__ void pack_umma_dx_kernel(const float* __restrict__ w, float* __restri
     }
 }
 
+// 3x3, tf32: [column block][dx*cout + co][16], column = ((g*3 + dy)*4 + k)*8 + e, for the weights-in-tensor-memory kernel
+__global__ void pack_umma_t_kernel(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int k_offset,
+                                   int k_total) {
+    const int total = 9 * cin * cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int rows = 3 * cout;
+        const int c_in = i % 16, row = (i / 16) % rows, c16 = i / (16 * rows);
+        int r = c16 * 16 + c_in;
+        const int e = r % 8; r /= 8;
+        const int k = r % 4; r /= 4;
+        const int dy = r % 3; r /= 3;
+        const int g = r;
+        const int dx = row / cout, co = row - dx * cout, ci = g * 32 + k * 8 + e;
+        out[i] = w[((size_t)co * k_total + k_offset + ci) * 9 + dy * 3 + dx];
+    }
+}
+
 // ---- batched variant: one launch packs every convolution of a trunk (blockIdx.y = job) ----
 __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
     const PackJob j = jobs[blockIdx.y];
@@ -113,6 +130,19 @@ __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
                 const float val = j.src[((size_t)co * j.k_total + j.k_off + ci) * 9 + dy * 3 + dx];
                 if (v == 0) j.tf32_dx[i] = val;
                 else j.tf32_dx32[i] = val;
+            }
+            if (j.tf32_t != nullptr) {
+                // [column block c16][row = dx*cout + co][16]: column ((g*3 + dy)*4 + k)*8 + e, cin = g*32 + k*8 + e (conv3_wt.cu:
+                // weights in tensor memory; a warp reads 2 KB contiguous per column block)
+                const int rows = 3 * j.cout;
+                const int c_in = i % 16, row = (i / 16) % rows, c16 = i / (16 * rows);
+                int r = c16 * 16 + c_in;
+                const int e = r % 8; r /= 8;
+                const int k = r % 4; r /= 4;
+                const int dy = r % 3; r /= 3;
+                const int g = r;
+                const int dx = row / j.cout, co = row - dx * j.cout, ci = g * 32 + k * 8 + e;
+                j.tf32_t[i] = j.src[((size_t)co * j.k_total + j.k_off + ci) * 9 + dy * 3 + dx];
             }
         }
 #pragma unroll
@@ -144,6 +174,7 @@ PackJob make_pack_job(const float* w_oihw, const ConvW& cw, int k_offset, int k_
     j.src = w_oihw; j.ffma = cw.w_ffma; j.tf32 = reinterpret_cast<float*>(cw.w_tf32);
     j.tf32_dx = reinterpret_cast<float*>(cw.w_tf32_dx);
     j.tf32_dx32 = reinterpret_cast<float*>(cw.w_tf32_dx32);
+    j.tf32_t = reinterpret_cast<float*>(cw.w_tf32_t);
     j.bf16 = reinterpret_cast<__nv_bfloat16*>(cw.w_bf16); j.dgrad = cw.w_dgrad;
     j.cin = cw.cin; j.cout = cw.cout; j.taps = cw.taps; j.k_off = k_offset; j.k_total = k_total;
     j.bn = cw.taps == 9 ? 32 : (cw.cout < 128 ? cw.cout : 128);
@@ -197,6 +228,11 @@ int pack_conv_weights(smg_handle* h, const float* w_oihw, ConvW& cw, int k_offse
         pack_umma_dx_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_tf32_dx32), cw.cout, cw.cin, k_offset,
                                                         k_total, 32);
         h->launches += 2;
+        if (cw.w_tf32_t != nullptr) {
+            pack_umma_t_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_tf32_t), cw.cout, cw.cin, k_offset,
+                                                           k_total);
+            h->launches++;
+        }
     }
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;
