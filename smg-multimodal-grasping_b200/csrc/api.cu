@@ -72,6 +72,10 @@ static int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
             const int status = launch_conv1_persist(h, a, st);
             if (status != SMG_ERR_UNSUPPORTED) return status;
         }
+        if (a.taps == 1 && (h->use_tma & 128)) {
+            const int status = launch_conv1_t(h, a, st);
+            if (status != SMG_ERR_UNSUPPORTED) return status;
+        }
         if (a.taps == 1 && (h->use_tma & 32)) {
             const int status = launch_conv_umma_ts(h, a, st);
             if (status != SMG_ERR_UNSUPPORTED) return status;
@@ -308,9 +312,10 @@ static void plan_conv(ArenaPlanner& p, ConvW& cw, int cin, int cout, int taps, u
     const size_t o4 = p.take(conv_packed_bytes_ffma(cin, cout, taps));
     const size_t o5 = taps == 9 ? p.take(conv_packed_bytes_umma(cin, cout, taps, 4)) : 0;
     const size_t o6 = taps == 9 ? p.take(conv_packed_bytes_umma(cin, cout, taps, 4)) : 0;
-    const size_t o7 = taps == 9 ? p.take(conv_packed_bytes_umma(cin, cout, taps, 4)) : 0;
+    const bool has_t = taps == 9 || (taps == 1 && cout == 128);
+    const size_t o7 = has_t ? p.take(conv_packed_bytes_umma(cin, cout, taps, 4)) : 0;
     if (base) {
-        if (taps == 9) cw.w_tf32_t = base + o7;
+        if (has_t) cw.w_tf32_t = base + o7;
         if (taps == 9) cw.w_tf32_dx = base + o5;
         if (taps == 9) cw.w_tf32_dx32 = base + o6;
         cw.w_ffma = reinterpret_cast<float*>(base + o1);

@@ -45,7 +45,7 @@ struct Tile1 {
 
 template <bool RES>
 __global__ void __launch_bounds__(Q_THREADS, 1)
-conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int total_tiles, int n_samples) {
+conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int total_tiles, int n_samples, long long* __restrict__ trace) {
     constexpr int BN = 128;
     using Q = Q1<RES>;
     constexpr int Q_NA = Q::NA, Q_NB = Q::NB;
@@ -72,6 +72,10 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
     const int tile_begin = (int)(((long long)blockIdx.x * total_tiles) / gridDim.x);
     const int tile_end = (int)(((long long)(blockIdx.x + 1) * total_tiles) / gridDim.x);
     const int ntiles = tile_end - tile_begin;
+    // optional timeline of CTA 0 (SMG_CONV3_TRACE): trace[event][index], clock64 stamps of the first 64 stages / tiles
+    auto stamp = [&](int event, int idx) {
+        if (trace != nullptr && blockIdx.x == 0 && idx < 64) trace[event * 64 + idx] = clock64();
+    };
     auto coord = [&](int tile) {
         Tile1 c;
         const int per_nt = tps * n_samples;
@@ -112,6 +116,7 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
             while (qa < total_stages || qb < total_stages) {
                 if (qa < total_stages && mbar_test(&a_empty[qa % Q_NA], ((qa / Q_NA) & 1) ^ 1)) {
                     const int slot = qa % Q_NA;
+                    stamp(0, qa);
                     mbar_arrive_expect_tx(&raw_full[slot], Q_STAGE);
                     tma_tile_3d(sA + slot * Q_STAGE, &tmA, ka * KC, ca.m0, ca.s, &raw_full[slot]);
                     ++qa;
@@ -177,6 +182,7 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 const float4 sc = *reinterpret_cast<const float4*>(s_sc + kg * KC + chunk * 4);
                 const float4 sh = *reinterpret_cast<const float4*>(s_sh + kg * KC + chunk * 4);
                 mbar_wait_sleep(&raw_full[slot], (q / Q_NA) & 1, 64);
+                if (gt == 0) stamp(1, q);
                 uint8_t* base = sA + slot * Q_STAGE + rbase * 128 + j * 16;
                 float4 x[8];
 #pragma unroll
@@ -192,6 +198,7 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 }
                 fence_proxy_async();
                 mbar_arrive(&a_ready[slot]);
+                if (gt == 0) stamp(2, q);
             }
         }
     } else if (warp == 8) {
@@ -211,6 +218,7 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                 for (int kg = 0; kg < KG; ++kg, ++q) {
                     const int sa = q % Q_NA, sb = RES ? kg : q % Q_NB;
                     mbar_wait(&a_ready[sa], (q / Q_NA) & 1);
+                    stamp(3, q);
                     if (!RES) mbar_wait(&b_full[sb], (q / Q_NB) & 1);
                     tc_fence_after();
 #pragma unroll
@@ -221,6 +229,7 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                         accum = 1;
                     }
                     umma_commit(&a_empty[sa]);
+                    stamp(4, q);
                     if (!RES) umma_commit(&b_empty[sb]);
                 }
                 umma_commit(&t_full[buf]);
@@ -257,6 +266,7 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
             float* orow = a.out + ((size_t)c.s * hw_out + c.m0 + row) * a.out_cstride + a.out_coff + c.nt * BN;
             mbar_wait_sleep(&t_full[eg], (it >> 1) & 1, 128);
             tc_fence_after();
+            if (e == 0 && lane == 0) stamp(5, it);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float v[32];
@@ -283,6 +293,7 @@ conv1_persist_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int tot
                     acc_ss[k] += (double)warp_transpose_sum(sq, lane);
                 }
             }
+            if (e == 0 && lane == 0) stamp(6, it);
         }
         if (cur_s >= 0) flush(cur_s, cur_nt);
     }
@@ -330,12 +341,29 @@ int launch_conv1_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
         attr = true;
     }
     const int grid = total < h->num_sms ? total : h->num_sms;
-    if (a.cout == 128 && a.cin / KC <= Q_RES_MAX)
-        conv1_persist_kernel<true><<<grid, Q_THREADS, Q1<true>::TOTAL, st>>>(tm, d, total, a.n);
-    else
-        conv1_persist_kernel<false><<<grid, Q_THREADS, Q1<false>::TOTAL, st>>>(tm, d, total, a.n);
+    // debugging aid: SMG_CONV1_TRACE=<file> appends the clock64 timeline of CTA 0 of every launch (synchronises!)
+    static const char* trace_path = getenv("SMG_CONV1_TRACE");
+    static long long* trace_dev = nullptr;
+    if (trace_path != nullptr && trace_dev == nullptr) SMG_CUDA(cudaMalloc(&trace_dev, 7 * 64 * sizeof(long long)));
+    if (trace_dev != nullptr) SMG_CUDA(cudaMemsetAsync(trace_dev, 0, 7 * 64 * sizeof(long long), st));
+    const bool res = a.cout == 128 && a.cin / KC <= Q_RES_MAX;
+    if (res) conv1_persist_kernel<true><<<grid, Q_THREADS, Q1<true>::TOTAL, st>>>(tm, d, total, a.n, trace_dev);
+    else conv1_persist_kernel<false><<<grid, Q_THREADS, Q1<false>::TOTAL, st>>>(tm, d, total, a.n, trace_dev);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
+    if (trace_dev != nullptr) {
+        long long host[7 * 64];
+        SMG_CUDA(cudaMemcpyAsync(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost, st));
+        SMG_CUDA(cudaStreamSynchronize(st));
+        if (FILE* f = fopen(trace_path, "a")) {
+            fprintf(f, "launch hin=%d n=%d cin=%d resident=%d total_tiles=%d grid=%d\n", a.hin, a.n, a.cin, (int)res, total, grid);
+            for (int e = 0; e < 7; ++e) {
+                for (int i = 0; i < 64; ++i) fprintf(f, "%lld ", host[e * 64 + i]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     return SMG_OK;
 }
 

@@ -101,6 +101,15 @@ __global__ void pack_umma_t_kernel(const float* __restrict__ w, float* __restric
     }
 }
 
+// 1x1, cout = 128, tf32: [cin/16][128 rows][16] for conv1_t.cu
+__global__ void pack_umma_t1_kernel(const float* __restrict__ w, float* __restrict__ out, int cin, int k_offset, int k_total) {
+    const int total = cin * 128;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c_in = i % 16, row = (i / 16) % 128, c16 = i / (16 * 128);
+        out[i] = w[(size_t)row * k_total + k_offset + c16 * 16 + c_in];
+    }
+}
+
 // ---- batched variant: one launch packs every convolution of a trunk (blockIdx.y = job) ----
 __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
     const PackJob j = jobs[blockIdx.y];
@@ -144,6 +153,11 @@ __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
                 const int dx = row / j.cout, co = row - dx * j.cout, ci = g * 32 + k * 8 + e;
                 j.tf32_t[i] = j.src[((size_t)co * j.k_total + j.k_off + ci) * 9 + dy * 3 + dx];
             }
+        }
+        if ((mask & SMG_PACK_TF32) && j.taps == 1 && j.cout == 128 && j.tf32_t != nullptr) {
+            // [cin/16][128 rows][16]: the [cout][cin] matrix in 16-column blocks (conv1_t.cu: weights as the A operand)
+            const int c_in = i % 16, row = (i / 16) % 128, c16 = i / (16 * 128);
+            j.tf32_t[i] = j.src[(size_t)row * j.k_total + j.k_off + c16 * 16 + c_in];
         }
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
@@ -222,6 +236,10 @@ int pack_conv_weights(smg_handle* h, const float* w_oihw, ConvW& cw, int k_offse
                                                                 cw.cout, cw.cin, cw.taps, k_offset, k_total, bn);
     pack_dgrad_kernel<<<blocks, threads, 0, st>>>(w_oihw, cw.w_dgrad, cw.cout, cw.cin, cw.taps, k_offset, k_total);
     h->launches += 4;
+    if (cw.taps == 1 && cw.cout == 128 && cw.w_tf32_t != nullptr) {
+        pack_umma_t1_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_tf32_t), cw.cin, k_offset, k_total);
+        h->launches++;
+    }
     if (cw.taps == 9 && cw.w_tf32_dx != nullptr) {
         pack_umma_dx_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_tf32_dx), cw.cout, cw.cin, k_offset,
                                                         k_total, 16);

@@ -71,7 +71,8 @@ struct ConvW {
     // (conv3_persist.cu)
     uint8_t* w_tf32_dx = nullptr;
     uint8_t* w_tf32_dx32 = nullptr;
-    // 3x3 only, tf32, for the weights-in-tensor-memory kernel (conv3_wt.cu): [column block of 16][dx*32 + cout][16], column = ((g*3 + dy)*4 + k)*8 + e
+    // tf32, weights as the A operand in tensor memory: 1x1 with cout = 128 (conv1_t.cu): [cin/16][128][16] = w[row][16 c16 + c];
+    // 3x3 (conv3_wt.cu): [column block of 16][dx*32 + cout][16], column = ((g*3 + dy)*4 + k)*8 + e
     uint8_t* w_tf32_t = nullptr;   // same with 32-channel groups: [kgroup][dy][chunk (8)][dx*32 + cout][4]
     uint8_t* w_bf16 = nullptr;
     // data-gradient weights for the fp32 kernels, in the same [taps][K][N] layout with the roles swapped:
@@ -146,12 +147,13 @@ struct smg_handle {
     int pack_mask = 15;            // weight layouts written by smg_set_*_weights (SMG_PACK_*)
     void* job_buf = nullptr;       // device table for the batched weight packer
     size_t job_bytes = 0;
-    int use_tma = 119;              // tuning bit mask, tf32 layers with tensor-map TMA activations: 1 = 1x1, 2 = one-tile 3x3
+    int use_tma = 247;              // tuning bit mask, tf32 layers with tensor-map TMA activations: 1 = 1x1, 2 = one-tile 3x3
                                    // (conv_umma_tma.cu), 4 = persistent 3x3 with resident weights (conv3_persist.cu),
                                    // 8 = persistent 1x1 (conv1_persist.cu; opt-in: measured 2 % slower than the one-tile 1x1 kernel),
                                    // 16 = tensor-core 7x7 stem for identical input channels (stem_umma.cu),
                                    // 32 = 1x1 with the activation operand in tensor memory (conv_umma_ts.cu; needs bit 0 as fallback),
-                                   // 64 = 3x3 with the weights resident in tensor memory (conv3_wt.cu)
+                                   // 64 = 3x3 with the weights resident in tensor memory (conv3_wt.cu),
+                                   // 128 = persistent 1x1 with swapped operand roles, weights in tensor memory for cin <= 256 (conv1_t.cu)
     int conv3_slot_channels = 32;  // tuning: channels per patch slot of conv3_persist.cu (32: 3 slots, 128-byte swizzle; 16: 6 slots, 64-byte)
     int l2_prefetch = 0;           // tuning: how many TMA boxes ahead of its shared-memory ring a persistent loader prefetches into L2
     int tiles_per_cta = 0;         // tuning: 0 auto, 1 one-tile kernel only, >1 fixed tiles per CTA for the multi-tile kernel
@@ -284,6 +286,7 @@ int launch_conv_umma_ts(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv3_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv1_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv3_wt(smg_handle* h, const ConvArgs& a, cudaStream_t st);
+int launch_conv1_t(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 
 // head
 int launch_head_prepare(smg_handle* h, int n, const double* stats4, int stats_stride, const BnP& norm5,
