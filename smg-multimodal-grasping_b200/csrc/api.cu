@@ -66,12 +66,9 @@ static int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     ProfScope ps(h, st, a.taps == 9 ? 2 : 1, 2.0 * px * a.cout * a.cin * a.taps, bytes);
     if (h->precision == SMG_PREC_FP32) return launch_conv_ffma(h, a, st);
     // tf32: activations fetched by tensor-map TMA (conv_umma_tma.cu; SMG_TMA bit 0 = 1x1 layers, bit 1 = one-tile 3x3, bit 2 = persistent 3x3 of conv3_persist.cu,
-    // bit 3 = persistent 1x1 of conv1_persist.cu)
+    // bit 4 = tensor-core stem, bit 5 = 1x1 with the operand in tensor memory, bit 6 = 3x3 with the weights in tensor memory,
+    // bit 7 = persistent 1x1 with swapped operand roles)
     if (h->precision == SMG_PREC_TF32 && !a.pool) {
-        if (a.taps == 1 && (h->use_tma & 8)) {
-            const int status = launch_conv1_persist(h, a, st);
-            if (status != SMG_ERR_UNSUPPORTED) return status;
-        }
         if (a.taps == 1 && (h->use_tma & 128)) {
             const int status = launch_conv1_t(h, a, st);
             if (status != SMG_ERR_UNSUPPORTED) return status;

@@ -149,7 +149,7 @@ struct smg_handle {
     size_t job_bytes = 0;
     int use_tma = 247;              // tuning bit mask, tf32 layers with tensor-map TMA activations: 1 = 1x1, 2 = one-tile 3x3
                                    // (conv_umma_tma.cu), 4 = persistent 3x3 with resident weights (conv3_persist.cu),
-                                   // 8 = persistent 1x1 (conv1_persist.cu; opt-in: measured 2 % slower than the one-tile 1x1 kernel),
+                                   // (8: unused),
                                    // 16 = tensor-core 7x7 stem for identical input channels (stem_umma.cu),
                                    // 32 = 1x1 with the activation operand in tensor memory (conv_umma_ts.cu; needs bit 0 as fallback),
                                    // 64 = 3x3 with the weights resident in tensor memory (conv3_wt.cu),
@@ -284,7 +284,6 @@ int launch_conv_umma_tma(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv3_umma_tma(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv_umma_ts(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv3_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st);
-int launch_conv1_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv3_wt(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv1_t(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 

@@ -105,13 +105,13 @@ def test_multi_tile_kernel_matches_torch(precision, case, tiles_per_cta, monkeyp
     del eng
 
 
-@pytest.mark.parametrize("tma_mask", [0, 1, 3, 7, 15, 33, 64, 128])
+@pytest.mark.parametrize("tma_mask", [0, 1, 3, 7, 33, 64, 128])
 @pytest.mark.parametrize("case", [(5, 80, 224, 256, 128, 1, 0), (2, 40, 96, 256, 128, 1, 0), (4, 80, 128, 128, 32, 3, 0),
                                   (1, 160, 128, 128, 32, 3, 0), (3, 20, 128, 128, 32, 3, 0), (2, 20, 1024, 1024, 128, 1, 0)],
                          ids=lambda c: "n%d_h%d_cin%d_cs%d_cout%d_k%d_pool%d" % c)
 def test_tma_kernel_variants_match_torch(case, tma_mask, monkeypatch):
     """Every tf32 kernel selectable through SMG_TMA: 0 register producers (conv_umma.cu / conv_umma_mt.cu), 1 one-tile 1x1
-    TMA, 2 one-tile 3x3 TMA (conv_umma_tma.cu), 4 persistent 3x3 (conv3_persist.cu), 8 persistent 1x1 (conv1_persist.cu), 32 1x1 with the A operand in tensor memory
+    TMA, 2 one-tile 3x3 TMA (conv_umma_tma.cu), 4 persistent 3x3 (conv3_persist.cu), 32 1x1 with the A operand in tensor memory
     (conv_umma_ts.cu), 64 3x3 with the weights in tensor memory (conv3_wt.cu),
     128 persistent 1x1 with the weights as the A operand (conv1_t.cu: tensor-memory resident for cin <= 256, streamed above).
     The multi-sample cases make persistent CTAs cross sample boundaries (table re-computation, statistics flush)."""
