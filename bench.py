@@ -357,15 +357,14 @@ def run_gpu_arm(args):
         ridge = tensor_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)
         ai = d["flops"] / max(1.0, d["bytes"])
         # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of a representative launch of this class from one
-        # `ncu --set full` capture of the kernels that serve the class now (profiles/r01_tma1_ncu_summary.csv,
-        # profiles/r01_persist3_ncu_summary.csv), next to the algorithmic bytes of the same launch: traffic ~= algorithmic,
-        # i.e. no wasted re-reads (halo re-reads of the 3x3 patches are absorbed by L2)
-        ncu_traffic = {"conv1x1": {"launch": "block-1 1x1 conv K=192, 17 samples (conv_umma_tma_kernel; conv_umma_ts_kernel moves the "
-                                             "same bytes, only the operand staging differs)", "dram_bytes": 517.5e6,
+        # `ncu --set full` capture of the kernels that serve the class now (profiles/r01_conv1_t_ncu_summary.csv,
+        # profiles/r01_conv3_wt_ncu_summary.csv), next to the algorithmic bytes of the same launch: traffic ~= algorithmic,
+        # i.e. no wasted re-reads (halo re-reads of the 3x3 patches are mostly absorbed by L2)
+        ncu_traffic = {"conv1x1": {"launch": "block-1 1x1 conv K=192, 17 samples (conv1_t_kernel, 96.6 us under ncu)", "dram_bytes": 512.0e6,
                                    "algorithmic_bytes": 557.1e6,
                                    # profiles/r01_tma_rate.csv pattern 5: this launch's reads + writes with no compute at all
                                    "pattern_peak_gbs": 5822.0},
-                       "conv3x3": {"launch": "block-1 3x3 conv, 17 samples (conv3_persist_kernel)", "dram_bytes": 307.7e6,
+                       "conv3x3": {"launch": "block-1 3x3 conv, 17 samples (conv3_wt_kernel, 110.2 us under ncu)", "dram_bytes": 313.1e6,
                                    "algorithmic_bytes": 278.5e6}}
         if dom == "stem" or ai < ridge:
             achieved = d["bytes"] / 1e9 / (d["ms"] / 1e3)
