@@ -518,17 +518,35 @@ conv_umma_kernel(UmmaDev a) {
 // host
 // ------------------------------------------------------------------------------------------
 void umma_patch_geometry(int hw, int* wp, int* ht) {
-    // patch width wp = tile width + 2 halo columns; ht*wp <= 128 output rows per MMA tile
-    if (hw + 2 <= MAX_WP) {
-        *wp = hw + 2;
-    } else {
-        // split the row into equal column tiles of at most MAX_WP-2 pixels
-        const int nt = (hw + (MAX_WP - 2) - 1) / (MAX_WP - 2);
-        const int wt = (hw + nt - 1) / nt;
-        *wp = wt + 2;
+    // patch width wp = tile width + 2 halo columns; ht*wp <= 128 output rows per MMA tile; the patch a tile loads is
+    // (ht+2) x wp pixels.  The 3x3 kernels are bound by the bytes they pull in, so the tile shape is chosen to minimise
+    // loaded pixels per output pixel (squarer tiles: 18 x 7 loads 1.46 pixels per output at 160^2, the widest tile 42 x 3
+    // loads 1.77), with a mild penalty on the number of tiles (= MMA work).  SMG_PATCH_GEOM=0 restores the widest-tile rule.
+    static const bool widest = getenv("SMG_PATCH_GEOM") != nullptr && atoi(getenv("SMG_PATCH_GEOM")) == 0;
+    int best_wp = 0, best_ht = 0;
+    double best_cost = 1e30;
+    int min_tiles = 1 << 30;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int nt = 1; nt <= hw; ++nt) {
+            const int wt = (hw + nt - 1) / nt, w = wt + 2;
+            if (w > MAX_WP) continue;
+            int t = UM / w;
+            if (t > hw) t = hw;
+            if (t < 1 || (t + 2) * w > 5 * MAX_WP || 2 * w + UM > 212) continue;
+            const int tiles = ((hw + wt - 1) / wt) * ((hw + t - 1) / t);
+            if (pass == 0) {
+                if (tiles < min_tiles) min_tiles = tiles;
+                if (widest) { best_wp = w; best_ht = t; nt = hw; }   // first admissible = fewest column tiles
+                continue;
+            }
+            const double loaded = (double)tiles * (t + 2) * w / ((double)hw * hw);
+            const double cost = loaded + 0.8 * ((double)tiles / min_tiles - 1.0);
+            if (cost < best_cost) { best_cost = cost; best_wp = w; best_ht = t; }
+        }
+        if (widest) break;
     }
-    *ht = UM / *wp;
-    if (*ht > hw) *ht = hw;
+    *wp = best_wp;
+    *ht = best_ht;
 }
 
 template <int ELT, int BN, int TAPS, int POOL>
