@@ -334,7 +334,7 @@ static size_t plan_trunk(smg_handle* h, TrunkW& T, uint8_t* base) {
     ArenaPlanner p;
     const size_t o = p.take(147 * 64 * 4);
     const size_t of = p.take(49 * 64 * 4);
-    const size_t ou = p.take(2 * 14 * 64 * 16);
+    const size_t ou = p.take(64 * 128 * 4);
     if (base) {
         T.conv0 = reinterpret_cast<float*>(base + o);
         T.conv0_folded = reinterpret_cast<float*>(base + of);

@@ -104,7 +104,7 @@ struct TrunkW {
     int packed = 0;  // SMG_PACK_* layouts that are current
     float* conv0 = nullptr;  // [147][64], k = (c*7+kh)*7+kw
     float* conv0_folded = nullptr;  // [49][64]: weights summed over the input channel (identical channels)
-    float* conv0_umma = nullptr;    // the folded weights as two tcgen05 B images (hi, lo) [14 chunks][64][4], k = kh*8 + kw (stem_umma.cu)
+    float* conv0_umma = nullptr;    // the folded weights as a tensor-memory A image [4 column blocks][128 rows = w_hi | w_lo][16], k = kh*8 + kw (stem_umma.cu)
     BnP norm0;
     std::vector<DenseLayerW> layers[kNumBlocks];
     TransitionW trans[kNumBlocks - 1];
