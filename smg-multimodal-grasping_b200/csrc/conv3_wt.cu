@@ -40,25 +40,6 @@ constexpr int W_TOTAL = W_OFF_BAR + 256;
 constexpr int W_THREADS = 512;
 static_assert(W_TOTAL <= 232448, "shared-memory plan exceeds the 227 KB of one SM");
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float4& a, const float4& b, const float4& c, const float4& d) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-        "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)),
-        "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)), "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w)),
-        "r"(__float_as_uint(c.x)), "r"(__float_as_uint(c.y)), "r"(__float_as_uint(c.z)), "r"(__float_as_uint(c.w)),
-        "r"(__float_as_uint(d.x)), "r"(__float_as_uint(d.y)), "r"(__float_as_uint(d.z)), "r"(__float_as_uint(d.w))
-        : "memory");
-}
-
-// A operand from tensor memory, B from shared memory
-__device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-
 struct TileCoord {
     int s, h0, w0;
 };

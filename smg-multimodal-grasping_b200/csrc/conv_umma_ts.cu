@@ -19,7 +19,7 @@ namespace {
 constexpr int NA_T = 4;   // activation stages in flight (16 KB each) = operand slots in tensor memory
 constexpr int NB_T = 2;   // weight stages (16 KB each at N = 128)
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+__device__ __forceinline__ void tmem_st16_wait(uint32_t taddr, const float* v) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
         "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
@@ -28,15 +28,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
         "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// A operand from tensor memory, B from shared memory
-__device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
 }
 
 template <int BN>
@@ -191,7 +182,7 @@ conv_umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a) {
             mbar_arrive(&raw_empty[slot]);                    // the raw stage is in registers: the next TMA may overwrite it
             mbar_wait_sleep(&a_empty[slot], ((kg / NA_T) & 1) ^ 1, 32);   // the MMAs that read this operand slot have retired
             tc_fence_after();
-            tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + slot * 32 + half * 16), y);
+            tmem_st16_wait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + slot * 32 + half * 16), y);
             tc_fence_before();
             mbar_arrive(&a_ready[slot]);
         }

@@ -52,24 +52,6 @@ constexpr int S_THREADS = 576;
 static_assert(S_OFF_A % 128 == 0 && S_OFF_X % 128 == 0 && S_OFF_BAR % 8 == 0, "alignment");
 static_assert(S_TOTAL <= 232448, "shared-memory plan exceeds the 227 KB of one SM");
 
-__device__ __forceinline__ void stem_tmem_st16(uint32_t taddr, const float4& a, const float4& b, const float4& c, const float4& d) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-        "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)),
-        "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)), "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w)),
-        "r"(__float_as_uint(c.x)), "r"(__float_as_uint(c.y)), "r"(__float_as_uint(c.z)), "r"(__float_as_uint(c.w)),
-        "r"(__float_as_uint(d.x)), "r"(__float_as_uint(d.y)), "r"(__float_as_uint(d.z)), "r"(__float_as_uint(d.w))
-        : "memory");
-}
-
-__device__ __forceinline__ void stem_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-
 __global__ void __launch_bounds__(S_THREADS, 1)
 conv0_umma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w_t, float* __restrict__ out,
                   double* __restrict__ stats, int stats_stride, int Ho, int total_tiles) {
@@ -169,8 +151,8 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
                 for (int k = 0; k < S_CH / 2; ++k) {
                     const uint64_t x_hi = make_desc(sA_u + as * S_ASLOT + 2 * k * S_LBO, S_LBO, 128);
                     const uint64_t x_lo = make_desc(sA_u + as * S_ASLOT + S_AHALF + 2 * k * S_LBO, S_LBO, 128);
-                    stem_umma_ts(d_tmem, tmem_w + (uint32_t)(k * 8), x_lo, idesc, k > 0 ? 1u : 0u);   // small term first
-                    stem_umma_ts(d_tmem, tmem_w + (uint32_t)(k * 8), x_hi, idesc, 1u);
+                    umma_ts_tf32(d_tmem, tmem_w + (uint32_t)(k * 8), x_lo, idesc, k > 0 ? 1u : 0u);   // small term first
+                    umma_ts_tf32(d_tmem, tmem_w + (uint32_t)(k * 8), x_hi, idesc, 1u);
                 }
                 umma_commit(&a_empty[as]);
                 umma_commit(&t_full[buf]);
@@ -187,7 +169,7 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
             const float4* wsrc = reinterpret_cast<const float4*>(w_t) + (size_t)(q4 * 32 + lane) * 4;
             for (int c16 = eg; c16 < S_WCOLS / 16; c16 += 2) {
                 const float4* p4 = wsrc + (size_t)c16 * 128 * 4;
-                stem_tmem_st16(tmem_w + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c16 * 16), __ldg(p4), __ldg(p4 + 1), __ldg(p4 + 2),
+                tmem_st16(tmem_w + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c16 * 16), __ldg(p4), __ldg(p4 + 1), __ldg(p4 + 2),
                                __ldg(p4 + 3));
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
