@@ -120,3 +120,16 @@ def test_running_stat_ema_weights_match_sequential_batchnorm():
     assert torch.allclose(rm.float(), bn.running_mean, atol=1e-6)
     assert torch.allclose(rv.float(), bn.running_var, atol=1e-5)
     assert int(bn.num_batches_tracked) == k
+
+
+def test_every_cuda_source_is_built():
+    """Every .cu under csrc/ is listed in the Makefile (a kernel file that is not linked would silently leave its launcher
+    undefined only at load time on the GPU box)."""
+    import glob
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "smg-multimodal-grasping_b200", "csrc")
+    mk = open(os.path.join(root, "Makefile")).read()
+    srcs = re.search(r"^SRCS\s*:=\s*(.*)$", mk, flags=re.M).group(1).split()
+    on_disk = sorted(os.path.basename(p) for p in glob.glob(os.path.join(root, "*.cu")))
+    assert sorted(srcs) == on_disk, (sorted(set(on_disk) - set(srcs)), sorted(set(srcs) - set(on_disk)))
