@@ -51,6 +51,8 @@ def test_tensor_core_kernels_are_tcgen05():
     sass = subprocess.check_output(["cuobjdump", "-sass", lib], text=True)
     assert "UTCHMMA" in sass or "UTCQMMA" in sass, "no tcgen05.mma in the SASS"
     assert "LDTM" in sass and "UBLKCP" in sass
+    assert "UTMALDG" in sass, "no tensor-map TMA load (cp.async.bulk.tensor) in the SASS"
+    assert "STTM" in sass, "no tcgen05.st (operands in tensor memory) in the SASS"
     assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync found"
 
 
