@@ -62,8 +62,10 @@ const char* smg_last_error(void);
 
 /* ---- lifetime ------------------------------------------------------------------ */
 /* Allocate workspace for up to `max_samples` samples of H x H input (H multiple of 32;
- * the heads need H = 640, code/models.py:322).  `train_samples` > 0 additionally
- * reserves the saved activations needed by smg_qbackward for that many samples.   */
+ * the heads need H = 640, code/models.py:322).  max_samples = 0 creates a handle without
+ * trunk workspace for the stateless kernels (smg_heightmap*, smg_nms, smg_argmax,
+ * smg_adam_step, smg_geometry_*).  The training workspace is allocated by the first
+ * smg_qforward_train.                                                              */
 int smg_create(int device, int max_samples, int H, smg_handle** out);
 int smg_destroy(smg_handle* h);
 int smg_set_precision(smg_handle* h, int precision);
@@ -150,6 +152,10 @@ int smg_qforward_train(smg_handle* h, int trunk_id, int head_id, const float* de
                        void* stream);
 int smg_qbackward(smg_handle* h, const float* dev_dq, float* const* dev_trunk_grads, float* const* dev_head_grads,
                   void* stream);
+/* Stamp of the pending smg_qforward_train result (incremented by every such call), or -1 if there is none - any
+ * other forward on the handle overwrites the saved activations and invalidates it; smg_qbackward then fails with
+ * SMG_ERR_STATE instead of differentiating another pass.  Only ONE grad-enabled pass may be in flight per handle. */
+int64_t smg_train_pass_id(smg_handle* h);
 /* fused Adam over a flat list of tensors (torch.optim.Adam, code/trainer.py:99,383) */
 int smg_adam_step(smg_handle* h, float* const* dev_params, const float* const* dev_grads, float* const* dev_m,
                   float* const* dev_v, const int64_t* host_numel, int n_tensors, int step, float lr, float beta1,

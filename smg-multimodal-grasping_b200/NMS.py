@@ -10,7 +10,7 @@ def py_cpu_nms(boxes, pred_score, co_thresh, min_area, max_area, device=None):
     n = len(pred_score)
     if n == 0:
         return []
-    eng = _engine.get_engine(torch.cuda.current_device() if device is None else device)
+    eng = _engine.stateless_engine(torch.cuda.current_device() if device is None else device)
     b = torch.from_numpy(np.ascontiguousarray(np.asarray(boxes)[:n], dtype=np.float32))
     keep, cnt = eng.nms(b, co_thresh, min_area, max_area)
     k = int(cnt.item())

@@ -36,6 +36,7 @@ PROTOTYPES = {
     "smg_head_bn_stats": (I, [VP, VP, I, VP]),
     "smg_qforward_train": (I, [VP, I, I, VP, VP, I, I, VP, VP, VP, VP]),
     "smg_qbackward": (I, [VP, VP, c_void_pp, c_void_pp, VP]),
+    "smg_train_pass_id": (ctypes.c_int64, [VP]),
     "smg_adam_step": (I, [VP, c_void_pp, c_void_pp, c_void_pp, c_void_pp, c_int64_p, I, I,
                           ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, VP]),
     "smg_argmax": (I, [VP, VP, I, VP, VP, VP]),

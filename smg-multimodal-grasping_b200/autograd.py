@@ -19,6 +19,7 @@ class _QPass(torch.autograd.Function):
     def forward(ctx, eng, style, scene, mask, rot, nrot, n_trunk, *params):
         q, mean, var = eng.qforward_train(style, scene, mask, rot, nrot)
         ctx.eng = eng
+        ctx.pass_id = eng.train_pass_id()
         ctx.n_trunk = n_trunk
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.mark_non_differentiable(mean, var)
@@ -27,6 +28,10 @@ class _QPass(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dq, _dm, _dv):
         eng = ctx.eng
+        if eng.train_pass_id() != ctx.pass_id:
+            raise RuntimeError("smg_b200: the activations saved by this grad-enabled forward were overwritten by another "
+                               "forward on the same model (or its engine was re-created) before backward(); only one "
+                               "grad-enabled pass may be in flight per model")
         grads = [torch.empty(s, dtype=torch.float32, device=eng.device) for s in ctx.shapes]
         eng.qbackward(dq.contiguous().view(-1), grads[:ctx.n_trunk], grads[ctx.n_trunk:])
         return (None,) * 7 + tuple(grads)

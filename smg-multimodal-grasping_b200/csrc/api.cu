@@ -65,48 +65,15 @@ static int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     const double bytes = 4.0 * ((double)a.n * a.hin * a.hin * a.cin + px * a.cout);
     ProfScope ps(h, st, a.taps == 9 ? 2 : 1, 2.0 * px * a.cout * a.cin * a.taps, bytes);
     if (h->precision == SMG_PREC_FP32) return launch_conv_ffma(h, a, st);
-    // tf32: activations fetched by tensor-map TMA (conv_umma_tma.cu; SMG_TMA bit 0 = 1x1 layers, bit 1 = one-tile 3x3, bit 2 = persistent 3x3 of conv3_persist.cu,
-    // bit 4 = tensor-core stem, bit 5 = 1x1 with the operand in tensor memory, bit 6 = 3x3 with the weights in tensor memory,
-    // bit 7 = persistent 1x1 with swapped operand roles)
+    // tf32 dense layers: the persistent TMA-fed kernels (SMG_TMA bits: 64 = conv3_wt.cu, 128 = conv1_t.cu); everything they
+    // do not serve (pooled transitions, the head's 1x1, bf16 mode, odd shapes) runs on the register-producer kernel.
     if (h->precision == SMG_PREC_TF32 && !a.pool) {
         if (a.taps == 1 && (h->use_tma & 128)) {
             const int status = launch_conv1_t(h, a, st);
             if (status != SMG_ERR_UNSUPPORTED) return status;
         }
-        if (a.taps == 1 && (h->use_tma & 32)) {
-            const int status = launch_conv_umma_ts(h, a, st);
-            if (status != SMG_ERR_UNSUPPORTED) return status;
-        }
-        if (a.taps == 1 && (h->use_tma & 1)) {
-            const int status = launch_conv_umma_tma(h, a, st);
-            if (status != SMG_ERR_UNSUPPORTED) return status;
-        }
         if (a.taps == 9 && (h->use_tma & 64)) {
             const int status = launch_conv3_wt(h, a, st);
-            if (status != SMG_ERR_UNSUPPORTED) return status;
-        }
-        if (a.taps == 9 && (h->use_tma & 4)) {
-            const int status = launch_conv3_persist(h, a, st);
-            if (status != SMG_ERR_UNSUPPORTED) return status;
-        }
-        if (a.taps == 9 && (h->use_tma & 2)) {
-            const int status = launch_conv3_umma_tma(h, a, st);
-            if (status != SMG_ERR_UNSUPPORTED) return status;
-        }
-    }
-    // large 3x3 launches: multi-tile CTAs (setup amortised, epilogue overlapped with the next tile).  Measured on B200
-    // (profiles/README.md): 3-7 % faster for the 3x3 convolutions, 3 % slower for the 1x1 ones, which therefore stay
-    // on the one-tile kernel unless SMG_TILES_PER_CTA forces a value.
-    if (!a.pool && h->tiles_per_cta != 1 && (a.taps == 9 || h->tiles_per_cta > 1)) {
-        const int tiles = a.taps == 9 ? 0 : (int)((px / a.n + 127) / 128);
-        int T = h->tiles_per_cta;
-        if (T == 0) {
-            const double per_launch = (a.taps == 9 ? px / 120.0 : (double)tiles * a.n) * (a.taps == 9 ? 1 : a.cout / 128.0);
-            T = (int)(per_launch / (3.0 * 2 * h->num_sms));
-            if (T > 4) T = 4;
-        }
-        if (T >= 2) {
-            const int status = launch_conv_umma_mt(h, a, h->precision, T, st);
             if (status != SMG_ERR_UNSUPPORTED) return status;
         }
     }
@@ -134,6 +101,9 @@ static int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cu
     TrunkW& T = h->trunks[trunk_id];
     SMG_CHECK(T.set, SMG_ERR_STATE, "trunk %d: weights not set (call smg_set_trunk_weights)", trunk_id);
     SMG_CHECK(n >= 1 && n <= h->max_samples, SMG_ERR_INVALID, "trunk_forward: n=%d outside [1,%d]", n, h->max_samples);
+    // every pass overwrites the workspace a pending smg_qforward_train result lives in: its backward must fail, not
+    // silently differentiate another pass's activations (smg_qforward_train re-validates after its own pass)
+    h->train.valid = false;
     {
         const int need = h->precision == SMG_PREC_FP32 ? SMG_PACK_FFMA : (h->precision == SMG_PREC_TF32 ? SMG_PACK_TF32 : SMG_PACK_BF16);
         SMG_CHECK(T.packed & need, SMG_ERR_STATE,
@@ -248,6 +218,7 @@ static int heads_forward(smg_handle* h, int trunk_id, int head_id, int n_rot, in
     TrunkW& T = h->trunks[trunk_id];
     HeadW& Hd = h->heads[head_id];
     SMG_CHECK(Hd.set, SMG_ERR_STATE, "head %d: weights not set (call smg_set_head_weights)", head_id);
+    h->train.valid = false;
     const BlockGeom& g = h->geom[3];
     SMG_CHECK(g.hw == kHeadK, SMG_ERR_INVALID, "heads need H=640 (block-4 spatial %d != %d)", g.hw, kHeadK);
     const int n = groups * (n_rot + n_masks);
@@ -371,7 +342,7 @@ const char* smg_last_error(void) { return smg::get_error(); }
 
 int smg_create(int device, int max_samples, int H, smg_handle** out) {
     SMG_CHECK(out != nullptr, SMG_ERR_INVALID, "smg_create: out is NULL");
-    SMG_CHECK(max_samples >= 1 && max_samples <= 4096, SMG_ERR_INVALID, "smg_create: max_samples %d", max_samples);
+    SMG_CHECK(max_samples >= 0 && max_samples <= 4096, SMG_ERR_INVALID, "smg_create: max_samples %d", max_samples);
     SMG_CHECK(H >= 64 && H % 32 == 0 && H <= 1024, SMG_ERR_INVALID, "smg_create: H=%d must be a multiple of 32 in [64,1024]", H);
     int ndev = 0;
     SMG_CUDA(cudaGetDeviceCount(&ndev));
@@ -397,6 +368,11 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
         h->geom[b].c_tot = c + kBlockLayers[b] * kGrowth;
         c = h->geom[b].c_tot / 2;
         hw /= 2;
+    }
+    if (max_samples == 0) {
+        // a handle for the stateless kernels only (heightmap, NMS, argmax, Adam): no trunk workspace
+        *out = h;
+        return SMG_OK;
     }
     const size_t S = max_samples;
     // stats arena layout (double2 per sample)
@@ -446,10 +422,7 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming);
     if (const char* e = getenv("SMG_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
     if (const char* e = getenv("SMG_ASYNC")) h->force_async = atoi(e);
-    if (const char* e = getenv("SMG_TILES_PER_CTA")) h->tiles_per_cta = atoi(e);
     if (const char* e = getenv("SMG_TMA")) h->use_tma = atoi(e);
-    if (const char* e = getenv("SMG_L2_PREFETCH")) h->l2_prefetch = atoi(e);
-    if (const char* e = getenv("SMG_CONV3_SLOT")) h->conv3_slot_channels = atoi(e) == 16 ? 16 : 32;
     *out = h;
     return SMG_OK;
 }
@@ -668,6 +641,7 @@ int smg_qforward_maps_batch(smg_handle* h, int trunk_id, int head_id, const doub
     cudaStream_t st = (cudaStream_t)stream;
     const size_t hm_elems = (size_t)hm_size * hm_size;
     SMG_CHECK(2 * hm_size <= h->H, SMG_ERR_INVALID, "smg_qforward_maps: hm_size %d too large for H %d", hm_size, h->H);
+    h->train.valid = false;   // also on the graph-replay path, which does not go through trunk_forward
     const bool graphable = h->use_graphs && !h->profile && !dev_bn_mean && !dev_bn_var;
     if (!graphable) return qforward_maps_body(h, trunk_id, head_id, dev_scene_hm, dev_mask_hms, n_masks, hm_size, mean, stddev,
                                               host_rot_idx, n_rot, num_rotations, dev_q, dev_bn_mean, dev_bn_var, st, groups);
@@ -984,6 +958,7 @@ int smg_qforward_train(smg_handle* h, int trunk_id, int head_id, const float* de
     h->train.trunk_id = trunk_id;
     h->train.head_id = head_id;
     h->train.valid = true;
+    h->train.pass_id++;
     return SMG_OK;
 }
 
@@ -998,6 +973,8 @@ int smg_qbackward(smg_handle* h, const float* dev_dq, float* const* dev_trunk_gr
     h->train.valid = false;
     return status;
 }
+
+int64_t smg_train_pass_id(smg_handle* h) { return (h && h->train.valid) ? h->train.pass_id : -1; }
 
 int smg_adam_step(smg_handle* h, float* const* dev_params, const float* const* dev_grads, float* const* dev_m,
                   float* const* dev_v, const int64_t* host_numel, int n_tensors, int step, float lr, float beta1,

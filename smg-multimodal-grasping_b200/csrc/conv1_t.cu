@@ -332,12 +332,8 @@ int launch_conv1_t(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     d.tiles_per_sample = (hw + UM - 1) / UM;
     d.tiles_per_cta = 0;
     const int total = d.tiles_per_sample * a.n;
-    static bool attr = false;
-    if (!attr) {
-        SMG_CUDA(cudaFuncSetAttribute(conv1_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1<true>::TOTAL));
-        SMG_CUDA(cudaFuncSetAttribute(conv1_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1<false>::TOTAL));
-        attr = true;
-    }
+    SMG_TRY(ensure_dyn_smem(h, (const void*)conv1_t_kernel<true>, T1<true>::TOTAL));
+    SMG_TRY(ensure_dyn_smem(h, (const void*)conv1_t_kernel<false>, T1<false>::TOTAL));
     const int grid = total < h->num_sms ? total : h->num_sms;
     const float* w_t = reinterpret_cast<const float*>(a.w->w_tf32_t);
     if (a.cin <= T_RES_MAXK) conv1_t_kernel<true><<<grid, T_THREADS, T1<true>::TOTAL, st>>>(tm, d, w_t, total);

@@ -340,11 +340,7 @@ int launch_conv3_wt(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
                                    (cuuint64_t)a.hin * a.hin * a.in_cstride * 4};
     const cuuint32_t box[4] = {KC, (cuuint32_t)d.wp, (cuuint32_t)(d.ht + 2), 1};
     SMG_TRY(make_tensor_map_f32(&tm, a.in, 4, dims, strides, box, 128));
-    static bool attr = false;
-    if (!attr) {
-        SMG_CUDA(cudaFuncSetAttribute(conv3_wt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_TOTAL));
-        attr = true;
-    }
+    SMG_TRY(ensure_dyn_smem(h, (const void*)conv3_wt_kernel, W_TOTAL));
     const int grid = total < h->num_sms ? total : h->num_sms;
     // debugging aid: SMG_CONV3_TRACE=<file> appends the clock64 timeline of CTA 0 of every launch (synchronises!)
     static const char* trace_path = getenv("SMG_CONV3_TRACE");

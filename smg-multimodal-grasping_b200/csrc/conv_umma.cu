@@ -552,12 +552,7 @@ void umma_patch_geometry(int hw, int* wp, int* ht) {
 template <int ELT, int BN, int TAPS, int POOL>
 static int launch_umma(smg_handle* h, const UmmaDev& d, int n, cudaStream_t st) {
     using P = SmemPlan<ELT, BN, TAPS>;
-    static bool attr = false;
-    if (!attr) {
-        SMG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<ELT, BN, TAPS, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      P::TOTAL));
-        attr = true;
-    }
+    SMG_TRY(ensure_dyn_smem(h, (const void*)conv_umma_kernel<ELT, BN, TAPS, POOL>, P::TOTAL));
     dim3 grid;
     if (TAPS == 9) {
         const int wt = d.wp - 2;

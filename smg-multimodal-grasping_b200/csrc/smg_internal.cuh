@@ -147,17 +147,12 @@ struct smg_handle {
     int pack_mask = 15;            // weight layouts written by smg_set_*_weights (SMG_PACK_*)
     void* job_buf = nullptr;       // device table for the batched weight packer
     size_t job_bytes = 0;
-    int use_tma = 247;              // tuning bit mask, tf32 layers with tensor-map TMA activations: 1 = 1x1, 2 = one-tile 3x3
-                                   // (conv_umma_tma.cu), 4 = persistent 3x3 with resident weights (conv3_persist.cu),
-                                   // (8: unused),
-                                   // 16 = tensor-core 7x7 stem for identical input channels (stem_umma.cu),
-                                   // 32 = 1x1 with the activation operand in tensor memory (conv_umma_ts.cu; needs bit 0 as fallback),
-                                   // 64 = 3x3 with the weights resident in tensor memory (conv3_wt.cu),
-                                   // 128 = persistent 1x1 with swapped operand roles, weights in tensor memory for cin <= 256 (conv1_t.cu)
-    int conv3_slot_channels = 32;  // tuning: channels per patch slot of conv3_persist.cu (32: 3 slots, 128-byte swizzle; 16: 6 slots, 64-byte)
-    int l2_prefetch = 0;           // tuning: how many TMA boxes ahead of its shared-memory ring a persistent loader prefetches into L2
-    int tiles_per_cta = 0;         // tuning: 0 auto, 1 one-tile kernel only, >1 fixed tiles per CTA for the multi-tile kernel
+    int use_tma = 208;             // A/B bit mask of the persistent TMA-fed tf32 kernels (SMG_TMA): 16 = tensor-core 7x7 stem for
+                                   // identical input channels (stem_umma.cu), 64 = 3x3 with the weights resident in tensor memory
+                                   // (conv3_wt.cu), 128 = persistent 1x1 with swapped operand roles (conv1_t.cu); a cleared bit
+                                   // routes the layer to the register-producer kernel of conv_umma.cu
     int force_async = 0;           // tuning: -1 auto by grid size, 0 register producers (default: measured fastest), 1 cp.async producers
+    std::vector<const void*> smem_opt_in;   // kernels whose >48 KB dynamic shared memory opt-in was set on this handle's device
 
     smg::BlockGeom geom[smg::kNumBlocks];
     smg::TrunkW trunks[SMG_NUM_TRUNKS];
@@ -215,6 +210,7 @@ struct smg_handle {
         double* sums = nullptr;              // BN backward reductions, zeroed once per backward
         size_t sums_bytes = 0;
         bool valid = false;                  // a training forward is waiting for its backward
+        int64_t pass_id = 0;                 // stamp of the last smg_qforward_train (smg_train_pass_id)
         int trunk_id = -1, head_id = -1, in_channels = 3;
     } train;
 
@@ -279,11 +275,7 @@ struct ConvArgs {
 };
 int launch_conv_ffma(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv_umma(smg_handle* h, const ConvArgs& a, int precision, cudaStream_t st);
-int launch_conv_umma_mt(smg_handle* h, const ConvArgs& a, int precision, int tiles_per_cta, cudaStream_t st);
-int launch_conv_umma_tma(smg_handle* h, const ConvArgs& a, cudaStream_t st);
-int launch_conv3_umma_tma(smg_handle* h, const ConvArgs& a, cudaStream_t st);
-int launch_conv_umma_ts(smg_handle* h, const ConvArgs& a, cudaStream_t st);
-int launch_conv3_persist(smg_handle* h, const ConvArgs& a, cudaStream_t st);
+int ensure_dyn_smem(smg_handle* h, const void* kernel, int bytes);   // tma_common.cu
 int launch_conv3_wt(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int launch_conv1_t(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 

@@ -197,11 +197,7 @@ static int launch_conv0_t(smg_handle* h, const float* in, int n, const float* w,
     const size_t operands = (size_t)(CIN * 49 * 64 + CIN * C0_PATCH * C0_PLD);
     const size_t staging = (size_t)256 * C0_STAGE_LD + 512;
     const size_t smem = (operands > staging ? operands : staging) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        SMG_CUDA(cudaFuncSetAttribute(conv0_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    SMG_TRY(ensure_dyn_smem(h, (const void*)conv0_kernel<CIN>, (int)smem));
     dim3 grid((Ho / C0_TILE) * (Ho / C0_TILE), n);
     conv0_kernel<CIN><<<grid, 256, smem, st>>>(in, w, out, stats, h->H, 64);
     h->launches++;

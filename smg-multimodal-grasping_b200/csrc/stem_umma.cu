@@ -287,11 +287,7 @@ int launch_conv0_umma(smg_handle* h, const float* in, int n, const float* w_umma
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SMG_CHECK(r == CUDA_SUCCESS, SMG_ERR_CUDA, "conv0_umma: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    static bool attr = false;
-    if (!attr) {
-        SMG_CUDA(cudaFuncSetAttribute(conv0_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_TOTAL));
-        attr = true;
-    }
+    SMG_TRY(ensure_dyn_smem(h, (const void*)conv0_umma_kernel, S_TOTAL));
     const int total = (Ho / S_TC) * (Ho / S_TR) * n;
     const int grid = total < h->num_sms ? total : h->num_sms;
     conv0_umma_kernel<<<grid, S_THREADS, S_TOTAL, st>>>(tm, w_umma, out, stats, 64, Ho, total);

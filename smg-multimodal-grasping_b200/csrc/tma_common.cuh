@@ -1,5 +1,5 @@
 // tma_common.cuh - tensor-map TMA helpers shared by the kernels whose activation operand is fetched by
-// cp.async.bulk.tensor (conv_umma_tma.cu, conv3_persist.cu, conv1_persist.cu): tile loads, the 128-byte-swizzle UMMA
+// cp.async.bulk.tensor (conv1_t.cu, conv3_wt.cu, stem_umma.cu): tile loads, the 128-byte-swizzle UMMA
 // descriptor, the warp transpose-reduction used by the register epilogues and the driver entry point for
 // cuTensorMapEncodeTiled (resolved through the runtime, so the library does not link libcuda).
 #pragma once
@@ -104,7 +104,7 @@ __device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, u
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn();   // conv_umma_tma.cu; nullptr if the driver does not export it
+EncodeTiledFn encode_tiled_fn();   // tma_common.cu; nullptr if the driver does not export it
 
 // fp32 tensor map with 128- or 64-byte swizzle and zero fill; dims/strides innermost first (strides in bytes, rank-1 of them)
 int make_tensor_map_f32(CUtensorMap* tm, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,

@@ -50,7 +50,7 @@ class Engine:
             raise _lib.SmgError("smg_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
-        self.max_samples = int(max_samples)
+        self.max_samples = int(max_samples)   # 0: stateless kernels only (heightmap, NMS, argmax)
         self.H = int(H)
         h = ctypes.c_void_p()
         _lib.check(self.lib.smg_create(self.device.index, self.max_samples, self.H, ctypes.byref(h)))
@@ -234,6 +234,12 @@ class Engine:
                                                self._stream()))
         return q, mean, var
 
+    def train_pass_id(self):
+        """Stamp of the pending grad-enabled pass on this handle, -1 if none (any other forward invalidates it)."""
+        if getattr(self, "h", None) is None or not self.h:
+            return -1
+        return int(self.lib.smg_train_pass_id(self.h))
+
     def head_bn_stats(self, n_pairs):
         """(mean, biased var) [n_pairs, 2, 64] of the head's BatchNorm2d(64) for the last Q pass on this handle."""
         out = torch.empty((n_pairs, 2, 64), dtype=torch.float32, device=self.device)
@@ -333,6 +339,11 @@ def drop_engine(owner):
     """Release the engines of a model that is going away."""
     for key in [k for k in _engines if k[2] == owner]:
         _engines.pop(key).__del__()
+
+
+def stateless_engine(device=0):
+    """A handle without trunk workspace for the kernels that need none (heightmap, NMS, argmax)."""
+    return get_engine(device, 0, 640, owner="stateless")
 
 
 def get_engine(device=0, max_samples=32, H=640, precision=None, owner=None):

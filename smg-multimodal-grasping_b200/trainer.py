@@ -72,10 +72,34 @@ class Trainer(object):
         self.episode_success_log = []
         self.training_loss_log = []
 
+    # (log file stem, attribute, layout): "rows" = 2-D log cut to the first `iteration` rows, "col" = 1-D log cut to
+    # `iteration` entries and stored as a column, "col_all" = 1-D log kept whole (the reference does not cut clearance)
+    _LOGS = (("executed-action", "executed_action_log", "rows"), ("label-value", "label_value_log", "col"),
+             ("predicted-value", "predicted_value_log", "col"), ("reward-value", "reward_value_log", "col"),
+             ("use-heuristic", "use_heuristic_log", "col"), ("is-exploit", "is_exploit_log", "col"),
+             ("clearance", "clearance_log", "col_all"), ("grasping_type", "grasping_type_log", "col"),
+             ("episode_success", "episode_success_log", "rows"), ("training_loss", "training_loss_log", "rows"))
+
     def preload(self, transitions_directory):
+        """Resume the ten `*.log.txt` files written by the reference's logger (code/trainer.py:118-158,
+        code/logger.py:118-119): `iteration` = rows of the executed-action log minus two, every log becomes a Python
+        list again (main.py appends to them and `logger.write_to_log` rewrites the whole file each step)."""
         import os
-        self.executed_action_log = np.loadtxt(os.path.join(transitions_directory, 'executed-action.log.txt'), delimiter=' ')
-        self.iteration = self.executed_action_log.shape[0] - 2
+
+        def load(stem):
+            return np.loadtxt(os.path.join(transitions_directory, stem + '.log.txt'), delimiter=' ')
+
+        self.iteration = load(self._LOGS[0][0]).shape[0] - 2
+        n = self.iteration
+        for stem, attr, layout in self._LOGS:
+            a = load(stem)
+            if layout == "rows":
+                a = a[0:n, :]
+            elif layout == "col":
+                a = a[0:n].reshape(n, 1)
+            else:
+                a = a.reshape(a.shape[0], 1)
+            setattr(self, attr, a.tolist())
 
     # ------------------------------------------------------------------ forward
     def _rotations(self, model, style, specific_rotation):

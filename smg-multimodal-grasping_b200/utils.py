@@ -19,7 +19,7 @@ def get_heightmap(color_img, depth_img, cam_intrinsics, cam_pose, workspace_limi
     reference's numpy + cv2 result.  The two colour warps (consumed only by Mask R-CNN / logging, outside the
     Q path) reproduce cv2's 15-bit fixed-point bilinear remap bit for bit; `color_img=None` skips them (None, None).
     """
-    eng = _engine.get_engine(torch.cuda.current_device() if device is None else device)
+    eng = _engine.stateless_engine(torch.cuda.current_device() if device is None else device)
     d = torch.from_numpy(np.ascontiguousarray(depth_img, dtype=np.float64))
     o224, o448, A = eng.heightmap(d, np.asarray(cam_intrinsics, dtype=np.float64)[:3, :3], np.asarray(cam_pose, dtype=np.float64))
     c224 = c448 = None
