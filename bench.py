@@ -17,8 +17,13 @@ latency configuration) on seeded synthetic 224x224 heightmaps with random-init w
   cpu_baseline  the oracle port of the reference path (recomputing the mask pass per rotation, as the
                 reference does) timed on this box's host cores on a bounded sample
 
-`--impl reference` times that CPU path alone (the reference is CUDA-only as written and cannot be
-imported on the GPU box; the oracle is its pinned restatement).  N > 1 (torchrun): every rank
+  gpu_reference the unmodified reference on torch.cuda (stock PyTorch + cuDNN, TF32 off and on) on the same GPU, same
+                unit and same Trainer.backprop call: the bar BASELINE.md section 4 names (N = 1, rank 0)
+  fp32_mode     the <= 1e-4 mode of this library on the same input: units/s and its error against the tf32 result's reference
+
+`--impl reference` times the CPU path alone: the UNMODIFIED reference modules (a build-time copy under baseline/_ref/,
+imported through oracle/refshim.py; kind "reference") or, if that copy is absent, the oracle port (kind "port").
+`--impl reference-gpu` prints the gpu_reference object alone.  N > 1 (torchrun): every rank
 evaluates its own units (weak scaling over independent scenes - the rotations / replay samples shard
 without a data-path collective); the per-rank best (Q, rotation) tuples are exchanged with one tiny
 NCCL all_gather per step, which is the path's only real exchange (code/main.py:170-173).
@@ -54,6 +59,33 @@ def measured_peaks():
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
                 "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def ncu_traffic(cls):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one representative launch of a kernel class, read from
+    the newest committed `ncu --set full` summary of that kernel under profiles/ (never a literal in this file), next to
+    the algorithmic bytes of the same launch (block-1 layer, 17 samples: the launch profiles/profile_step.py captures)."""
+    import csv
+    import glob
+    stem = {"conv1x1": "conv1_t", "conv3x3": "conv3_wt"}.get(cls)
+    if stem is None:
+        return None
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_%s_ncu_summary.csv" % stem)))
+    if not files:
+        return None
+    vals = {}
+    with open(files[-1]) as f:
+        for row in csv.reader(f):
+            if len(row) >= 3 and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"):
+                scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0, "us": 1.0, "ms": 1e3}.get(row[2], 1.0)
+                vals[row[0]] = float(row[1]) * scale
+    if "dram__bytes_read.sum" not in vals or "dram__bytes_write.sum" not in vals:
+        return None
+    px = 17 * 160 * 160
+    algo = {"conv1x1": px * (192 + 128) * 4.0, "conv3x3": px * (128 + 32) * 4.0}[cls]
+    return {"source": os.path.relpath(files[-1], ROOT), "dram_bytes": vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"],
+            "algorithmic_bytes": algo, "launch_us_under_ncu": vals.get("gpu__time_duration.sum"),
+            "launch": "block-1 %s layer, 17 samples" % ("1x1 K=192" if cls == "conv1x1" else "3x3")}
 
 
 class ClockSampler:
@@ -123,9 +155,18 @@ def make_units(n_units, seed0):
 _CPU_CACHE = {}
 
 
+def cpu_kind():
+    from baseline import ref_arms
+    return "reference" if ref_arms.available() else "port"
+
+
 def cpu_reference_time(rotations_per_sample, repeats=1):
     """Seconds for `rotations_per_sample` rotations of one unit executed the way the reference does:
-    per rotation: rotate, trunk(scene), trunk(mask), cat, head (code/models.py:371-389)."""
+    per rotation: rotate, trunk(scene), trunk(mask), cat, head (code/models.py:371-389).  Runs the unmodified reference
+    when its build-time copy is present, the oracle port otherwise."""
+    from baseline import ref_arms
+    if ref_arms.available():
+        return ref_arms.cpu_rotations_seconds(rotations_per_sample, repeats)
     import torch
     from oracle import qnet
     import smg_b200.models as models
@@ -165,16 +206,34 @@ def run_reference_arm(args):
     dt = time.perf_counter() - t0
     units = args.steps * rps / float(R)
     value = units / dt
-    sample = ("%d of %d rotations per step (each: rotate + trunk(scene) + trunk(mask) + head, fp32, torch %s CPU), "
-              "scaled by 16/%d" % (rps, R, torch.__version__, rps))
+    kind = cpu_kind()
+    sample = ("%d of %d rotations per step (each: rotate + trunk(scene) + trunk(mask) + head, fp32, torch %s CPU, %s), "
+              "scaled by 16/%d" % (rps, R, torch.__version__,
+                                   "unmodified reference modules" if kind == "reference" else "oracle port", rps))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+    return 0
+
+
+def run_reference_gpu_arm(args):
+    """The unmodified reference on torch.cuda, alone (rank 0)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from baseline import ref_arms
+    if not ref_arms.available():
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "baseline/_ref/code is absent (built only where /root/reference exists)"}))
+        return 0
+    g = ref_arms.gpu_reference(steps=max(2, min(args.steps, 5)), warmup=1)
+    v = g["fp32"]["forward_e2e_units_per_s"]
+    print(json.dumps({"impl": "reference-gpu", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": WORKLOAD}, "gpu_reference": g}))
     return 0
 
 
@@ -306,8 +365,102 @@ def run_gpu_arm(args):
     h2d = int(U * (scenes[0].nbytes + masks[0].nbytes))
     d2h = int(qh.size * 4)
 
-    # ---- backprop steps/s (second half of BASELINE.json's metric): Trainer.backprop through the public API
     line_extra = {}
+    # ---- roofline of the dominant kernel class (rank 0, separate short pass with event pairs per launch)
+    eng = tr.model._engine(R + 1)
+    if rank == 0:
+        peaks = measured_peaks()
+        eng.profile_enable(True)
+        nprof = min(3, args.steps)
+        for i in range(nprof):
+            step_resident(i, exchange=False)   # rank 0 only: no collective inside the profiled pass
+        prof = eng.profile_read()
+        eng.profile_enable(False)
+        total_ms = sum(v["ms"] for v in prof.values())
+        dom = max(("conv1x1", "conv3x3", "stem"), key=lambda k: prof[k]["ms"])
+        d = prof[dom]
+        per_launch_ms = d["ms"] / max(1, d["launches"])
+        # bound by arithmetic intensity against the measured ridge: fp32-stored activations make the DenseNet convolutions
+        # memory-bound (block-1 1x1, K=224: 41 FLOP/B; 3x3: 115 FLOP/B; ridge 209 FLOP/B at the bf16 peak, 105 at tf32 rate)
+        tensor_peak = peaks["bf16_tflops_sustained"] * (0.5 if precision == "tf32" else 1.0)
+        ridge = tensor_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)
+        ai = d["flops"] / max(1.0, d["bytes"])
+        traffic = ncu_traffic(dom)
+        if dom == "stem" or ai < ridge:
+            achieved = d["bytes"] / 1e9 / (d["ms"] / 1e3)
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"],
+                    "traffic": traffic["dram_bytes"] if traffic else None, "traffic_detail": traffic,
+                    "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
+                    "tensor_tflops": d["flops"] / 1e12 / (d["ms"] / 1e3)}
+        else:
+            achieved = d["flops"] / 1e12 / (d["ms"] / 1e3)
+            roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16_tflops_sustained"],
+                    "traffic": traffic["dram_bytes"] if traffic else None, "traffic_detail": traffic}
+        roof.update({"kernel": dom, "avg_launch_ms": per_launch_ms, "launches_per_step": d["launches"] // nprof,
+                     "share_of_step": d["ms"] / total_ms if total_ms else None, "peak_source": peaks["source"],
+                     "note": "peak = dense bf16 cuBLAS sustained; tf32 operands run at half the bf16 tensor rate" if precision == "tf32" else None,
+                     "classes": {k: {"ms_per_step": v["ms"] / nprof, "launches_per_step": v["launches"] // nprof,
+                                     "tflops": (v["flops"] / 1e12 / (v["ms"] / 1e3)) if v["ms"] else None,
+                                     "algo_gbs": (v["bytes"] / 1e9 / (v["ms"] / 1e3)) if v["ms"] else None}
+                                 for k, v in prof.items()}})
+        line_extra["roofline"] = roof
+        line_extra["whole_step_tflops"] = GFLOP_PER_UNIT * value / 1e3 / world
+
+        # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
+        if world == 1 and not args.no_cpu_baseline:
+            rps = 2
+            dt = cpu_reference_time(rps)
+            line_extra["cpu_baseline"] = {
+                "value": (rps / float(R)) / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": cpu_kind(),
+                "sample": "%d of %d rotations of one unit (each: rotate + trunk(scene) + trunk(mask) + head, fp32 torch CPU, "
+                          "all host threads), scaled by 16/%d; %.1f s of CPU work" % (rps, R, rps, dt)}
+
+        # ---- the unmodified reference on torch.cuda, same GPU (rank 0, N = 1 only): the real bar
+        ref_q = None
+        if world == 1 and not args.no_gpu_reference:
+            try:
+                from baseline import ref_arms
+                if ref_arms.available():
+                    g = ref_arms.gpu_reference(steps=3, warmup=1)
+                    ref_q = g.pop("q_unit0", None)
+                    line_extra["gpu_reference"] = g
+                else:
+                    line_extra["gpu_reference"] = {"unavailable": "baseline/_ref/code is absent"}
+            except Exception as exc:
+                line_extra["gpu_reference"] = {"error": repr(exc)[:300]}
+
+        # ---- fp32 mode (north_star: <= 1e-4 of scale) on the same input, and both modes against the reference's own Q
+        if world == 1 and not args.no_extras:
+            try:
+                tr.model.precision = "fp32"
+                eng32 = tr.model._engine(U * (R + 1))
+                def step32(i):
+                    sl = unit_slice(i)
+                    return eng32.qforward_maps_batch(0, scenes_d[sl], masks_d[sl][:, None], MEAN, STD, rots, R)
+                for i in range(2):
+                    step32(i)
+                torch.cuda.synchronize()
+                n32 = 3
+                e0.record()
+                for i in range(n32):
+                    step32(i)
+                e1.record()
+                torch.cuda.synchronize()
+                q32 = tr.forward(scenes[0], masks[0], 0, True, False)
+                fp32 = {"value": n32 * U / (e0.elapsed_time(e1) / 1e3), "unit": UNIT, "steps": n32}
+                if ref_q is not None:
+                    refq = np.asarray(ref_q, np.float64)
+                    fp32["err"] = float(np.abs(q32 - refq).max() / np.abs(refq).max())
+                    fp32["err_what"] = "max|dQ|/max|Q_ref| over the 16 rotations of unit 0 vs the unmodified reference on torch.cuda, TF32 off"
+                    line_extra["precision_err_vs_reference"] = float(np.abs(q_fast - refq).max() / np.abs(refq).max())
+                line_extra["fp32_mode"] = fp32
+            except Exception as exc:
+                line_extra["fp32_mode"] = {"error": repr(exc)[:300]}
+            tr.model.precision = precision
+
+    # ---- backprop steps/s (second half of BASELINE.json's metric): Trainer.backprop through the public API
     if not args.no_backprop:
         try:
             # fp32 mode: the gradients of this net are only meaningful against the fp32 reference when the forward is fp32
@@ -337,66 +490,6 @@ def run_gpu_arm(args):
             line_extra["backprop"] = {"error": repr(exc)[:300]}
         tr.model.precision = precision
 
-    # ---- roofline of the dominant kernel class (rank 0, separate short pass with event pairs per launch)
-    eng = tr.model._engine(R + 1)
-    if rank == 0:
-        peaks = measured_peaks()
-        eng.profile_enable(True)
-        nprof = min(3, args.steps)
-        for i in range(nprof):
-            step_resident(i, exchange=False)   # rank 0 only: no collective inside the profiled pass
-        prof = eng.profile_read()
-        eng.profile_enable(False)
-        total_ms = sum(v["ms"] for v in prof.values())
-        dom = max(("conv1x1", "conv3x3", "stem"), key=lambda k: prof[k]["ms"])
-        d = prof[dom]
-        per_launch_ms = d["ms"] / max(1, d["launches"])
-        # bound by arithmetic intensity against the measured ridge: fp32-stored activations make the DenseNet convolutions
-        # memory-bound (block-1 1x1, K=224: 41 FLOP/B; 3x3: 115 FLOP/B; ridge 209 FLOP/B at the bf16 peak, 105 at tf32 rate)
-        tensor_peak = peaks["bf16_tflops_sustained"] * (0.5 if precision == "tf32" else 1.0)
-        ridge = tensor_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)
-        ai = d["flops"] / max(1.0, d["bytes"])
-        # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of a representative launch of this class from one
-        # `ncu --set full` capture of the kernels that serve the class now (profiles/r01_conv1_t_ncu_summary.csv,
-        # profiles/r01_conv3_wt_ncu_summary.csv), next to the algorithmic bytes of the same launch: traffic ~= algorithmic,
-        # i.e. no wasted re-reads (halo re-reads of the 3x3 patches are mostly absorbed by L2)
-        ncu_traffic = {"conv1x1": {"launch": "block-1 1x1 conv K=192, 17 samples (conv1_t_kernel, 96.6 us under ncu)", "dram_bytes": 512.0e6,
-                                   "algorithmic_bytes": 557.1e6,
-                                   # profiles/r01_tma_rate.csv pattern 5: this launch's reads + writes with no compute at all
-                                   "pattern_peak_gbs": 5822.0},
-                       "conv3x3": {"launch": "block-1 3x3 conv, 17 samples (conv3_wt_kernel, 110.2 us under ncu)", "dram_bytes": 313.1e6,
-                                   "algorithmic_bytes": 278.5e6}}
-        if dom == "stem" or ai < ridge:
-            achieved = d["bytes"] / 1e9 / (d["ms"] / 1e3)
-            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"],
-                    "traffic": ncu_traffic.get(dom, {}).get("dram_bytes"), "traffic_detail": ncu_traffic.get(dom),
-                    "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
-                    "tensor_tflops": d["flops"] / 1e12 / (d["ms"] / 1e3)}
-        else:
-            achieved = d["flops"] / 1e12 / (d["ms"] / 1e3)
-            roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["bf16_tflops_sustained"],
-                    "traffic": ncu_traffic.get(dom, {}).get("dram_bytes"), "traffic_detail": ncu_traffic.get(dom)}
-        roof.update({"kernel": dom, "avg_launch_ms": per_launch_ms, "launches_per_step": d["launches"] // nprof,
-                     "share_of_step": d["ms"] / total_ms if total_ms else None, "peak_source": peaks["source"],
-                     "note": "peak = dense bf16 cuBLAS sustained; tf32 operands run at half the bf16 tensor rate" if precision == "tf32" else None,
-                     "classes": {k: {"ms_per_step": v["ms"] / nprof, "launches_per_step": v["launches"] // nprof,
-                                     "tflops": (v["flops"] / 1e12 / (v["ms"] / 1e3)) if v["ms"] else None,
-                                     "algo_gbs": (v["bytes"] / 1e9 / (v["ms"] / 1e3)) if v["ms"] else None}
-                                 for k, v in prof.items()}})
-        line_extra["roofline"] = roof
-        line_extra["whole_step_tflops"] = GFLOP_PER_UNIT * value / 1e3 / world
-
-        # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
-        if world == 1 and not args.no_cpu_baseline:
-            rps = 2
-            dt = cpu_reference_time(rps)
-            line_extra["cpu_baseline"] = {
-                "value": (rps / float(R)) / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                "sample": "%d of %d rotations of one unit (each: rotate + trunk(scene) + trunk(mask) + head, fp32 torch CPU, "
-                          "all host threads), scaled by 16/%d; %.1f s of CPU work" % (rps, R, rps, dt)}
-
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -420,16 +513,20 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-backprop", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip fp32_mode / running-stats / decision / replay extras")
     ap.add_argument("--units", type=int, default=4,
                     help="independent (scene, mask) units evaluated per step and GPU as one batch (1 = latency mode)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.impl == "reference-gpu":
+        return run_reference_gpu_arm(args)
     return run_gpu_arm(args)
 
 

@@ -212,9 +212,11 @@ class Trainer(object):
             elif exploit_action == 'suction':
                 m = depth_heightmap * mask_depth[bests_id[0]]
                 future_reward = self.forward(depth_heightmap, m, 1, True, True, bests_id[1])[0]
-            else:
+            elif exploit_action == 'grasp_then_suction':
                 m = depth_heightmap * (mask_depth[bestgs_g_id[0]] + mask_depth[bestgs_s_id[0]])
                 future_reward = self.forward(depth_heightmap, m, 2, True, True, bestgs_g_id[1])[0]
+            else:   # the reference leaves future_reward unbound here (UnboundLocalError)
+                raise ValueError("unknown exploit_action %r" % (exploit_action,))
         expected_reward = current_reward + self.future_reward_discount * future_reward
         return expected_reward, current_reward
 

@@ -74,46 +74,14 @@ def test_conv_matches_torch(eng, precision, case):
     assert float((q_got - q_ref).abs().max() / q_ref.abs().max()) <= 1e-4
 
 
-@pytest.mark.parametrize("tiles_per_cta", [2, 3])
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
-@pytest.mark.parametrize("case", [(2, 40, 96, 256, 128, 1, 0), (1, 80, 224, 256, 128, 1, 0), (2, 80, 128, 128, 32, 3, 0),
-                                  (1, 160, 128, 128, 32, 3, 0), (3, 20, 128, 128, 32, 3, 0), (1, 20, 512, 1024, 256, 1, 0)],
-                         ids=lambda c: "n%d_h%d_cin%d_cs%d_cout%d_k%d_pool%d" % c)
-def test_multi_tile_kernel_matches_torch(precision, case, tiles_per_cta, monkeypatch):
-    """The multi-tile tcgen05 kernel (conv_umma_mt.cu): T tiles per CTA, double-buffered TMEM accumulators."""
-    from smg_b200 import engine
-    monkeypatch.setenv("SMG_TILES_PER_CTA", str(tiles_per_cta))
-    monkeypatch.setenv("SMG_TMA", "0")          # otherwise the tf32 cases are served by the TMA kernels
-    eng = engine.Engine(0, 4, 640, "fp32")      # a private handle so the environment knob is read
-    n, hin, cin, cstride, cout, k, pool = case
-    g = torch.Generator(device="cuda").manual_seed(hash(case) % 1000 + tiles_per_cta)
-    x = torch.randn((n, hin, hin, cstride), generator=g, device="cuda")
-    scale = torch.rand((n, cin), generator=g, device="cuda") + 0.5
-    shift = torch.randn((n, cin), generator=g, device="cuda") * 0.3
-    w = torch.randn((cout, cin, k, k), generator=g, device="cuda") / (cin * k * k) ** 0.5
-    out_cstride, out_coff = cout + 64, 32
-    out, stats = eng.debug_conv(precision, x, cin, scale, shift, True, pool, w, out_cstride, out_coff)
-    ref = reference(x, cin, scale, shift, True, pool, w)
-    got = out[..., out_coff:out_coff + cout]
-    err = float((got - ref).abs().max() / ref.abs().max())
-    print("mt T=%d %s %s: rel-max err %.2e" % (tiles_per_cta, precision, case, err))
-    assert err <= TOL[precision]
-    assert float(out[..., :out_coff].abs().max()) == 0 and float(out[..., out_coff + cout:].abs().max()) == 0
-    s_ref, q_ref = got.double().sum((1, 2)), (got.double() ** 2).sum((1, 2))
-    assert float((stats[:, out_coff:out_coff + cout, 0] - s_ref).abs().max() / s_ref.abs().max()) <= 1e-4
-    assert float((stats[:, out_coff:out_coff + cout, 1] - q_ref).abs().max() / q_ref.abs().max()) <= 1e-4
-    del eng
-
-
-@pytest.mark.parametrize("tma_mask", [0, 1, 3, 7, 33, 64, 128])
+@pytest.mark.parametrize("tma_mask", [0, 64, 128])
 @pytest.mark.parametrize("case", [(5, 80, 224, 256, 128, 1, 0), (2, 40, 96, 256, 128, 1, 0), (4, 80, 128, 128, 32, 3, 0),
                                   (1, 160, 128, 128, 32, 3, 0), (3, 20, 128, 128, 32, 3, 0), (2, 20, 1024, 1024, 128, 1, 0)],
                          ids=lambda c: "n%d_h%d_cin%d_cs%d_cout%d_k%d_pool%d" % c)
 def test_tma_kernel_variants_match_torch(case, tma_mask, monkeypatch):
-    """Every tf32 kernel selectable through SMG_TMA: 0 register producers (conv_umma.cu / conv_umma_mt.cu), 1 one-tile 1x1
-    TMA, 2 one-tile 3x3 TMA (conv_umma_tma.cu), 4 persistent 3x3 (conv3_persist.cu), 32 1x1 with the A operand in tensor memory
-    (conv_umma_ts.cu), 64 3x3 with the weights in tensor memory (conv3_wt.cu),
-    128 persistent 1x1 with the weights as the A operand (conv1_t.cu: tensor-memory resident for cin <= 256, streamed above).
+    """Every tf32 kernel selectable through SMG_TMA: 0 register producers (conv_umma.cu), 64 persistent 3x3 with the weights
+    in tensor memory (conv3_wt.cu), 128 persistent 1x1 with the weights as the A operand (conv1_t.cu: tensor-memory resident
+    for cin <= 256, streamed above).
     The multi-sample cases make persistent CTAs cross sample boundaries (table re-computation, statistics flush)."""
     from smg_b200 import engine
     monkeypatch.setenv("SMG_TMA", str(tma_mask))

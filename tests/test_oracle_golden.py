@@ -182,3 +182,57 @@ def test_action_selection_rules():
     assert a["bestgs_g_id"][0] == 1 and a["bestgs_s_id"][0] == 0
     a = oaction.select_action(gra, suc, gs * 0 + 0.25, is_ets=True, method="reactive")
     assert a["primitive"] == "suction"  # 2*0.25 = 0.5 < 0.6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2 fixtures (tests/golden/golden_r02.json, made by tests/golden/make_golden_r02.py from the unmodified reference)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gold2():
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "golden_r02.json")) as f:
+        return json.load(f)
+
+
+def test_oracle_highly_cluttered_k10_entries(gold2, rl_state_dict):
+    """The oracle on the K = 10 highly-cluttered scene: one object's grasp row (R = 4) and one ES pair."""
+    import smg_b200.synth as synth
+    g = gold2["hc"]
+    sc = synth.make_scene(g["scene_seed"], num_objects=g["K"], cluttered=True)
+    scene, masks = sc["scene"], sc["masks"].astype(np.float64)
+    x = qnet.preprocess(scene, MEAN, STD)
+    with torch.no_grad():
+        row = qnet.q_forward(rl_state_dict, x, qnet.preprocess(scene * masks[1], MEAN, STD), 0, range(g["R"]), g["R"])
+        pair = qnet.model_forward(rl_state_dict, x, qnet.preprocess(scene * (masks[0] + masks[9]), MEAN, STD), 2, True, -1,
+                                  gnum_rotations=g["R"], snum_rotations=g["R"])
+    assert np.abs(np.asarray([float(o.view(-1)[0]) for o in row]) - np.asarray(g["gra_conf"][1])).max() <= 2e-5
+    assert abs(float(pair[0].view(-1)[0]) - g["gs_conf"][0][9]) <= 2e-5
+
+
+def test_oracle_label_value_cases(gold2, rl_state_dict, scene_inputs):
+    from oracle import labels
+    g = gold2["label_value"]
+    scene, _, _, sc = scene_inputs
+    for c in g["cases"]:
+        lv, rv = labels.label_value(c["method"], rl_state_dict, c["args"], scene, sc["masks"].astype(np.float64),
+                                    num_rotations=g["num_rotations"], mean=MEAN, std=STD)
+        assert float(rv) == c["reward_value"]
+        assert abs(float(lv) - c["label_value"]) <= 2e-5, c
+
+
+def test_preload_restores_the_ten_logs(gold2):
+    """Trainer.preload (code/trainer.py:118-158) on log files written by the reference's logger: same iteration, same lists."""
+    import os
+    import types
+    from conftest import GOLDEN_DIR
+    from smg_b200.trainer import Trainer
+    g = gold2["preload"]
+    t = types.SimpleNamespace(_LOGS=Trainer._LOGS)
+    Trainer.preload(t, os.path.join(GOLDEN_DIR, g["dir"]))
+    assert t.iteration == g["iteration"]
+    for attr, want in g["logs"].items():
+        got = getattr(t, attr)
+        assert isinstance(got, list) and got == want, attr
+    t.executed_action_log.append([1, 2, 3, 4])      # main.py:369 appends to the restored list
