@@ -460,34 +460,44 @@ def run_gpu_arm(args):
                 line_extra["fp32_mode"] = {"error": repr(exc)[:300]}
             tr.model.precision = precision
 
-    # ---- backprop steps/s (second half of BASELINE.json's metric): Trainer.backprop through the public API
+    # ---- backprop steps/s (second half of BASELINE.json's metric): Trainer.backprop through the public API, in the
+    # benchmarked precision (tf32 forward + tensor-core data gradients) and in fp32 mode
     if not args.no_backprop:
-        try:
-            # fp32 mode: the gradients of this net are only meaningful against the fp32 reference when the forward is fp32
-            # too (a tf32 forward moves ~1e-3 of the pre-activations across their ReLU kinks; tests/test_gpu_backward.py)
-            tr.model.precision = "fp32"
-            import smg_b200.synth as synth
-            sc = synth.make_scene(100 + 1000 * rank, num_objects=4, cluttered=False)
-            obj_masks = sc["masks"].astype(np.float64)
-            nb = max(3, min(args.steps, 10))
-            for i in range(3):
-                tr.backprop(sc["scene"], "grasp", [i % 4, i % R], [0, 0], [], [], 1.0, obj_masks.copy(), [0] * 4, [0] * 4, [])
-            barrier()
-            e0.record()
-            for i in range(nb):
-                tr.backprop(sc["scene"], "grasp", [i % 4, i % R], [0, 0], [], [], 1.0, obj_masks.copy(), [0] * 4, [0] * 4, [])
-            e1.record()
-            barrier()
-            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            line_extra["backprop"] = {
-                "value": world * nb / (float(t.item()) / 1e3), "unit": "steps/s", "steps": nb,
-                "ms_per_step": float(t.item()) / nb, "gflop_per_step": 6 * GFLOP_PER_PASS, "precision": "fp32",
-                "what": "Trainer.backprop: grad-enabled forward (2 trunk passes + head) + backward + Adam + weight re-pack, "
-                        "host heightmaps in, loss out"}
-        except Exception as exc:  # the training path must never take the inference numbers down with it
-            line_extra["backprop"] = {"error": repr(exc)[:300]}
+        import smg_b200.synth as synth
+        sc = synth.make_scene(100 + 1000 * rank, num_objects=4, cluttered=False)
+        obj_masks = sc["masks"].astype(np.float64)
+        nb = max(5, min(args.steps, 20))
+
+        def bp(i):
+            return tr.backprop(sc["scene"], "grasp", [i % 4, i % R], [0, 0], [], [], 1.0, obj_masks.copy(), [0] * 4, [0] * 4, [])
+
+        for key, prec in (("backprop", precision), ("backprop_fp32", "fp32")):
+            if key == "backprop_fp32" and (precision == "fp32" or args.no_extras):
+                continue
+            try:
+                tr.model.precision = prec
+                eng_t = tr.model._engine(2, 0)
+                for i in range(2 * R):                  # first sight of each rotation runs eagerly, the second captures
+                    bp(i)
+                barrier()
+                l0 = eng_t.launch_count()
+                e0.record()
+                for i in range(nb):
+                    bp(i)
+                e1.record()
+                barrier()
+                t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                line_extra[key] = {
+                    "value": world * nb / (float(t.item()) / 1e3), "unit": "steps/s", "steps": nb,
+                    "ms_per_step": float(t.item()) / nb, "gflop_per_step": 6 * GFLOP_PER_PASS, "precision": prec,
+                    "launches_per_step": (eng_t.launch_count() - l0) // nb,
+                    "tflops": 6 * GFLOP_PER_PASS / 1e3 / (float(t.item()) / nb / 1e3),
+                    "what": "Trainer.backprop (fused smg_train_step, CUDA-graph replay): host heightmaps in, grad-enabled forward "
+                            "(2 trunk passes + head), loss, backward, Adam, weight re-pack, BN running statistics, loss out"}
+            except Exception as exc:  # the training path must never take the inference numbers down with it
+                line_extra[key] = {"error": repr(exc)[:300]}
         tr.model.precision = precision
 
     if rank == 0:

@@ -152,6 +152,33 @@ int smg_qforward_train(smg_handle* h, int trunk_id, int head_id, const float* de
                        void* stream);
 int smg_qbackward(smg_handle* h, const float* dev_dq, float* const* dev_trunk_grads, float* const* dev_head_grads,
                   void* stream);
+/* ---- the whole training step in one call (code/trainer.py:338-383) ----------------
+ * Trainer.backprop's device work: Trainer.forward pre-processing of the two 224x224 float64 heightmaps (scene and masked
+ * scene), the grad-enabled Q pass at rotation rot_idx, the loss (0: hand-written Huber, delta 1, on Q - label,
+ * trainer.py:345-348; 1: CrossEntropyLoss2d with class weights on the 3 logits, trainer.py:284-299), backward, Adam
+ * (torch.optim.Adam semantics, trainer.py:99) and the re-pack of the updated weights.  The whole sequence is captured in a
+ * CUDA graph per configuration and replayed.
+ * dev_params / dev_grads / dev_exp_avg / dev_exp_avg_sq: n_tensors = SMG_TRUNK_NUM_PARAMS + SMG_HEAD_NUM_PARAMS device
+ * pointers (trunk tensors in smg_set_trunk_weights order, then the head's) to caller-owned float32 buffers of the parameter
+ * shapes; dev_params must be the tensors the packed weights were set from.  Gradients are WRITTEN, parameters and moments
+ * updated in place.  dev_loss [1], dev_q [n_out]; dev_bn_mean / dev_bn_var optional [2, SMG_TRUNK_BN_CHANNELS]
+ * (scene pass, then mask pass) for the caller's running-statistics update.                                              */
+typedef struct smg_train_step_args {
+    int32_t trunk_id, head_id;      /* routing of the sample's primitive (code/models.py:513-586) */
+    int32_t rot_idx, num_rotations; /* rotation of the scene pass: angle = rot_idx * 360 / num_rotations */
+    int32_t hm_size;                /* the heightmaps are hm_size x hm_size float64 */
+    int32_t loss_kind;              /* 0 Huber on the scalar Q, 1 weighted cross-entropy on 3 logits */
+    int32_t adam_step;              /* 1-based step count of this update (bias corrections) */
+    float label;                    /* target value (loss 0) or class index (loss 1) */
+    double mean, stddev;            /* (x - mean) / stddev of Trainer.forward */
+    float class_weight[3];          /* loss 1 only */
+    float lr, beta1, beta2, eps;    /* Adam hyper-parameters */
+} smg_train_step_args;
+int smg_train_step(smg_handle* h, const smg_train_step_args* args, const double* dev_scene_hm, const double* dev_mask_hm,
+                   float* const* dev_params, float* const* dev_grads, float* const* dev_exp_avg,
+                   float* const* dev_exp_avg_sq, int n_tensors, float* dev_loss, float* dev_q, float* dev_bn_mean,
+                   float* dev_bn_var, void* stream);
+
 /* Stamp of the pending smg_qforward_train result (incremented by every such call), or -1 if there is none - any
  * other forward on the handle overwrites the saved activations and invalidates it; smg_qbackward then fails with
  * SMG_ERR_STATE instead of differentiating another pass.  Only ONE grad-enabled pass may be in flight per handle. */
@@ -212,6 +239,13 @@ int smg_debug_conv(smg_handle* h, int precision, const float* dev_in, int n, int
                    const float* dev_scale, const float* dev_shift, int relu, int pool, int taps,
                    const float* dev_w_oihw, int cout, float* dev_out, int out_cstride, int out_coff,
                    double* dev_out_stats, void* stream);
+
+/* unit-test hook for the data-gradient convolutions of the backward pass: g NHWC [n,hin,hin,g_cstride] (channels
+ * [g_coff, g_coff+cout) used) is the gradient w.r.t. the OUTPUT of a convolution with torch OIHW weights [cout,cin,k,k]
+ * (k = 1 or 3, pad k/2); writes the gradient w.r.t. its input, NHWC [n,hin,hin,cin].  tf32: tcgen05 kernel on the
+ * w_dgrad_tf32 image; fp32: CUDA cores.  Synchronous.                                                              */
+int smg_debug_dgrad(smg_handle* h, int precision, const float* dev_g, int n, int hin, int cout, int g_cstride, int g_coff,
+                    int taps, const float* dev_w_oihw, int cin, float* dev_dx, void* stream);
 
 /* unit-test hook for the BatchNorm(+ReLU) backward kernels (backward.cu): x NHWC [S,hw,hw,x_cstride] is the raw
  * BN input, dev_stats its (sum,sumsq) [S,stats_stride,2] doubles, da the gradient w.r.t. relu(bn(x)) (at half

@@ -14,6 +14,15 @@ c_void_pp = ctypes.POINTER(ctypes.c_void_p)
 VP = ctypes.c_void_p
 I = ctypes.c_int
 
+class TrainStepArgs(ctypes.Structure):
+    """smg_train_step_args of include/smg_b200.h."""
+    _fields_ = [("trunk_id", ctypes.c_int32), ("head_id", ctypes.c_int32), ("rot_idx", ctypes.c_int32),
+                ("num_rotations", ctypes.c_int32), ("hm_size", ctypes.c_int32), ("loss_kind", ctypes.c_int32),
+                ("adam_step", ctypes.c_int32), ("label", ctypes.c_float), ("mean", ctypes.c_double),
+                ("stddev", ctypes.c_double), ("class_weight", ctypes.c_float * 3), ("lr", ctypes.c_float),
+                ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float)]
+
+
 # name -> (restype, argtypes); must list every symbol include/smg_b200.h declares
 PROTOTYPES = {
     "smg_version": (I, []),
@@ -37,6 +46,8 @@ PROTOTYPES = {
     "smg_qforward_train": (I, [VP, I, I, VP, VP, I, I, VP, VP, VP, VP]),
     "smg_qbackward": (I, [VP, VP, c_void_pp, c_void_pp, VP]),
     "smg_train_pass_id": (ctypes.c_int64, [VP]),
+    "smg_train_step": (I, [VP, ctypes.POINTER(TrainStepArgs), VP, VP, c_void_pp, c_void_pp, c_void_pp, c_void_pp, I, VP, VP,
+                           VP, VP, VP]),
     "smg_adam_step": (I, [VP, c_void_pp, c_void_pp, c_void_pp, c_void_pp, c_int64_p, I, I,
                           ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, VP]),
     "smg_argmax": (I, [VP, VP, I, VP, VP, VP]),
@@ -47,6 +58,7 @@ PROTOTYPES = {
     "smg_debug_read": (I, [VP, ctypes.c_char_p, I, VP, ctypes.c_int64, VP]),
     "smg_profile_enable": (I, [VP, I]),
     "smg_profile_read": (I, [VP, c_double_p, c_int64_p, c_double_p, c_double_p]),
+    "smg_debug_dgrad": (I, [VP, I, VP, I, I, I, I, I, I, VP, I, VP, VP]),
     "smg_debug_bn_bwd": (I, [VP, VP, I, I, VP, I, VP, I, VP, VP, I, I, I, I, VP, VP, I, I, VP, VP, VP]),
     "smg_debug_conv": (I, [VP, I, VP, I, I, I, I, VP, VP, I, I, I, VP, I, VP, I, I, VP, VP]),
 }

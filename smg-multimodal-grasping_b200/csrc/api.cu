@@ -26,18 +26,6 @@ const char* get_error() { return g_err; }
 int launch_bn_export_region(smg_handle* h, int n, const double* stats, int stats_stride, int c_count, double cnt,
                             float* mean, float* var, int out_stride, int out_off, cudaStream_t st);
 
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
 // brackets the launches issued inside its lifetime with CUDA events when profiling is enabled
 struct ProfScope {
     smg_handle* h;
@@ -58,7 +46,7 @@ struct ProfScope {
     }
 };
 
-static int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
+int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     const int hout = a.pool ? a.hin / 2 : a.hin;
     const double px = (double)a.n * hout * hout;
     // algorithmic traffic: every input element of the layer read once, every output written once (fp32)
@@ -97,7 +85,7 @@ static int chunk_samples(const smg_handle* h, int b, int n) {
     return cs;
 }
 
-static int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cudaStream_t st, bool save_bott = false) {
+int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cudaStream_t st, bool save_bott) {
     TrunkW& T = h->trunks[trunk_id];
     SMG_CHECK(T.set, SMG_ERR_STATE, "trunk %d: weights not set (call smg_set_trunk_weights)", trunk_id);
     SMG_CHECK(n >= 1 && n <= h->max_samples, SMG_ERR_INVALID, "trunk_forward: n=%d outside [1,%d]", n, h->max_samples);
@@ -186,7 +174,7 @@ static int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cu
 }
 
 // per-sample BN statistics of all 121 BatchNorm layers in module order
-static int export_bn_stats(smg_handle* h, int n, float* mean, float* var, cudaStream_t st) {
+int export_bn_stats(smg_handle* h, int n, float* mean, float* var, cudaStream_t st) {
     int off = 0;
     const int total = SMG_TRUNK_BN_CHANNELS;
     const double cnt0 = (double)(h->H / 2) * (h->H / 2);
@@ -213,8 +201,8 @@ static int export_bn_stats(smg_handle* h, int n, float* mean, float* var, cudaSt
 }
 
 // heads for all (mask, rotation) pairs; samples [0,n_rot) are scenes, [n_rot, n_rot+n_masks) masks
-static int heads_forward(smg_handle* h, int trunk_id, int head_id, int n_rot, int n_masks, float* dev_q,
-                         cudaStream_t st, int groups = 1) {
+int heads_forward(smg_handle* h, int trunk_id, int head_id, int n_rot, int n_masks, float* dev_q, cudaStream_t st,
+                  int groups) {
     TrunkW& T = h->trunks[trunk_id];
     HeadW& Hd = h->heads[head_id];
     SMG_CHECK(Hd.set, SMG_ERR_STATE, "head %d: weights not set (call smg_set_head_weights)", head_id);
@@ -278,14 +266,12 @@ static void plan_conv(ArenaPlanner& p, ConvW& cw, int cin, int cout, int taps, u
     const size_t o2 = p.take(conv_packed_bytes_umma(cin, cout, taps, 4));
     const size_t o3 = p.take(conv_packed_bytes_umma(cin, cout, taps, 2));
     const size_t o4 = p.take(conv_packed_bytes_ffma(cin, cout, taps));
-    const size_t o5 = taps == 9 ? p.take(conv_packed_bytes_umma(cin, cout, taps, 4)) : 0;
-    const size_t o6 = taps == 9 ? p.take(conv_packed_bytes_umma(cin, cout, taps, 4)) : 0;
+    const size_t o5 = p.take(conv_packed_bytes_umma(dgrad_cin_padded(cin, taps), cout, taps, 4));
     const bool has_t = taps == 9 || (taps == 1 && cout == 128);
     const size_t o7 = has_t ? p.take(conv_packed_bytes_umma(cin, cout, taps, 4)) : 0;
     if (base) {
         if (has_t) cw.w_tf32_t = base + o7;
-        if (taps == 9) cw.w_tf32_dx = base + o5;
-        if (taps == 9) cw.w_tf32_dx32 = base + o6;
+        cw.w_dgrad_tf32 = base + o5;
         cw.w_ffma = reinterpret_cast<float*>(base + o1);
         cw.w_tf32 = base + o2;
         cw.w_bf16 = base + o3;
@@ -329,6 +315,34 @@ static size_t plan_trunk(smg_handle* h, TrunkW& T, uint8_t* base) {
     }
     plan_bn(p, T.norm5, kFeatC, base);
     return p.off;
+}
+
+int repack_trunk(smg_handle* h, int trunk_id, cudaStream_t st) {
+    TrunkW& T = h->trunks[trunk_id];
+    SMG_CHECK(T.jobs_dev != nullptr && T.src.size() == SMG_TRUNK_NUM_PARAMS, SMG_ERR_STATE, "trunk %d: no packing tables", trunk_id);
+    pack_conv0_kernel<<<(147 * 64 + 255) / 256, 256, 0, st>>>(T.src[0], T.conv0, T.conv0_folded);
+    h->launches++;
+    SMG_TRY(pack_conv0_umma(h, T.conv0_folded, T.conv0_umma, st));
+    const PackJob* pj = reinterpret_cast<const PackJob*>(T.jobs_dev);
+    const CopyJob* cj = reinterpret_cast<const CopyJob*>(reinterpret_cast<const uint8_t*>(T.jobs_dev) + T.pack_jobs.size() * sizeof(PackJob));
+    SMG_TRY(launch_pack_tables(h, pj, (int)T.pack_jobs.size(), cj, (int)T.copy_jobs.size(), st));
+    return SMG_OK;
+}
+
+int repack_head(smg_handle* h, int head_id, cudaStream_t st) {
+    HeadW& Hd = h->heads[head_id];
+    SMG_CHECK(Hd.src.size() == SMG_HEAD_NUM_PARAMS && Hd.arena != nullptr, SMG_ERR_STATE, "head %d: weights never set", head_id);
+    const float* const* dev_params = Hd.src.data();
+    SMG_CUDA(cudaMemcpyAsync(Hd.norm0.gamma, dev_params[0], 2 * kFeatC * 4, cudaMemcpyDeviceToDevice, st));
+    SMG_CUDA(cudaMemcpyAsync(Hd.norm0.beta, dev_params[1], 2 * kFeatC * 4, cudaMemcpyDeviceToDevice, st));
+    SMG_TRY(pack_conv_weights(h, dev_params[2], Hd.conv0[0], 0, 2 * kFeatC, st));
+    SMG_TRY(pack_conv_weights(h, dev_params[2], Hd.conv0[1], kFeatC, 2 * kFeatC, st));
+    SMG_CUDA(cudaMemcpyAsync(Hd.norm1.gamma, dev_params[3], kHeadMid * 4, cudaMemcpyDeviceToDevice, st));
+    SMG_CUDA(cudaMemcpyAsync(Hd.norm1.beta, dev_params[4], kHeadMid * 4, cudaMemcpyDeviceToDevice, st));
+    pack_head_conv1_kernel<<<64, 256, 0, st>>>(dev_params[5], Hd.conv1, Hd.n_out, kHeadK * kHeadK);
+    h->launches++;
+    SMG_CUDA(cudaGetLastError());
+    return SMG_OK;
 }
 
 }  // namespace smg
@@ -431,15 +445,20 @@ int smg_destroy(smg_handle* h) {
     if (!h) return SMG_OK;
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
-    if (h->job_buf) cudaFree(h->job_buf);
     for (auto& g : h->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto& g : h->step.graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (h->step.tables) cudaFree(h->step.tables);
+    if (h->train.arena) cudaFree(h->train.arena);
     if (h->gstream) cudaStreamDestroy(h->gstream);
     if (h->g_in) cudaEventDestroy(h->g_in);
     if (h->g_out) cudaEventDestroy(h->g_out);
     if (h->input) cudaFree(h->input);  // base of the workspace arena
-    for (int t = 0; t < SMG_NUM_TRUNKS; ++t)
+    for (int t = 0; t < SMG_NUM_TRUNKS; ++t) {
         if (h->trunks[t].arena) cudaFree(h->trunks[t].arena);
+        if (h->trunks[t].jobs_dev) cudaFree(h->trunks[t].jobs_dev);
+    }
     for (int t = 0; t < SMG_NUM_HEADS; ++t)
         if (h->heads[t].arena) cudaFree(h->heads[t].arena);
     delete h;
@@ -468,32 +487,41 @@ int smg_set_trunk_weights(smg_handle* h, int trunk_id, const float* const* dev_p
         SMG_CUDA(cudaMalloc(&T.arena, T.arena_bytes));
         plan_trunk(h, T, reinterpret_cast<uint8_t*>(T.arena));
     }
-    int i = 0;
-    std::vector<PackJob> pj;
-    std::vector<CopyJob> cj;
-    auto copy_bn = [&](BnP& b) {
-        cj.push_back(CopyJob{dev_params[i++], b.gamma, b.c});
-        cj.push_back(CopyJob{dev_params[i++], b.beta, b.c});
-    };
-    pack_conv0_kernel<<<(147 * 64 + 255) / 256, 256, 0, st>>>(dev_params[i++], T.conv0, T.conv0_folded);
-    SMG_TRY(pack_conv0_umma(h, T.conv0_folded, T.conv0_umma, st));
-    h->launches++;
-    copy_bn(T.norm0);
-    for (int b = 0; b < kNumBlocks; ++b) {
-        for (int l = 0; l < kBlockLayers[b]; ++l) {
-            DenseLayerW& L = T.layers[b][l];
-            copy_bn(L.norm1);
-            pj.push_back(make_pack_job(dev_params[i++], L.conv1, 0, L.conv1.cin));
-            copy_bn(L.norm2);
-            pj.push_back(make_pack_job(dev_params[i++], L.conv2, 0, L.conv2.cin));
+    // the job tables live in the trunk (host copy + device copy): they are rebuilt only when a source pointer changes, so
+    // that repack_trunk() can re-run the packing kernels alone - e.g. inside the captured training step
+    std::vector<const float*> src(dev_params, dev_params + n);
+    int i = SMG_TRUNK_NUM_PARAMS;
+    if (src != T.src) {
+        i = 0;
+        T.pack_jobs.clear();
+        T.copy_jobs.clear();
+        auto copy_bn = [&](BnP& b) {
+            T.copy_jobs.push_back(CopyJob{dev_params[i++], b.gamma, b.c});
+            T.copy_jobs.push_back(CopyJob{dev_params[i++], b.beta, b.c});
+        };
+        i++;  // conv0.weight: packed by its own two kernels
+        copy_bn(T.norm0);
+        for (int b = 0; b < kNumBlocks; ++b) {
+            for (int l = 0; l < kBlockLayers[b]; ++l) {
+                DenseLayerW& L = T.layers[b][l];
+                copy_bn(L.norm1);
+                T.pack_jobs.push_back(make_pack_job(dev_params[i++], L.conv1, 0, L.conv1.cin));
+                copy_bn(L.norm2);
+                T.pack_jobs.push_back(make_pack_job(dev_params[i++], L.conv2, 0, L.conv2.cin));
+            }
+            if (b < kNumBlocks - 1) {
+                copy_bn(T.trans[b].norm);
+                T.pack_jobs.push_back(make_pack_job(dev_params[i++], T.trans[b].conv, 0, T.trans[b].conv.cin));
+            }
         }
-        if (b < kNumBlocks - 1) {
-            copy_bn(T.trans[b].norm);
-            pj.push_back(make_pack_job(dev_params[i++], T.trans[b].conv, 0, T.trans[b].conv.cin));
-        }
+        copy_bn(T.norm5);
+        const size_t pb = T.pack_jobs.size() * sizeof(PackJob), cb = T.copy_jobs.size() * sizeof(CopyJob);
+        if (!T.jobs_dev) SMG_CUDA(cudaMalloc(&T.jobs_dev, pb + cb));
+        SMG_CUDA(cudaMemcpy(T.jobs_dev, T.pack_jobs.data(), pb, cudaMemcpyHostToDevice));
+        SMG_CUDA(cudaMemcpy(reinterpret_cast<uint8_t*>(T.jobs_dev) + pb, T.copy_jobs.data(), cb, cudaMemcpyHostToDevice));
+        T.src = src;
     }
-    copy_bn(T.norm5);
-    SMG_TRY(launch_pack_batch(h, pj, cj, st));
+    SMG_TRY(repack_trunk(h, trunk_id, st));
     SMG_CHECK(i == SMG_TRUNK_NUM_PARAMS, SMG_ERR_STATE, "consumed %d trunk tensors", i);
     SMG_CUDA(cudaGetLastError());
     T.set = true;
@@ -527,15 +555,8 @@ int smg_set_head_weights(smg_handle* h, int head_id, const float* const* dev_par
         }
         Hd.n_out = n_out;
     }
-    SMG_CUDA(cudaMemcpyAsync(Hd.norm0.gamma, dev_params[0], 2 * kFeatC * 4, cudaMemcpyDeviceToDevice, st));
-    SMG_CUDA(cudaMemcpyAsync(Hd.norm0.beta, dev_params[1], 2 * kFeatC * 4, cudaMemcpyDeviceToDevice, st));
-    SMG_TRY(pack_conv_weights(h, dev_params[2], Hd.conv0[0], 0, 2 * kFeatC, st));
-    SMG_TRY(pack_conv_weights(h, dev_params[2], Hd.conv0[1], kFeatC, 2 * kFeatC, st));
-    SMG_CUDA(cudaMemcpyAsync(Hd.norm1.gamma, dev_params[3], kHeadMid * 4, cudaMemcpyDeviceToDevice, st));
-    SMG_CUDA(cudaMemcpyAsync(Hd.norm1.beta, dev_params[4], kHeadMid * 4, cudaMemcpyDeviceToDevice, st));
-    pack_head_conv1_kernel<<<64, 256, 0, st>>>(dev_params[5], Hd.conv1, n_out, npix);
-    h->launches++;
-    SMG_CUDA(cudaGetLastError());
+    Hd.src.assign(dev_params, dev_params + SMG_HEAD_NUM_PARAMS);
+    SMG_TRY(repack_head(h, head_id, st));
     Hd.set = true;
     Hd.packed = SMG_PACK_ALL;  // the head's few tensors are always packed in every layout
     return SMG_OK;
@@ -708,10 +729,14 @@ int smg_qforward_maps_batch(smg_handle* h, int trunk_id, int head_id, const doub
     return SMG_OK;
 }
 
+}  // extern "C" (reopened below)
+
+namespace smg {
+
 // ---------------------------------------------------------------------------------------
 // training: forward that keeps what the backward needs, backward, Adam
 // ---------------------------------------------------------------------------------------
-static int ensure_train_workspace(smg_handle* h) {
+int ensure_train_workspace(smg_handle* h) {
     smg_handle::TrainWs& W = h->train;
     if (W.arena) return SMG_OK;
     const size_t S = 2;
@@ -751,10 +776,6 @@ static int ensure_train_workspace(smg_handle* h) {
     return SMG_OK;
 }
 
-}  // extern "C" (reopened below)
-
-namespace smg {
-
 // gradient pointer cursor over the smg_set_trunk_weights parameter order
 struct TrunkGradMap {
     float* conv0;
@@ -779,16 +800,31 @@ struct TrunkGradMap {
     }
 };
 
+// a data-gradient convolution: identity prologue, flipped / transposed weights.  tf32 mode: the tcgen05 kernel of
+// conv_umma.cu on the w_dgrad_tf32 stage image; fp32 mode: CUDA cores on w_dgrad.
+static int dgrad_conv(smg_handle* h, ConvArgs a, const ConvW& cw, cudaStream_t st) {
+    a.prologue_mode = 2;
+    a.relu = 0;
+    a.w = nullptr;
+    const double px = (double)a.n * a.hin * a.hin;
+    ProfScope ps(h, st, 3, 2.0 * px * a.cout * a.cin * a.taps, 4.0 * px * (a.cin + a.cout));
+    if (h->precision == SMG_PREC_TF32 && cw.w_dgrad_tf32 != nullptr) {
+        a.w_umma = cw.w_dgrad_tf32;
+        return launch_conv_umma(h, a, SMG_PREC_TF32, st);
+    }
+    a.w_raw = cw.w_dgrad;
+    return launch_conv_ffma(h, a, st);
+}
+
 // one BatchNorm(+ReLU) backward: reduce -> parameter grads -> apply
 static int bn_backward(smg_handle* h, BnBwd a, int S, double*& sums_cursor, float* dgamma, float* dbeta, cudaStream_t st) {
     a.sums = sums_cursor;
     sums_cursor += (size_t)2 * S * a.C;
-    SMG_TRY(launch_bn_bwd(h, a, S, false, st));
-    SMG_TRY(launch_bn_param_grad(h, a.sums, S, a.C, dgamma, dbeta, st));
-    return launch_bn_bwd(h, a, S, true, st);
+    SMG_TRY(launch_bn_bwd(h, a, S, false, nullptr, nullptr, st));
+    return launch_bn_bwd(h, a, S, true, dgamma, dbeta, st);
 }
 
-static int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* const* hg, cudaStream_t st) {
+int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* const* hg, cudaStream_t st) {
     smg_handle::TrainWs& W = h->train;
     TrunkW& T = h->trunks[W.trunk_id];
     HeadW& Hd = h->heads[W.head_id];
@@ -812,11 +848,11 @@ static int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, floa
         wg.relu = 1; wg.dw = hg[2]; wg.k_total = 2 * kFeatC; wg.k_off = half * kFeatC;
         SMG_TRY(launch_wgrad(h, wg, 1, 1, 0, st));
         ConvArgs a;
-        a.in = W.dP; a.in_cstride = kHeadMid; a.cin = kHeadMid; a.hin = g4.hw; a.prologue_mode = 2; a.relu = 0;
-        a.taps = 1; a.w_raw = Hd.conv0[half].w_dgrad;
+        a.in = W.dP; a.in_cstride = kHeadMid; a.cin = kHeadMid; a.hin = g4.hw;
+        a.taps = 1;
         a.out = W.t_c + (size_t)s * npix4 * kFeatC; a.out_cstride = kFeatC; a.out_coff = 0; a.cout = kFeatC;
         a.n = 1;
-        SMG_TRY(launch_conv_ffma(h, a, st));
+        SMG_TRY(dgrad_conv(h, a, Hd.conv0[half], st));
     }
     SMG_TRY(launch_head_norm_bwd(h, W.t_c, h->block[3], stats_ptr(h, h->st_block[3]), g4.c_tot, T.norm5, Hd.norm0,
                                  W.dblk[3], G.norm5[0], G.norm5[1], hg[0], hg[1], st));
@@ -837,10 +873,10 @@ static int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, floa
             // (1) 3x3 dgrad: d relu(bn2(y1)) = conv3x3(dX[:, cin:cin+32], flipped W2)
             {
                 ConvArgs a;
-                a.in = W.dblk[b] + cin; a.in_cstride = g.c_tot; a.cin = kGrowth; a.hin = g.hw; a.prologue_mode = 2; a.relu = 0;
-                a.taps = 9; a.w_raw = L.conv2.w_dgrad;
+                a.in = W.dblk[b] + cin; a.in_cstride = g.c_tot; a.cin = kGrowth; a.hin = g.hw;
+                a.taps = 9;
                 a.out = W.t_a; a.out_cstride = kBottleneck; a.out_coff = 0; a.cout = kBottleneck; a.n = S;
-                SMG_TRY(launch_conv_ffma(h, a, st));
+                SMG_TRY(dgrad_conv(h, a, L.conv2, st));
             }
             // (2) 3x3 wgrad
             SMG_CUDA(cudaMemsetAsync(GL.c2, 0, (size_t)kGrowth * kBottleneck * 9 * 4, st));
@@ -873,10 +909,10 @@ static int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, floa
             // (5) 1x1 dgrad: d relu(bn1(X[:, :cin])) = dy1 . W1
             {
                 ConvArgs a;
-                a.in = W.t_b; a.in_cstride = kBottleneck; a.cin = kBottleneck; a.hin = g.hw; a.prologue_mode = 2; a.relu = 0;
-                a.taps = 1; a.w_raw = L.conv1.w_dgrad;
+                a.in = W.t_b; a.in_cstride = kBottleneck; a.cin = kBottleneck; a.hin = g.hw;
+                a.taps = 1;
                 a.out = W.t_c; a.out_cstride = cin; a.out_coff = 0; a.cout = cin; a.n = S;
-                SMG_TRY(launch_conv_ffma(h, a, st));
+                SMG_TRY(dgrad_conv(h, a, L.conv1, st));
             }
             // (6) BN1 + ReLU backward, accumulated into the block gradient
             {
@@ -904,10 +940,10 @@ static int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, floa
             }
             {
                 ConvArgs a;
-                a.in = W.dblk[b]; a.in_cstride = g.c_tot; a.cin = Co; a.hin = g.hw; a.prologue_mode = 2; a.relu = 0;
-                a.taps = 1; a.w_raw = R.conv.w_dgrad;
+                a.in = W.dblk[b]; a.in_cstride = g.c_tot; a.cin = Co; a.hin = g.hw;
+                a.taps = 1;
                 a.out = W.t_c; a.out_cstride = C; a.out_coff = 0; a.cout = C; a.n = S;
-                SMG_TRY(launch_conv_ffma(h, a, st));
+                SMG_TRY(dgrad_conv(h, a, R.conv, st));
             }
             {
                 BnBwd bb{};
@@ -930,8 +966,16 @@ static int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, floa
         bb.C = 64; bb.hw = Hc; bb.relu = 1; bb.dst = W.dconv0; bb.dst_cstride = 64; bb.accumulate = 0;
         SMG_TRY(bn_backward(h, bb, S, sums, G.norm0[0], G.norm0[1], st));
     }
-    SMG_CUDA(cudaMemsetAsync(G.conv0, 0, (size_t)64 * 147 * 4, st));
-    SMG_TRY(launch_conv0_wgrad(h, S, W.dconv0, h->input, 3, G.conv0, st));
+    if (W.in_channels == 1) {
+        // Trainer.forward feeds three identical channels: one 49-tap gradient, replicated into [64][3][7][7]
+        float* g1 = W.t_a;
+        SMG_CUDA(cudaMemsetAsync(g1, 0, (size_t)64 * 49 * 4, st));
+        SMG_TRY(launch_conv0_wgrad(h, S, W.dconv0, h->input, 1, g1, st));
+        SMG_TRY(launch_replicate_conv0_grad(h, g1, G.conv0, st));
+    } else {
+        SMG_CUDA(cudaMemsetAsync(G.conv0, 0, (size_t)64 * 147 * 4, st));
+        SMG_TRY(launch_conv0_wgrad(h, S, W.dconv0, h->input, 3, G.conv0, st));
+    }
     return SMG_OK;
 }
 
@@ -957,6 +1001,7 @@ int smg_qforward_train(smg_handle* h, int trunk_id, int head_id, const float* de
     if (dev_bn_mean && dev_bn_var) SMG_TRY(export_bn_stats(h, 2, dev_bn_mean, dev_bn_var, st));
     h->train.trunk_id = trunk_id;
     h->train.head_id = head_id;
+    h->train.in_channels = 3;
     h->train.valid = true;
     h->train.pass_id++;
     return SMG_OK;
@@ -1124,6 +1169,40 @@ int smg_debug_conv(smg_handle* h, int precision, const float* dev_in, int n, int
     return status;
 }
 
+int smg_debug_dgrad(smg_handle* h, int precision, const float* dev_g, int n, int hin, int cout, int g_cstride, int g_coff,
+                    int taps, const float* dev_w_oihw, int cin, float* dev_dx, void* stream) {
+    SMG_CHECK(h && dev_g && dev_w_oihw && dev_dx, SMG_ERR_INVALID, "smg_debug_dgrad: NULL argument");
+    SMG_CHECK(taps == 1 || taps == 9, SMG_ERR_INVALID, "smg_debug_dgrad: taps %d", taps);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ConvW cw;
+    ArenaPlanner p;
+    plan_conv(p, cw, cin, cout, taps, nullptr);
+    uint8_t* base = nullptr;
+    SMG_CUDA(cudaMalloc(&base, p.off));
+    ArenaPlanner p2;
+    plan_conv(p2, cw, cin, cout, taps, base);
+    int status = pack_conv_weights(h, dev_w_oihw, cw, 0, cin, st);
+    if (status == SMG_OK) {
+        ConvArgs a;
+        a.in = dev_g + g_coff; a.in_cstride = g_cstride; a.cin = cout; a.hin = hin;
+        a.taps = taps;
+        a.out = dev_dx; a.out_cstride = cin; a.out_coff = 0; a.cout = cin;
+        a.n = n;
+        const int saved = h->precision;
+        h->precision = precision;
+        status = dgrad_conv(h, a, cw, st);
+        h->precision = saved;
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(base);
+    if (status == SMG_OK && e != cudaSuccess) {
+        set_error("smg_debug_dgrad: %s", cudaGetErrorString(e));
+        return SMG_ERR_CUDA;
+    }
+    return status;
+}
+
 int smg_debug_bn_bwd(smg_handle* h, const float* dev_da, int da_cstride, int da_pooled, const float* dev_x,
                      int x_cstride, const double* dev_stats, int stats_stride, const float* dev_gamma,
                      const float* dev_beta, int C, int hw, int relu, int S, double* dev_sums, float* dev_dst,
@@ -1137,9 +1216,8 @@ int smg_debug_bn_bwd(smg_handle* h, const float* dev_da, int da_cstride, int da_
     bb.stats = dev_stats; bb.stats_stride = stats_stride; bb.gamma = dev_gamma; bb.beta = dev_beta;
     bb.C = C; bb.hw = hw; bb.relu = relu; bb.sums = dev_sums; bb.dst = dev_dst; bb.dst_cstride = dst_cstride;
     bb.accumulate = accumulate;
-    SMG_TRY(launch_bn_bwd(h, bb, S, false, st));
-    SMG_TRY(launch_bn_param_grad(h, dev_sums, S, C, dev_dgamma, dev_dbeta, st));
-    SMG_TRY(launch_bn_bwd(h, bb, S, true, st));
+    SMG_TRY(launch_bn_bwd(h, bb, S, false, nullptr, nullptr, st));
+    SMG_TRY(launch_bn_bwd(h, bb, S, true, dev_dgamma, dev_dbeta, st));
     SMG_CUDA(cudaStreamSynchronize(st));
     return SMG_OK;
 }

@@ -41,78 +41,108 @@ __device__ __forceinline__ float bn_da(const BnBwd& a, const float* da_s, int p,
     return da_s[(size_t)p * a.da_cstride + c];
 }
 
-// block = 32 channel lanes x 8 pixel lanes
+// One CTA = a chunk of pixels of one sample x ALL channels.  A thread owns four consecutive channels (float4 loads and
+// stores) and every PL-th pixel of the chunk; Q = C/4 channel quads x PL = 256/Q pixel lanes.
+//   APPLY = 0: S1 += dz, S2 += dz * xhat per channel -> shared-memory combine over the pixel lanes -> one double atomic
+//              pair per channel and CTA.
+//   APPLY = 1: dx = gamma * rstd * (dz - S1/n - xhat * S2/n); the CTA (0, sample 0) also writes the parameter gradients
+//              dgamma = sum_s S2, dbeta = sum_s S1 (the reductions are complete once this kernel runs).
 template <int APPLY>
 __global__ void __launch_bounds__(256)
-bn_bwd_kernel(BnBwd a) {
-    __shared__ float red[2][8][32];
+bn_bwd_kernel(BnBwd a, int S, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    extern __shared__ __align__(16) float4 red[];   // APPLY = 0: [2][PL][Q]
     const int s = blockIdx.y;
-    const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    const int Q = a.C >> 2;
+    const int PL = 256 / Q;
+    const int q = threadIdx.x % Q, pl = threadIdx.x / Q;
+    const bool active = pl < PL;
     const int npix = a.hw * a.hw;
     const int p0 = blockIdx.x * a.pix_per_cta;
     const int p1 = min(p0 + a.pix_per_cta, npix);
     const int hw_da = a.da_pooled ? (a.hw >> 1) : a.hw;
-    const float* da_s = a.da + (size_t)s * hw_da * hw_da * a.da_cstride;
-    const float* x_s = a.x + (size_t)s * npix * a.x_cstride;
-    float* dst_s = APPLY ? a.dst + (size_t)s * npix * a.dst_cstride : nullptr;
+    const float* da_s = a.da + (size_t)s * hw_da * hw_da * a.da_cstride + 4 * q;
+    const float* x_s = a.x + (size_t)s * npix * a.x_cstride + 4 * q;
     const float inv_n = 1.0f / (float)npix;
-    for (int c0 = 0; c0 < a.C; c0 += 32) {
-        const int c = c0 + cl;
-        const bool cv = c < a.C;
-        float mean = 0.f, rstd = 0.f, sc = 0.f, sh = 0.f, m1 = 0.f, m2 = 0.f;
-        if (cv) {
-            bn_channel_consts(a, s, c, mean, rstd, sc, sh);
-            if (APPLY) {
-                const double* sm = a.sums + 2 * ((size_t)s * a.C + c);
-                m1 = (float)(sm[0] * (double)inv_n);
-                m2 = (float)(sm[1] * (double)inv_n);
-            }
-        }
-        float s1 = 0.f, s2 = 0.f;
-        if (cv) {
-            for (int p = p0 + pl; p < p1; p += 8) {
-                const float xv = x_s[(size_t)p * a.x_cstride + c];
-                float dz = bn_da(a, da_s, p, c);
-                if (a.relu && !(fmaf(xv, sc, sh) > 0.f)) dz = 0.f;
-                const float xh = (xv - mean) * rstd;
-                if (APPLY) {
-                    const float dx = a.gamma[c] * rstd * (dz - m1 - xh * m2);
-                    float* d = dst_s + (size_t)p * a.dst_cstride + c;
-                    *d = a.accumulate ? *d + dx : dx;
-                } else {
-                    s1 += dz;
-                    s2 = fmaf(dz, xh, s2);
-                }
-            }
-        }
-        if (!APPLY) {
-            red[0][pl][cl] = s1;
-            red[1][pl][cl] = s2;
-            __syncthreads();
-            if (pl == 0 && cv) {
-                double t1 = 0, t2 = 0;
+    float mean[4], rstd[4], sc[4], sh[4], m1[4], m2[4], gr[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { t1 += (double)red[0][i][cl]; t2 += (double)red[1][i][cl]; }
-                double* sm = a.sums + 2 * ((size_t)s * a.C + c);
-                atomicAdd(sm, t1);
-                atomicAdd(sm + 1, t2);
-            }
-            __syncthreads();
+    for (int j = 0; j < 4; ++j) {
+        bn_channel_consts(a, s, 4 * q + j, mean[j], rstd[j], sc[j], sh[j]);
+        m1[j] = m2[j] = gr[j] = 0.f;
+        if (APPLY) {
+            const double* sm = a.sums + 2 * ((size_t)s * a.C + 4 * q + j);
+            m1[j] = (float)(sm[0] * (double)inv_n);
+            m2[j] = (float)(sm[1] * (double)inv_n);
+            gr[j] = a.gamma[4 * q + j] * rstd[j];
         }
     }
-}
-
-__global__ void bn_param_grad_kernel(const double* __restrict__ sums, int S, int C, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double g = 0, b = 0;
-    for (int s = 0; s < S; ++s) {
-        b += sums[2 * ((size_t)s * C + c)];
-        g += sums[2 * ((size_t)s * C + c) + 1];
+    if (APPLY && blockIdx.x == 0 && s == 0 && pl == 0 && dgamma != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double g = 0, b = 0;
+            for (int t = 0; t < S; ++t) {
+                b += a.sums[2 * ((size_t)t * a.C + 4 * q + j)];
+                g += a.sums[2 * ((size_t)t * a.C + 4 * q + j) + 1];
+            }
+            dgamma[4 * q + j] = (float)g;
+            dbeta[4 * q + j] = (float)b;
+        }
     }
-    dgamma[c] = (float)g;
-    dbeta[c] = (float)b;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+        float* dst_s = APPLY ? a.dst + (size_t)s * npix * a.dst_cstride + 4 * q : nullptr;
+        for (int p = p0 + pl; p < p1; p += PL) {
+            const float4 xv4 = *reinterpret_cast<const float4*>(x_s + (size_t)p * a.x_cstride);
+            float4 dv4;
+            if (a.da_pooled) {
+                const int y = p / a.hw, x = p - y * a.hw;
+                dv4 = *reinterpret_cast<const float4*>(da_s + ((size_t)(y >> 1) * hw_da + (x >> 1)) * a.da_cstride);
+                dv4.x *= 0.25f; dv4.y *= 0.25f; dv4.z *= 0.25f; dv4.w *= 0.25f;
+            } else {
+                dv4 = *reinterpret_cast<const float4*>(da_s + (size_t)p * a.da_cstride);
+            }
+            const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+            float dz[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (a.relu && !(fmaf(xv[j], sc[j], sh[j]) > 0.f)) dz[j] = 0.f;
+                const float xh = (xv[j] - mean[j]) * rstd[j];
+                o[j] = gr[j] * (dz[j] - m1[j] - xh * m2[j]);
+                s1[j] += dz[j];
+                s2[j] = fmaf(dz[j], xh, s2[j]);
+            }
+            if (APPLY) {
+                float4* d = reinterpret_cast<float4*>(dst_s + (size_t)p * a.dst_cstride);
+                float4 r = make_float4(o[0], o[1], o[2], o[3]);
+                if (a.accumulate) {
+                    const float4 old = *d;
+                    r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+                }
+                *d = r;
+            }
+        }
+    }
+    if (!APPLY) {
+        if (active) {
+            red[pl * Q + q] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+            red[(PL + pl) * Q + q] = make_float4(s2[0], s2[1], s2[2], s2[3]);
+        }
+        __syncthreads();
+        if (pl == 0) {
+            double t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
+            for (int i = 0; i < PL; ++i) {
+                const float4 u = red[i * Q + q], v = red[(PL + i) * Q + q];
+                t1[0] += u.x; t1[1] += u.y; t1[2] += u.z; t1[3] += u.w;
+                t2[0] += v.x; t2[1] += v.y; t2[2] += v.z; t2[3] += v.w;
+            }
+            double* sm = a.sums + 2 * ((size_t)s * a.C + 4 * q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(sm + 2 * j, t1[j]);
+                atomicAdd(sm + 2 * j + 1, t2[j]);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -288,7 +318,10 @@ conv0_wgrad_kernel(const float* __restrict__ d, const float* __restrict__ in, fl
     const int Ho = H / 2;
     const int K = cin * 49;
     const int p0 = blockIdx.x * pix_per_cta, p1 = min(p0 + pix_per_cta, Ho * Ho);
-    const int k = tid;
+    // K = cin * 49 taps; with one input channel three pixel lanes share the 147 busy threads
+    const int nl = cin == 1 ? 3 : 1;
+    const int lane_p = tid / K;
+    const int k = lane_p < nl ? tid - lane_p * K : K;
     const int c = k / 49, kh = (k % 49) / 7, kw = k % 7;
     const float* d_s = d + (size_t)s * Ho * Ho * 64;
     const float* in_s = in + (size_t)s * cin * H * H;
@@ -304,7 +337,7 @@ conv0_wgrad_kernel(const float* __restrict__ d, const float* __restrict__ in, fl
         }
         __syncthreads();
         if (k < K) {
-            for (int px = 0; px < 32 && pb + px < p1; ++px) {
+            for (int px = lane_p; px < 32 && pb + px < p1; px += nl) {
                 const int p = pb + px;
                 const int y = 2 * (p / Ho) + kh - 3, x = 2 * (p % Ho) + kw - 3;
                 if (y < 0 || y >= H || x < 0 || x >= H) continue;
@@ -466,21 +499,19 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-int launch_bn_bwd(smg_handle* h, BnBwd a, int S, bool apply, cudaStream_t st) {
+int launch_bn_bwd(smg_handle* h, BnBwd a, int S, bool apply, float* dgamma, float* dbeta, cudaStream_t st) {
+    SMG_CHECK(a.C % 4 == 0 && a.C >= 4 && a.C <= 1024 && a.da_cstride % 4 == 0 && a.x_cstride % 4 == 0 &&
+                  (!apply || a.dst_cstride % 4 == 0),
+              SMG_ERR_INVALID, "bn_bwd: C %d / strides must be multiples of 4 (C <= 1024)", a.C);
     const int npix = a.hw * a.hw;
-    int ppc = 256;
-    while (ppc > 32 && (npix + ppc - 1) / ppc * S < 2 * h->num_sms) ppc >>= 1;
+    const int Q = a.C / 4, PL = 256 / Q;
+    // pixels per CTA: at least 8 per pixel lane, and enough CTAs to fill the GPU twice
+    int ppc = 2048;
+    while (ppc > 8 * PL && (npix + ppc - 1) / ppc * S < 2 * h->num_sms) ppc >>= 1;
     a.pix_per_cta = ppc;
     dim3 grid((npix + ppc - 1) / ppc, S);
-    if (apply) bn_bwd_kernel<1><<<grid, 256, 0, st>>>(a);
-    else bn_bwd_kernel<0><<<grid, 256, 0, st>>>(a);
-    h->launches++;
-    SMG_CUDA(cudaGetLastError());
-    return SMG_OK;
-}
-
-int launch_bn_param_grad(smg_handle* h, const double* sums, int S, int C, float* dgamma, float* dbeta, cudaStream_t st) {
-    bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, S, C, dgamma, dbeta);
+    if (apply) bn_bwd_kernel<1><<<grid, 256, 0, st>>>(a, S, dgamma, dbeta);
+    else bn_bwd_kernel<0><<<grid, 256, 2 * PL * Q * sizeof(float4), st>>>(a, S, nullptr, nullptr);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;
@@ -517,6 +548,18 @@ int launch_pool0_bwd(smg_handle* h, int S, const float* g, int g_cstride, const 
     const int Hc = h->H / 2, Hp = Hc / 2;
     dim3 grid((Hp * Hp + 15) / 16, S);
     pool0_bwd_kernel<<<grid, 256, 0, st>>>(g, g_cstride, conv0, stats, gamma, beta, da0, Hc);
+    h->launches++;
+    SMG_CUDA(cudaGetLastError());
+    return SMG_OK;
+}
+
+__global__ void replicate_conv0_grad_kernel(const float* __restrict__ g1, float* __restrict__ g3) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [64][3][49]
+    if (i < 64 * 147) g3[i] = g1[(i / 147) * 49 + i % 49];
+}
+
+int launch_replicate_conv0_grad(smg_handle* h, const float* g1, float* g3, cudaStream_t st) {
+    replicate_conv0_grad_kernel<<<(64 * 147 + 255) / 256, 256, 0, st>>>(g1, g3);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;

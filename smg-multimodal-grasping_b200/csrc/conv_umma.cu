@@ -97,10 +97,15 @@ conv_umma_kernel(UmmaDev a) {
             s_sc[c] = sc;
             s_sh[c] = a.beta[c] - (float)m * sc;
         }
-    } else {
+    } else if (a.prologue_mode == 1) {
         for (int c = tid; c < a.cin; c += 448) {
             s_sc[c] = a.scale[(size_t)s * a.cin + c];
             s_sh[c] = a.shift[(size_t)s * a.cin + c];
+        }
+    } else {   // identity prologue (data-gradient convolutions): fmaf(x, 1, 0) == x
+        for (int c = tid; c < a.cin; c += 448) {
+            s_sc[c] = 1.f;
+            s_sh[c] = 0.f;
         }
     }
     tc_fence_before();
@@ -278,8 +283,8 @@ conv_umma_kernel(UmmaDev a) {
                         if (poff[i] >= 0) cp_async16(dst + (r0 + i * RSTEP) * 16, src + poff[i]);
                     cp_async_commit();
                 };
-                issue(pgroup);  // producer group g owns patch slot g: channel groups g and g+2
-                for (int g = pgroup; g < 4; g += 2) {
+                if (pgroup < KG) issue(pgroup);  // producer group g owns patch slot g: channel groups g and g+2
+                for (int g = pgroup; g < KG; g += 2) {
                     const int slot = g & 1;
                     cp_async_wait<0>();
                     const int ch0 = g * KC + c * E::EPC;
@@ -303,7 +308,7 @@ conv_umma_kernel(UmmaDev a) {
                     }
                     fence_proxy_async();
                     mbar_arrive(&a_full[slot]);
-                    if (g + 2 < 4) {
+                    if (g + 2 < KG) {
                         mbar_wait(&a_empty[slot], 0);
                         issue(g + 2);
                     } else {
@@ -311,7 +316,7 @@ conv_umma_kernel(UmmaDev a) {
                     }
                 }
             } else
-            for (int g = pgroup; g < 4; g += 2) {
+            for (int g = pgroup; g < KG; g += 2) {
                 const int slot = g & 1;
                 if (g >= 2) mbar_wait(&a_empty[slot], 0);
                 const int ch0 = g * KC + c * E::EPC;
@@ -372,7 +377,7 @@ conv_umma_kernel(UmmaDev a) {
     } else if (warp == 9) {
         // =============================== weight loader ===============================
         if (lane == 0) {
-            const int nstages = TAPS == 9 ? 36 : KG;
+            const int nstages = TAPS == 9 ? 9 * KG : KG;
             const uint8_t* wsrc = a.w + (size_t)ntile * nstages * P::B_STAGE;
             for (int j = 0; j < nstages; ++j) {
                 const int slot = j % P::B_SLOTS;
@@ -407,7 +412,7 @@ conv_umma_kernel(UmmaDev a) {
                     umma_commit(&b_empty[sb]);
                 }
             } else {
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < KG; ++g) {
                     const int sa = g & 1;
                     mbar_wait(&a_full[sa], (g >> 1) & 1);
                     for (int t = 0; t < 9; ++t) {
@@ -471,8 +476,10 @@ conv_umma_kernel(UmmaDev a) {
             }
             if (!ok) continue;
             float* o = a.out + ((size_t)s * hw_out + pix) * a.out_cstride + a.out_coff + ntile * BN;
+            const int nvalid = a.cout - ntile * BN;   // < BN only on the zero-padded last tile of a data-gradient convolution
 #pragma unroll
-            for (int cb = 0; cb < BN; cb += 32) o[cb + lane] = s_out[r * (BN + 1) + cb + lane];
+            for (int cb = 0; cb < BN; cb += 32)
+                if (cb + lane < nvalid) o[cb + lane] = s_out[r * (BN + 1) + cb + lane];
         }
         // per-channel statistics of this tile (invalid rows were staged as zeros): partial column sums by all
         // threads, combined in shared memory (the scale/shift tables are dead by now), ONE double atomic pair per
@@ -494,7 +501,7 @@ conv_umma_kernel(UmmaDev a) {
                 red[(GROUPS + g) * BN + cidx] = sq;
             }
             __syncthreads();
-            if (tid < BN) {
+            if (tid < BN && ntile * BN + tid < a.cout) {
                 double su = 0.0, sq = 0.0;
 #pragma unroll
                 for (int g2 = 0; g2 < GROUPS; ++g2) {
@@ -559,7 +566,7 @@ static int launch_umma(smg_handle* h, const UmmaDev& d, int n, cudaStream_t st) 
         const int tx = (d.hout + wt - 1) / wt, ty = (d.hout + d.ht - 1) / d.ht;
         grid = dim3(tx * ty, 1, n);
     } else {
-        grid = dim3((d.hout * d.hout + UM - 1) / UM, d.cout / BN, n);
+        grid = dim3((d.hout * d.hout + UM - 1) / UM, (d.cout + BN - 1) / BN, n);
     }
     UmmaDev dd = d;
     dd.async_producer = h->force_async >= 0 ? h->force_async : ((int)(grid.x * grid.y * grid.z) < 2 * h->num_sms ? 1 : 0);
@@ -571,18 +578,25 @@ static int launch_umma(smg_handle* h, const UmmaDev& d, int n, cudaStream_t st) 
 
 template <int ELT>
 static int dispatch(smg_handle* h, const ConvArgs& a, UmmaDev& d, cudaStream_t st) {
-    d.w = ELT == 4 ? a.w->w_tf32 : a.w->w_bf16;
+    d.w = a.w_umma != nullptr ? a.w_umma : (ELT == 4 ? a.w->w_tf32 : a.w->w_bf16);
     SMG_CHECK(d.w != nullptr, SMG_ERR_STATE, "conv_umma: weights not packed");
     if (a.taps == 9) {
-        SMG_CHECK(a.cin == 128 && a.cout == 32 && !a.pool, SMG_ERR_UNSUPPORTED, "conv_umma: 3x3 expects 128->32");
+        const bool fwd = a.cin == 128 && a.cout == 32, dgrad = ELT == 4 && a.cin == 32 && a.cout == 128 && a.w_umma != nullptr;
+        SMG_CHECK((fwd || dgrad) && !a.pool, SMG_ERR_UNSUPPORTED, "conv_umma: 3x3 expects 128->32 (or its 32->128 data gradient)");
         umma_patch_geometry(d.hout, &d.wp, &d.ht);
         SMG_CHECK((d.ht + 2) * d.wp <= 5 * MAX_WP && d.ht * d.wp <= UM, SMG_ERR_STATE, "conv_umma: patch %dx%d too large",
                   d.ht, d.wp);
         const int wt = d.wp - 2;
         d.tiles_x = (d.hout + wt - 1) / wt;
+        if (dgrad) return launch_umma<4, 128, 9, 0>(h, d, a.n, st);
         return launch_umma<ELT, 32, 9, 0>(h, d, a.n, st);
     }
     SMG_CHECK(a.cin % KC == 0 && a.cin <= 1024, SMG_ERR_UNSUPPORTED, "conv_umma: cin %d unsupported", a.cin);
+    if (a.w_umma != nullptr) {
+        // data-gradient 1x1: the packed image is zero-padded to whole 128-channel output tiles
+        SMG_CHECK(ELT == 4 && !a.pool, SMG_ERR_UNSUPPORTED, "conv_umma: packed-image override is tf32, unpooled only");
+        return launch_umma<4, 128, 1, 0>(h, d, a.n, st);
+    }
     if (a.cout == 64) {
         SMG_CHECK(!a.pool, SMG_ERR_UNSUPPORTED, "conv_umma: pooled N=64 not built");
         return launch_umma<ELT, 64, 1, 0>(h, d, a.n, st);
@@ -593,7 +607,7 @@ static int dispatch(smg_handle* h, const ConvArgs& a, UmmaDev& d, cudaStream_t s
 }
 
 int launch_conv_umma(smg_handle* h, const ConvArgs& a, int precision, cudaStream_t st) {
-    SMG_CHECK(a.w != nullptr, SMG_ERR_STATE, "conv_umma: no weights");
+    SMG_CHECK(a.w != nullptr || a.w_umma != nullptr, SMG_ERR_STATE, "conv_umma: no weights");
     UmmaDev d;
     d.in = a.in; d.in_cstride = a.in_cstride; d.cin = a.cin; d.hin = a.hin;
     d.prologue_mode = a.prologue_mode; d.in_stats = a.in_stats; d.in_stats_stride = a.in_stats_stride;

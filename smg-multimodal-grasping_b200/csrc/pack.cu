@@ -5,7 +5,7 @@
 //   w_tf32 / w_bf16 : stage images in the UMMA no-swizzle K-major layout (conv_umma.cu):
 //       1x1 : [ntile][kgroup(32 ch)][chunk(16 B)][n (BN rows)][elements of the chunk]
 //       3x3 : [kgroup][tap][chunk][n (32 rows)][elements of the chunk]
-//   w_tf32_dx (3x3): [16-channel group][dy][chunk][dx*32 + n][4 floats]: the three dx taps as one N = 96 operand (conv3_persist.cu)
+//   w_tf32_t : weights as the tensor-memory A operand of conv1_t.cu / conv3_wt.cu;  w_dgrad_tf32 : data-gradient stage image
 #include "smg_internal.cuh"
 
 namespace smg {
@@ -68,20 +68,26 @@ __global__ void pack_umma_kernel(const float* __restrict__ w, T* __restrict__ ou
     }
 }
 
-// 3x3, tf32: [channel group of gc][dy][chunk][n = dx*cout + co][4] ( the three dx taps side by side as one wide N operand)
-__global__ void pack_umma_dx_kernel(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int k_offset,
-                                    int k_total, int gc) {
-    const int total = 9 * cin * cout;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int r = i;
-        const int e = r % 4; r /= 4;
-        const int n = r % (3 * cout); r /= 3 * cout;
-        const int c = r % (gc / 4); r /= gc / 4;
-        const int dy = r % 3; r /= 3;
-        const int kg = r;
-        const int dx = n / cout, co = n - dx * cout, ci = kg * gc + c * 4 + e;
-        out[i] = w[((size_t)co * k_total + k_offset + ci) * 9 + dy * 3 + dx];
-    }
+// data-gradient weights as a tf32 stage image for conv_umma.cu (see ConvW::w_dgrad_tf32): element i of the image
+__device__ __forceinline__ float dgrad_image_value(const float* __restrict__ w, int i, int cout, int cin, int taps, int k_offset,
+                                                   int k_total) {
+    int r = i;
+    const int e = r % 4; r /= 4;
+    const int n = r % 128; r /= 128;
+    const int c = r % 8; r /= 8;
+    int ntile, kg, tap;
+    if (taps == 1) { kg = r % (cout / 32); ntile = r / (cout / 32); tap = 0; }
+    else { tap = r % 9; kg = r / 9; ntile = 0; }
+    const int oc = ntile * 128 + n;          // output channel of the data gradient = input channel of the convolution
+    const int ic = kg * 32 + c * 4 + e;      // input channel of the data gradient = output channel of the convolution
+    return oc < cin ? w[((size_t)ic * k_total + k_offset + oc) * taps + (taps - 1 - tap)] : 0.f;
+}
+
+__global__ void pack_dgrad_umma_kernel(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int taps,
+                                       int k_offset, int k_total) {
+    const int total = taps * cout * dgrad_cin_padded(cin, taps);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+        out[i] = dgrad_image_value(w, i, cout, cin, taps, k_offset, k_total);
 }
 
 // 3x3, tf32: [column block][dx*cout + co][16], column = ((g*3 + dy)*4 + k)*8 + e, for the weights-in-tensor-memory kernel
@@ -115,6 +121,11 @@ __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
     const PackJob j = jobs[blockIdx.y];
     const int total = j.taps * j.cin * j.cout;
     const int kgs = j.cin / 32;
+    if ((mask & SMG_PACK_DGRAD) && j.dgrad_tf32 != nullptr) {
+        const int total_pad = j.taps * j.cout * dgrad_cin_padded(j.cin, j.taps);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total_pad; i += gridDim.x * blockDim.x)
+            j.dgrad_tf32[i] = dgrad_image_value(j.src, i, j.cout, j.cin, j.taps, j.k_off, j.k_total);
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         if (mask & SMG_PACK_FFMA) {
             const int co = i % j.cout, ci = (i / j.cout) % j.cin, t = i / (j.cout * j.cin);
@@ -124,22 +135,7 @@ __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
             const int ci = i % j.cin, co = (i / j.cin) % j.cout, t = i / (j.cout * j.cin);
             j.dgrad[i] = j.src[((size_t)co * j.k_total + j.k_off + ci) * j.taps + (j.taps - 1 - t)];
         }
-        if ((mask & SMG_PACK_TF32) && j.taps == 9 && j.tf32_dx != nullptr) {
-            // [channel group][dy][chunk][n = dx*cout + co][e] with 16- and 32-channel groups
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                const int gc = v == 0 ? 16 : 32;
-                int r = i;
-                const int e = r % 4; r /= 4;
-                const int n = r % (3 * j.cout); r /= 3 * j.cout;
-                const int c = r % (gc / 4); r /= gc / 4;
-                const int dy = r % 3; r /= 3;
-                const int kg = r;
-                const int dx = n / j.cout, co = n - dx * j.cout, ci = kg * gc + c * 4 + e;
-                const float val = j.src[((size_t)co * j.k_total + j.k_off + ci) * 9 + dy * 3 + dx];
-                if (v == 0) j.tf32_dx[i] = val;
-                else j.tf32_dx32[i] = val;
-            }
+        if ((mask & SMG_PACK_TF32) && j.taps == 9) {
             if (j.tf32_t != nullptr) {
                 // [column block c16][row = dx*cout + co][16]: column ((g*3 + dy)*4 + k)*8 + e, cin = g*32 + k*8 + e (conv3_wt.cu:
                 // weights in tensor memory; a warp reads 2 KB contiguous per column block)
@@ -186,32 +182,22 @@ __global__ void copy_batch_kernel(const CopyJob* __restrict__ jobs) {
 PackJob make_pack_job(const float* w_oihw, const ConvW& cw, int k_offset, int k_total) {
     PackJob j;
     j.src = w_oihw; j.ffma = cw.w_ffma; j.tf32 = reinterpret_cast<float*>(cw.w_tf32);
-    j.tf32_dx = reinterpret_cast<float*>(cw.w_tf32_dx);
-    j.tf32_dx32 = reinterpret_cast<float*>(cw.w_tf32_dx32);
     j.tf32_t = reinterpret_cast<float*>(cw.w_tf32_t);
+    j.dgrad_tf32 = reinterpret_cast<float*>(cw.w_dgrad_tf32);
     j.bf16 = reinterpret_cast<__nv_bfloat16*>(cw.w_bf16); j.dgrad = cw.w_dgrad;
     j.cin = cw.cin; j.cout = cw.cout; j.taps = cw.taps; j.k_off = k_offset; j.k_total = k_total;
     j.bn = cw.taps == 9 ? 32 : (cw.cout < 128 ? cw.cout : 128);
     return j;
 }
 
-int launch_pack_batch(smg_handle* h, const std::vector<PackJob>& pj, const std::vector<CopyJob>& cj, cudaStream_t st) {
-    const size_t need = pj.size() * sizeof(PackJob) + cj.size() * sizeof(CopyJob);
-    if (need > h->job_bytes) {
-        if (h->job_buf) cudaFree(h->job_buf);
-        h->job_bytes = need * 2;
-        SMG_CUDA(cudaMalloc(&h->job_buf, h->job_bytes));
-    }
-    uint8_t* base = reinterpret_cast<uint8_t*>(h->job_buf);
-    if (!pj.empty()) {
-        SMG_CUDA(cudaMemcpyAsync(base, pj.data(), pj.size() * sizeof(PackJob), cudaMemcpyHostToDevice, st));
-        pack_batch_kernel<<<dim3(48, (unsigned)pj.size()), 256, 0, st>>>(reinterpret_cast<const PackJob*>(base), h->pack_mask);
+// packs every convolution / copies every BatchNorm affine of a trunk from job tables that already live on the device
+int launch_pack_tables(smg_handle* h, const PackJob* dev_pj, int n_pj, const CopyJob* dev_cj, int n_cj, cudaStream_t st) {
+    if (n_pj > 0) {
+        pack_batch_kernel<<<dim3(48, (unsigned)n_pj), 256, 0, st>>>(dev_pj, h->pack_mask);
         h->launches++;
     }
-    if (!cj.empty()) {
-        uint8_t* cb = base + pj.size() * sizeof(PackJob);
-        SMG_CUDA(cudaMemcpyAsync(cb, cj.data(), cj.size() * sizeof(CopyJob), cudaMemcpyHostToDevice, st));
-        copy_batch_kernel<<<(unsigned)cj.size(), 256, 0, st>>>(reinterpret_cast<const CopyJob*>(cb));
+    if (n_cj > 0) {
+        copy_batch_kernel<<<(unsigned)n_cj, 256, 0, st>>>(dev_cj);
         h->launches++;
     }
     SMG_CUDA(cudaGetLastError());
@@ -240,17 +226,15 @@ int pack_conv_weights(smg_handle* h, const float* w_oihw, ConvW& cw, int k_offse
         pack_umma_t1_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_tf32_t), cw.cin, k_offset, k_total);
         h->launches++;
     }
-    if (cw.taps == 9 && cw.w_tf32_dx != nullptr) {
-        pack_umma_dx_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_tf32_dx), cw.cout, cw.cin, k_offset,
-                                                        k_total, 16);
-        pack_umma_dx_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_tf32_dx32), cw.cout, cw.cin, k_offset,
-                                                        k_total, 32);
-        h->launches += 2;
-        if (cw.w_tf32_t != nullptr) {
-            pack_umma_t_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_tf32_t), cw.cout, cw.cin, k_offset,
-                                                           k_total);
-            h->launches++;
-        }
+    if (cw.taps == 9 && cw.w_tf32_t != nullptr) {
+        pack_umma_t_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_tf32_t), cw.cout, cw.cin, k_offset,
+                                                       k_total);
+        h->launches++;
+    }
+    if (cw.w_dgrad_tf32 != nullptr) {
+        pack_dgrad_umma_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_dgrad_tf32), cw.cout, cw.cin,
+                                                           cw.taps, k_offset, k_total);
+        h->launches++;
     }
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;

@@ -67,10 +67,6 @@ struct ConvW {
     // tcgen05 layouts: a sequence of ready-to-copy shared-memory stage images
     // (no-swizzle K-major core matrices, see conv_umma.cu), tf32 (4-byte) and bf16
     uint8_t* w_tf32 = nullptr;
-    // 3x3 only, tf32: [16-channel group][dy][chunk][dx*32 + cout][4] - the three dx taps side by side as one N = 96 operand
-    // (conv3_persist.cu)
-    uint8_t* w_tf32_dx = nullptr;
-    uint8_t* w_tf32_dx32 = nullptr;
     // tf32, weights as the A operand in tensor memory: 1x1 with cout = 128 (conv1_t.cu): [cin/16][128][16] = w[row][16 c16 + c];
     // 3x3 (conv3_wt.cu): [column block of 16][dx*32 + cout][16], column = ((g*3 + dy)*4 + k)*8 + e
     uint8_t* w_tf32_t = nullptr;   // same with 32-channel groups: [kgroup][dy][chunk (8)][dx*32 + cout][4]
@@ -78,9 +74,29 @@ struct ConvW {
     // data-gradient weights for the fp32 kernels, in the same [taps][K][N] layout with the roles swapped:
     // 1x1: [cout][cin] (the torch layout); 3x3: [flipped tap][cout][cin]
     float* w_dgrad = nullptr;
+    // the same data-gradient weights as a tf32 stage image for conv_umma.cu (N = 128 tiles, zero-padded to a whole tile):
+    // 1x1: [ntile over cin/128][kgroup over cout/32][chunk][n][4], value w[kgroup*32 + ..][ntile*128 + n];
+    // 3x3: [kgroup over cout/32][flipped tap][chunk][n = cin][4]
+    uint8_t* w_dgrad_tf32 = nullptr;
     int cin = 0, cout = 0, taps = 1;
 };
 
+// weight-packing job tables (pack.cu)
+struct PackJob {
+    const float* src;
+    float* ffma;
+    float* tf32;
+    float* tf32_t;
+    float* dgrad_tf32;
+    __nv_bfloat16* bf16;
+    float* dgrad;
+    int cin, cout, taps, k_off, k_total, bn;
+};
+struct CopyJob {
+    const float* src;
+    float* dst;
+    int n;
+};
 struct BnP {
     float* gamma = nullptr;
     float* beta = nullptr;
@@ -111,6 +127,11 @@ struct TrunkW {
     BnP norm5;
     void* arena = nullptr;
     size_t arena_bytes = 0;
+    // packing tables of the last smg_set_trunk_weights (sources = the caller's parameter tensors)
+    std::vector<const float*> src;
+    std::vector<PackJob> pack_jobs;
+    std::vector<CopyJob> copy_jobs;
+    void* jobs_dev = nullptr;
 };
 
 struct HeadW {
@@ -123,6 +144,7 @@ struct HeadW {
     float* conv1 = nullptr;  // [n_out][400][64]  (pixel-major, channel fastest)
     void* arena = nullptr;
     size_t arena_bytes = 0;
+    std::vector<const float*> src;   // parameter tensors of the last smg_set_head_weights
 };
 
 // geometry of one dense block
@@ -145,8 +167,6 @@ struct smg_handle {
     int64_t workspace_bytes = 0;
     double l2_chunk_bytes = 0.0;   // >0: run each dense block over sample chunks of about this footprint (L2 residency)
     int pack_mask = 15;            // weight layouts written by smg_set_*_weights (SMG_PACK_*)
-    void* job_buf = nullptr;       // device table for the batched weight packer
-    size_t job_bytes = 0;
     int use_tma = 208;             // A/B bit mask of the persistent TMA-fed tf32 kernels (SMG_TMA): 16 = tensor-core 7x7 stem for
                                    // identical input channels (stem_umma.cu), 64 = 3x3 with the weights resident in tensor memory
                                    // (conv3_wt.cu), 128 = persistent 1x1 with swapped operand roles (conv1_t.cu); a cleared bit
@@ -214,6 +234,32 @@ struct smg_handle {
         int trunk_id = -1, head_id = -1, in_channels = 3;
     } train;
 
+    // smg_train_step: device tables of the caller's tensors, per-call scalars, staged outputs, captured steps
+    struct StepGraph {
+        uint64_t sig;
+        int seen;
+        int64_t n_launches;
+        cudaGraphExec_t exec;
+    };
+    struct StepState {
+        void* tables = nullptr;
+        size_t tables_bytes = 0;
+        uint64_t tables_sig = 0;
+        int tables_n_out = 0;
+        float** d_params = nullptr;
+        float** d_grads = nullptr;
+        float** d_m = nullptr;
+        float** d_v = nullptr;
+        uint8_t* d_chunks = nullptr;
+        int n_chunks = 0;
+        float* dyn = nullptr;      // [0] label, [1] 1 - beta1^t, [2] sqrt(1 - beta2^t)
+        float* out = nullptr;      // [0..3] Q / logits, [4] loss, [8..11] dLoss/dQ
+        float* bn_mean = nullptr;  // [2][SMG_TRUNK_BN_CHANNELS] batch statistics of the two passes
+        float* bn_var = nullptr;
+        std::vector<float*> host_grads;
+        std::vector<StepGraph> graphs;
+    } step;
+
     // optional per-kernel-class timing (bench.py roofline): CUDA events around every launch of a class
     bool profile = false;
     struct ProfRec {
@@ -230,6 +276,19 @@ inline double* stats_ptr(const smg_handle* h, size_t off_double2) {
     return h->stats + 2 * off_double2 * (size_t)h->max_samples;
 }
 // stats layout: for a region with C channels: [S][C] double2, region base = off * S
+
+// makes the handle's device current for the lifetime of an ABI call
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 
 // ---- kernels (defined in the .cu files) ---------------------------------------------
 // K1
@@ -265,6 +324,7 @@ struct ConvArgs {
     int taps = 1;  // 1 or 9 (3x3, pad 1)
     const ConvW* w = nullptr;
     const float* w_raw = nullptr;  // conv_ffma only: overrides w->w_ffma ([taps][cin][cout] fp32)
+    const uint8_t* w_umma = nullptr;  // conv_umma only (tf32): overrides w->w_tf32 with another packed stage image (w_dgrad_tf32)
     float* out = nullptr;
     int out_cstride = 0;
     int out_coff = 0;
@@ -334,12 +394,13 @@ struct Wgrad {
     int pix_per_cta, chunks_per_sample;
 };
 
-int launch_bn_bwd(smg_handle* h, BnBwd a, int S, bool apply, cudaStream_t st);
-int launch_bn_param_grad(smg_handle* h, const double* sums, int S, int C, float* dgamma, float* dbeta, cudaStream_t st);
+// reduce (apply = false) then apply (apply = true; also writes dgamma / dbeta [C] from the completed reductions)
+int launch_bn_bwd(smg_handle* h, BnBwd a, int S, bool apply, float* dgamma, float* dbeta, cudaStream_t st);
 int launch_wgrad(smg_handle* h, Wgrad a, int S, int taps, int pool, cudaStream_t st);
 int launch_pool0_bwd(smg_handle* h, int S, const float* g, int g_cstride, const float* conv0, const double* stats,
                      const float* gamma, const float* beta, float* da0, cudaStream_t st);
 int launch_conv0_wgrad(smg_handle* h, int S, const float* d, const float* in, int cin, float* dw, cudaStream_t st);
+int launch_replicate_conv0_grad(smg_handle* h, const float* g1, float* g3, cudaStream_t st);   // [64][49] -> [64][3][49]
 int launch_head_tail_bwd(smg_handle* h, const float* p, const HeadW& hw, const float* dq, float* dP, float* dg1,
                          float* db1, float* dw1, cudaStream_t st);
 int launch_head_norm_bwd(smg_handle* h, const float* da0, const float* x4, const double* stats, int stats_stride,
@@ -348,26 +409,22 @@ int launch_head_norm_bwd(smg_handle* h, const float* da0, const float* x4, const
 int launch_adam(smg_handle* h, float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float b1,
                 float b2, float eps, cudaStream_t st);
 
+// schedule pieces shared by api.cu and train.cu
+int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st);
+int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cudaStream_t st, bool save_bott = false);
+int heads_forward(smg_handle* h, int trunk_id, int head_id, int n_rot, int n_masks, float* dev_q, cudaStream_t st,
+                  int groups = 1);
+int export_bn_stats(smg_handle* h, int n, float* mean, float* var, cudaStream_t st);
+int ensure_train_workspace(smg_handle* h);
+int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* const* hg, cudaStream_t st);
+int repack_trunk(smg_handle* h, int trunk_id, cudaStream_t st);   // kernels only (graph-capturable), tables from the last set
+int repack_head(smg_handle* h, int head_id, cudaStream_t st);
+
 // weight packing
 enum { SMG_PACK_FFMA = 1, SMG_PACK_TF32 = 2, SMG_PACK_BF16 = 4, SMG_PACK_DGRAD = 8, SMG_PACK_ALL = 15 };
-struct PackJob {
-    const float* src;
-    float* ffma;
-    float* tf32;
-    float* tf32_dx;
-    float* tf32_dx32;
-    float* tf32_t;
-    __nv_bfloat16* bf16;
-    float* dgrad;
-    int cin, cout, taps, k_off, k_total, bn;
-};
-struct CopyJob {
-    const float* src;
-    float* dst;
-    int n;
-};
+__host__ __device__ inline int dgrad_cin_padded(int cin, int taps) { return taps == 9 ? cin : (cin + 127) / 128 * 128; }
 PackJob make_pack_job(const float* w_oihw, const ConvW& cw, int k_offset, int k_total);
-int launch_pack_batch(smg_handle* h, const std::vector<PackJob>& pj, const std::vector<CopyJob>& cj, cudaStream_t st);
+int launch_pack_tables(smg_handle* h, const PackJob* dev_pj, int n_pj, const CopyJob* dev_cj, int n_cj, cudaStream_t st);
 int pack_conv_weights(smg_handle* h, const float* w_oihw, ConvW& cw, int k_offset, int k_total, cudaStream_t st);
 size_t conv_packed_bytes_ffma(int cin, int cout, int taps);
 size_t conv_packed_bytes_umma(int cin, int cout, int taps, int elt_bytes);

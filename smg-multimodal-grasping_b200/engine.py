@@ -58,6 +58,7 @@ class Engine:
         self._sig = {}
         self._param_lists = {}
         self._staged = {}
+        self._mean_std = (0.01, 0.03)   # Trainer.image_mean / image_std, set by the Trainer before a fused step
         self.set_precision(precision)
 
     def __del__(self):
@@ -239,6 +240,29 @@ class Engine:
         if getattr(self, "h", None) is None or not self.h:
             return -1
         return int(self.lib.smg_train_pass_id(self.h))
+
+    def train_step(self, style, scene_hm, mask_hm, rot, num_rotations, loss_kind, label, class_weight, ptrs, n_tensors,
+                   step, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, want_bn_stats=True):
+        """One whole training step (smg_train_step): pre-processing, grad-enabled Q pass, loss, backward, Adam, re-pack.
+        scene_hm / mask_hm: [hs,hs] float64 on this device; ptrs: (params, grads, exp_avg, exp_avg_sq) ctypes pointer
+        arrays of `n_tensors` device tensors.  Returns (loss [1], q [n_out], bn_mean, bn_var [2, C] or None)."""
+        tid, hid = STYLE_ROUTE[int(style)]
+        args = _lib.TrainStepArgs(tid, hid, int(rot), int(num_rotations), int(scene_hm.shape[-1]), int(loss_kind), int(step),
+                                  float(label), float(self._mean_std[0]), float(self._mean_std[1]),
+                                  (ctypes.c_float * 3)(*[float(w) for w in class_weight]), float(lr), float(beta1),
+                                  float(beta2), float(eps))
+        loss = torch.empty((1,), dtype=torch.float32, device=self.device)
+        q = torch.empty((self.n_out,), dtype=torch.float32, device=self.device)
+        mean = var = None
+        pm = pv = None
+        if want_bn_stats:
+            mean = torch.empty((2, TRUNK_BN_CHANNELS), dtype=torch.float32, device=self.device)
+            var = torch.empty_like(mean)
+            pm, pv = mean.data_ptr(), var.data_ptr()
+        _lib.check(self.lib.smg_train_step(self.h, ctypes.byref(args), scene_hm.data_ptr(), mask_hm.data_ptr(), ptrs[0],
+                                           ptrs[1], ptrs[2], ptrs[3], int(n_tensors), loss.data_ptr(), q.data_ptr(), pm, pv,
+                                           self._stream()))
+        return loss, q, mean, var
 
     def head_bn_stats(self, n_pairs):
         """(mean, biased var) [n_pairs, 2, 64] of the head's BatchNorm2d(64) for the last Q pass on this handle."""

@@ -23,6 +23,15 @@ from .models import reactive_net, reinforcement_net
 from .utils import CrossEntropyLoss2d
 
 
+def group_is_plain_adam(opt):
+    """The fused step implements exactly the reference's optimizer: one param group of plain Adam (code/trainer.py:99)."""
+    if type(opt) is not torch.optim.Adam or len(opt.param_groups) != 1:
+        return False
+    g = opt.param_groups[0]
+    return not g.get("amsgrad") and not g.get("maximize") and g.get("weight_decay", 0) == 0 and not g.get("capturable") \
+        and not torch.is_tensor(g["lr"])
+
+
 class Trainer(object):
     def __init__(self, method, future_reward_discount, load_snapshot, snapshot_file, force_cpu,
                  precision="fp32", device=None):
@@ -60,6 +69,11 @@ class Trainer(object):
             self.model_target.precision = precision
         self.model.train()
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0)
+        # backprop() runs the whole step as ONE library call (smg_train_step: forward, loss, backward, Adam, re-pack inside a
+        # CUDA graph).  False = the reference's own sequence: autograd node + loss.backward() + optimizer.step().
+        self.fused_step = True
+        self._fused = {}
+        self._fused_last_style = None
         self.iteration = 0
         self.executed_action_log = []
         self.label_value_log = []
@@ -220,6 +234,90 @@ class Trainer(object):
         expected_reward = current_reward + self.future_reward_discount * future_reward
         return expected_reward, current_reward
 
+    # ------------------------------------------------------------------ fused step plumbing
+    def _fused_state(self, style):
+        """Per primitive: the 368 parameters the sample touches (trunk tensors in smg_set_trunk_weights order, then the
+        head's) with flat gradient / Adam-moment buffers.  `p.grad` and `optimizer.state[p]` are views of those buffers in
+        torch.optim.Adam's own format, so `optimizer.step()` / `state_dict()` keep working on the same state."""
+        import ctypes
+        model = self.model
+        tid, hid = _engine.STYLE_ROUTE[int(style)]
+        params = _engine.trunk_param_list(getattr(model, _engine.TRUNK_ATTRS[tid])) + \
+            _engine.head_param_list(getattr(model, _engine.HEAD_ATTRS[hid]))
+        key = (int(style), tuple(p.data_ptr() for p in params))
+        st = self._fused.get(int(style))
+        if st is not None and st["key"] == key:
+            return st
+        for p in params:
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("smg_b200: training needs contiguous float32 parameters on the GPU")
+        total = sum(p.numel() for p in params)
+        dev = params[0].device
+        flat = {k: torch.zeros(total, dtype=torch.float32, device=dev) for k in ("grad", "exp_avg", "exp_avg_sq")}
+        views = {k: [] for k in flat}
+        off = 0
+        for p in params:
+            for k in flat:
+                views[k].append(flat[k][off:off + p.numel()].view_as(p))
+            off += p.numel()
+        steps = []
+        for i, p in enumerate(params):
+            s = self.optimizer.state[p]
+            if len(s) != 0:                       # already stepped by torch: adopt its moments
+                views["exp_avg"][i].copy_(s["exp_avg"])
+                views["exp_avg_sq"][i].copy_(s["exp_avg_sq"])
+                step = s["step"] if torch.is_tensor(s["step"]) else torch.tensor(float(s["step"]))
+            else:
+                step = torch.tensor(0.0, dtype=torch.float32)
+            s["step"], s["exp_avg"], s["exp_avg_sq"] = step, views["exp_avg"][i], views["exp_avg_sq"][i]
+            steps.append(step)
+
+        def arr(ts):
+            a = (ctypes.c_void_p * len(ts))()
+            for i, t in enumerate(ts):
+                a[i] = t.data_ptr()
+            return a
+
+        st = {"key": key, "params": params, "flat": flat, "views": views, "steps": steps,
+              "ptrs": (arr(params), arr(views["grad"]), arr(views["exp_avg"]), arr(views["exp_avg_sq"]))}
+        self._fused[int(style)] = st
+        return st
+
+    def _backprop_fused(self, depth_heightmap, m_depth_heightmap, style, rot, label_value, attr):
+        model = self.model
+        eng = model._engine(2, style)
+        st = self._fused_state(style)
+        if self._fused_last_style != style:
+            # optimizer.zero_grad() + a backward that only reaches this primitive's trunk and head (code/trainer.py:338-351):
+            # every other parameter ends the step without a gradient, so Adam skips it
+            self.optimizer.zero_grad()
+            for p, g in zip(st["params"], st["views"]["grad"]):
+                p.grad = g
+            self._fused_last_style = style
+        hm = torch.from_numpy(np.stack([np.asarray(depth_heightmap, np.float64), np.asarray(m_depth_heightmap, np.float64)]))
+        hm = hm.to(eng.device, non_blocking=True)
+        rot = 0 if style == 2 else int(rot)                 # ES is pinned to rotation 0 (code/models.py:567)
+        group = self.optimizer.param_groups[0]
+        step = int(st["steps"][0]) + 1
+        eng._mean_std = (self.image_mean, self.image_std)
+        if self.method == 'reactive':
+            w = {0: self.grasp_criterion, 1: self.suction_criterion, 2: self.gs_criterion}[style].weight
+            kind, cw = 1, [float(v) for v in w.cpu()]
+        else:
+            kind, cw = 0, [1.0, 1.0, 1.0]
+        loss, q, mean, var = eng.train_step(style, hm[0], hm[1], rot, model.gnum_rotations, kind, float(label_value), cw,
+                                            st["ptrs"], len(st["params"]), step, group["lr"], group["betas"][0],
+                                            group["betas"][1], group["eps"], want_bn_stats=model.update_running_stats)
+        torch._foreach_add_(st["steps"], 1)
+        if model.update_running_stats:
+            tid, hid = _engine.STYLE_ROUTE[int(style)]
+            trunk, head = getattr(model, _engine.TRUNK_ATTRS[tid]), getattr(model, _engine.HEAD_ATTRS[hid])
+            model._apply_running_stats(trunk, mean, var, [0, 1])
+            model._apply_head_running_stats(head, trunk, var, [(0, 1)], eng.head_bn_stats(1))
+        model.gra_prob, model.suc_prob, model.gs_prob = [], [], []
+        setattr(model, attr, q.view(1, model.N_OUT, 1, 1))
+        return loss.view(()).cpu().numpy()
+
     # ------------------------------------------------------------------ backprop (code/trainer.py:278-384)
     def backprop(self, depth_heightmap, primitive_action, bestg_id, bests_id, bestgs_g_id, bestgs_s_id,
                  label_value, objects_mask, sro_best, gro_best, bestgs_num):
@@ -235,6 +333,9 @@ class Trainer(object):
             rot, attr = bestgs_g_id[1], 'gs_prob'
         else:
             raise ValueError(primitive_action)
+        if self.fused_step and group_is_plain_adam(self.optimizer):
+            return self._backprop_fused(depth_heightmap, m, style, rot, label_value, attr)
+        self._fused_last_style = None
         self.forward(depth_heightmap, m, style=style, is_volatile=False, is_target=False, specific_rotation=rot)
         out = getattr(self.model, attr)
         if self.method == 'reactive':

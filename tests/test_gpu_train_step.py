@@ -1,0 +1,142 @@
+"""GPU parity of the round-2 training path: tensor-core data-gradient convolutions (conv_umma.cu on the w_dgrad_tf32
+images) against torch autograd, and the fused `smg_train_step` (forward + loss + backward + Adam + re-pack in one captured
+call, what `Trainer.backprop` runs) against the reference's own sequence (autograd node, loss.backward(), optimizer.step())."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import MEAN, STD
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from smg_b200 import engine
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return engine.get_engine(0, 4, 640, "fp32", owner="dgrad")
+
+
+DGRAD_CASES = [
+    # (n, hin, cout, g_cstride, g_coff, k, cin): gradient of conv(cin -> cout) w.r.t. its input
+    (2, 40, 128, 128, 0, 1, 96),       # dense 1x1, partial output tile (96 of 128)
+    (2, 20, 128, 128, 0, 1, 992),      # 8 output tiles, last one partial
+    (1, 80, 128, 128, 0, 1, 256),
+    (2, 16, 256, 512, 0, 1, 512),      # transition conv (K = 256 -> 8 groups)
+    (1, 20, 64, 64, 0, 1, 1024),       # head half
+    (2, 40, 32, 512, 256, 3, 128),     # dense 3x3: gradient slice [256, 288) of the block buffer
+    (1, 160, 32, 256, 96, 3, 128),
+    (2, 20, 32, 1024, 992, 3, 128),
+]
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("tf32", 3e-3)])
+@pytest.mark.parametrize("case", DGRAD_CASES, ids=lambda c: "n%d_h%d_cout%d_gs%d_off%d_k%d_cin%d" % c)
+def test_dgrad_matches_autograd(eng, case, precision, tol):
+    from smg_b200 import _lib, engine
+    n, hin, cout, gcs, goff, k, cin = case
+    gen = torch.Generator(device="cuda").manual_seed(hash(case) % 1000)
+    g_full = torch.randn((n, hin, hin, gcs), generator=gen, device="cuda")
+    w = torch.randn((cout, cin, k, k), generator=gen, device="cuda") / (cout * k * k) ** 0.5
+    dx = torch.full((n, hin, hin, cin), 7.0, device="cuda")
+    _lib.check(eng.lib.smg_debug_dgrad(eng.h, engine.PRECISIONS[precision], g_full.data_ptr(), n, hin, cout, gcs, goff,
+                                       k * k, w.data_ptr(), cin, dx.data_ptr(), None))
+    g = g_full[..., goff:goff + cout].permute(0, 3, 1, 2).double()
+    ref = F.conv_transpose2d(g, w.double(), padding=k // 2).permute(0, 2, 3, 1).float()
+    err = float((dx - ref).abs().max() / ref.abs().max())
+    print("dgrad %s %s: rel-max err %.2e" % (precision, case, err))
+    assert err <= tol
+
+
+def _trainers(method, precision):
+    from smg_b200.trainer import Trainer
+    out = []
+    for fused in (True, False):
+        torch.manual_seed(0)
+        tr = Trainer(method, 0.5, False, None, False, precision=precision)
+        tr.fused_step = fused
+        out.append(tr)
+    return out
+
+
+@pytest.mark.parametrize("method,prim,label", [("reinforcement", "grasp", 1.0), ("reinforcement", "grasp_then_suction", 2.5),
+                                                ("reactive", "suction", 1)])
+def test_fused_step_equals_autograd_sequence(scene_inputs, method, prim, label):
+    """Same seed, same sample, three consecutive steps (eager, captured, replayed): the fused call and the reference's
+    sequence must leave the same loss, gradients, Adam state and weights (fp32 mode; both run the same kernels, so the
+    only differences are the atomics' summation order and conv0's folded input channel)."""
+    scene, _, _, sc = scene_inputs
+    masks = sc["masks"].astype(np.float64)
+    fused, plain = _trainers(method, "fp32")
+    args = (scene, prim, [1, 0], [2, 0], [0, 0], [3, 0], label, masks, [0] * 4, [0] * 4, [])
+    for it in range(3):
+        lf = float(fused.backprop(*args))
+        lp = float(plain.backprop(*args))
+        assert abs(lf - lp) <= 2e-4 * max(1.0, abs(lp)), (it, lf, lp)
+    pf, pp = dict(fused.model.named_parameters()), dict(plain.model.named_parameters())
+    touched = [k for k, p in pp.items() if p.grad is not None]
+    assert len(touched) == 368 and sorted(k for k, p in pf.items() if p.grad is not None) == sorted(touched)
+    worst_g = worst_w = 0.0
+    gscale = max(float(pp[k].grad.abs().max()) for k in touched)
+    for k in touched:
+        gs = max(float(pp[k].grad.abs().max()), 1e-3 * gscale)
+        worst_g = max(worst_g, float((pf[k].grad - pp[k].grad).abs().max()) / gs)
+        # three Adam steps move a weight by at most 3 lr; entries whose gradient is within noise of 0 may flip sign
+        # (norm5 feeds another BatchNorm: its gradient is analytically zero, i.e. nothing but noise)
+        frac = float(((pf[k].detach() - pp[k].detach()).abs() <= 0.2e-4).float().mean())
+        assert frac >= 0.8 or ".norm5." in k, (k, frac)
+        worst_w = max(worst_w, float((pf[k].detach() - pp[k].detach()).abs().max()))
+        sf, sp = fused.optimizer.state[pf[k]], plain.optimizer.state[pp[k]]
+        assert float(sf["step"]) == float(sp["step"]) == 3.0
+        m = max(float(sp["exp_avg"].abs().max()), 1e-3 * gscale)
+        assert float((sf["exp_avg"] - sp["exp_avg"]).abs().max()) <= 0.1 * m, k
+    print("fused vs autograd sequence (%s/%s): grads %.2e of scale, weights max |d| %.2e" % (method, prim, worst_g, worst_w))
+    assert worst_g <= 0.1 and worst_w <= 6.1e-4
+    untouched = [k for k in pp if k not in touched][0]
+    assert torch.equal(pf[untouched].detach(), pp[untouched].detach())
+    # BatchNorm running statistics: same side effect on both paths
+    bf, bp = dict(fused.model.named_buffers()), dict(plain.model.named_buffers())
+    for k in ("grasp_depth_trunk.features.denseblock2.denselayer3.norm1.running_mean",
+              "gs_depth_trunk.features.norm5.running_var", "suction_depth_trunk.features.norm0.running_mean"):
+        assert torch.allclose(bf[k], bp[k], rtol=1e-4, atol=1e-6), k
+    # the optimizer object is still a working torch.optim.Adam on the same state
+    fused.fused_step = False
+    fused.backprop(*args)
+    assert float(fused.optimizer.state[pf[touched[0]]]["step"]) == 4.0
+
+
+def test_fused_step_tf32_gradients_kink_free(scene_inputs, rl_state_dict):
+    """tf32 training step (tf32 forward, tensor-core dgrad) against the fp32 CPU oracle on the kink-free network
+    (see test_gpu_parity_r02.py): stated gradient tolerance 3e-2 per tensor (tf32 rounds operands to 10 mantissa bits)."""
+    from oracle import qnet
+    from smg_b200.trainer import Trainer
+    from test_gpu_parity_r02 import _kink_free_state
+    scene, mask, _, sc = scene_inputs
+    sd = _kink_free_state(rl_state_dict)
+    torch.manual_seed(0)
+    tr = Trainer("reinforcement", 0.5, False, None, False, precision="tf32")
+    tr.model.load_state_dict(sd)
+    tr.model.gnum_rotations = tr.model.snum_rotations = 16
+    masks = sc["masks"].astype(np.float64)
+    loss = float(tr.backprop(scene, "grasp", [0, 3], [0, 0], [], [], 1.0, masks, [0] * 4, [0] * 4, []))
+    x, m = qnet.preprocess(scene, MEAN, STD), qnet.preprocess(mask, MEAN, STD)
+    ref_loss, ref = qnet.backprop_grads(sd, x, m, 0, 3, 1.0, "reinforcement", gnum_rotations=16)
+    assert abs(loss - ref_loss) <= 2e-2 * max(1.0, abs(ref_loss))
+    grads = {n: p.grad.detach().cpu() for n, p in tr.model.named_parameters() if p.grad is not None}
+    assert set(grads) == set(ref)
+    gscale = max(float(v.abs().max()) for v in ref.values())
+    worst = []
+    for k, r in ref.items():
+        if k.endswith("features.norm5.weight") or k.endswith("features.norm5.bias"):
+            assert float(grads[k].abs().max()) <= 1e-3 * gscale, k
+            continue
+        scale = r.double().abs().max()
+        if ".norm" in k and k.endswith(".bias"):
+            scale = torch.maximum(scale, ref[k[:-len("bias")] + "weight"].double().abs().max())
+        worst.append((float((grads[k].double() - r.double()).abs().max() / scale.clamp_min(1e-30)), k))
+    worst.sort(reverse=True)
+    print("tf32 fused step, kink-free gradients: worst %s, median %.2e" % ([("%.2e" % e, k) for e, k in worst[:3]],
+                                                                           worst[len(worst) // 2][0]))
+    assert worst[0][0] <= 3e-2, worst[0]
