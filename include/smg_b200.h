@@ -247,6 +247,15 @@ int smg_debug_conv(smg_handle* h, int precision, const float* dev_in, int n, int
 int smg_debug_dgrad(smg_handle* h, int precision, const float* dev_g, int n, int hin, int cout, int g_cstride, int g_coff,
                     int taps, const float* dev_w_oihw, int cin, float* dev_dx, void* stream);
 
+/* unit-test hook for the tensor-core weight gradients of the dense layers (wgrad_umma.cu, tf32): g NHWC
+ * [S,hw,hw,g_cstride] (channels [g_coff, g_coff+cout) used) is the gradient w.r.t. the convolution's output, x the RAW
+ * input activation NHWC [S,hw,hw,x_cstride] (channels [0,cin)), normalised as relu(bn(x)) from dev_stats (sum, sumsq)
+ * [S,stats_stride,2] doubles and gamma/beta.  taps = 1: cout = 128, dev_dw [128,cin]; taps = 9: cin = 128, cout = 32, dev_dw
+ * [32,128,3,3].  Synchronous.                                                                                        */
+int smg_debug_wgrad(smg_handle* h, int taps, const float* dev_g, int g_cstride, int g_coff, const float* dev_x, int x_cstride,
+                    int cin, int hw, int S, const double* dev_stats, int stats_stride, const float* dev_gamma,
+                    const float* dev_beta, float* dev_dw, void* stream);
+
 /* unit-test hook for the BatchNorm(+ReLU) backward kernels (backward.cu): x NHWC [S,hw,hw,x_cstride] is the raw
  * BN input, dev_stats its (sum,sumsq) [S,stats_stride,2] doubles, da the gradient w.r.t. relu(bn(x)) (at half
  * resolution and spread x0.25 if da_pooled).  Writes dx into dev_dst (accumulating if requested), the two

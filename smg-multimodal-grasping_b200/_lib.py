@@ -59,6 +59,7 @@ PROTOTYPES = {
     "smg_profile_enable": (I, [VP, I]),
     "smg_profile_read": (I, [VP, c_double_p, c_int64_p, c_double_p, c_double_p]),
     "smg_debug_dgrad": (I, [VP, I, VP, I, I, I, I, I, I, VP, I, VP, VP]),
+    "smg_debug_wgrad": (I, [VP, I, VP, I, I, VP, I, I, I, I, VP, I, VP, VP, VP, VP]),
     "smg_debug_bn_bwd": (I, [VP, VP, I, I, VP, I, VP, I, VP, VP, I, I, I, I, VP, VP, I, I, VP, VP, VP]),
     "smg_debug_conv": (I, [VP, I, VP, I, I, I, I, VP, VP, I, I, I, VP, I, VP, I, I, VP, VP]),
 }

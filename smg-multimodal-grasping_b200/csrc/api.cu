@@ -758,6 +758,8 @@ int ensure_train_workspace(smg_handle* h) {
         const size_t o_a = p.take(S * hq * kBottleneck * 4), o_b = p.take(S * hq * kBottleneck * 4);
         const size_t o_c = p.take(S * hq * h->geom[0].c_tot * 4);
         const size_t o_p = p.take((size_t)kHeadK * kHeadK * kHeadMid * 4);
+        const size_t o_w3 = p.take((size_t)58 * 288 * 128 * 4);
+        const size_t o_wj = p.take((size_t)58 * 2 * sizeof(void*));
         W.sums_bytes = S * (size_t)SMG_TRUNK_BN_CHANNELS * 2 * sizeof(double);
         const size_t o_s = p.take(W.sums_bytes);
         if (base) {
@@ -766,6 +768,9 @@ int ensure_train_workspace(smg_handle* h) {
             W.t_b = reinterpret_cast<float*>(base + o_b);
             W.t_c = reinterpret_cast<float*>(base + o_c);
             W.dP = reinterpret_cast<float*>(base + o_p);
+            W.wg3_scratch = reinterpret_cast<float*>(base + o_w3);
+            W.wg3_jobs_dev = base + o_wj;
+            W.wg3_jobs.assign(58 * 2, nullptr);
             W.sums = reinterpret_cast<double*>(base + o_s);
         } else {
             W.bytes = p.off;
@@ -833,6 +838,11 @@ int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* cons
     G.fill(tg);
     SMG_CUDA(cudaMemsetAsync(W.sums, 0, W.sums_bytes, st));
     double* sums = W.sums;
+    // tf32 mode: the dense layers' weight gradients run on the tensor cores (wgrad_umma.cu; SMG_WGRAD_TC=0 keeps CUDA cores)
+    static const bool wgrad_tc_env = getenv("SMG_WGRAD_TC") == nullptr || atoi(getenv("SMG_WGRAD_TC")) != 0;
+    const bool wgrad_tc = wgrad_tc_env && h->precision == SMG_PREC_TF32;
+    int n_wg3 = 0;
+    if (wgrad_tc) SMG_CUDA(cudaMemsetAsync(W.wg3_scratch, 0, (size_t)58 * 288 * 128 * 4, st));
     const BlockGeom& g4 = h->geom[3];
     const int npix4 = g4.hw * g4.hw;
 
@@ -879,8 +889,21 @@ int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* cons
                 SMG_TRY(dgrad_conv(h, a, L.conv2, st));
             }
             // (2) 3x3 wgrad
-            SMG_CUDA(cudaMemsetAsync(GL.c2, 0, (size_t)kGrowth * kBottleneck * 9 * 4, st));
-            {
+            int wg3_status = SMG_ERR_UNSUPPORTED;
+            if (wgrad_tc) {
+                float* scratch = W.wg3_scratch + (size_t)n_wg3 * 288 * 128;
+                wg3_status = launch_wgrad3_umma(h, W.dblk[b], g.c_tot, cin, y1, g.hw, S, st_bott, kBottleneck, L.norm2.gamma,
+                                                L.norm2.beta, scratch, st);
+                if (wg3_status == SMG_OK) {
+                    W.wg3_jobs[2 * n_wg3] = scratch;
+                    W.wg3_jobs[2 * n_wg3 + 1] = GL.c2;
+                    ++n_wg3;
+                } else if (wg3_status != SMG_ERR_UNSUPPORTED) {
+                    return wg3_status;
+                }
+            }
+            if (wg3_status == SMG_ERR_UNSUPPORTED) {
+                SMG_CUDA(cudaMemsetAsync(GL.c2, 0, (size_t)kGrowth * kBottleneck * 9 * 4, st));
                 Wgrad wg{};
                 wg.g = W.dblk[b]; wg.g_cstride = g.c_tot; wg.g_coff = cin; wg.cout = kGrowth;
                 wg.x = y1; wg.x_cstride = kBottleneck; wg.cin = kBottleneck; wg.hin = g.hw; wg.hout = g.hw;
@@ -898,7 +921,13 @@ int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* cons
             }
             // (4) 1x1 wgrad
             SMG_CUDA(cudaMemsetAsync(GL.c1, 0, (size_t)kBottleneck * cin * 4, st));
-            {
+            int wg1_status = SMG_ERR_UNSUPPORTED;
+            if (wgrad_tc) {
+                wg1_status = launch_wgrad1_umma(h, W.t_b, h->block[b], g.c_tot, cin, g.hw, S, st_blk, g.c_tot, L.norm1.gamma,
+                                                L.norm1.beta, GL.c1, st);
+                if (wg1_status != SMG_OK && wg1_status != SMG_ERR_UNSUPPORTED) return wg1_status;
+            }
+            if (wg1_status == SMG_ERR_UNSUPPORTED) {
                 Wgrad wg{};
                 wg.g = W.t_b; wg.g_cstride = kBottleneck; wg.g_coff = 0; wg.cout = kBottleneck;
                 wg.x = h->block[b]; wg.x_cstride = g.c_tot; wg.cin = cin; wg.hin = g.hw; wg.hout = g.hw;
@@ -953,6 +982,11 @@ int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* cons
                 SMG_TRY(bn_backward(h, bb, S, sums, G.trans[b - 1].n[0], G.trans[b - 1].n[1], st));
             }
         }
+    }
+    if (n_wg3 > 0) {
+        // the table lives in the handle (stable host address): a captured copy node re-reads it at every replay
+        SMG_CUDA(cudaMemcpyAsync(W.wg3_jobs_dev, W.wg3_jobs.data(), (size_t)n_wg3 * 2 * sizeof(void*), cudaMemcpyHostToDevice, st));
+        SMG_TRY(launch_wgrad3_finish(h, W.wg3_jobs_dev, n_wg3, st));
     }
     // ---- stem: maxpool -> relu/bn0 -> conv0 wgrad (no data gradient is needed for the input image)
     const int Hc = h->H / 2;
@@ -1201,6 +1235,41 @@ int smg_debug_dgrad(smg_handle* h, int precision, const float* dev_g, int n, int
         return SMG_ERR_CUDA;
     }
     return status;
+}
+
+int smg_debug_wgrad(smg_handle* h, int taps, const float* dev_g, int g_cstride, int g_coff, const float* dev_x, int x_cstride,
+                    int cin, int hw, int S, const double* dev_stats, int stats_stride, const float* dev_gamma,
+                    const float* dev_beta, float* dev_dw, void* stream) {
+    SMG_CHECK(h && dev_g && dev_x && dev_stats && dev_gamma && dev_beta && dev_dw, SMG_ERR_INVALID, "smg_debug_wgrad: NULL argument");
+    SMG_CHECK(taps == 1 || taps == 9, SMG_ERR_INVALID, "smg_debug_wgrad: taps %d", taps);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int status;
+    if (taps == 1) {
+        SMG_CHECK(g_cstride == 128 && g_coff == 0, SMG_ERR_INVALID, "smg_debug_wgrad: the 1x1 gradient operand is dense [..,128]");
+        SMG_CUDA(cudaMemsetAsync(dev_dw, 0, (size_t)128 * cin * 4, st));
+        status = launch_wgrad1_umma(h, dev_g, dev_x, x_cstride, cin, hw, S, dev_stats, stats_stride, dev_gamma, dev_beta, dev_dw, st);
+    } else {
+        SMG_CHECK(x_cstride == 128 && cin == 128, SMG_ERR_INVALID, "smg_debug_wgrad: the 3x3 activation operand is dense [..,128]");
+        uint8_t* base = nullptr;
+        const size_t sb = (size_t)288 * 128 * 4;
+        SMG_CUDA(cudaMalloc(&base, sb + 64));
+        SMG_CUDA(cudaMemsetAsync(base, 0, sb, st));
+        float* scratch = reinterpret_cast<float*>(base);
+        status = launch_wgrad3_umma(h, dev_g, g_cstride, g_coff, dev_x, hw, S, dev_stats, stats_stride, dev_gamma, dev_beta,
+                                    scratch, st);
+        if (status == SMG_OK) {
+            void* job[2] = {scratch, dev_dw};
+            SMG_CUDA(cudaMemcpyAsync(base + sb, job, sizeof(job), cudaMemcpyHostToDevice, st));
+            status = launch_wgrad3_finish(h, base + sb, 1, st);
+        }
+        cudaStreamSynchronize(st);
+        cudaFree(base);
+    }
+    if (status == SMG_ERR_UNSUPPORTED) set_error("smg_debug_wgrad: shape not served by the tensor-core kernels");
+    if (status != SMG_OK) return status;
+    SMG_CUDA(cudaStreamSynchronize(st));
+    return SMG_OK;
 }
 
 int smg_debug_bn_bwd(smg_handle* h, const float* dev_da, int da_cstride, int da_pooled, const float* dev_x,

@@ -227,6 +227,9 @@ struct smg_handle {
         float* t_b = nullptr;                // [2,H/4,H/4,128] scratch (d conv1 output)
         float* t_c = nullptr;                // [2,H/4,H/4,256] scratch (d relu(bn1) / transition dgrad)
         float* dP = nullptr;                 // [400,64]
+        float* wg3_scratch = nullptr;        // [58][(tap, co) 288][ci 128]: 3x3 weight gradients before the final transpose
+        std::vector<void*> wg3_jobs;         // host copy of the {scratch, gradient tensor} table of wgrad3_finish_kernel
+        void* wg3_jobs_dev = nullptr;
         double* sums = nullptr;              // BN backward reductions, zeroed once per backward
         size_t sums_bytes = 0;
         bool valid = false;                  // a training forward is waiting for its backward
@@ -406,6 +409,13 @@ int launch_head_tail_bwd(smg_handle* h, const float* p, const HeadW& hw, const f
 int launch_head_norm_bwd(smg_handle* h, const float* da0, const float* x4, const double* stats, int stats_stride,
                          const BnP& norm5, const BnP& hnorm0, float* dx4, float* dg5, float* db5, float* dgh, float* dbh,
                          cudaStream_t st);
+// tensor-core weight gradients of the dense layers (wgrad_umma.cu); SMG_ERR_UNSUPPORTED for shapes they do not serve
+int launch_wgrad1_umma(smg_handle* h, const float* g, const float* x, int x_cstride, int cin, int hw, int S, const double* stats,
+                       int stats_stride, const float* gamma, const float* beta, float* dw, cudaStream_t st);
+int launch_wgrad3_umma(smg_handle* h, const float* g, int g_cstride, int g_coff, const float* y, int hw, int S,
+                       const double* stats, int stats_stride, const float* gamma, const float* beta, float* scratch,
+                       cudaStream_t st);
+int launch_wgrad3_finish(smg_handle* h, const void* dev_jobs, int n_jobs, cudaStream_t st);
 int launch_adam(smg_handle* h, float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float b1,
                 float b2, float eps, cudaStream_t st);
 

@@ -140,3 +140,47 @@ def test_fused_step_tf32_gradients_kink_free(scene_inputs, rl_state_dict):
     print("tf32 fused step, kink-free gradients: worst %s, median %.2e" % ([("%.2e" % e, k) for e, k in worst[:3]],
                                                                            worst[len(worst) // 2][0]))
     assert worst[0][0] <= 3e-2, worst[0]
+
+
+WGRAD_CASES = [
+    # (taps, S, hw, cin, x_cstride, g_cstride, g_coff)
+    (1, 2, 40, 96, 256, 128, 0),       # one partial N tile (96 channels)
+    (1, 2, 20, 992, 1024, 128, 0),     # four N tiles, the last one 224 wide; 20 units over 2 samples
+    (1, 1, 80, 256, 256, 128, 0),
+    (1, 2, 160, 64, 256, 128, 0),      # block-1 size: 1280 units split over the SMs
+    (9, 2, 40, 128, 128, 512, 256),    # gradient slice [256, 288) of the block buffer, full-row units
+    (9, 1, 160, 128, 128, 256, 96),    # four units per row
+    (9, 2, 20, 128, 128, 1024, 992),   # two-row units
+    (9, 2, 80, 128, 128, 512, 480),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=lambda c: "k%d_S%d_h%d_cin%d_xs%d_gs%d_off%d" % c)
+def test_tensor_core_wgrad_matches_autograd(eng, case):
+    """wgrad_umma.cu (MN-major tf32 operands straight from TMA boxes, split-K with global reductions) vs torch autograd of
+    conv2d(relu(bn(x)), w) w.r.t. w, per-sample train-mode BatchNorm, in float64."""
+    from smg_b200 import _lib
+    taps, S, hw, cin, xcs, gcs, goff = case
+    k = 3 if taps == 9 else 1
+    cout = 32 if taps == 9 else 128
+    gen = torch.Generator(device="cuda").manual_seed(sum(case))
+    x_full = torch.randn((S, hw, hw, xcs), generator=gen, device="cuda") * 1.3 + 0.2
+    g_full = torch.randn((S, hw, hw, gcs), generator=gen, device="cuda")
+    gamma = torch.rand(cin, generator=gen, device="cuda") + 0.5
+    beta = torch.randn(cin, generator=gen, device="cuda") * 0.3
+    xs = x_full[..., :cin].double()
+    stats = torch.zeros((S, xcs, 2), dtype=torch.float64, device="cuda")
+    stats[:, :cin, 0] = xs.sum((1, 2))
+    stats[:, :cin, 1] = (xs * xs).sum((1, 2))
+    dw = torch.full((cout, cin, k, k), 3.0, device="cuda")
+    _lib.check(eng.lib.smg_debug_wgrad(eng.h, taps, g_full.data_ptr(), gcs, goff, x_full.data_ptr(), xcs, cin, hw, S,
+                                       stats.data_ptr(), xcs, gamma.data_ptr(), beta.data_ptr(), dw.data_ptr(), None))
+    w = torch.zeros((cout, cin, k, k), dtype=torch.float64, device="cuda", requires_grad=True)
+    xn = xs.permute(0, 3, 1, 2)
+    a = torch.cat([F.relu(F.batch_norm(xn[s:s + 1], None, None, gamma.double(), beta.double(), training=True, momentum=0.0,
+                                       eps=1e-5)) for s in range(S)])
+    y = F.conv2d(a, w, padding=k // 2)
+    y.backward(g_full[..., goff:goff + cout].permute(0, 3, 1, 2).double())
+    err = float((dw.double() - w.grad).abs().max() / w.grad.abs().max())
+    print("wgrad %s: rel-max err %.2e" % (case, err))
+    assert err <= 3e-3
