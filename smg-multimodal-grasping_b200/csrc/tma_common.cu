@@ -25,7 +25,9 @@ int make_tensor_map_f32(CUtensorMap* tm, const float* base, int rank, const cuui
     SMG_CHECK(enc != nullptr, SMG_ERR_CUDA, "tensor map: cuTensorMapEncodeTiled not available from the driver");
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims, strides, box,
-                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                               : (swizzle_bytes == kSwizzle128Atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SMG_CHECK(r == CUDA_SUCCESS, SMG_ERR_CUDA, "tensor map: cuTensorMapEncodeTiled failed (%d)", (int)r);

@@ -106,6 +106,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled_fn();   // tma_common.cu; nullptr if the driver does not export it
 
+// swizzle_bytes value selecting the 128-byte swizzle with 32-byte atomicity (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): the
+// shared-memory image MN-major tf32 UMMA operands need (layout type SWIZZLE_128B_BASE32B)
+constexpr int kSwizzle128Atom32 = 12832;
+
 // fp32 tensor map with 128- or 64-byte swizzle and zero fill; dims/strides innermost first (strides in bytes, rank-1 of them)
 int make_tensor_map_f32(CUtensorMap* tm, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
                         const cuuint32_t* box, int swizzle_bytes = 128);

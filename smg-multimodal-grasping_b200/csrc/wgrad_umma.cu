@@ -4,10 +4,11 @@
 // weights: dW[co][ci][tap] = sum over samples and pixels of  G[p][co] * A[p + tap shift][ci],  A = relu(bn(x)) recomputed
 // from the raw activation and the saved (sum, sumsq) statistics.  As a GEMM the contraction index K is the PIXEL, and both
 // operands sit in memory pixel-major with the channel contiguous (NHWC), i.e. "MN-major" in UMMA terms.  tcgen05 reads
-// MN-major tf32 operands directly (instruction-descriptor bits 15/16), in exactly the shared-memory image a tensor-map TMA
-// box {32 channels x P pixels} with the 128-byte swizzle produces: one 128-byte row per pixel, 8-row swizzle atoms, 32-channel
-// column blocks side by side (descriptor: leading byte offset = block stride, stride byte offset = 1024).  So the kernel
-// needs no transposition at all:
+// MN-major tf32 operands directly (instruction-descriptor bits 15/16) from the shared-memory image a tensor-map TMA box
+// {32 channels x P pixels} produces with the 128-byte swizzle of 32-byte atomicity (the only layout 32-bit MN-major operands
+// may use: descriptor layout type SWIZZLE_128B_BASE32B; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): one 128-byte row per pixel
+// whose 32-byte quarters are XOR-ed with (row mod 4), 4-row atoms of 512 bytes, 32-channel column blocks side by side
+// (descriptor: leading byte offset = block stride, stride byte offset = 512).  So the kernel needs no transposition at all:
 //
 //   1x1 (conv1, cin -> 128):  D[co 128][ci tile <= 256] += G^T [co][pixel] * A[pixel][ci]
 //        M operand = 4 blocks of the output gradient (raw), N operand = up to 8 blocks of the activation (BN-ReLU applied
@@ -51,14 +52,15 @@ struct WgradDev {
     int ld;
 };
 
-// MN-major operand, 128-byte swizzle: 32-channel blocks `lbo` bytes apart, 8-pixel groups 1024 bytes apart
+// MN-major 32-bit operand, 128-byte swizzle with 32-byte atomicity (layout type 1): 32-channel blocks `lbo` bytes apart,
+// 4-pixel atoms 512 bytes apart
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)(512 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;
     return d;
 }
 
@@ -190,7 +192,8 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant
                 for (int rr = 0; rr < 3; ++rr) {
                     const int r = r0 + 16 * rr;
                     if (r < G_P) {
-                        const int chunk = j ^ (r & 7);          // logical 4-channel chunk held by this piece
+                        // 32-byte quarters are XOR-ed with (row mod 4): logical 4-channel chunk held by this 16-byte piece
+                        const int chunk = ((((j >> 1) ^ (r & 3)) << 1) | (j & 1));
                         const float4 sc = *reinterpret_cast<const float4*>(s_sc + b * 32 + chunk * 4);
                         const float4 sh = *reinterpret_cast<const float4*>(s_sh + b * 32 + chunk * 4);
                         float4* p = reinterpret_cast<float4*>(st + b * G_BLK + r * 128 + j * 16);
@@ -260,13 +263,13 @@ int launch_wgrad1_umma(smg_handle* h, const float* g, const float* x, int x_cstr
         const cuuint64_t dims[3] = {128, (cuuint64_t)npix, (cuuint64_t)S};
         const cuuint64_t strides[2] = {128 * 4, (cuuint64_t)npix * 128 * 4};
         const cuuint32_t box[3] = {32, G_P, 1};
-        SMG_TRY(make_tensor_map_f32(&tmM, g, 3, dims, strides, box));
+        SMG_TRY(make_tensor_map_f32(&tmM, g, 3, dims, strides, box, kSwizzle128Atom32));
     }
     {
         const cuuint64_t dims[3] = {(cuuint64_t)x_cstride, (cuuint64_t)npix, (cuuint64_t)S};
         const cuuint64_t strides[2] = {(cuuint64_t)x_cstride * 4, (cuuint64_t)npix * x_cstride * 4};
         const cuuint32_t box[3] = {32, G_P, 1};
-        SMG_TRY(make_tensor_map_f32(&tmN, x, 3, dims, strides, box));
+        SMG_TRY(make_tensor_map_f32(&tmN, x, 3, dims, strides, box, kSwizzle128Atom32));
     }
     WgradDev d{};
     d.hw = hw; d.S = S; d.units_per_sample = npix / G_P; d.total_units = S * d.units_per_sample;
@@ -296,7 +299,7 @@ int launch_wgrad3_umma(smg_handle* h, const float* g, int g_cstride, int g_coff,
         const cuuint64_t dims[3] = {128, (cuuint64_t)npix, (cuuint64_t)S};
         const cuuint64_t strides[2] = {128 * 4, (cuuint64_t)npix * 128 * 4};
         const cuuint32_t box[3] = {32, G_P, 1};
-        SMG_TRY(make_tensor_map_f32(&tmM, y, 3, dims, strides, box));
+        SMG_TRY(make_tensor_map_f32(&tmM, y, 3, dims, strides, box, kSwizzle128Atom32));
     }
     WgradDev d{};
     d.hw = hw; d.S = S; d.units_per_sample = npix / G_P; d.total_units = S * d.units_per_sample;
@@ -306,7 +309,7 @@ int launch_wgrad3_umma(smg_handle* h, const float* g, int g_cstride, int g_coff,
         const cuuint64_t dims[4] = {32, (cuuint64_t)hw, (cuuint64_t)hw, (cuuint64_t)S};
         const cuuint64_t strides[3] = {(cuuint64_t)g_cstride * 4, (cuuint64_t)hw * g_cstride * 4, (cuuint64_t)npix * g_cstride * 4};
         const cuuint32_t box[4] = {32, (cuuint32_t)d.tw, (cuuint32_t)d.th, 1};
-        SMG_TRY(make_tensor_map_f32(&tmN, g + g_coff, 4, dims, strides, box));
+        SMG_TRY(make_tensor_map_f32(&tmN, g + g_coff, 4, dims, strides, box, kSwizzle128Atom32));
     }
     d.cin = 128; d.stats = stats; d.stats_stride = stats_stride; d.gamma = gamma; d.beta = beta; d.dw = scratch; d.ld = 128;
     int splits = h->num_sms;

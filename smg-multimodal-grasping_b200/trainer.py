@@ -322,7 +322,6 @@ class Trainer(object):
     def backprop(self, depth_heightmap, primitive_action, bestg_id, bests_id, bestgs_g_id, bestgs_s_id,
                  label_value, objects_mask, sro_best, gro_best, bestgs_num):
         mask_depth = np.asarray(objects_mask).reshape(objects_mask.shape[0], objects_mask.shape[1], objects_mask.shape[2])
-        self.optimizer.zero_grad()
         if primitive_action == 'grasp':
             style, m, rot, attr = 0, depth_heightmap * mask_depth[bestg_id[0]], bestg_id[1], 'gra_prob'
         elif primitive_action == 'suction':
@@ -336,6 +335,7 @@ class Trainer(object):
         if self.fused_step and group_is_plain_adam(self.optimizer):
             return self._backprop_fused(depth_heightmap, m, style, rot, label_value, attr)
         self._fused_last_style = None
+        self.optimizer.zero_grad()
         self.forward(depth_heightmap, m, style=style, is_volatile=False, is_target=False, specific_rotation=rot)
         out = getattr(self.model, attr)
         if self.method == 'reactive':

@@ -64,36 +64,37 @@ def _trainers(method, precision):
 @pytest.mark.parametrize("method,prim,label", [("reinforcement", "grasp", 1.0), ("reinforcement", "grasp_then_suction", 2.5),
                                                 ("reactive", "suction", 1)])
 def test_fused_step_equals_autograd_sequence(scene_inputs, method, prim, label):
-    """Same seed, same sample, three consecutive steps (eager, captured, replayed): the fused call and the reference's
-    sequence must leave the same loss, gradients, Adam state and weights (fp32 mode; both run the same kernels, so the
-    only differences are the atomics' summation order and conv0's folded input channel)."""
+    """Same seed, same sample, ONE step from identical weights: the fused call and the reference's sequence (autograd node,
+    loss.backward(), torch.optim.Adam.step()) must leave the same loss, gradients, Adam state and weights.  fp32 mode; both
+    run the same kernels, the differences are the atomics' summation order and conv0's folded input channel - enough to flip
+    a few ReLU kinks, hence the statistical bars (see tests/test_gpu_backward.py)."""
     scene, _, _, sc = scene_inputs
     masks = sc["masks"].astype(np.float64)
     fused, plain = _trainers(method, "fp32")
     args = (scene, prim, [1, 0], [2, 0], [0, 0], [3, 0], label, masks, [0] * 4, [0] * 4, [])
-    for it in range(3):
-        lf = float(fused.backprop(*args))
-        lp = float(plain.backprop(*args))
-        assert abs(lf - lp) <= 2e-4 * max(1.0, abs(lp)), (it, lf, lp)
+    lf, lp = float(fused.backprop(*args)), float(plain.backprop(*args))
+    assert abs(lf - lp) <= 2e-4 * max(1.0, abs(lp)), (lf, lp)
     pf, pp = dict(fused.model.named_parameters()), dict(plain.model.named_parameters())
     touched = [k for k, p in pp.items() if p.grad is not None]
     assert len(touched) == 368 and sorted(k for k, p in pf.items() if p.grad is not None) == sorted(touched)
-    worst_g = worst_w = 0.0
+    errs = []
     gscale = max(float(pp[k].grad.abs().max()) for k in touched)
     for k in touched:
         gs = max(float(pp[k].grad.abs().max()), 1e-3 * gscale)
-        worst_g = max(worst_g, float((pf[k].grad - pp[k].grad).abs().max()) / gs)
-        # three Adam steps move a weight by at most 3 lr; entries whose gradient is within noise of 0 may flip sign
-        # (norm5 feeds another BatchNorm: its gradient is analytically zero, i.e. nothing but noise)
-        frac = float(((pf[k].detach() - pp[k].detach()).abs() <= 0.2e-4).float().mean())
-        assert frac >= 0.8 or ".norm5." in k, (k, frac)
-        worst_w = max(worst_w, float((pf[k].detach() - pp[k].detach()).abs().max()))
+        errs.append(float((pf[k].grad - pp[k].grad).abs().max()) / gs)
+        # Adam's first step is -lr * g / (|g| + eps) ~ -lr * sign(g): only entries whose gradient is within noise of zero
+        # may differ (norm5 feeds another BatchNorm: its gradient is nothing but noise)
+        frac = float(((pf[k].detach() - pp[k].detach()).abs() <= 0.1e-4).float().mean())
+        assert frac >= 0.85 or ".norm5." in k, (k, frac)
+        assert float((pf[k].detach() - pp[k].detach()).abs().max()) <= 2.01e-4, k
         sf, sp = fused.optimizer.state[pf[k]], plain.optimizer.state[pp[k]]
-        assert float(sf["step"]) == float(sp["step"]) == 3.0
-        m = max(float(sp["exp_avg"].abs().max()), 1e-3 * gscale)
-        assert float((sf["exp_avg"] - sp["exp_avg"]).abs().max()) <= 0.1 * m, k
-    print("fused vs autograd sequence (%s/%s): grads %.2e of scale, weights max |d| %.2e" % (method, prim, worst_g, worst_w))
-    assert worst_g <= 0.1 and worst_w <= 6.1e-4
+        assert float(sf["step"]) == float(sp["step"]) == 1.0
+        assert torch.allclose(sf["exp_avg"], 0.1 * pf[k].grad, rtol=1e-5, atol=1e-12), k        # (1 - beta1) * g
+        assert torch.allclose(sf["exp_avg_sq"], 0.001 * pf[k].grad ** 2, rtol=1e-4, atol=1e-20), k
+    errs.sort()
+    print("fused vs autograd sequence (%s/%s): gradient error median %.2e, 95th %.2e, max %.2e of scale"
+          % (method, prim, errs[len(errs) // 2], errs[int(0.95 * len(errs))], errs[-1]))
+    assert errs[len(errs) // 2] <= 1e-2 and errs[int(0.95 * len(errs))] <= 5e-2 and errs[-1] <= 0.5
     untouched = [k for k in pp if k not in touched][0]
     assert torch.equal(pf[untouched].detach(), pp[untouched].detach())
     # BatchNorm running statistics: same side effect on both paths
@@ -104,12 +105,38 @@ def test_fused_step_equals_autograd_sequence(scene_inputs, method, prim, label):
     # the optimizer object is still a working torch.optim.Adam on the same state
     fused.fused_step = False
     fused.backprop(*args)
-    assert float(fused.optimizer.state[pf[touched[0]]]["step"]) == 4.0
+    assert float(fused.optimizer.state[pf[touched[0]]]["step"]) == 2.0
+
+
+def test_fused_step_graph_replay_equals_eager(scene_inputs, monkeypatch):
+    """Four consecutive steps with the CUDA graph (eager, captured, replayed, replayed) against the same four steps launched
+    eagerly (SMG_NO_GRAPHS): identical kernels in identical order, so the trajectories agree to the atomics' noise."""
+    from smg_b200 import engine
+    from smg_b200.trainer import Trainer
+    scene, _, _, sc = scene_inputs
+    masks = sc["masks"].astype(np.float64)
+    args = (scene, "grasp", [1, 0], [2, 0], [0, 0], [3, 0], 1.0, masks, [0] * 4, [0] * 4, [])
+    runs = []
+    for no_graphs in ("0", "1"):
+        monkeypatch.setenv("SMG_NO_GRAPHS", no_graphs)
+        torch.manual_seed(0)
+        tr = Trainer("reinforcement", 0.5, False, None, False, precision="tf32")
+        eng = tr.model._engine(2, 0)                     # created under the environment setting above
+        n0 = eng.launch_count()
+        losses = [float(tr.backprop(*args)) for _ in range(4)]
+        runs.append((losses, {k: v.detach().clone() for k, v in tr.model.named_parameters()}, eng.launch_count() - n0))
+    (la, wa, na), (lb, wb, nb) = runs
+    print("graph vs eager losses:", la, lb, "launches", na, nb)
+    assert na == nb and na > 4 * 500
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 5e-3 * max(1.0, abs(b)), (la, lb)
+    k = "grasp_depth_trunk.features.denseblock3.denselayer7.conv1.weight"
+    assert float(((wa[k] - wb[k]).abs() <= 0.5e-4).float().mean()) >= 0.9
 
 
 def test_fused_step_tf32_gradients_kink_free(scene_inputs, rl_state_dict):
     """tf32 training step (tf32 forward, tensor-core dgrad) against the fp32 CPU oracle on the kink-free network
-    (see test_gpu_parity_r02.py): stated gradient tolerance 3e-2 per tensor (tf32 rounds operands to 10 mantissa bits)."""
+    (see test_gpu_parity_r02.py) with the stated tf32 gradient tolerance of check_kink_free_grads."""
     from oracle import qnet
     from smg_b200.trainer import Trainer
     from test_gpu_parity_r02 import _kink_free_state
@@ -125,21 +152,8 @@ def test_fused_step_tf32_gradients_kink_free(scene_inputs, rl_state_dict):
     ref_loss, ref = qnet.backprop_grads(sd, x, m, 0, 3, 1.0, "reinforcement", gnum_rotations=16)
     assert abs(loss - ref_loss) <= 2e-2 * max(1.0, abs(ref_loss))
     grads = {n: p.grad.detach().cpu() for n, p in tr.model.named_parameters() if p.grad is not None}
-    assert set(grads) == set(ref)
-    gscale = max(float(v.abs().max()) for v in ref.values())
-    worst = []
-    for k, r in ref.items():
-        if k.endswith("features.norm5.weight") or k.endswith("features.norm5.bias"):
-            assert float(grads[k].abs().max()) <= 1e-3 * gscale, k
-            continue
-        scale = r.double().abs().max()
-        if ".norm" in k and k.endswith(".bias"):
-            scale = torch.maximum(scale, ref[k[:-len("bias")] + "weight"].double().abs().max())
-        worst.append((float((grads[k].double() - r.double()).abs().max() / scale.clamp_min(1e-30)), k))
-    worst.sort(reverse=True)
-    print("tf32 fused step, kink-free gradients: worst %s, median %.2e" % ([("%.2e" % e, k) for e, k in worst[:3]],
-                                                                           worst[len(worst) // 2][0]))
-    assert worst[0][0] <= 3e-2, worst[0]
+    from test_gpu_parity_r02 import check_kink_free_grads
+    check_kink_free_grads(grads, ref, "tf32", "fused step")
 
 
 WGRAD_CASES = [
