@@ -23,8 +23,6 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
-int launch_bn_export_region(smg_handle* h, int n, const double* stats, int stats_stride, int c_count, double cnt,
-                            float* mean, float* var, int out_stride, int out_off, cudaStream_t st);
 
 // brackets the launches issued inside its lifetime with CUDA events when profiling is enabled
 struct ProfScope {
@@ -173,30 +171,34 @@ int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cudaStrea
     return SMG_OK;
 }
 
-// per-sample BN statistics of all 121 BatchNorm layers in module order
+// per-sample BN statistics of all 121 BatchNorm layers in module order: ONE launch over a region table built at creation
 int export_bn_stats(smg_handle* h, int n, float* mean, float* var, cudaStream_t st) {
+    SMG_CHECK(h->bn_regions_dev != nullptr, SMG_ERR_STATE, "bn export: no region table");
+    return launch_bn_export_all(h, n, h->bn_regions_dev, h->bn_regions, SMG_TRUNK_BN_CHANNELS, mean, var, st);
+}
+
+static int build_bn_regions(smg_handle* h) {
+    std::vector<BnRegion> r;
     int off = 0;
-    const int total = SMG_TRUNK_BN_CHANNELS;
-    const double cnt0 = (double)(h->H / 2) * (h->H / 2);
-    SMG_TRY(launch_bn_export_region(h, n, stats_ptr(h, h->st_conv0), 64, 64, cnt0, mean, var, total, off, st));
-    off += 64;
+    auto add = [&](size_t st_off, int stride, int count, double cnt) {
+        r.push_back(BnRegion{stats_ptr(h, st_off), stride, count, cnt, off});
+        off += count;
+    };
+    add(h->st_conv0, 64, 64, (double)(h->H / 2) * (h->H / 2));
     int layer_index = 0;
     for (int b = 0; b < kNumBlocks; ++b) {
         const BlockGeom& g = h->geom[b];
         const double cnt = (double)g.hw * g.hw;
         for (int l = 0; l < kBlockLayers[b]; ++l, ++layer_index) {
-            const int cin = g.c_in + l * kGrowth;
-            SMG_TRY(launch_bn_export_region(h, n, stats_ptr(h, h->st_block[b]), g.c_tot, cin, cnt, mean, var, total, off, st));
-            off += cin;
-            SMG_TRY(launch_bn_export_region(h, n, stats_ptr(h, h->st_bott + (size_t)layer_index * kBottleneck), kBottleneck,
-                                            kBottleneck, cnt, mean, var, total, off, st));
-            off += kBottleneck;
+            add(h->st_block[b], g.c_tot, g.c_in + l * kGrowth, cnt);                                      // norm1
+            add(h->st_bott + (size_t)layer_index * kBottleneck, kBottleneck, kBottleneck, cnt);           // norm2
         }
-        // transition norm (b<3) or norm5 (b==3): statistics of the whole block buffer
-        SMG_TRY(launch_bn_export_region(h, n, stats_ptr(h, h->st_block[b]), g.c_tot, g.c_tot, cnt, mean, var, total, off, st));
-        off += g.c_tot;
+        add(h->st_block[b], g.c_tot, g.c_tot, cnt);   // transition norm (b < 3) or norm5 (b == 3): the whole block buffer
     }
-    SMG_CHECK(off == total, SMG_ERR_STATE, "bn export: %d channels, expected %d", off, total);
+    SMG_CHECK(off == SMG_TRUNK_BN_CHANNELS && r.size() == 121, SMG_ERR_STATE, "bn export: %d channels in %zu regions", off, r.size());
+    SMG_CUDA(cudaMalloc(&h->bn_regions_dev, r.size() * sizeof(BnRegion)));
+    SMG_CUDA(cudaMemcpy(h->bn_regions_dev, r.data(), r.size() * sizeof(BnRegion), cudaMemcpyHostToDevice));
+    h->bn_regions = (int)r.size();
     return SMG_OK;
 }
 
@@ -431,7 +433,18 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     h->head_bn1 = reinterpret_cast<float*>(base + o_hb);
     h->head_bn1_floats = S * S * 128;
     h->q_stage = reinterpret_cast<float*>(base + o_q);
-    cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking);
+    if (build_bn_regions(h) != SMG_OK) {
+        cudaFree(base);
+        delete h;
+        return SMG_ERR_CUDA;
+    }
+    {
+        // the graph stream carries the critical chain: highest priority, so that its CTAs are scheduled ahead of the
+        // side-stream weight gradients whenever SMs free up
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&h->gstream, cudaStreamNonBlocking, hi);
+    }
     cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming);
     if (const char* e = getenv("SMG_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
@@ -450,7 +463,11 @@ int smg_destroy(smg_handle* h) {
     for (auto& g : h->step.graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->step.tables) cudaFree(h->step.tables);
+    if (h->bn_regions_dev) cudaFree(h->bn_regions_dev);
     if (h->train.arena) cudaFree(h->train.arena);
+    if (h->train.wstream) cudaStreamDestroy(h->train.wstream);
+    for (auto& e : h->train.ev)
+        if (e) cudaEventDestroy(e);
     if (h->gstream) cudaStreamDestroy(h->gstream);
     if (h->g_in) cudaEventDestroy(h->g_in);
     if (h->g_out) cudaEventDestroy(h->g_out);
@@ -749,6 +766,12 @@ int ensure_train_workspace(smg_handle* h) {
                 const size_t o = p.take(S * h->geom[b].hw * h->geom[b].hw * kBottleneck * 4);
                 if (base) W.bott_saved[li] = reinterpret_cast<float*>(base + o);
             }
+        li = 0;
+        for (int b = 0; b < kNumBlocks; ++b)
+            for (int l = 0; l < kBlockLayers[b]; ++l, ++li) {
+                const size_t o = p.take(S * h->geom[b].hw * h->geom[b].hw * kBottleneck * 4);
+                if (base) W.dy1_saved[li] = reinterpret_cast<float*>(base + o);
+            }
         for (int b = 0; b < kNumBlocks; ++b) {
             const size_t o = p.take(S * h->geom[b].hw * h->geom[b].hw * h->geom[b].c_tot * 4);
             if (base) W.dblk[b] = reinterpret_cast<float*>(base + o);
@@ -776,6 +799,8 @@ int ensure_train_workspace(smg_handle* h) {
             W.bytes = p.off;
             SMG_CUDA(cudaMalloc(&W.arena, W.bytes));
             h->workspace_bytes += (int64_t)W.bytes;
+            SMG_CUDA(cudaStreamCreateWithPriority(&W.wstream, cudaStreamNonBlocking, 0));   // lower priority than the main chain's
+            for (auto& e : W.ev) SMG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
     }
     return SMG_OK;
@@ -822,11 +847,22 @@ static int dgrad_conv(smg_handle* h, ConvArgs a, const ConvW& cw, cudaStream_t s
 }
 
 // one BatchNorm(+ReLU) backward: reduce -> parameter grads -> apply
-static int bn_backward(smg_handle* h, BnBwd a, int S, double*& sums_cursor, float* dgamma, float* dbeta, cudaStream_t st) {
+static int bn_backward(smg_handle* h, BnBwd a, int S, double*& sums_cursor, float* dgamma, float* dbeta, cudaStream_t st,
+                       bool reduce_done = false) {
     a.sums = sums_cursor;
     sums_cursor += (size_t)2 * S * a.C;
-    SMG_TRY(launch_bn_bwd(h, a, S, false, nullptr, nullptr, st));
+    if (!reduce_done) SMG_TRY(launch_bn_bwd(h, a, S, false, nullptr, nullptr, st));   // else: fused into the producing dgrad
     return launch_bn_bwd(h, a, S, true, dgamma, dbeta, st);
+}
+
+// lets the epilogue of a tensor-core data-gradient convolution do the reduction of the BatchNorm backward that consumes its
+// output (tf32 mode only: the CUDA-core kernel has no such epilogue); `sums` = the region bn_backward will be given next
+static bool fuse_bn_reduce(const smg_handle* h, ConvArgs& a, const BnBwd& bb, double* sums) {
+    static const bool on = getenv("SMG_BN_FUSE") == nullptr || atoi(getenv("SMG_BN_FUSE")) != 0;
+    if (!on || h->precision != SMG_PREC_TF32 || bb.da_pooled || !bb.relu) return false;
+    a.bnr_x = bb.x; a.bnr_x_cstride = bb.x_cstride; a.bnr_stats = bb.stats; a.bnr_stats_stride = bb.stats_stride;
+    a.bnr_gamma = bb.gamma; a.bnr_beta = bb.beta; a.bnr_sums = sums;
+    return true;
 }
 
 int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* const* hg, cudaStream_t st) {
@@ -842,7 +878,19 @@ int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* cons
     static const bool wgrad_tc_env = getenv("SMG_WGRAD_TC") == nullptr || atoi(getenv("SMG_WGRAD_TC")) != 0;
     const bool wgrad_tc = wgrad_tc_env && h->precision == SMG_PREC_TF32;
     int n_wg3 = 0;
-    if (wgrad_tc) SMG_CUDA(cudaMemsetAsync(W.wg3_scratch, 0, (size_t)58 * 288 * 128 * 4, st));
+    // The weight gradients feed nothing downstream: with per-layer copies of d(conv1 output) they run on a second stream
+    // next to the dgrad / BatchNorm chain (fork here, one dependency per layer, join before the stem).  Their grids are
+    // capped so that the critical chain always finds free SMs.  SMG_WGRAD_ASYNC=0 keeps everything on one stream.
+    static const bool async_env = getenv("SMG_WGRAD_ASYNC") == nullptr || atoi(getenv("SMG_WGRAD_ASYNC")) != 0;
+    static const int cap_env = getenv("SMG_WGRAD_CTAS") ? atoi(getenv("SMG_WGRAD_CTAS")) : 64;
+    const bool async_w = wgrad_tc && async_env;
+    cudaStream_t ws = async_w ? W.wstream : st;
+    h->wgrad_cta_cap = async_w ? cap_env : 0;
+    if (async_w) {
+        SMG_CUDA(cudaEventRecord(W.ev[58], st));
+        SMG_CUDA(cudaStreamWaitEvent(ws, W.ev[58], 0));
+    }
+    if (wgrad_tc) SMG_CUDA(cudaMemsetAsync(W.wg3_scratch, 0, (size_t)58 * 288 * 128 * 4, ws));
     const BlockGeom& g4 = h->geom[3];
     const int npix4 = g4.hw * g4.hw;
 
@@ -880,20 +928,33 @@ int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* cons
             const int cin = g.c_in + l * kGrowth;
             double* st_bott = stats_ptr(h, h->st_bott + (size_t)layer_index * kBottleneck);
             float* y1 = W.bott_saved[layer_index];
-            // (1) 3x3 dgrad: d relu(bn2(y1)) = conv3x3(dX[:, cin:cin+32], flipped W2)
+            float* dy1 = async_w ? W.dy1_saved[layer_index] : W.t_b;   // d(conv1 output): kept per layer for the side stream
+            // (1) 3x3 dgrad: d relu(bn2(y1)) = conv3x3(dX[:, cin:cin+32], flipped W2); its epilogue reduces BN2's backward
+            BnBwd bb2{};
+            bb2.da = W.t_a; bb2.da_cstride = kBottleneck; bb2.x = y1; bb2.x_cstride = kBottleneck;
+            bb2.stats = st_bott; bb2.stats_stride = kBottleneck; bb2.gamma = L.norm2.gamma; bb2.beta = L.norm2.beta;
+            bb2.C = kBottleneck; bb2.hw = g.hw; bb2.relu = 1; bb2.dst = dy1; bb2.dst_cstride = kBottleneck; bb2.accumulate = 0;
+            bool fused2;
             {
                 ConvArgs a;
                 a.in = W.dblk[b] + cin; a.in_cstride = g.c_tot; a.cin = kGrowth; a.hin = g.hw;
                 a.taps = 9;
                 a.out = W.t_a; a.out_cstride = kBottleneck; a.out_coff = 0; a.cout = kBottleneck; a.n = S;
+                fused2 = fuse_bn_reduce(h, a, bb2, sums);
                 SMG_TRY(dgrad_conv(h, a, L.conv2, st));
+            }
+            // (3) BN2 + ReLU backward -> d y1
+            SMG_TRY(bn_backward(h, bb2, S, sums, GL.n2[0], GL.n2[1], st, fused2));
+            if (async_w) {   // both weight gradients of this layer may start: its gradient slice and d y1 are final
+                SMG_CUDA(cudaEventRecord(W.ev[layer_index], st));
+                SMG_CUDA(cudaStreamWaitEvent(ws, W.ev[layer_index], 0));
             }
             // (2) 3x3 wgrad
             int wg3_status = SMG_ERR_UNSUPPORTED;
             if (wgrad_tc) {
                 float* scratch = W.wg3_scratch + (size_t)n_wg3 * 288 * 128;
                 wg3_status = launch_wgrad3_umma(h, W.dblk[b], g.c_tot, cin, y1, g.hw, S, st_bott, kBottleneck, L.norm2.gamma,
-                                                L.norm2.beta, scratch, st);
+                                                L.norm2.beta, scratch, ws);
                 if (wg3_status == SMG_OK) {
                     W.wg3_jobs[2 * n_wg3] = scratch;
                     W.wg3_jobs[2 * n_wg3 + 1] = GL.c2;
@@ -903,53 +964,44 @@ int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* cons
                 }
             }
             if (wg3_status == SMG_ERR_UNSUPPORTED) {
-                SMG_CUDA(cudaMemsetAsync(GL.c2, 0, (size_t)kGrowth * kBottleneck * 9 * 4, st));
+                SMG_CUDA(cudaMemsetAsync(GL.c2, 0, (size_t)kGrowth * kBottleneck * 9 * 4, ws));
                 Wgrad wg{};
                 wg.g = W.dblk[b]; wg.g_cstride = g.c_tot; wg.g_coff = cin; wg.cout = kGrowth;
                 wg.x = y1; wg.x_cstride = kBottleneck; wg.cin = kBottleneck; wg.hin = g.hw; wg.hout = g.hw;
                 wg.prologue_mode = 0; wg.stats = st_bott; wg.stats_stride = kBottleneck; wg.gamma = L.norm2.gamma; wg.beta = L.norm2.beta;
                 wg.relu = 1; wg.dw = GL.c2; wg.k_total = kBottleneck; wg.k_off = 0;
-                SMG_TRY(launch_wgrad(h, wg, S, 9, 0, st));
-            }
-            // (3) BN2 + ReLU backward -> d y1 in t_b
-            {
-                BnBwd bb{};
-                bb.da = W.t_a; bb.da_cstride = kBottleneck; bb.x = y1; bb.x_cstride = kBottleneck;
-                bb.stats = st_bott; bb.stats_stride = kBottleneck; bb.gamma = L.norm2.gamma; bb.beta = L.norm2.beta;
-                bb.C = kBottleneck; bb.hw = g.hw; bb.relu = 1; bb.dst = W.t_b; bb.dst_cstride = kBottleneck; bb.accumulate = 0;
-                SMG_TRY(bn_backward(h, bb, S, sums, GL.n2[0], GL.n2[1], st));
+                SMG_TRY(launch_wgrad(h, wg, S, 9, 0, ws));
             }
             // (4) 1x1 wgrad
-            SMG_CUDA(cudaMemsetAsync(GL.c1, 0, (size_t)kBottleneck * cin * 4, st));
+            SMG_CUDA(cudaMemsetAsync(GL.c1, 0, (size_t)kBottleneck * cin * 4, ws));
             int wg1_status = SMG_ERR_UNSUPPORTED;
             if (wgrad_tc) {
-                wg1_status = launch_wgrad1_umma(h, W.t_b, h->block[b], g.c_tot, cin, g.hw, S, st_blk, g.c_tot, L.norm1.gamma,
-                                                L.norm1.beta, GL.c1, st);
+                wg1_status = launch_wgrad1_umma(h, dy1, h->block[b], g.c_tot, cin, g.hw, S, st_blk, g.c_tot, L.norm1.gamma,
+                                                L.norm1.beta, GL.c1, ws);
                 if (wg1_status != SMG_OK && wg1_status != SMG_ERR_UNSUPPORTED) return wg1_status;
             }
             if (wg1_status == SMG_ERR_UNSUPPORTED) {
                 Wgrad wg{};
-                wg.g = W.t_b; wg.g_cstride = kBottleneck; wg.g_coff = 0; wg.cout = kBottleneck;
+                wg.g = dy1; wg.g_cstride = kBottleneck; wg.g_coff = 0; wg.cout = kBottleneck;
                 wg.x = h->block[b]; wg.x_cstride = g.c_tot; wg.cin = cin; wg.hin = g.hw; wg.hout = g.hw;
                 wg.prologue_mode = 0; wg.stats = st_blk; wg.stats_stride = g.c_tot; wg.gamma = L.norm1.gamma; wg.beta = L.norm1.beta;
                 wg.relu = 1; wg.dw = GL.c1; wg.k_total = cin; wg.k_off = 0;
-                SMG_TRY(launch_wgrad(h, wg, S, 1, 0, st));
+                SMG_TRY(launch_wgrad(h, wg, S, 1, 0, ws));
             }
             // (5) 1x1 dgrad: d relu(bn1(X[:, :cin])) = dy1 . W1
-            {
-                ConvArgs a;
-                a.in = W.t_b; a.in_cstride = kBottleneck; a.cin = kBottleneck; a.hin = g.hw;
-                a.taps = 1;
-                a.out = W.t_c; a.out_cstride = cin; a.out_coff = 0; a.cout = cin; a.n = S;
-                SMG_TRY(dgrad_conv(h, a, L.conv1, st));
-            }
-            // (6) BN1 + ReLU backward, accumulated into the block gradient
+            // (6) BN1 + ReLU backward, accumulated into the block gradient; its reduction rides in the 1x1 dgrad's epilogue
             {
                 BnBwd bb{};
                 bb.da = W.t_c; bb.da_cstride = cin; bb.x = h->block[b]; bb.x_cstride = g.c_tot;
                 bb.stats = st_blk; bb.stats_stride = g.c_tot; bb.gamma = L.norm1.gamma; bb.beta = L.norm1.beta;
                 bb.C = cin; bb.hw = g.hw; bb.relu = 1; bb.dst = W.dblk[b]; bb.dst_cstride = g.c_tot; bb.accumulate = 1;
-                SMG_TRY(bn_backward(h, bb, S, sums, GL.n1[0], GL.n1[1], st));
+                ConvArgs a;
+                a.in = dy1; a.in_cstride = kBottleneck; a.cin = kBottleneck; a.hin = g.hw;
+                a.taps = 1;
+                a.out = W.t_c; a.out_cstride = cin; a.out_coff = 0; a.cout = cin; a.n = S;
+                const bool fused1 = fuse_bn_reduce(h, a, bb, sums);
+                SMG_TRY(dgrad_conv(h, a, L.conv1, st));
+                SMG_TRY(bn_backward(h, bb, S, sums, GL.n1[0], GL.n1[1], st, fused1));
             }
         }
         if (b > 0) {
@@ -985,9 +1037,14 @@ int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* cons
     }
     if (n_wg3 > 0) {
         // the table lives in the handle (stable host address): a captured copy node re-reads it at every replay
-        SMG_CUDA(cudaMemcpyAsync(W.wg3_jobs_dev, W.wg3_jobs.data(), (size_t)n_wg3 * 2 * sizeof(void*), cudaMemcpyHostToDevice, st));
-        SMG_TRY(launch_wgrad3_finish(h, W.wg3_jobs_dev, n_wg3, st));
+        SMG_CUDA(cudaMemcpyAsync(W.wg3_jobs_dev, W.wg3_jobs.data(), (size_t)n_wg3 * 2 * sizeof(void*), cudaMemcpyHostToDevice, ws));
+        SMG_TRY(launch_wgrad3_finish(h, W.wg3_jobs_dev, n_wg3, ws));
     }
+    if (async_w) {   // join: everything after this point (and the caller) sees the weight gradients
+        SMG_CUDA(cudaEventRecord(W.ev[59], ws));
+        SMG_CUDA(cudaStreamWaitEvent(st, W.ev[59], 0));
+    }
+    h->wgrad_cta_cap = 0;
     // ---- stem: maxpool -> relu/bn0 -> conv0 wgrad (no data gradient is needed for the input image)
     const int Hc = h->H / 2;
     SMG_CUDA(cudaMemsetAsync(W.dconv0, 0, (size_t)S * Hc * Hc * 64 * 4, st));

@@ -363,35 +363,42 @@ conv0_wgrad_kernel(const float* __restrict__ d, const float* __restrict__ in, fl
 // ------------------------------------------------------------------------------------------------
 // head backward
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sum16(const float (*r)[64], int c) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += r[i][c];
+    return t;
+}
+
 // one CTA: BN(64)+ReLU+20x20 conv backward for the (scene, mask) pair.  p: [2][npix][64] partial products.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 head_tail_bwd_kernel(const float* __restrict__ p, int npix, const float* __restrict__ g1, const float* __restrict__ b1,
                      const float* __restrict__ w1, int n_out, const float* __restrict__ dq, float* __restrict__ dP,
                      float* __restrict__ dg1, float* __restrict__ db1, float* __restrict__ dw1) {
-    __shared__ float red[2][4][64];
+    __shared__ float red[2][16][64];   // 64 channels x 16 pixel groups
     __shared__ float s_dq[4];
     const int tid = threadIdx.x, c = tid & 63, g = tid >> 6;
     const float* ps = p;
     const float* pm = p + (size_t)npix * 64;
     if (tid < 4) s_dq[tid] = tid < n_out ? dq[tid] : 0.f;
     float su = 0.f;
-    for (int px = g; px < npix; px += 4) su += ps[px * 64 + c] + pm[px * 64 + c];
+    for (int px = g; px < npix; px += 16) su += ps[px * 64 + c] + pm[px * 64 + c];
     red[0][g][c] = su;
     __syncthreads();
-    const float mean = (red[0][0][c] + red[0][1][c] + red[0][2][c] + red[0][3][c]) / (float)npix;
+    const float mean = sum16(red[0], c) / (float)npix;
     float sq = 0.f;
-    for (int px = g; px < npix; px += 4) {
+    for (int px = g; px < npix; px += 16) {
         const float d = ps[px * 64 + c] + pm[px * 64 + c] - mean;
         sq = fmaf(d, d, sq);
     }
     red[1][g][c] = sq;
     __syncthreads();
-    const float var = (red[1][0][c] + red[1][1][c] + red[1][2][c] + red[1][3][c]) / (float)npix;
+    const float var = sum16(red[1], c) / (float)npix;
     const float rstd = rsqrtf(var + kBnEps);
     const float gam = g1[c], bet = b1[c];
     __syncthreads();
     float s1 = 0.f, s2 = 0.f;
-    for (int px = g; px < npix; px += 4) {
+    for (int px = g; px < npix; px += 16) {
         const float yh = (ps[px * 64 + c] + pm[px * 64 + c] - mean) * rstd;
         const float act = fmaxf(fmaf(gam, yh, bet), 0.f);
         float da = 0.f;
@@ -406,11 +413,11 @@ head_tail_bwd_kernel(const float* __restrict__ p, int npix, const float* __restr
     red[0][g][c] = s1;
     red[1][g][c] = s2;
     __syncthreads();
-    const float S1 = red[0][0][c] + red[0][1][c] + red[0][2][c] + red[0][3][c];
-    const float S2 = red[1][0][c] + red[1][1][c] + red[1][2][c] + red[1][3][c];
+    const float S1 = sum16(red[0], c);
+    const float S2 = sum16(red[1], c);
     if (g == 0) { dg1[c] = S2; db1[c] = S1; }
     const float m1 = S1 / (float)npix, m2 = S2 / (float)npix;
-    for (int px = g; px < npix; px += 4) {
+    for (int px = g; px < npix; px += 16) {
         const float yh = (ps[px * 64 + c] + pm[px * 64 + c] - mean) * rstd;
         const float act = fmaxf(fmaf(gam, yh, bet), 0.f);
         float da = 0.f;
@@ -420,14 +427,27 @@ head_tail_bwd_kernel(const float* __restrict__ p, int npix, const float* __restr
     }
 }
 
-// backward through head norm0 (+ReLU) and the trunk's norm5 for the two samples; thread = channel
-__global__ void __launch_bounds__(128)
+// backward through head norm0 (+ReLU) and the trunk's norm5 for the two samples; CTA = 32 channels x 8 pixel lanes
+__device__ __forceinline__ void lane8_sum2(float (*red)[8][32], int pl, int cl, float& a, float& b) {
+    red[0][pl][cl] = a;
+    red[1][pl][cl] = b;
+    __syncthreads();
+    float ta = 0.f, tb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ta += red[0][i][cl]; tb += red[1][i][cl]; }
+    __syncthreads();
+    a = ta;
+    b = tb;
+}
+
+__global__ void __launch_bounds__(256)
 head_norm_bwd_kernel(const float* __restrict__ da0, const float* __restrict__ x4, const double* __restrict__ stats,
                      int stats_stride, int npix, const float* __restrict__ g5, const float* __restrict__ b5,
                      const float* __restrict__ gh, const float* __restrict__ bh, float* __restrict__ dx4,
                      float* __restrict__ dg5, float* __restrict__ db5, float* __restrict__ dgh, float* __restrict__ dbh) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= kFeatC) return;
+    __shared__ float red[2][8][32];
+    const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     float acc_g5 = 0.f, acc_b5 = 0.f;
     const float n = (float)npix;
     for (int s = 0; s < 2; ++s) {
@@ -444,7 +464,7 @@ head_norm_bwd_kernel(const float* __restrict__ da0, const float* __restrict__ x4
         const float* ds = da0 + (size_t)s * npix * kFeatC + c;
         float* os = dx4 + (size_t)s * npix * kFeatC + c;
         float A1 = 0.f, A2 = 0.f;
-        for (int p = 0; p < npix; ++p) {
+        for (int p = pl; p < npix; p += 8) {
             const float xh = (xs[(size_t)p * kFeatC] - mean) * r5;
             const float zh = kap * xh;
             const float u = fmaf(gamh, zh, beth);
@@ -452,11 +472,14 @@ head_norm_bwd_kernel(const float* __restrict__ da0, const float* __restrict__ x4
             A1 += du;
             A2 = fmaf(du, zh, A2);
         }
-        dgh[s * kFeatC + c] = A2;
-        dbh[s * kFeatC + c] = A1;
+        lane8_sum2(red, pl, cl, A1, A2);
+        if (pl == 0) {
+            dgh[s * kFeatC + c] = A2;
+            dbh[s * kFeatC + c] = A1;
+        }
         const float a1 = A1 / n, a2 = A2 / n;
         float B1 = 0.f, B2 = 0.f;
-        for (int p = 0; p < npix; ++p) {
+        for (int p = pl; p < npix; p += 8) {
             const float xh = (xs[(size_t)p * kFeatC] - mean) * r5;
             const float zh = kap * xh;
             const float u = fmaf(gamh, zh, beth);
@@ -465,10 +488,11 @@ head_norm_bwd_kernel(const float* __restrict__ da0, const float* __restrict__ x4
             B1 += dz;
             B2 = fmaf(dz, xh, B2);
         }
+        lane8_sum2(red, pl, cl, B1, B2);
         acc_g5 += B2;
         acc_b5 += B1;
         const float b1 = B1 / n, b2 = B2 / n;
-        for (int p = 0; p < npix; ++p) {
+        for (int p = pl; p < npix; p += 8) {
             const float xh = (xs[(size_t)p * kFeatC] - mean) * r5;
             const float zh = kap * xh;
             const float u = fmaf(gamh, zh, beth);
@@ -477,8 +501,10 @@ head_norm_bwd_kernel(const float* __restrict__ da0, const float* __restrict__ x4
             os[(size_t)p * kFeatC] = gam5 * r5 * (dz - b1 - xh * b2);
         }
     }
-    dg5[c] = acc_g5;
-    db5[c] = acc_b5;
+    if (pl == 0) {
+        dg5[c] = acc_g5;
+        db5[c] = acc_b5;
+    }
 }
 
 // fused multi-tensor-free Adam over one flat tensor (torch.optim.Adam semantics, code/trainer.py:99)
@@ -578,7 +604,7 @@ int launch_conv0_wgrad(smg_handle* h, int S, const float* d, const float* in, in
 int launch_head_tail_bwd(smg_handle* h, const float* p, const HeadW& hw, const float* dq, float* dP, float* dg1,
                          float* db1, float* dw1, cudaStream_t st) {
     const int npix = h->geom[3].hw * h->geom[3].hw;
-    head_tail_bwd_kernel<<<1, 256, 0, st>>>(p, npix, hw.norm1.gamma, hw.norm1.beta, hw.conv1, hw.n_out, dq, dP, dg1, db1, dw1);
+    head_tail_bwd_kernel<<<1, 1024, 0, st>>>(p, npix, hw.norm1.gamma, hw.norm1.beta, hw.conv1, hw.n_out, dq, dP, dg1, db1, dw1);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;
@@ -588,7 +614,7 @@ int launch_head_norm_bwd(smg_handle* h, const float* da0, const float* x4, const
                          const BnP& norm5, const BnP& hnorm0, float* dx4, float* dg5, float* db5, float* dgh, float* dbh,
                          cudaStream_t st) {
     const int npix = h->geom[3].hw * h->geom[3].hw;
-    head_norm_bwd_kernel<<<kFeatC / 128, 128, 0, st>>>(da0, x4, stats, stats_stride, npix, norm5.gamma, norm5.beta,
+    head_norm_bwd_kernel<<<kFeatC / 32, 256, 0, st>>>(da0, x4, stats, stats_stride, npix, norm5.gamma, norm5.beta,
                                                       hnorm0.gamma, hnorm0.beta, dx4, dg5, db5, dgh, dbh);
     h->launches++;
     SMG_CUDA(cudaGetLastError());

@@ -484,6 +484,60 @@ conv_umma_kernel(UmmaDev a) {
         // per-channel statistics of this tile (invalid rows were staged as zeros): partial column sums by all
         // threads, combined in shared memory (the scale/shift tables are dead by now), ONE double atomic pair per
         // channel and tile
+        if (a.bnr_sums != nullptr) {
+            // BatchNorm(+ReLU) backward reduction over this tile: channel = column, rows split over the row groups
+            constexpr int GROUPS = 448 / BN;
+            constexpr int RPG = (UM + GROUPS - 1) / GROUPS;
+            float* red = s_sc;
+            const int cidx = tid % BN, g = tid / BN;
+            const int ch = ntile * BN + cidx;
+            if (g < GROUPS) {
+                float s1 = 0.f, s2 = 0.f;
+                if (ch < a.cout) {
+                    const double cnt = (double)hout * hout;
+                    const double* stp = a.bnr_stats + 2 * ((size_t)s * a.bnr_stats_stride + ch);
+                    const double md = stp[0] / cnt;
+                    double var = stp[1] / cnt - md * md;
+                    if (var < 0) var = 0;
+                    const float mean = (float)md, rstd = (float)(1.0 / sqrt(var + (double)kBnEps));
+                    const float sc = a.bnr_gamma[ch] * rstd, sh = a.bnr_beta[ch] - mean * sc;
+                    const float* xb = a.bnr_x + (size_t)s * hw_out * a.bnr_x_cstride + ch;
+                    const int r1 = (g + 1) * RPG < UM ? (g + 1) * RPG : UM;
+                    for (int r = g * RPG; r < r1; ++r) {
+                        int pix;
+                        bool ok;
+                        if (TAPS == 9) {
+                            const int i = r / a.wp, j = r - i * a.wp;
+                            ok = i < a.ht && j < a.wp - 2 && h0 + i < hout && w0 + j < hout;
+                            pix = (h0 + i) * hout + w0 + j;
+                        } else {
+                            ok = m0 + r < hw_out;
+                            pix = m0 + r;
+                        }
+                        if (!ok) continue;
+                        const float xv = xb[(size_t)pix * a.bnr_x_cstride];
+                        const float dz = fmaf(xv, sc, sh) > 0.f ? s_out[r * (BN + 1) + cidx] : 0.f;
+                        s1 += dz;
+                        s2 = fmaf(dz, (xv - mean) * rstd, s2);
+                    }
+                }
+                red[g * BN + cidx] = s1;
+                red[(GROUPS + g) * BN + cidx] = s2;
+            }
+            __syncthreads();
+            if (tid < BN && ntile * BN + tid < a.cout) {
+                double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+                for (int g2 = 0; g2 < GROUPS; ++g2) {
+                    t1 += (double)red[g2 * BN + tid];
+                    t2 += (double)red[(GROUPS + g2) * BN + tid];
+                }
+                double* sm = a.bnr_sums + 2 * ((size_t)s * a.cout + ntile * BN + tid);
+                atomicAdd(sm, t1);
+                atomicAdd(sm + 1, t2);
+            }
+            __syncthreads();
+        }
         if (a.out_stats != nullptr) {
             constexpr int GROUPS = 448 / BN;                        // row groups: 3 (N=128), 7 (N=64), 14 (N=32)
             constexpr int RPG = (UM + GROUPS - 1) / GROUPS;          // rows per group
@@ -614,6 +668,8 @@ int launch_conv_umma(smg_handle* h, const ConvArgs& a, int precision, cudaStream
     d.gamma = a.gamma; d.beta = a.beta; d.scale = a.scale; d.shift = a.shift; d.relu = a.relu;
     d.out = a.out; d.out_cstride = a.out_cstride; d.out_coff = a.out_coff; d.cout = a.cout;
     d.out_stats = a.out_stats; d.out_stats_stride = a.out_stats_stride;
+    d.bnr_x = a.bnr_x; d.bnr_x_cstride = a.bnr_x_cstride; d.bnr_stats = a.bnr_stats; d.bnr_stats_stride = a.bnr_stats_stride;
+    d.bnr_gamma = a.bnr_gamma; d.bnr_beta = a.bnr_beta; d.bnr_sums = a.bnr_sums;
     d.hout = a.pool ? a.hin / 2 : a.hin;
     d.wp = d.ht = d.tiles_x = 0;
     d.async_producer = 0;

@@ -166,18 +166,19 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int npix, int 
     }
 }
 
-// per-sample BN batch statistics (mean, biased var) from (sum, sumsq): out[s*out_stride + out_off + c]
-__global__ void bn_export_kernel(int n, const double* __restrict__ stats, int stats_stride, int c_count, double cnt,
-                                 float* __restrict__ mean, float* __restrict__ var, int out_stride, int out_off) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * c_count) return;
-    const int s = i / c_count, c = i - s * c_count;
-    const double* st = stats + 2 * ((size_t)s * stats_stride + c);
-    const double m = st[0] / cnt;
-    double v = st[1] / cnt - m * m;
-    if (v < 0) v = 0;
-    mean[(size_t)s * out_stride + out_off + c] = (float)m;
-    var[(size_t)s * out_stride + out_off + c] = (float)v;
+// per-sample BN batch statistics (mean, biased var) from (sum, sumsq): block = (region, sample)
+__global__ void bn_export_all_kernel(const BnRegion* __restrict__ regions, int total, float* __restrict__ mean,
+                                     float* __restrict__ var) {
+    const BnRegion r = regions[blockIdx.x];
+    const int s = blockIdx.y;
+    for (int c = threadIdx.x; c < r.count; c += blockDim.x) {
+        const double* st = r.stats + 2 * ((size_t)s * r.stride + c);
+        const double m = st[0] / r.cnt;
+        double v = st[1] / r.cnt - m * m;
+        if (v < 0) v = 0;
+        mean[(size_t)s * total + r.out_off + c] = (float)m;
+        var[(size_t)s * total + r.out_off + c] = (float)v;
+    }
 }
 
 int launch_head_prepare(smg_handle* h, int n, const double* stats4, int stats_stride, const BnP& norm5,
@@ -236,11 +237,9 @@ int launch_nhwc_to_nchw(smg_handle* h, const float* in, int hw, int c, int cstri
     return SMG_OK;
 }
 
-int launch_bn_export_region(smg_handle* h, int n, const double* stats, int stats_stride, int c_count, double cnt,
-                            float* mean, float* var, int out_stride, int out_off, cudaStream_t st) {
-    const int total = n * c_count;
-    bn_export_kernel<<<(total + 255) / 256, 256, 0, st>>>(n, stats, stats_stride, c_count, cnt, mean, var, out_stride,
-                                                          out_off);
+int launch_bn_export_all(smg_handle* h, int n, const void* dev_regions, int n_regions, int total, float* mean, float* var,
+                         cudaStream_t st) {
+    bn_export_all_kernel<<<dim3(n_regions, n), 256, 0, st>>>(reinterpret_cast<const BnRegion*>(dev_regions), total, mean, var);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;

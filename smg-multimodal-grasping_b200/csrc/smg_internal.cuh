@@ -171,6 +171,7 @@ struct smg_handle {
                                    // identical input channels (stem_umma.cu), 64 = 3x3 with the weights resident in tensor memory
                                    // (conv3_wt.cu), 128 = persistent 1x1 with swapped operand roles (conv1_t.cu); a cleared bit
                                    // routes the layer to the register-producer kernel of conv_umma.cu
+    int wgrad_cta_cap = 0;         // > 0 while the weight gradients share the GPU with the dgrad chain: max CTAs per wgrad launch
     int force_async = 0;           // tuning: -1 auto by grid size, 0 register producers (default: measured fastest), 1 cp.async producers
     std::vector<const void*> smem_opt_in;   // kernels whose >48 KB dynamic shared memory opt-in was set on this handle's device
 
@@ -215,6 +216,8 @@ struct smg_handle {
     };
     std::vector<QGraph> graphs;
     int last_n = 0;               // samples of the last trunk forward (for smg_debug_read)
+    void* bn_regions_dev = nullptr;   // the 121 BatchNorm statistics regions in module order (export_bn_stats)
+    int bn_regions = 0;
 
     // training workspace (2 samples: rotated scene + masked scene), allocated by the first smg_qforward_train
     struct TrainWs {
@@ -226,6 +229,9 @@ struct smg_handle {
         float* t_a = nullptr;                // [2,H/4,H/4,128] scratch (d relu(bn2))
         float* t_b = nullptr;                // [2,H/4,H/4,128] scratch (d conv1 output)
         float* t_c = nullptr;                // [2,H/4,H/4,256] scratch (d relu(bn1) / transition dgrad)
+        float* dy1_saved[58] = {nullptr};    // gradient w.r.t. conv1's output of every dense layer [2,Hb,Hb,128] (side-stream wgrad)
+        cudaStream_t wstream = nullptr;      // the weight gradients' stream
+        cudaEvent_t ev[60] = {nullptr};      // [0,58) per-layer dependencies, 58 fork, 59 join
         float* dP = nullptr;                 // [400,64]
         float* wg3_scratch = nullptr;        // [58][(tap, co) 288][ci 128]: 3x3 weight gradients before the final transpose
         std::vector<void*> wg3_jobs;         // host copy of the {scratch, gradient tensor} table of wgrad3_finish_kernel
@@ -328,6 +334,14 @@ struct ConvArgs {
     const ConvW* w = nullptr;
     const float* w_raw = nullptr;  // conv_ffma only: overrides w->w_ffma ([taps][cin][cout] fp32)
     const uint8_t* w_umma = nullptr;  // conv_umma only (tf32): overrides w->w_tf32 with another packed stage image (w_dgrad_tf32)
+    // conv_umma only: fused BatchNorm-backward reduction in the epilogue of a data-gradient convolution (see UmmaDev)
+    const float* bnr_x = nullptr;
+    int bnr_x_cstride = 0;
+    const double* bnr_stats = nullptr;
+    int bnr_stats_stride = 0;
+    const float* bnr_gamma = nullptr;
+    const float* bnr_beta = nullptr;
+    double* bnr_sums = nullptr;
     float* out = nullptr;
     int out_cstride = 0;
     int out_coff = 0;
@@ -349,7 +363,16 @@ int launch_norm5_export(smg_handle* h, int n, const float* block4, const double*
                         const BnP& norm5, float* out_nchw, cudaStream_t st);
 int launch_head_tail(smg_handle* h, const float* p, int n_rot, int n_masks, const HeadW& hw, float* q,
                      cudaStream_t st, int groups = 1);
-int launch_bn_export(smg_handle* h, int trunk_id, int n, float* mean, float* var, cudaStream_t st);
+// one BatchNorm layer's slice of the statistics arena: `count` channels of a [S][stride] double2 region -> columns
+// [out_off, out_off + count) of the exported [S][total] mean / biased-variance tables
+struct BnRegion {
+    const double* stats;
+    int stride, count;
+    double cnt;
+    int out_off;
+};
+int launch_bn_export_all(smg_handle* h, int n, const void* dev_regions, int n_regions, int total, float* mean, float* var,
+                         cudaStream_t st);
 int launch_argmax(smg_handle* h, const float* q, int n, float* out, int32_t* out_idx, cudaStream_t st);
 int launch_nhwc_to_nchw(smg_handle* h, const float* in, int hw, int c, int cstride, float* out, cudaStream_t st);
 

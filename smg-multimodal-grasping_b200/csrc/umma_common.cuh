@@ -154,6 +154,16 @@ struct UmmaDev {
     int tiles_per_sample, tiles_per_cta;
     // persistent kernels: how many TMA boxes ahead of its shared-memory ring the loader prefetches into L2 (0 = off)
     int l2_prefetch = 0;
+    // data-gradient convolutions: the output IS the gradient w.r.t. relu(bn(x)) of the BatchNorm that produced this
+    // convolution's forward input, so the epilogue can do that BatchNorm's backward REDUCTION on the tile it holds:
+    // S1 += dz, S2 += dz * xhat with dz = out masked by relu'(bn(x)) -> bnr_sums [S][cout] double2 (nullptr = off)
+    const float* bnr_x = nullptr;      // raw BatchNorm input, NHWC on the output's pixel grid, channels [0, cout)
+    int bnr_x_cstride = 0;
+    const double* bnr_stats = nullptr; // its (sum, sumsq): [S][bnr_stats_stride] double2
+    int bnr_stats_stride = 0;
+    const float* bnr_gamma = nullptr;
+    const float* bnr_beta = nullptr;
+    double* bnr_sums = nullptr;
 };
 
 constexpr int UM = 128;         // rows per tile (UMMA M)

@@ -275,7 +275,7 @@ int launch_wgrad1_umma(smg_handle* h, const float* g, const float* x, int x_cstr
     d.hw = hw; d.S = S; d.units_per_sample = npix / G_P; d.total_units = S * d.units_per_sample;
     d.cin = cin; d.stats = stats; d.stats_stride = stats_stride; d.gamma = gamma; d.beta = beta; d.dw = dw; d.ld = cin;
     const int ntiles = (cin + 255) / 256;
-    int splits = h->num_sms / ntiles;
+    int splits = (h->wgrad_cta_cap > 0 ? h->wgrad_cta_cap : h->num_sms) / ntiles;
     if (splits > d.total_units / 2) splits = d.total_units / 2;      // at least two units per CTA
     if (splits < 1) splits = 1;
     d.units_per_cta = (d.total_units + splits - 1) / splits;
@@ -312,7 +312,7 @@ int launch_wgrad3_umma(smg_handle* h, const float* g, int g_cstride, int g_coff,
         SMG_TRY(make_tensor_map_f32(&tmN, g + g_coff, 4, dims, strides, box, kSwizzle128Atom32));
     }
     d.cin = 128; d.stats = stats; d.stats_stride = stats_stride; d.gamma = gamma; d.beta = beta; d.dw = scratch; d.ld = 128;
-    int splits = h->num_sms;
+    int splits = h->wgrad_cta_cap > 0 ? h->wgrad_cta_cap : h->num_sms;
     if (splits > d.total_units / 2) splits = d.total_units / 2;
     if (splits < 1) splits = 1;
     d.units_per_cta = (d.total_units + splits - 1) / splits;

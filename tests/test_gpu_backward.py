@@ -132,6 +132,8 @@ def test_trainer_backprop_rl_dropin(scene_inputs, golden):
     # Adam's first step is -lr * g / (|g| + eps) ~ -lr * sign(g): entries whose gradient is within the fp32 noise of
     # zero may flip; everything else must match what the reference recorded
     for k, fp in g["param_delta"].items():
+        if ".norm5." in k:      # norm5 feeds another BatchNorm: its gradient is analytically zero, Adam steps on noise
+            continue
         d = (after[k] - before[k]).cpu().double().numpy().ravel()[np.asarray(fp["pos"])]
         ok = np.abs(d - np.asarray(fp["val"])) <= 0.05 * 1e-4
         assert ok.mean() >= 0.85, (k, ok.mean())
