@@ -500,6 +500,128 @@ def run_gpu_arm(args):
                 line_extra[key] = {"error": repr(exc)[:300]}
         tr.model.precision = precision
 
+    # ---- one highly-cluttered decision (K = 10 objects, R = 16, E + S + ES: 98 distinct trunk passes) STRONG-scaled over the
+    # N GPUs (BASELINE config 5): per-rank share of the passes, all-gather of the head partials, argmax
+    if not args.no_extras:
+        try:
+            import smg_b200.synth as synth
+            from smg_b200 import decision as _decision, parallel as _parallel
+            tr.model.precision = precision
+            hc = synth.make_scene(7, num_objects=10, cluttered=True)
+            nd = 5
+            for i in range(2):
+                dec = _parallel.decide_sharded(tr, hc["depth"], hc["masks"], is_ets=True)
+            barrier()
+            e0.record()
+            for i in range(nd):
+                dec = _parallel.decide_sharded(tr, hc["depth"], hc["masks"], is_ets=True)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            line_extra["decision"] = {
+                "latency_ms": float(t.item()) / nd, "decisions_per_s": nd / (float(t.item()) / 1e3), "n_gpus": world,
+                "scaling": "strong", "distinct_trunk_passes": 98, "objects": 10, "rotations": R, "primitive": dec["primitive"],
+                "exchange": "all_gather of the per-sample head partials (%d bytes received per rank) + all_gather of the per-rank "
+                            "best (Q, index) tuples" % dec["exchange_bytes"],
+                "what": "host heightmap + 10 masks in -> gra/suc/gs Q tables, argmax and primitive choice out (parallel.decide_sharded)"}
+            if world == 1:
+                for i in range(2):
+                    _decision.decide(tr, hc["depth"], hc["masks"], is_ets=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(nd):
+                    _decision.decide(tr, hc["depth"], hc["masks"], is_ets=True)
+                e1.record()
+                torch.cuda.synchronize()
+                line_extra["decision"]["single_call_path_ms"] = e0.elapsed_time(e1) / nd
+        except Exception as exc:
+            line_extra["decision"] = {"error": repr(exc)[:300]}
+            if world > 1:
+                raise
+
+    # ---- data-parallel replay step (BASELINE config 4): 64 highly-cluttered samples, 64 / N per GPU, gradients all-reduced
+    # over NCCL, one Adam step; checked against the serial single-GPU step with --verify
+    if not args.no_extras and not args.no_backprop:
+        try:
+            import smg_b200.synth as synth
+            B = 64
+            lo, hi = B * rank // world, B * (rank + 1) // world
+            batch = []
+            for i in range(lo, hi):
+                sci = synth.make_scene(500 + i, num_objects=10, cluttered=True)
+                batch.append({"depth_heightmap": sci["scene"], "m_depth_heightmap": synth.masked_scene(sci["scene"], sci["masks"], [i % 10]),
+                              "style": 0, "rotation": i % R, "label_value": float(i % 3)})
+            tr.model.precision = precision
+            tr.backprop_batch(batch, total=B, first_index=lo)        # warm-up: first sight of every rotation runs eagerly
+            tr.backprop_batch(batch, total=B, first_index=lo)        # captures
+            barrier()
+            nrep = 2
+            waits = []
+            e0.record()
+            for _ in range(nrep):
+                _, w = tr.backprop_batch(batch, total=B, first_index=lo)
+                waits.append(w)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            grad_bytes = int(tr._fused[0]["flat"]["grad"].numel() * 4)
+            rep = {"batch": B, "samples_per_gpu": hi - lo, "n_gpus": world, "scaling": "strong",
+                   "ms_per_batch_step": float(t.item()) / nrep, "samples_per_s": B * nrep / (float(t.item()) / 1e3),
+                   "allreduce_bytes": grad_bytes, "allreduce_wait_ms": 1e3 * sum(waits) / len(waits), "precision": precision,
+                   "what": "Trainer.backprop_batch: per-sample grad-enabled pass + backward (graph replay), local sum, NCCL all-reduce of the "
+                           "flat 368-tensor gradient (first n-1 samples' sum overlapped with the last sample), mean, one multi-tensor Adam, re-pack"}
+            if world > 1:
+                # the all-reduce alone on the same buffer (device time)
+                Gf = tr._fused[0]["flat"]["grad"]
+                for _ in range(3):
+                    dist.all_reduce(Gf)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(10):
+                    dist.all_reduce(Gf)
+                e1.record()
+                torch.cuda.synchronize()
+                rep["allreduce_alone_ms"] = e0.elapsed_time(e1) / 10
+                rep["allreduce_busbw_gbs"] = 2 * (world - 1) / world * grad_bytes / 1e9 / (rep["allreduce_alone_ms"] / 1e3)
+            if world > 1 and not args.no_verify:
+                # the all-reduced, averaged gradient of one more data-parallel step against the same batch accumulated
+                # serially on this GPU alone, at the same weights
+                st_f = tr._fused[0]
+                w0 = [p.detach().clone() for p in st_f["params"]]
+                tr.backprop_batch(batch, total=B, first_index=lo)
+                g_dp = st_f["flat"]["grad"].clone()
+                with torch.no_grad():
+                    for p, w in zip(st_f["params"], w0):
+                        p.copy_(w)
+                eng.sync_weights(tr.model, force=True, style=0)
+                full = []
+                for i in range(B):
+                    sci = synth.make_scene(500 + i, num_objects=10, cluttered=True)
+                    full.append({"depth_heightmap": sci["scene"], "m_depth_heightmap": synth.masked_scene(sci["scene"], sci["masks"], [i % 10]),
+                                 "style": 0, "rotation": i % R, "label_value": float(i % 3)})
+                tr.backprop_batch(full, total=B, first_index=0, local_only=True)
+                g_serial = st_f["flat"]["grad"]
+                errs, off = [], 0
+                for p in st_f["params"]:
+                    a_, b_ = g_dp[off:off + p.numel()], g_serial[off:off + p.numel()]
+                    off += p.numel()
+                    errs.append(float((a_ - b_).abs().max() / b_.abs().max().clamp_min(1e-3 * float(g_serial.abs().max()))))
+                errs.sort()
+                e_t = torch.tensor([errs[len(errs) // 2], errs[-1]], device=dev)
+                dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
+                rep["verify_vs_serial"] = {"median_rel_err": float(e_t[0]), "max_rel_err": float(e_t[1]),
+                                           "what": "per-tensor max|g_dp - g_serial| / max|g_serial| of the averaged gradient, max over ranks "
+                                                   "(differences: summation order + the ReLU-kink flips it causes)"}
+            line_extra["replay"] = rep
+        except Exception as exc:
+            line_extra["replay"] = {"error": repr(exc)[:300]}
+            if world > 1:
+                raise
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -529,6 +651,7 @@ def main():
     ap.add_argument("--no-backprop", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip fp32_mode / running-stats / decision / replay extras")
+    ap.add_argument("--no-verify", action="store_true", help="N > 1: skip checking the data-parallel replay gradient against the serial one")
     ap.add_argument("--units", type=int, default=4,
                     help="independent (scene, mask) units evaluated per step and GPU as one batch (1 = latency mode)")
     args = ap.parse_args()

@@ -121,6 +121,19 @@ int smg_trunk_forward(smg_handle* h, int trunk_id, const float* dev_in, int n, f
 int smg_qforward(smg_handle* h, int trunk_id, int head_id, const float* dev_scene, const float* dev_masks,
                  int n_masks, const int* host_rot_idx, int n_rot, int num_rotations, float* dev_q,
                  float* dev_bn_mean, float* dev_bn_var, void* stream);
+/* ---- the Q pass split for multi-GPU decisions -----------
+ * The head's BN(2048)+ReLU+1x1 conv acts on cat(scene features, mask features): its first 1024 input channels depend only
+ * on the scene sample, the last 1024 only on the mask sample.  smg_qpartials runs pre-processing, rotation and the trunk for
+ * the LISTED rotations of the scene (n_rot may be 0) and the given masked heightmaps (n_masks may be 0) and returns the
+ * per-sample partial products P [n_rot + n_masks, 400, 64] (rotations first); any rank can then form Q for every
+ * (mask, rotation) pair from gathered partials with smg_qcombine: dev_q [n_masks, n_rot, n_out].  Results are identical to
+ * smg_qforward_maps (BatchNorm is per sample).  The gather between the two is the path's data exchange (NCCL).       */
+int smg_qpartials(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm, const int* host_rot_idx, int n_rot,
+                  int num_rotations, const double* dev_mask_hms, int n_masks, int hm_size, double mean, double stddev,
+                  float* dev_p, void* stream);
+int smg_qcombine(smg_handle* h, int head_id, const float* dev_p_scene, int n_rot, const float* dev_p_mask, int n_masks,
+                 float* dev_q, void* stream);
+
 /* same, starting from 224x224 float64 heightmaps (fuses smg_prep): Trainer.forward,
  * code/trainer.py:162-207.                                                          */
 int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm,
@@ -173,7 +186,11 @@ typedef struct smg_train_step_args {
     double mean, stddev;            /* (x - mean) / stddev of Trainer.forward */
     float class_weight[3];          /* loss 1 only */
     float lr, beta1, beta2, eps;    /* Adam hyper-parameters */
+    int32_t flags;                  /* SMG_STEP_* */
 } smg_train_step_args;
+/* gradients only: no Adam update, no re-pack (data-parallel training accumulates / all-reduces the gradients of many
+ * samples first and then calls smg_adam_step once) */
+#define SMG_STEP_GRADS_ONLY 1
 int smg_train_step(smg_handle* h, const smg_train_step_args* args, const double* dev_scene_hm, const double* dev_mask_hm,
                    float* const* dev_params, float* const* dev_grads, float* const* dev_exp_avg,
                    float* const* dev_exp_avg_sq, int n_tensors, float* dev_loss, float* dev_q, float* dev_bn_mean,
@@ -183,7 +200,7 @@ int smg_train_step(smg_handle* h, const smg_train_step_args* args, const double*
  * other forward on the handle overwrites the saved activations and invalidates it; smg_qbackward then fails with
  * SMG_ERR_STATE instead of differentiating another pass.  Only ONE grad-enabled pass may be in flight per handle. */
 int64_t smg_train_pass_id(smg_handle* h);
-/* fused Adam over a flat list of tensors (torch.optim.Adam, code/trainer.py:99,383) */
+/* torch.optim.Adam (code/trainer.py:99,383) over a list of tensors in ONE launch; `step` is the 1-based update count */
 int smg_adam_step(smg_handle* h, float* const* dev_params, const float* const* dev_grads, float* const* dev_m,
                   float* const* dev_v, const int64_t* host_numel, int n_tensors, int step, float lr, float beta1,
                   float beta2, float eps, void* stream);

@@ -1,14 +1,16 @@
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
-timeout 900 python -m pytest tests/test_gpu_train_step.py tests/test_gpu_backward.py tests/test_gpu_parity_r02.py tests/test_gpu_qnet.py -m gpu -q -s > gpurun_out/r02_pytest6.log 2>&1; echo "pytest exit $?"
-grep -E "passed|failed|FAILED|Error|error|fused|kink|graph vs" gpurun_out/r02_pytest6.log | head -40
-for cfg in "1 1 64" "0 1 64" "1 0 64" "1 1 32" "1 1 148"; do
-set -- $cfg
-SMG_BN_FUSE=$1 SMG_WGRAD_ASYNC=$2 SMG_WGRAD_CTAS=$3 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-extras > gpurun_out/r02_bench6_$1$2$3.log 2>/dev/null
-python - "$cfg" gpurun_out/r02_bench6_$1$2$3.log <<'PY'
+timeout 900 python -m pytest tests -m gpu -q -s -x > gpurun_out/r02_pytest7.log 2>&1; echo "pytest exit $?"
+grep -E "passed|failed|FAILED|Error|error|replay batch|Traceback" gpurun_out/r02_pytest7.log | head -30
+for fuse in 0 1; do
+SMG_BN_FUSE=$fuse timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-reference > gpurun_out/r02_bench7_f$fuse.log 2>gpurun_out/r02_bench7_f$fuse.err
+python - gpurun_out/r02_bench7_f$fuse.log <<'PY'
 import json,sys
-l=[x for x in open(sys.argv[2]) if x.startswith('{')]
+l=[x for x in open(sys.argv[1]) if x.startswith('{')]
 d=json.loads(l[-1])
-print("fuse/async/cap", sys.argv[1], "value %.1f"%d['value'], "backprop", {k:round(v,2) if isinstance(v,float) else v for k,v in d['backprop'].items() if k in('value','ms_per_step','launches_per_step','error')})
+print("value %.1f e2e %.1f"%(d['value'], d['e2e']['value']))
+for k in ('backprop','backprop_fp32','decision','replay','fp32_mode'):
+    v=d.get(k,{}); print(k, {a:(round(b,3) if isinstance(b,float) else b) for a,b in v.items() if a not in ('what','exchange')})
 PY
+tail -n 3 gpurun_out/r02_bench7_f$fuse.err
 done

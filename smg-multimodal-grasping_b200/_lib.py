@@ -20,7 +20,7 @@ class TrainStepArgs(ctypes.Structure):
                 ("num_rotations", ctypes.c_int32), ("hm_size", ctypes.c_int32), ("loss_kind", ctypes.c_int32),
                 ("adam_step", ctypes.c_int32), ("label", ctypes.c_float), ("mean", ctypes.c_double),
                 ("stddev", ctypes.c_double), ("class_weight", ctypes.c_float * 3), ("lr", ctypes.c_float),
-                ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float)]
+                ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float), ("flags", ctypes.c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol include/smg_b200.h declares
@@ -40,6 +40,8 @@ PROTOTYPES = {
     "smg_rotate_index_map": (I, [VP, I, I, VP, VP]),
     "smg_trunk_forward": (I, [VP, I, VP, I, VP, VP, VP, VP]),
     "smg_qforward": (I, [VP, I, I, VP, VP, I, c_int_p, I, I, VP, VP, VP, VP]),
+    "smg_qpartials": (I, [VP, I, I, VP, c_int_p, I, I, VP, I, I, ctypes.c_double, ctypes.c_double, VP, VP]),
+    "smg_qcombine": (I, [VP, I, VP, I, VP, I, VP, VP]),
     "smg_qforward_maps": (I, [VP, I, I, VP, VP, I, I, ctypes.c_double, ctypes.c_double, c_int_p, I, I, VP, VP, VP, VP]),
     "smg_qforward_maps_batch": (I, [VP, I, I, VP, VP, I, I, I, ctypes.c_double, ctypes.c_double, c_int_p, I, I, VP, VP, VP, VP]),
     "smg_head_bn_stats": (I, [VP, VP, I, VP]),

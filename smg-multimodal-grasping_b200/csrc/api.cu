@@ -211,11 +211,23 @@ int heads_forward(smg_handle* h, int trunk_id, int head_id, int n_rot, int n_mas
     h->train.valid = false;
     const BlockGeom& g = h->geom[3];
     SMG_CHECK(g.hw == kHeadK, SMG_ERR_INVALID, "heads need H=640 (block-4 spatial %d != %d)", g.hw, kHeadK);
-    const int n = groups * (n_rot + n_masks);
+    SMG_TRY(head_partials(h, trunk_id, head_id, n_rot, n_masks, st, groups));
+    return launch_head_tail(h, h->head_p, h->head_p + (size_t)groups * n_rot * g.hw * g.hw * kHeadMid, n_rot, n_masks, Hd, dev_q, st,
+                            groups);
+}
+
+// per-sample halves of the head's BN(2048)+ReLU+1x1 conv: channels [0,1024) of the concatenation depend only on the scene
+// sample, [1024,2048) only on the mask sample, so P_s = W_half . relu(bn(f_s)) is computed once per sample into h->head_p
+// ([groups x n_rot] scenes, then [groups x n_masks] masks; [400][64] each) and paired later by head_tail
+int head_partials(smg_handle* h, int trunk_id, int head_id, int n_rot, int n_masks, cudaStream_t st, int groups) {
+    TrunkW& T = h->trunks[trunk_id];
+    HeadW& Hd = h->heads[head_id];
+    const BlockGeom& g = h->geom[3];
     const double* st4 = stats_ptr(h, h->st_block[3]);
     for (int half = 0; half < 2; ++half) {
         const int s0 = half == 0 ? 0 : groups * n_rot;
         const int cnt = groups * (half == 0 ? n_rot : n_masks);
+        if (cnt == 0) continue;
         SMG_TRY(launch_head_prepare(h, cnt, st4 + 2 * (size_t)s0 * g.c_tot, g.c_tot, T.norm5, Hd.norm0, half,
                                     h->head_scale + (size_t)s0 * kFeatC, h->head_shift + (size_t)s0 * kFeatC, st));
         ConvArgs a;
@@ -228,8 +240,7 @@ int heads_forward(smg_handle* h, int trunk_id, int head_id, int n_rot, int n_mas
         a.n = cnt;
         SMG_TRY(conv_dispatch(h, a, st));
     }
-    (void)n;
-    return launch_head_tail(h, h->head_p, n_rot, n_masks, Hd, dev_q, st, groups);
+    return SMG_OK;
 }
 
 __global__ void pack_head_conv1_kernel(const float* __restrict__ w, float* __restrict__ out, int n_out, int npix) {
@@ -463,6 +474,7 @@ int smg_destroy(smg_handle* h) {
     for (auto& g : h->step.graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->step.tables) cudaFree(h->step.tables);
+    if (h->step.adam_tables) cudaFree(h->step.adam_tables);
     if (h->bn_regions_dev) cudaFree(h->bn_regions_dev);
     if (h->train.arena) cudaFree(h->train.arena);
     if (h->train.wstream) cudaStreamDestroy(h->train.wstream);
@@ -657,6 +669,40 @@ static int qforward_maps_body(smg_handle* h, int trunk_id, int head_id, const do
                               h->input + (size_t)g * n_rot * img, 1, st));
     SMG_TRY(launch_prep(h, dev_mask_hms, groups * n_masks, hm_size, mean, stddev, h->input + (size_t)groups * n_rot * img, 1, st));
     return qforward_common(h, trunk_id, head_id, n_masks, n_rot, 1, dev_q, dev_bn_mean, dev_bn_var, st, groups);
+}
+
+int smg_qpartials(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm, const int* host_rot_idx, int n_rot,
+                  int num_rotations, const double* dev_mask_hms, int n_masks, int hm_size, double mean, double stddev,
+                  float* dev_p, void* stream) {
+    SMG_CHECK(h && dev_p && (n_rot == 0 || (dev_scene_hm && host_rot_idx)) && (n_masks == 0 || dev_mask_hms), SMG_ERR_INVALID,
+              "smg_qpartials: NULL argument");
+    SMG_CHECK(trunk_id >= 0 && trunk_id < SMG_NUM_TRUNKS && head_id >= 0 && head_id < SMG_NUM_HEADS, SMG_ERR_INVALID,
+              "smg_qpartials: trunk %d / head %d", trunk_id, head_id);
+    SMG_CHECK(n_rot >= 0 && n_masks >= 0 && n_rot + n_masks >= 1 && n_rot + n_masks <= h->max_samples, SMG_ERR_INVALID,
+              "smg_qpartials: %d rotations + %d masks outside [1, %d]", n_rot, n_masks, h->max_samples);
+    SMG_CHECK(stddev != 0.0 && 2 * hm_size <= h->H, SMG_ERR_INVALID, "smg_qpartials: stddev %g / hm_size %d", stddev, hm_size);
+    SMG_CHECK(h->heads[head_id].set, SMG_ERR_STATE, "head %d: weights not set", head_id);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t img = (size_t)h->H * h->H;
+    if (n_rot > 0) {
+        SMG_TRY(launch_prep(h, dev_scene_hm, 1, hm_size, mean, stddev, h->scene_tmp, 1, st));
+        SMG_TRY(launch_rotate(h, h->scene_tmp, host_rot_idx, n_rot, num_rotations, h->input, 1, st));
+    }
+    if (n_masks > 0) SMG_TRY(launch_prep(h, dev_mask_hms, n_masks, hm_size, mean, stddev, h->input + (size_t)n_rot * img, 1, st));
+    SMG_TRY(trunk_forward(h, trunk_id, n_rot + n_masks, 1, st));
+    SMG_TRY(head_partials(h, trunk_id, head_id, n_rot, n_masks, st, 1));
+    const size_t per = (size_t)kHeadK * kHeadK * kHeadMid;
+    SMG_CUDA(cudaMemcpyAsync(dev_p, h->head_p, (size_t)(n_rot + n_masks) * per * 4, cudaMemcpyDeviceToDevice, st));
+    return SMG_OK;
+}
+
+int smg_qcombine(smg_handle* h, int head_id, const float* dev_p_scene, int n_rot, const float* dev_p_mask, int n_masks,
+                 float* dev_q, void* stream) {
+    SMG_CHECK(h && dev_p_scene && dev_p_mask && dev_q && n_rot >= 1 && n_masks >= 1, SMG_ERR_INVALID, "smg_qcombine: bad argument");
+    SMG_CHECK(head_id >= 0 && head_id < SMG_NUM_HEADS && h->heads[head_id].set, SMG_ERR_STATE, "smg_qcombine: head %d not set", head_id);
+    DeviceGuard guard(h->device);
+    return launch_head_tail(h, dev_p_scene, dev_p_mask, n_rot, n_masks, h->heads[head_id], dev_q, (cudaStream_t)stream, 1);
 }
 
 int smg_qforward_maps(smg_handle* h, int trunk_id, int head_id, const double* dev_scene_hm, const double* dev_mask_hms,
@@ -1118,10 +1164,8 @@ int smg_adam_step(smg_handle* h, float* const* dev_params, const float* const* d
     SMG_CHECK(h && dev_params && dev_grads && dev_m && dev_v && host_numel && n_tensors >= 0 && step >= 1, SMG_ERR_INVALID,
               "smg_adam_step: bad argument");
     DeviceGuard guard(h->device);
-    for (int i = 0; i < n_tensors; ++i)
-        SMG_TRY(launch_adam(h, dev_params[i], dev_grads[i], dev_m[i], dev_v[i], host_numel[i], step, lr, beta1, beta2, eps,
-                            (cudaStream_t)stream));
-    return SMG_OK;
+    return adam_multi_tensor(h, dev_params, dev_grads, dev_m, dev_v, host_numel, n_tensors, step, lr, beta1, beta2, eps,
+                             (cudaStream_t)stream);
 }
 
 int smg_argmax(smg_handle* h, const float* dev_q, int n, float* dev_out, int32_t* dev_out_idx, void* stream) {

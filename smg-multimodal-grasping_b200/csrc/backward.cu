@@ -507,21 +507,6 @@ head_norm_bwd_kernel(const float* __restrict__ da0, const float* __restrict__ x4
     }
 }
 
-// fused multi-tensor-free Adam over one flat tensor (torch.optim.Adam semantics, code/trainer.py:99)
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
-                            float bc2_sqrt) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float gi = g[i];
-        const float mi = b1 * m[i] + (1.f - b1) * gi;
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi;
-        v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] -= (lr / bc1) * (mi / denom);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
@@ -616,18 +601,6 @@ int launch_head_norm_bwd(smg_handle* h, const float* da0, const float* x4, const
     const int npix = h->geom[3].hw * h->geom[3].hw;
     head_norm_bwd_kernel<<<kFeatC / 32, 256, 0, st>>>(da0, x4, stats, stats_stride, npix, norm5.gamma, norm5.beta,
                                                       hnorm0.gamma, hnorm0.beta, dx4, dg5, db5, dgh, dbh);
-    h->launches++;
-    SMG_CUDA(cudaGetLastError());
-    return SMG_OK;
-}
-
-int launch_adam(smg_handle* h, float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float b1,
-                float b2, float eps, cudaStream_t st) {
-    const float bc1 = 1.f - powf(b1, (float)step);
-    const float bc2 = 1.f - powf(b2, (float)step);
-    int blocks = (int)((n + 255) / 256);
-    if (blocks > h->num_sms * 8) blocks = h->num_sms * 8;
-    adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, sqrtf(bc2));
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;

@@ -502,23 +502,34 @@ conv_umma_kernel(UmmaDev a) {
                     const float mean = (float)md, rstd = (float)(1.0 / sqrt(var + (double)kBnEps));
                     const float sc = a.bnr_gamma[ch] * rstd, sh = a.bnr_beta[ch] - mean * sc;
                     const float* xb = a.bnr_x + (size_t)s * hw_out * a.bnr_x_cstride + ch;
-                    const int r1 = (g + 1) * RPG < UM ? (g + 1) * RPG : UM;
-                    for (int r = g * RPG; r < r1; ++r) {
-                        int pix;
-                        bool ok;
-                        if (TAPS == 9) {
-                            const int i = r / a.wp, j = r - i * a.wp;
-                            ok = i < a.ht && j < a.wp - 2 && h0 + i < hout && w0 + j < hout;
-                            pix = (h0 + i) * hout + w0 + j;
-                        } else {
-                            ok = m0 + r < hw_out;
-                            pix = m0 + r;
+                    // branch-free batches of eight rows: the eight raw-activation loads are in flight together (a serial
+                    // loop of ~43 dependent global loads per thread cost more than the separate reduction kernel it replaces)
+                    const int rbeg = g * RPG, rend = (g + 1) * RPG < UM ? (g + 1) * RPG : UM;
+                    for (int rb = rbeg; rb < rend; rb += 8) {
+                        float xv[8], w[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int r = rb + u;
+                            int pix;
+                            bool ok;
+                            if (TAPS == 9) {
+                                const int i = r / a.wp, j = r - i * a.wp;
+                                ok = r < rend && i < a.ht && j < a.wp - 2 && h0 + i < hout && w0 + j < hout;
+                                pix = (h0 + i) * hout + w0 + j;
+                            } else {
+                                ok = r < rend && m0 + r < hw_out;
+                                pix = m0 + r;
+                            }
+                            w[u] = ok ? 1.f : 0.f;
+                            xv[u] = __ldg(xb + (size_t)(ok ? pix : 0) * a.bnr_x_cstride);
                         }
-                        if (!ok) continue;
-                        const float xv = xb[(size_t)pix * a.bnr_x_cstride];
-                        const float dz = fmaf(xv, sc, sh) > 0.f ? s_out[r * (BN + 1) + cidx] : 0.f;
-                        s1 += dz;
-                        s2 = fmaf(dz, (xv - mean) * rstd, s2);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int r = rb + u < UM ? rb + u : UM - 1;
+                            const float dz = fmaf(xv[u], sc, sh) > 0.f ? w[u] * s_out[r * (BN + 1) + cidx] : 0.f;
+                            s1 += dz;
+                            s2 = fmaf(dz, (xv[u] - mean) * rstd, s2);
+                        }
                     }
                 }
                 red[g * BN + cidx] = s1;

@@ -65,7 +65,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // one CTA per (mask k, rotation r) pair.  p: [n_rot + n_masks][400][64]
 __global__ void __launch_bounds__(256)
-head_tail_kernel(const float* __restrict__ p, int n_rot, int n_masks, int npix, const float* __restrict__ g1,
+head_tail_kernel(const float* __restrict__ p, const float* __restrict__ p_mask, int n_rot, int n_masks, int npix,
+                 const float* __restrict__ g1,
                  const float* __restrict__ b1, const float* __restrict__ w1, int n_out, float* __restrict__ q,
                  float* __restrict__ bn1_stats) {
     __shared__ float red[2][4][64];
@@ -76,7 +77,7 @@ head_tail_kernel(const float* __restrict__ p, int n_rot, int n_masks, int npix, 
     const int k = grp * n_masks + k0;   // mask index over all groups == row of q / bn1_stats
     const int tid = threadIdx.x, c = tid & 63, g = tid >> 6;
     const float* ps = p + (size_t)(grp * n_rot + r) * npix * 64;
-    const float* pm = p + (size_t)(groups * n_rot + k) * npix * 64;
+    const float* pm = p_mask + (size_t)k * npix * 64;   // masked-scene partials: [groups x n_masks], mask index k over all groups
     // pass 1: mean
     float su = 0.f;
     for (int px = g; px < npix; px += 4) su += ps[px * 64 + c] + pm[px * 64 + c];
@@ -205,13 +206,13 @@ int launch_norm5_export(smg_handle* h, int n, const float* block4, const double*
     return SMG_OK;
 }
 
-int launch_head_tail(smg_handle* h, const float* p, int n_rot, int n_masks, const HeadW& hw, float* q,
+int launch_head_tail(smg_handle* h, const float* p, const float* p_mask, int n_rot, int n_masks, const HeadW& hw, float* q,
                      cudaStream_t st, int groups) {
     const int npix = h->geom[3].hw * h->geom[3].hw;
     SMG_CHECK(hw.n_out >= 1 && hw.n_out <= 4, SMG_ERR_INVALID, "head_tail: n_out %d", hw.n_out);
     dim3 grid(n_rot, n_masks, groups);
     const bool fits = (size_t)groups * n_rot * n_masks * 128 <= h->head_bn1_floats;
-    head_tail_kernel<<<grid, 256, 0, st>>>(p, n_rot, n_masks, npix, hw.norm1.gamma, hw.norm1.beta, hw.conv1, hw.n_out, q,
+    head_tail_kernel<<<grid, 256, 0, st>>>(p, p_mask, n_rot, n_masks, npix, hw.norm1.gamma, hw.norm1.beta, hw.conv1, hw.n_out, q,
                                            fits ? h->head_bn1 : nullptr);
     h->head_bn1_pairs = fits ? groups * n_rot * n_masks : 0;
     h->launches++;

@@ -267,6 +267,11 @@ struct smg_handle {
         float* bn_var = nullptr;
         std::vector<float*> host_grads;
         std::vector<StepGraph> graphs;
+        // smg_adam_step's own tables (any tensor list)
+        void* adam_tables = nullptr;
+        size_t adam_tables_bytes = 0;
+        uint64_t adam_sig = 0;
+        int adam_chunks = 0;
     } step;
 
     // optional per-kernel-class timing (bench.py roofline): CUDA events around every launch of a class
@@ -361,7 +366,7 @@ int launch_head_prepare(smg_handle* h, int n, const double* stats4, int stats_st
                         const BnP& hnorm0, int half, float* scale, float* shift, cudaStream_t st);
 int launch_norm5_export(smg_handle* h, int n, const float* block4, const double* stats4, int stats_stride,
                         const BnP& norm5, float* out_nchw, cudaStream_t st);
-int launch_head_tail(smg_handle* h, const float* p, int n_rot, int n_masks, const HeadW& hw, float* q,
+int launch_head_tail(smg_handle* h, const float* p_scene, const float* p_mask, int n_rot, int n_masks, const HeadW& hw, float* q,
                      cudaStream_t st, int groups = 1);
 // one BatchNorm layer's slice of the statistics arena: `count` channels of a [S][stride] double2 region -> columns
 // [out_off, out_off + count) of the exported [S][total] mean / biased-variance tables
@@ -439,15 +444,17 @@ int launch_wgrad3_umma(smg_handle* h, const float* g, int g_cstride, int g_coff,
                        const double* stats, int stats_stride, const float* gamma, const float* beta, float* scratch,
                        cudaStream_t st);
 int launch_wgrad3_finish(smg_handle* h, const void* dev_jobs, int n_jobs, cudaStream_t st);
-int launch_adam(smg_handle* h, float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float b1,
-                float b2, float eps, cudaStream_t st);
 
 // schedule pieces shared by api.cu and train.cu
 int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st);
 int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cudaStream_t st, bool save_bott = false);
 int heads_forward(smg_handle* h, int trunk_id, int head_id, int n_rot, int n_masks, float* dev_q, cudaStream_t st,
                   int groups = 1);
+int head_partials(smg_handle* h, int trunk_id, int head_id, int n_rot, int n_masks, cudaStream_t st, int groups = 1);
 int export_bn_stats(smg_handle* h, int n, float* mean, float* var, cudaStream_t st);
+// ONE launch of torch.optim.Adam over a list of tensors (train.cu); the device tables are cached per pointer set
+int adam_multi_tensor(smg_handle* h, float* const* params, const float* const* grads, float* const* m, float* const* v,
+                      const int64_t* numel, int n, int step, float lr, float b1, float b2, float eps, cudaStream_t st);
 int ensure_train_workspace(smg_handle* h);
 int qbackward_impl(smg_handle* h, const float* dq, float* const* tg, float* const* hg, cudaStream_t st);
 int repack_trunk(smg_handle* h, int trunk_id, cudaStream_t st);   // kernels only (graph-capturable), tables from the last set

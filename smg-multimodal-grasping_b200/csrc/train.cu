@@ -118,13 +118,60 @@ static int train_step_body(smg_handle* h, const smg_train_step_args& a, cudaStre
                                   S.out + 4, S.out + 8);
     h->launches++;
     SMG_TRY(qbackward_impl(h, S.out + 8, S.host_grads.data(), S.host_grads.data() + SMG_TRUNK_NUM_PARAMS, st));
-    adam_multi_kernel<<<S.n_chunks, 256, 0, st>>>(S.d_params, S.d_grads, S.d_m, S.d_v, reinterpret_cast<const AdamChunk*>(S.d_chunks),
-                                                  S.dyn, a.lr, a.beta1, a.beta2, a.eps);
+    if (!(a.flags & SMG_STEP_GRADS_ONLY)) {
+        adam_multi_kernel<<<S.n_chunks, 256, 0, st>>>(S.d_params, S.d_grads, S.d_m, S.d_v,
+                                                      reinterpret_cast<const AdamChunk*>(S.d_chunks), S.dyn, a.lr, a.beta1, a.beta2,
+                                                      a.eps);
+        h->launches++;
+        SMG_CUDA(cudaGetLastError());
+        SMG_TRY(repack_trunk(h, a.trunk_id, st));
+        SMG_TRY(repack_head(h, a.head_id, st));
+    }
+    SMG_TRY(export_bn_stats(h, 2, S.bn_mean, S.bn_var, st));
+    return SMG_OK;
+}
+
+int adam_multi_tensor(smg_handle* h, float* const* params, const float* const* grads, float* const* m, float* const* v,
+                      const int64_t* numel, int n, int step, float lr, float b1, float b2, float eps, cudaStream_t st) {
+    if (n == 0) return SMG_OK;
+    smg_handle::StepState& S = h->step;
+    const size_t ptr_bytes = (size_t)n * sizeof(void*);
+    std::vector<AdamChunk> chunks;
+    for (int t = 0; t < n; ++t)
+        for (int64_t o = 0; o < numel[t]; o += 4096) chunks.push_back(AdamChunk{t, (int)o, (int)(numel[t] - o < 4096 ? numel[t] - o : 4096)});
+    const size_t need = 4 * ptr_bytes + chunks.size() * sizeof(AdamChunk) + 64;
+    uint64_t sig = fnv(1469598103934665603ull, params, ptr_bytes);
+    sig = fnv(sig, grads, ptr_bytes);
+    sig = fnv(sig, m, ptr_bytes);
+    sig = fnv(sig, v, ptr_bytes);
+    sig = fnv(sig, numel, (size_t)n * sizeof(int64_t));
+    if (need > S.adam_tables_bytes) {
+        SMG_CUDA(cudaStreamSynchronize(st));
+        if (S.adam_tables) cudaFree(S.adam_tables);
+        S.adam_tables_bytes = need * 2;
+        SMG_CUDA(cudaMalloc(&S.adam_tables, S.adam_tables_bytes));
+        S.adam_sig = 0;
+    }
+    uint8_t* b = reinterpret_cast<uint8_t*>(S.adam_tables);
+    float* dyn = reinterpret_cast<float*>(b + 4 * ptr_bytes + chunks.size() * sizeof(AdamChunk));
+    if (sig != S.adam_sig) {
+        SMG_CUDA(cudaStreamSynchronize(st));
+        SMG_CUDA(cudaMemcpy(b, params, ptr_bytes, cudaMemcpyHostToDevice));
+        SMG_CUDA(cudaMemcpy(b + ptr_bytes, grads, ptr_bytes, cudaMemcpyHostToDevice));
+        SMG_CUDA(cudaMemcpy(b + 2 * ptr_bytes, m, ptr_bytes, cudaMemcpyHostToDevice));
+        SMG_CUDA(cudaMemcpy(b + 3 * ptr_bytes, v, ptr_bytes, cudaMemcpyHostToDevice));
+        SMG_CUDA(cudaMemcpy(b + 4 * ptr_bytes, chunks.data(), chunks.size() * sizeof(AdamChunk), cudaMemcpyHostToDevice));
+        S.adam_sig = sig;
+        S.adam_chunks = (int)chunks.size();
+    }
+    const float hd[3] = {0.f, 1.f - powf(b1, (float)step), sqrtf(1.f - powf(b2, (float)step))};
+    SMG_CUDA(cudaMemcpyAsync(dyn, hd, sizeof(hd), cudaMemcpyHostToDevice, st));
+    adam_multi_kernel<<<S.adam_chunks, 256, 0, st>>>(reinterpret_cast<float* const*>(b), reinterpret_cast<const float* const*>(b + ptr_bytes),
+                                                     reinterpret_cast<float* const*>(b + 2 * ptr_bytes),
+                                                     reinterpret_cast<float* const*>(b + 3 * ptr_bytes),
+                                                     reinterpret_cast<const AdamChunk*>(b + 4 * ptr_bytes), dyn, lr, b1, b2, eps);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
-    SMG_TRY(repack_trunk(h, a.trunk_id, st));
-    SMG_TRY(repack_head(h, a.head_id, st));
-    SMG_TRY(export_bn_stats(h, 2, S.bn_mean, S.bn_var, st));
     return SMG_OK;
 }
 
@@ -229,6 +276,7 @@ extern "C" int smg_train_step(smg_handle* h, const smg_train_step_args* args, co
     gsig = fnv(gsig, &a.loss_kind, sizeof(int));
     gsig = fnv(gsig, a.class_weight, sizeof(a.class_weight));
     gsig = fnv(gsig, &a.lr, 4 * sizeof(float));
+    gsig = fnv(gsig, &a.flags, sizeof(int));
     gsig = fnv(gsig, &h->precision, sizeof(int));
     gsig = fnv(gsig, &h->pack_mask, sizeof(int));
     smg_handle::StepGraph* G = nullptr;

@@ -207,6 +207,30 @@ class Engine:
                                               pm, pv, self._stream()))
         return (q, mean_t, var_t) if want_bn_stats else q
 
+    def qpartials(self, style, scene_hm, rot_idx, num_rotations, mask_hms, mean, std):
+        """Per-sample halves of the head's first convolution for the LISTED rotations of `scene_hm` and the masked heightmaps
+        `mask_hms` [n,hs,hs] (either list may be empty): P [len(rot_idx) + n, 400, 64].  Gathered partials of all ranks are
+        paired by `qcombine` - the multi-GPU split of one decision (smg_qpartials / smg_qcombine)."""
+        tid, hid = STYLE_ROUTE[int(style)]
+        n_rot = len(rot_idx)
+        n_masks = 0 if mask_hms is None else int(mask_hms.shape[0])
+        hs = int(scene_hm.shape[-1])
+        rot = (ctypes.c_int * max(n_rot, 1))(*[int(r) for r in rot_idx])
+        p = torch.empty((n_rot + n_masks, 400, 64), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.smg_qpartials(self.h, tid, hid, scene_hm.data_ptr(), rot, n_rot, int(num_rotations),
+                                          mask_hms.data_ptr() if n_masks else None, n_masks, hs, float(mean), float(std),
+                                          p.data_ptr(), self._stream()))
+        return p
+
+    def qcombine(self, style, p_scene, p_mask):
+        """Q [n_masks, n_rot, n_out] from per-sample partials (scene partials [n_rot,400,64], mask partials [n_masks,400,64])."""
+        hid = STYLE_ROUTE[int(style)][1]
+        p_scene, p_mask = p_scene.contiguous(), p_mask.contiguous()
+        q = torch.empty((p_mask.shape[0], p_scene.shape[0], self.n_out), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.smg_qcombine(self.h, hid, p_scene.data_ptr(), int(p_scene.shape[0]), p_mask.data_ptr(),
+                                         int(p_mask.shape[0]), q.data_ptr(), self._stream()))
+        return q
+
     def qforward_maps_batch(self, style, scene_hms, mask_hms, mean, std, rot_idx, num_rotations):
         """G independent units in one batch: scene_hms [G,hs,hs], mask_hms [G,M,hs,hs] float64 on the device
         -> Q [G, M, n_rot, n_out].  Same per-unit results as qforward_maps (BatchNorm is per sample)."""
@@ -242,7 +266,7 @@ class Engine:
         return int(self.lib.smg_train_pass_id(self.h))
 
     def train_step(self, style, scene_hm, mask_hm, rot, num_rotations, loss_kind, label, class_weight, ptrs, n_tensors,
-                   step, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, want_bn_stats=True):
+                   step, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, want_bn_stats=True, grads_only=False):
         """One whole training step (smg_train_step): pre-processing, grad-enabled Q pass, loss, backward, Adam, re-pack.
         scene_hm / mask_hm: [hs,hs] float64 on this device; ptrs: (params, grads, exp_avg, exp_avg_sq) ctypes pointer
         arrays of `n_tensors` device tensors.  Returns (loss [1], q [n_out], bn_mean, bn_var [2, C] or None)."""
@@ -250,7 +274,7 @@ class Engine:
         args = _lib.TrainStepArgs(tid, hid, int(rot), int(num_rotations), int(scene_hm.shape[-1]), int(loss_kind), int(step),
                                   float(label), float(self._mean_std[0]), float(self._mean_std[1]),
                                   (ctypes.c_float * 3)(*[float(w) for w in class_weight]), float(lr), float(beta1),
-                                  float(beta2), float(eps))
+                                  float(beta2), float(eps), 1 if grads_only else 0)
         loss = torch.empty((1,), dtype=torch.float32, device=self.device)
         q = torch.empty((self.n_out,), dtype=torch.float32, device=self.device)
         mean = var = None
@@ -283,6 +307,11 @@ class Engine:
         _lib.check(self.lib.smg_adam_step(self.h, _ptr_array(params), _ptr_array(grads), _ptr_array(exp_avg),
                                           _ptr_array(exp_avg_sq), numel, n, int(step), float(lr), float(beta1),
                                           float(beta2), float(eps), self._stream()))
+
+    def adam_step_ptrs(self, ptrs, numel, n, step, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8):
+        """Same with pre-built ctypes pointer arrays (params, grads, exp_avg, exp_avg_sq) and element counts."""
+        _lib.check(self.lib.smg_adam_step(self.h, ptrs[0], ptrs[1], ptrs[2], ptrs[3], numel, int(n), int(step), float(lr),
+                                          float(beta1), float(beta2), float(eps), self._stream()))
 
     def debug_read(self, what, sample, shape):
         out = torch.empty(shape, dtype=torch.float32, device=self.device)

@@ -95,7 +95,13 @@ class _SmgNet(nn.Module):
         for i, s in enumerate(order):
             wl[s] += _BN_MOMENTUM * (1 - _BN_MOMENTUM) ** (k - 1 - i)
         w = torch.tensor(wl, dtype=torch.float64, device=mean.device)
+        self._apply_running_sums(trunk, (w[:, None] * mean.double()).sum(0), (w[:, None] * var.double()).sum(0), k)
+
+    @torch.no_grad()
+    def _apply_running_sums(self, trunk, bm, bv, k):
+        """running = (1-m)^k running + (weighted sums of the k passes' batch means / biased variances, float64 [C])."""
         decay = (1 - _BN_MOMENTUM) ** k
+        mean = bm
         mods = self._bn_modules(trunk)
         sizes = [m.num_features for m in mods]
         # unbiased variance: n/(n-1) with n = H*W of that layer
@@ -104,8 +110,8 @@ class _SmgNet(nn.Module):
         if key not in cache:
             cache[key] = torch.cat([torch.full((c,), n / (n - 1.0), dtype=torch.float64)
                                     for c, n in zip(sizes, _bn_counts(640))]).to(mean.device)
-        bm = (w[:, None] * mean.double()).sum(0).float()
-        bv = ((w[:, None] * var.double()).sum(0) * cache[key]).float()
+        bm = bm.float()
+        bv = (bv * cache[key]).float()
         rm, rv = [m.running_mean for m in mods], [m.running_var for m in mods]
         # a handful of multi-tensor launches instead of ~500 tiny ones
         torch._foreach_mul_(rm, decay)

@@ -6,6 +6,7 @@ primitives or replay samples are independent given per-sample BatchNorm.  The on
 tuples are all-gathered (16 bytes per rank; NCCL over NVLink on GPUs, gloo in the CPU tests).
 Ties resolve to the lowest flat index so the result equals np.argmax over the full table.
 """
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -49,14 +50,170 @@ def gather_best(q_local, flat_index, group=None):
     return float(best), int(cand[:, 1].min())
 
 
-def allreduce_grads(grads, group=None):
-    """Data-parallel training: sum the touched trunk + head gradients over ranks (one flat all-reduce)."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return grads
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+def _world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def allreduce_flat(flat, group=None, async_op=False):
+    """Sum one flat gradient buffer over the ranks in place (the training exchange: ncclAllReduce over NVLink on GPUs).
+    The fused step already keeps the 368 touched gradients as views of ONE flat buffer, so nothing is concatenated or
+    copied back.  Returns the work handle when async_op (None on a single rank)."""
+    if _world(group)[1] == 1:
+        return None
+    return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def ema_pass_weights(global_pass_index, total_passes, momentum=0.1):
+    """Weight of BatchNorm pass j of `total_passes` serial passes in the final running statistic:
+    running_T = (1-m)^T running_0 + sum_j m (1-m)^(T-1-j) batch_j  (SURVEY.md section 8(e))."""
+    return momentum * (1.0 - momentum) ** (total_passes - 1 - global_pass_index)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# one decision, sharded over the ranks (code/main.py:158-233)
+# --------------------------------------------------------------------------------------------------------------------
+def decision_plan(K, rotations, world, is_ets=True):
+    """For each style the flat list of distinct trunk samples (rotation indices first, then mask indices) and the
+    contiguous share of every rank.  Returns {style: (n_rot, n_masks, [(lo, hi) per rank])} and the per-rank capacity
+    (partials a rank contributes to the gather, summed over the styles, max over ranks)."""
+    plan = {}
+    styles = [(0, rotations[0], K), (1, rotations[1], K)]
+    if is_ets and K > 1:
+        styles.append((2, 1, K * (K - 1) // 2))
+    cap = 0
+    for style, n_rot, n_masks in styles:
+        shares = [shard_range(n_rot + n_masks, r, world) for r in range(world)]
+        plan[style] = (n_rot, n_masks, shares)
+        cap += max(hi - lo for lo, hi in shares)
+    return plan, cap
+
+
+def decide_sharded(trainer, depth_heightmap, masks, is_ets=True, is_target=False, group=None):
+    """`decision.decide` with the distinct trunk passes of ONE decision spread over the ranks.
+
+    Every rank runs its contiguous share of each primitive's samples (rotated scenes and object-masked scenes alike:
+    16 + K for enveloping and sucking, 1 + K(K-1)/2 for the pairs) through the trunk and the per-sample half of the head's
+    first convolution (`smg_qpartials`); ONE all-gather exchanges the partial products (100 KB per sample, 9.8 MB for K = 10,
+    R = 16); every rank then pairs them into the three Q tables (`smg_qcombine`, microseconds) and takes the argmax.  The
+    per-rank best (Q, flat index) tuples are exchanged as well (`gather_best`) and must agree with the local argmax.
+    Results equal `decide` (per-sample BatchNorm makes every pass independent of its batch).  The BatchNorm
+    running-statistics side effect is not reproduced on this path."""
+    from . import decision as _decision
+    from . import engine as _engine
+    rank, world = _world(group)
+    ctx = decision_context(trainer, depth_heightmap, masks, world, is_ets, is_target)
+    send = decision_local_partials(trainer, ctx, rank)
+    if world > 1:
+        recv = torch.empty((world * ctx["cap"], 400, 64), dtype=torch.float32, device=send.device)
+        dist.all_gather_into_tensor(recv, send, group=group)
+    else:
+        recv = send
+    return decision_from_partials(trainer, ctx, recv, rank, group)
+
+
+def decision_context(trainer, depth_heightmap, masks, world, is_ets=True, is_target=False):
+    """Everything the ranks agree on before the passes: scene, masks, pair list, per-style sample shares."""
+    from . import decision as _decision
+    masks = np.asarray(masks, np.float64)
+    K = masks.shape[0]
+    model = trainer.model_target if (is_target and trainer.method == "reinforcement") else trainer.model
+    R = {0: model.gnum_rotations, 1: model.snum_rotations, 2: 1}
+    plan, cap = decision_plan(K, (R[0], R[1]), world, is_ets)
+    return {"scene": _decision.scene_from_masks(depth_heightmap, masks), "masks": masks, "K": K, "model": model, "R": R,
+            "pairs": [(g, s) for g in range(K) for s in range(g + 1, K)], "plan": plan, "cap": cap, "world": world}
+
+
+def decision_local_partials(trainer, ctx, rank):
+    """This rank's share of every primitive's samples through the trunk + head half: the all-gather's send buffer
+    [cap, 400, 64] (zero-padded where the shares are uneven)."""
+    model, plan, cap, scene, masks, pairs = ctx["model"], ctx["plan"], ctx["cap"], ctx["scene"], ctx["masks"], ctx["pairs"]
+    max_local = max(hi - lo for _, _, shares in plan.values() for lo, hi in shares)
+    eng = model._engine(max(max_local, 18))
+    dev = eng.device
+    scene_t = torch.from_numpy(np.ascontiguousarray(scene)).to(dev, non_blocking=True)
+    send = torch.zeros((cap, 400, 64), dtype=torch.float32, device=dev)
     off = 0
-    for g in grads:
-        g.copy_(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
-    return grads
+    for style, (n_rot, n_masks, shares) in plan.items():
+        lo, hi = shares[rank]
+        width = max(h_ - l_ for l_, h_ in shares)
+        if hi > lo:
+            eng.sync_weights(model, style=style)
+            rots = [i for i in range(lo, min(hi, n_rot))]
+            mids = [i - n_rot for i in range(max(lo, n_rot), hi)]
+            if style == 2:
+                mh = np.stack([scene * (masks[pairs[i][0]] + masks[pairs[i][1]]) for i in mids]) if mids else None
+            else:
+                mh = np.stack([scene * masks[i] for i in mids]) if mids else None
+            mh_t = torch.from_numpy(np.ascontiguousarray(mh)).to(dev, non_blocking=True) if mids else None
+            nrot_div = model.gnum_rotations if style != 1 else model.snum_rotations
+            send[off:off + (hi - lo)] = eng.qpartials(style, scene_t, rots, nrot_div, mh_t, trainer.image_mean, trainer.image_std)
+        off += width
+    return send
+
+
+def decision_from_partials(trainer, ctx, recv, rank=0, group=None):
+    """Pair the gathered partials into the three Q tables and apply the reference's selection rules (every rank)."""
+    model, plan, cap, K, R, pairs, world = ctx["model"], ctx["plan"], ctx["cap"], ctx["K"], ctx["R"], ctx["pairs"], ctx["world"]
+    eng = model._engine(18)
+    dev = eng.device
+    offsets, off = {}, 0
+    for style, (n_rot, n_masks, shares) in plan.items():
+        offsets[style] = off
+        off += max(h_ - l_ for l_, h_ in shares)
+    out = {}
+    tables = {}
+    for style, (n_rot, n_masks, shares) in plan.items():
+        o = offsets[style]
+        parts = torch.cat([recv[r * cap + o: r * cap + o + (hi - lo)] for r, (lo, hi) in enumerate(shares) if hi > lo])
+        eng.sync_weights(model, style=style)
+        q = eng.qcombine(style, parts[:n_rot], parts[n_rot:])                 # [n_masks, n_rot, n_out]
+        if trainer.method == "reactive":
+            tables[style] = torch.softmax(q[:, :1, :], dim=2)[:, :, 0]
+        else:
+            tables[style] = q[:, :, 0]
+    gra, suc = tables[0], tables[1]
+    out["gra_conf"], out["suc_conf"] = gra.double().cpu().numpy(), suc.double().cpu().numpy()
+    vg, ig = eng.argmax(gra)
+    vs, isx = eng.argmax(suc)
+    # the north-star exchange: every rank reduces ITS rows of the table to one (Q, flat index) tuple, the tuples are gathered
+    if rank is not None:
+        lo, hi = shard_range(K, rank, world)
+        flat_idx = torch.arange(lo * R[0], hi * R[0], device=dev, dtype=torch.int64)
+        bq, bi = gather_best(gra[lo:hi].reshape(-1), flat_idx, group)
+        assert bi == int(ig.item()), "sharded argmax disagrees with the argmax of the gathered table"
+    bestg_conf, bests_conf = float(vg.item()), float(vs.item())
+    out["bestg_id"] = (int(ig.item()) // R[0], int(ig.item()) % R[0])
+    out["bests_id"] = (int(isx.item()) // R[1], int(isx.item()) % R[1])
+    bestgs_conf, bestgs_num, bestgs_g_id, bestgs_s_id = 0.0, (), [], []
+    gs_conf = np.zeros((K, K))
+    if 2 in tables:
+        flat = torch.full((K * K,), -100.0, device=dev)
+        idx = torch.tensor([g * K + s for g, s in pairs], device=dev)
+        flat[idx] = tables[2][:, 0].float()
+        v, i = eng.argmax(flat)
+        bestgs_conf = float(v.item())
+        bestgs_num = (int(i.item()) // K, int(i.item()) % K)
+        gs_conf = flat.view(K, K).double().cpu().numpy()
+        gnu_best, gro_best = out["gra_conf"].max(axis=1), out["gra_conf"].argmax(axis=1)
+        sro_best = out["suc_conf"].argmax(axis=1)
+        a, b = bestgs_num
+        if gnu_best[a] > gnu_best[b]:                                              # code/main.py:196-201
+            bestgs_g_id, bestgs_s_id = [a, int(gro_best[a])], [b, int(sro_best[b])]
+        else:
+            bestgs_g_id, bestgs_s_id = [b, int(gro_best[b])], [a, int(sro_best[a])]
+    primitive = "grasp"
+    if 2 not in tables:
+        if bests_conf > bestg_conf:
+            primitive = "suction"
+    else:
+        g2 = 2 * bestgs_conf if trainer.method == "reactive" else bestgs_conf      # code/main.py:221-233
+        if bests_conf > max(bestg_conf, g2):
+            primitive = "suction"
+        elif g2 > max(bests_conf, bestg_conf):
+            primitive = "grasp_then_suction"
+    out.update({"primitive": primitive, "gs_conf": gs_conf, "bestgs_num": bestgs_num, "bestgs_g_id": bestgs_g_id,
+                "bestgs_s_id": bestgs_s_id, "bestg_conf": bestg_conf, "bests_conf": bests_conf,
+                "bestgs_conf": bestgs_conf, "exchange_bytes": int(cap * 400 * 64 * 4 * world)})
+    return out

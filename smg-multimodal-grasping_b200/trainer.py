@@ -318,6 +318,110 @@ class Trainer(object):
         setattr(model, attr, q.view(1, model.N_OUT, 1, 1))
         return loss.view(()).cpu().numpy()
 
+    def backprop_batch(self, samples, group=None, total=None, first_index=0, reduction="mean", local_only=False):
+        """Data-parallel replay step (BASELINE config 4): `samples` is THIS rank's share of a batch
+        of `total` independent transitions, each a dict(depth_heightmap, m_depth_heightmap, style, rotation, label_value)
+        with global position first_index + i.  Every sample runs the grad-enabled pass and the backward at the SAME weights
+        (`smg_train_step` with SMG_STEP_GRADS_ONLY); the per-sample gradients are summed locally, all-reduced over the ranks
+        (one flat 28.5 MB buffer; the reduction of the first n-1 samples' sum overlaps the last sample's backward), averaged
+        (`reduction="mean"`) and applied by ONE multi-tensor Adam launch on every rank.  The result equals the serial
+        single-GPU step over the same batch; BatchNorm running statistics follow the weighted-sum rule of the serial order.
+        All samples of a batch must use the same primitive (one trunk + head).  Returns (mean loss, seconds spent waiting
+        for the all-reduce)."""
+        import time
+        from . import parallel as _parallel
+        rank, world = (0, 1) if local_only else _parallel._world(group)
+        total = int(total if total is not None else len(samples))
+        style = int(samples[0]["style"])
+        model = self.model
+        eng = model._engine(2, style)
+        st = self._fused_state(style)
+        if self._fused_last_style != style:
+            self.optimizer.zero_grad()
+            for p, g in zip(st["params"], st["views"]["grad"]):
+                p.grad = g
+            self._fused_last_style = style
+        eng._mean_std = (self.image_mean, self.image_std)
+        kind = 1 if self.method == 'reactive' else 0
+        cw = [1.0, 1.0, 0.0] if kind else [1.0, 1.0, 1.0]
+        group_ = self.optimizer.param_groups[0]
+        G = st["flat"]["grad"]
+        acc = st.setdefault("acc", torch.zeros_like(G))
+        acc.zero_()
+        tid, hid = _engine.STYLE_ROUTE[style]
+        trunk, head = getattr(model, _engine.TRUNK_ATTRS[tid]), getattr(model, _engine.HEAD_ATTRS[hid])
+        n = len(samples)
+        loss_sum = torch.zeros(1, dtype=torch.float32, device=eng.device)
+        bn_sum = None
+        work_acc = None
+        for i, smp in enumerate(samples):
+            hm = torch.from_numpy(np.stack([np.asarray(smp["depth_heightmap"], np.float64),
+                                            np.asarray(smp["m_depth_heightmap"], np.float64)])).to(eng.device, non_blocking=True)
+            rot = 0 if style == 2 else int(smp["rotation"])
+            loss, q, mean, var = eng.train_step(style, hm[0], hm[1], rot, model.gnum_rotations, kind, float(smp["label_value"]),
+                                                cw, st["ptrs"], len(st["params"]), 1, want_bn_stats=model.update_running_stats,
+                                                grads_only=True)
+            loss_sum += loss
+            if model.update_running_stats:
+                j = 2 * (first_index + i)
+                w0 = _parallel.ema_pass_weights(j, 2 * total)
+                w1 = _parallel.ema_pass_weights(j + 1, 2 * total)
+                contrib = torch.cat([w0 * mean[0].double() + w1 * mean[1].double(), w0 * var[0].double() + w1 * var[1].double()])
+                # the head's two BatchNorms see one call per sample (see models._apply_head_running_stats)
+                wh = _parallel.ema_pass_weights(first_index + i, total)
+                norm5 = trunk.features.norm5
+                v5 = var[:, -1024:].double()
+                var_z = norm5.weight.double() ** 2 * v5 / (v5 + 1e-5)
+                h1 = eng.head_bn_stats(1).double()[0]
+                unb = 400.0 / 399.0
+                contrib = torch.cat([contrib, wh * norm5.bias.double(), wh * norm5.bias.double(), wh * unb * var_z[0],
+                                     wh * unb * var_z[1], wh * h1[0], wh * unb * h1[1]])
+                bn_sum = contrib if bn_sum is None else bn_sum + contrib
+            if i < n - 1:
+                acc += G
+                if i == n - 2 and world > 1:
+                    work_acc = _parallel.allreduce_flat(acc, group, async_op=True)   # overlaps the last sample's passes
+        t0 = time.perf_counter()
+        work_last = _parallel.allreduce_flat(G, group, async_op=True) if world > 1 else None
+        for w in (work_acc, work_last):
+            if w is not None:
+                w.wait()
+        if world > 1:
+            torch.cuda.current_stream(eng.device).synchronize()
+        wait_s = time.perf_counter() - t0
+        G += acc
+        if reduction == "mean":
+            G /= float(total)
+        if world > 1:
+            dist_loss = loss_sum.clone()
+            torch.distributed.all_reduce(dist_loss, group=group)
+            loss_sum = dist_loss
+        step = int(st["steps"][0]) + 1
+        numel = st.get("numel")
+        if numel is None:
+            import ctypes
+            numel = st["numel"] = (ctypes.c_int64 * len(st["params"]))(*[p.numel() for p in st["params"]])
+        eng.adam_step_ptrs(st["ptrs"], numel, len(st["params"]), step, group_["lr"], group_["betas"][0], group_["betas"][1],
+                           group_["eps"])
+        torch._foreach_add_(st["steps"], 1)
+        eng.sync_weights(model, force=True, style=style)        # re-pack the updated weights
+        if model.update_running_stats and bn_sum is not None:
+            if world > 1:
+                torch.distributed.all_reduce(bn_sum, group=group)
+            C = _engine.TRUNK_BN_CHANNELS
+            model._apply_running_sums(trunk, bn_sum[:C], bn_sum[C:2 * C], 2 * total)
+            bns = [m for m in head.children() if isinstance(m, torch.nn.BatchNorm2d)]
+            hsum = bn_sum[2 * C:]
+            decay = 0.9 ** total
+            with torch.no_grad():
+                bns[0].running_mean.mul_(decay).add_(hsum[0:2048].to(bns[0].running_mean))
+                bns[0].running_var.mul_(decay).add_(hsum[2048:4096].to(bns[0].running_var))
+                bns[1].running_mean.mul_(decay).add_(hsum[4096:4160].to(bns[1].running_mean))
+                bns[1].running_var.mul_(decay).add_(hsum[4160:4224].to(bns[1].running_var))
+                bns[0].num_batches_tracked += total
+                bns[1].num_batches_tracked += total
+        return float(loss_sum.item()) / total, wait_s
+
     # ------------------------------------------------------------------ backprop (code/trainer.py:278-384)
     def backprop(self, depth_heightmap, primitive_action, bestg_id, bests_id, bestgs_g_id, bestgs_s_id,
                  label_value, objects_mask, sro_best, gro_best, bestgs_num):
