@@ -460,45 +460,13 @@ def run_gpu_arm(args):
                 line_extra["fp32_mode"] = {"error": repr(exc)[:300]}
             tr.model.precision = precision
 
-    # ---- backprop steps/s (second half of BASELINE.json's metric): Trainer.backprop through the public API, in the
-    # benchmarked precision (tf32 forward + tensor-core data gradients) and in fp32 mode
-    if not args.no_backprop:
-        import smg_b200.synth as synth
-        sc = synth.make_scene(100 + 1000 * rank, num_objects=4, cluttered=False)
-        obj_masks = sc["masks"].astype(np.float64)
-        nb = max(5, min(args.steps, 20))
-
-        def bp(i):
-            return tr.backprop(sc["scene"], "grasp", [i % 4, i % R], [0, 0], [], [], 1.0, obj_masks.copy(), [0] * 4, [0] * 4, [])
-
-        for key, prec in (("backprop", precision), ("backprop_fp32", "fp32")):
-            if key == "backprop_fp32" and (precision == "fp32" or args.no_extras):
-                continue
-            try:
-                tr.model.precision = prec
-                eng_t = tr.model._engine(2, 0)
-                for i in range(2 * R):                  # first sight of each rotation runs eagerly, the second captures
-                    bp(i)
-                barrier()
-                l0 = eng_t.launch_count()
-                e0.record()
-                for i in range(nb):
-                    bp(i)
-                e1.record()
-                barrier()
-                t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-                if world > 1:
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                line_extra[key] = {
-                    "value": world * nb / (float(t.item()) / 1e3), "unit": "steps/s", "steps": nb,
-                    "ms_per_step": float(t.item()) / nb, "gflop_per_step": 6 * GFLOP_PER_PASS, "precision": prec,
-                    "launches_per_step": (eng_t.launch_count() - l0) // nb,
-                    "tflops": 6 * GFLOP_PER_PASS / 1e3 / (float(t.item()) / nb / 1e3),
-                    "what": "Trainer.backprop (fused smg_train_step, CUDA-graph replay): host heightmaps in, grad-enabled forward "
-                            "(2 trunk passes + head), loss, backward, Adam, weight re-pack, BN running statistics, loss out"}
-            except Exception as exc:  # the training path must never take the inference numbers down with it
-                line_extra[key] = {"error": repr(exc)[:300]}
-        tr.model.precision = precision
+    # the modes below are ONE job spread over the ranks: every rank must hold the same weights (they do - same seed, nothing
+    # trained yet - but a broadcast from rank 0 makes it a property of the bench, not of the order of its sections)
+    if world > 1 and not args.no_extras:
+        with torch.no_grad():
+            for t_ in tr.model.state_dict().values():
+                dist.broadcast(t_, 0)
+        eng.sync_weights(tr.model, force=True)
 
     # ---- one highly-cluttered decision (K = 10 objects, R = 16, E + S + ES: 98 distinct trunk passes) STRONG-scaled over the
     # N GPUs (BASELINE config 5): per-rank share of the passes, all-gather of the head partials, argmax
@@ -621,6 +589,46 @@ def run_gpu_arm(args):
             line_extra["replay"] = {"error": repr(exc)[:300]}
             if world > 1:
                 raise
+
+    # ---- backprop steps/s (second half of BASELINE.json's metric): Trainer.backprop through the public API, in the
+    # benchmarked precision (tf32 forward + tensor-core data gradients) and in fp32 mode
+    if not args.no_backprop:
+        import smg_b200.synth as synth
+        sc = synth.make_scene(100 + 1000 * rank, num_objects=4, cluttered=False)
+        obj_masks = sc["masks"].astype(np.float64)
+        nb = max(5, min(args.steps, 20))
+
+        def bp(i):
+            return tr.backprop(sc["scene"], "grasp", [i % 4, i % R], [0, 0], [], [], 1.0, obj_masks.copy(), [0] * 4, [0] * 4, [])
+
+        for key, prec in (("backprop", precision), ("backprop_fp32", "fp32")):
+            if key == "backprop_fp32" and (precision == "fp32" or args.no_extras):
+                continue
+            try:
+                tr.model.precision = prec
+                eng_t = tr.model._engine(2, 0)
+                for i in range(2 * R):                  # first sight of each rotation runs eagerly, the second captures
+                    bp(i)
+                barrier()
+                l0 = eng_t.launch_count()
+                e0.record()
+                for i in range(nb):
+                    bp(i)
+                e1.record()
+                barrier()
+                t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                line_extra[key] = {
+                    "value": world * nb / (float(t.item()) / 1e3), "unit": "steps/s", "steps": nb,
+                    "ms_per_step": float(t.item()) / nb, "gflop_per_step": 6 * GFLOP_PER_PASS, "precision": prec,
+                    "launches_per_step": (eng_t.launch_count() - l0) // nb,
+                    "tflops": 6 * GFLOP_PER_PASS / 1e3 / (float(t.item()) / nb / 1e3),
+                    "what": "Trainer.backprop (fused smg_train_step, CUDA-graph replay): host heightmaps in, grad-enabled forward "
+                            "(2 trunk passes + head), loss, backward, Adam, weight re-pack, BN running statistics, loss out"}
+            except Exception as exc:  # the training path must never take the inference numbers down with it
+                line_extra[key] = {"error": repr(exc)[:300]}
+        tr.model.precision = precision
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
