@@ -223,6 +223,17 @@ int smg_heightmap(smg_handle* h, const double* dev_depth, const double* host_K, 
  * 15-bit fixed-point bilinear remap (consumed by Mask R-CNN / logging, not by the Q pass).                            */
 int smg_heightmap_color(smg_handle* h, const uint8_t* dev_color, uint8_t* dev_out224, uint8_t* dev_out448, void* stream);
 
+/* ---- PE / OO geometry after the argmax (code/utils.py:70-81, :316-366, :370-612) ----
+ * mode 0 global_position(host_pix = (_, row, col)) -> host_out[0..2] robot xyz;
+ * mode 1 get_best_grasp_angle(is_pe = flag, box_mask_cors, bestg_id[0] = best_id) -> xyz, [3] jaw angle (rad), [4] opening (m);
+ * mode 2 get_best_suction_angle(is_oo = flag, objects_number = n_objects, masks_cter, box_mask_cors, bests_id[0] = best_id)
+ *        -> xyz, [3] np.deg2rad(chosen direction).
+ * dev_depth: the camera depth image [img_h, img_w] float64 on the device; host_A_htor 3x3, host_K 3x3, host_pose 4x4 row-major;
+ * host_boxes [n,4,2] (x, y) min-area box corners, host_centers [n,2] (x, y); host_out 5 doubles.  Synchronous.           */
+int smg_geometry(smg_handle* h, int mode, const double* dev_depth, int img_h, int img_w, const double* host_A_htor,
+                 const double* host_K, const double* host_pose, const double* host_boxes, const double* host_centers,
+                 int n_objects, int best_id, int flag, const double* host_pix, double* host_out, void* stream);
+
 /* ---- K12: box NMS (code/NMS.py:8-59) ---------------------------------------------
  * boxes [n,2,2] float32 ((x1,y1),(x2,y2)); keeps index-order greedy survivors.
  * dev_keep [n] int32 receives kept indices, dev_n_keep[0] their count.  n <= 1024.   */

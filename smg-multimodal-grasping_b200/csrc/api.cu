@@ -476,6 +476,7 @@ int smg_destroy(smg_handle* h) {
     if (h->step.tables) cudaFree(h->step.tables);
     if (h->step.adam_tables) cudaFree(h->step.adam_tables);
     if (h->bn_regions_dev) cudaFree(h->bn_regions_dev);
+    if (h->geo_out) cudaFree(h->geo_out);
     if (h->train.arena) cudaFree(h->train.arena);
     if (h->train.wstream) cudaStreamDestroy(h->train.wstream);
     for (auto& e : h->train.ev)
@@ -1185,6 +1186,27 @@ int smg_heightmap(smg_handle* h, const double* dev_depth, const double* host_K, 
     SMG_CHECK(h && dev_depth && host_K && host_pose && dev_out224 && dev_out448, SMG_ERR_INVALID, "smg_heightmap: NULL argument");
     DeviceGuard guard(h->device);
     return launch_heightmap(h, dev_depth, host_K, host_pose, dev_out224, dev_out448, host_A_htor, (cudaStream_t)stream);
+}
+
+int smg_geometry(smg_handle* h, int mode, const double* dev_depth, int img_h, int img_w, const double* host_A_htor,
+                 const double* host_K, const double* host_pose, const double* host_boxes, const double* host_centers,
+                 int n_objects, int best_id, int flag, const double* host_pix, double* host_out, void* stream) {
+    SMG_CHECK(h && dev_depth && host_A_htor && host_K && host_pose && host_out, SMG_ERR_INVALID, "smg_geometry: NULL argument");
+    SMG_CHECK(mode >= 0 && mode <= 2 && (mode == 0 ? host_pix != nullptr : host_boxes != nullptr) && (mode != 2 || !flag || host_centers),
+              SMG_ERR_INVALID, "smg_geometry: mode %d with missing inputs", mode);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->geo_out) SMG_CUDA(cudaMalloc(&h->geo_out, 8 * sizeof(double)));
+    SMG_TRY(launch_geometry(h, mode, dev_depth, img_h, img_w, host_A_htor, host_K, host_pose, host_boxes, host_centers, n_objects,
+                            best_id, flag, host_pix, h->geo_out, st));
+    double out[6];
+    SMG_CUDA(cudaMemcpyAsync(out, h->geo_out, sizeof(out), cudaMemcpyDeviceToHost, st));
+    SMG_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 5; ++i) host_out[i] = out[i];
+    const int status = (int)out[5];
+    SMG_CHECK(!(status & 1), SMG_ERR_INVALID, "smg_geometry: a heightmap pixel maps outside the %d x %d camera image", img_w, img_h);
+    SMG_CHECK(!(status & 2), SMG_ERR_STATE, "smg_geometry: no free suction direction was found");
+    return SMG_OK;
 }
 
 int smg_nms(smg_handle* h, const float* dev_boxes, int n, float co_thresh, float min_area, float max_area,

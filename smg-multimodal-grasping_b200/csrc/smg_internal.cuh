@@ -216,6 +216,7 @@ struct smg_handle {
     };
     std::vector<QGraph> graphs;
     int last_n = 0;               // samples of the last trunk forward (for smg_debug_read)
+    double* geo_out = nullptr;        // result staging of smg_geometry
     void* bn_regions_dev = nullptr;   // the 121 BatchNorm statistics regions in module order (export_bn_stats)
     int bn_regions = 0;
 
@@ -381,6 +382,10 @@ int launch_bn_export_all(smg_handle* h, int n, const void* dev_regions, int n_re
 int launch_argmax(smg_handle* h, const float* q, int n, float* out, int32_t* out_idx, cudaStream_t st);
 int launch_nhwc_to_nchw(smg_handle* h, const float* in, int hw, int c, int cstride, float* out, cudaStream_t st);
 
+// PE / OO geometry (geometry.cu)
+int launch_geometry(smg_handle* h, int mode, const double* dev_depth, int img_h, int img_w, const double* A, const double* K,
+                    const double* P, const double* boxes, const double* centers, int n, int best, int flag, const double* pix,
+                    double* dev_out, cudaStream_t st);
 // K11 / K12
 int launch_heightmap_color(smg_handle* h, const uint8_t* color, uint8_t* out224, uint8_t* out448, cudaStream_t st);
 int launch_heightmap(smg_handle* h, const double* depth, const double* K, const double* pose, double* out224,

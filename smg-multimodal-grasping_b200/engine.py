@@ -378,6 +378,30 @@ class Engine:
         _lib.check(self.lib.smg_heightmap_color(self.h, c.data_ptr(), o224.data_ptr(), o448.data_ptr(), self._stream()))
         return o224, o448
 
+    def geometry(self, mode, depth_img, A_htor, intrinsics, pose, boxes=None, centers=None, best=0, flag=0, pix=None):
+        """smg_geometry: mode 0 global_position, 1 grasp angle / opening, 2 suction direction -> numpy [5]."""
+        d = depth_img if torch.is_tensor(depth_img) else torch.from_numpy(np.ascontiguousarray(depth_img, dtype=np.float64))
+        d = d.to(self.device, torch.float64).contiguous()
+        dp = ctypes.POINTER(ctypes.c_double)
+
+        def arr(a, n=None):
+            if a is None:
+                return None, None
+            v = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+            return v, v.ctypes.data_as(dp)
+
+        A, pA = arr(np.asarray(A_htor)[:3, :3])
+        K, pK = arr(np.asarray(intrinsics)[:3, :3])
+        P, pP = arr(np.asarray(pose)[:4, :4])
+        B, pB = arr(boxes)
+        C, pC = arr(centers)
+        X, pX = arr(pix)
+        n = 0 if boxes is None else int(np.asarray(boxes).shape[0])
+        out = np.zeros(5, dtype=np.float64)
+        _lib.check(self.lib.smg_geometry(self.h, int(mode), d.data_ptr(), int(d.shape[0]), int(d.shape[1]), pA, pK, pP, pB, pC, n,
+                                         int(best), int(bool(flag)), pX, out.ctypes.data_as(dp), self._stream()))
+        return out
+
     def nms(self, boxes, co_thresh, min_area, max_area):
         b = boxes.to(self.device, torch.float32).contiguous().view(-1, 4)
         n = b.shape[0]

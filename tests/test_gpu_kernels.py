@@ -125,3 +125,31 @@ def test_nms_matches_reference_lists(eng, golden):
         assert keep == case["keep"], case
     boxes, scores = synth.make_boxes(7, 1000)  # maximum supported size, against the oracle
     assert NMS.py_cpu_nms(boxes, scores, 0.40, 224 * 224 / 60, 224 * 224 / 5) == onms.nms(boxes, scores, 0.40, 224 * 224 / 60, 224 * 224 / 5)
+
+
+def test_pe_oo_geometry_matches_reference():
+    """utils.global_position / get_best_grasp_angle / get_best_suction_angle (csrc/geometry.cu, one device thread in fp64)
+    against the outputs of the unmodified reference functions (tests/golden/golden_r02.json)."""
+    import json
+    import os
+    import smg_b200.synth as synth
+    from smg_b200 import utils
+    with open(os.path.join(GOLDEN_DIR, "golden_r02.json")) as f:
+        geo = json.load(f)["geometry"]
+    n = 0
+    for e in geo:
+        cam = synth.make_camera(e["camera_seed"])
+        A, K, P, depth = np.asarray(e["A_htor"]), cam["intrinsics"], cam["pose"], cam["depth"]
+        box, cter = np.asarray(e["box_mask_cors"]), np.asarray(e["masks_cter"])
+        for gp in e["global_position"]:
+            assert np.allclose(utils.global_position(np.array(gp["pix"]), A, K, P, depth), gp["xyz"], rtol=0, atol=1e-12)
+        for gr in e["grasp"]:
+            c, ang, dist = utils.get_best_grasp_angle(gr["is_pe"], box, [gr["obj"], 0], A, K, P, depth)
+            assert np.allclose(c, gr["center"], atol=1e-12)
+            assert abs(ang - gr["angle"]) <= 1e-9 and abs(dist - gr["open_distance"]) <= 1e-12, gr
+        for su in e["suction"]:
+            c, ang = utils.get_best_suction_angle(su["is_oo"], e["K"], cter, box, [su["obj"], 0], A, K, P, depth)
+            assert np.allclose(c, su["center"], atol=1e-12)
+            assert abs(ang - su["angle"]) <= 1e-9, (e["scene_seed"], su, ang)    # whole degrees: any slip would be >= 0.017
+            n += 1
+    assert n == 40

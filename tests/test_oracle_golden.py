@@ -236,3 +236,60 @@ def test_preload_restores_the_ten_logs(gold2):
         got = getattr(t, attr)
         assert isinstance(got, list) and got == want, attr
     t.executed_action_log.append([1, 2, 3, 4])      # main.py:369 appends to the restored list
+
+
+def test_oracle_geometry_vs_reference(gold2):
+    """oracle/geometry.py (the step-by-step restatement csrc/geometry.cu follows) against the reference's own
+    global_position / get_best_grasp_angle / get_best_suction_angle outputs."""
+    import smg_b200.synth as synth
+    from oracle import geometry as ogeo
+    n_oo = 0
+    for e in gold2["geometry"]:
+        cam = synth.make_camera(e["camera_seed"])
+        A, K, P, depth = np.asarray(e["A_htor"]), cam["intrinsics"], cam["pose"], cam["depth"]
+        box, cter = np.asarray(e["box_mask_cors"]), np.asarray(e["masks_cter"])
+        for gp in e["global_position"]:
+            assert np.allclose(ogeo.global_position(gp["pix"], A, K, P, depth), gp["xyz"], rtol=0, atol=1e-12)
+        for gr in e["grasp"]:
+            c, ang, dist = ogeo.grasp_angle(gr["is_pe"], box, gr["obj"], A, K, P, depth)
+            assert np.allclose(c, gr["center"], atol=1e-12) and abs(ang - gr["angle"]) <= 1e-12 and abs(dist - gr["open_distance"]) <= 1e-12
+        for su in e["suction"]:
+            c, ang = ogeo.suction_angle(su["is_oo"], e["K"], cter, box, su["obj"], A, K, P, depth)
+            assert np.allclose(c, su["center"], atol=1e-12)
+            assert abs(float(ang) - su["angle"]) <= 1e-12, (e["scene_seed"], su, float(ang))
+            n_oo += su["is_oo"]
+    assert n_oo == 20
+
+
+def test_snapshot_round_trip_with_reference_logger(tmp_path):
+    """N4: a `.pth` written by the reference's own logger (code/logger.py:121-125) from the reference's own
+    net loads into this package's net unchanged, and a snapshot of ours loads back into the reference net (2217 keys, same
+    shapes and values).  Needs /root/reference: runs in the build container only."""
+    from oracle import refshim
+    if not os.path.isdir("/root/reference/code"):
+        pytest.skip("the reference tree is only present in the build container")
+    mods = refshim.install(cpu=True)
+    try:
+        import logger as ref_logger
+        import smg_b200.models as mine
+        torch.manual_seed(3)
+        ref = mods["models"].reinforcement_net(True)
+
+        class L:
+            models_directory = str(tmp_path)
+        ref_logger.Logger.save_model(L, 50, ref, "reinforcement")                     # model.cpu().state_dict()
+        ref_logger.Logger.save_backup_model(L, ref, "reinforcement")
+        snap = os.path.join(str(tmp_path), "snapshot-000050.reinforcement.pth")
+        net = mine.reinforcement_net(True)
+        missing = net.load_state_dict(torch.load(snap))                                 # code/trainer.py:85-87
+        assert not missing.missing_keys and not missing.unexpected_keys
+        sd_ref, sd_mine = ref.state_dict(), net.state_dict()
+        assert list(sd_ref.keys()) == list(sd_mine.keys()) and len(sd_mine) == 2217
+        assert all(torch.equal(sd_ref[k], sd_mine[k]) for k in sd_ref)
+        torch.save(net.state_dict(), os.path.join(str(tmp_path), "mine.pth"))
+        ref2 = mods["models"].reinforcement_net(True)
+        ref2.load_state_dict(torch.load(os.path.join(str(tmp_path), "mine.pth")))
+        assert all(torch.equal(v, ref2.state_dict()[k]) for k, v in sd_mine.items())
+        assert os.path.exists(os.path.join(str(tmp_path), "snapshot-backup.reinforcement.pth"))
+    finally:
+        refshim.set_cpu_mode(False)
