@@ -223,6 +223,11 @@ int smg_heightmap(smg_handle* h, const double* dev_depth, const double* host_K, 
  * 15-bit fixed-point bilinear remap (consumed by Mask R-CNN / logging, not by the Q pass).                            */
 int smg_heightmap_color(smg_handle* h, const uint8_t* dev_color, uint8_t* dev_out224, uint8_t* dev_out448, void* stream);
 
+/* ---- detector post-processing in front of the Q pass (code/masks.py:51) -----------
+ * F.interpolate(masks, size=[size_out, size_out], mode="bilinear", align_corners=True) of n float32 soft masks
+ * [n, size_in, size_in] (the reference resizes Mask R-CNN's 448x448 masks to the 224x224 heightmap grid).          */
+int smg_resize_masks(smg_handle* h, const float* dev_masks, int n, int size_in, int size_out, float* dev_out, void* stream);
+
 /* ---- PE / OO geometry after the argmax (code/utils.py:70-81, :316-366, :370-612) ----
  * mode 0 global_position(host_pix = (_, row, col)) -> host_out[0..2] robot xyz;
  * mode 1 get_best_grasp_angle(is_pe = flag, box_mask_cors, bestg_id[0] = best_id) -> xyz, [3] jaw angle (rad), [4] opening (m);

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "smg_argmax": (I, [VP, VP, I, VP, VP, VP]),
     "smg_heightmap": (I, [VP, VP, c_double_p, c_double_p, VP, VP, c_double_p, VP]),
     "smg_heightmap_color": (I, [VP, VP, VP, VP, VP]),
+    "smg_resize_masks": (I, [VP, VP, I, I, I, VP, VP]),
     "smg_geometry": (I, [VP, I, VP, I, I, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, I, I, I, c_double_p,
                          c_double_p, VP]),
     "smg_nms": (I, [VP, VP, I, ctypes.c_float, ctypes.c_float, ctypes.c_float, VP, VP, VP]),

@@ -1188,6 +1188,13 @@ int smg_heightmap(smg_handle* h, const double* dev_depth, const double* host_K, 
     return launch_heightmap(h, dev_depth, host_K, host_pose, dev_out224, dev_out448, host_A_htor, (cudaStream_t)stream);
 }
 
+int smg_resize_masks(smg_handle* h, const float* dev_masks, int n, int size_in, int size_out, float* dev_out, void* stream) {
+    SMG_CHECK(h && (n == 0 || (dev_masks && dev_out)) && n >= 0 && size_in >= 2 && size_out >= 1, SMG_ERR_INVALID,
+              "smg_resize_masks: bad argument");
+    DeviceGuard guard(h->device);
+    return launch_resize_masks(h, dev_masks, n, size_in, size_out, dev_out, (cudaStream_t)stream);
+}
+
 int smg_geometry(smg_handle* h, int mode, const double* dev_depth, int img_h, int img_w, const double* host_A_htor,
                  const double* host_K, const double* host_pose, const double* host_boxes, const double* host_centers,
                  int n_objects, int best_id, int flag, const double* host_pix, double* host_out, void* stream) {

@@ -128,4 +128,35 @@ int launch_rotate_index_map(smg_handle* h, int rot, int num_rot, int32_t* out, c
     return SMG_OK;
 }
 
+// Soft-mask resize of the detector front end (/root/reference/code/masks.py:51): F.interpolate(masks, size=[224, 224],
+// mode="bilinear", align_corners=True) of float32 [n,1,448,448] masks.  torch's float32 recipe: scale = (in-1)/(out-1);
+// src = scale * dst; i0 = (int)src; lambda1 = src - i0; lambda0 = 1 - lambda1; out = l0y*(l0x*p00 + l1x*p01) + l1y*(l0x*p10 + l1x*p11).
+__global__ void resize_bilinear_ac_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int hin, int hout) {
+    const float scale = hout > 1 ? (float)(hin - 1) / (float)(hout - 1) : 0.f;
+    const size_t total = (size_t)n * hout * hout;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % hout), y = (int)((i / hout) % hout);
+        const size_t m = i / ((size_t)hout * hout);
+        const float sy = scale * (float)y, sx = scale * (float)x;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int yp = y0 < hin - 1 ? 1 : 0, xp = x0 < hin - 1 ? 1 : 0;
+        const float ly1 = sy - (float)y0, ly0 = 1.f - ly1, lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+        const float* p = in + m * hin * hin + (size_t)y0 * hin + x0;
+        const float top = __fadd_rn(__fmul_rn(lx0, p[0]), __fmul_rn(lx1, p[xp]));
+        const float bot = __fadd_rn(__fmul_rn(lx0, p[(size_t)yp * hin]), __fmul_rn(lx1, p[(size_t)yp * hin + xp]));
+        out[i] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+    }
+}
+
+int launch_resize_masks(smg_handle* h, const float* in, int n, int hin, int hout, float* out, cudaStream_t st) {
+    const size_t total = (size_t)n * hout * hout;
+    if (total == 0) return SMG_OK;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > h->num_sms * 16) blocks = h->num_sms * 16;
+    resize_bilinear_ac_kernel<<<blocks, 256, 0, st>>>(in, out, n, hin, hout);
+    h->launches++;
+    SMG_CUDA(cudaGetLastError());
+    return SMG_OK;
+}
+
 }  // namespace smg

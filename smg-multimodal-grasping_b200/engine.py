@@ -378,6 +378,15 @@ class Engine:
         _lib.check(self.lib.smg_heightmap_color(self.h, c.data_ptr(), o224.data_ptr(), o448.data_ptr(), self._stream()))
         return o224, o448
 
+    def resize_masks(self, masks, size_out=224):
+        """[n,s,s] float32 -> [n,size_out,size_out]: bilinear, align_corners=True (code/masks.py:51)."""
+        m = masks.to(self.device, torch.float32).contiguous()
+        n, s = int(m.shape[0]), int(m.shape[-1])
+        out = torch.empty((n, size_out, size_out), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.smg_resize_masks(self.h, m.data_ptr() if n else None, n, s, int(size_out), out.data_ptr() if n else None,
+                                             self._stream()))
+        return out
+
     def geometry(self, mode, depth_img, A_htor, intrinsics, pose, boxes=None, centers=None, best=0, flag=0, pix=None):
         """smg_geometry: mode 0 global_position, 1 grasp angle / opening, 2 suction direction -> numpy [5]."""
         d = depth_img if torch.is_tensor(depth_img) else torch.from_numpy(np.ascontiguousarray(depth_img, dtype=np.float64))

@@ -153,3 +153,26 @@ def test_pe_oo_geometry_matches_reference():
             assert abs(ang - su["angle"]) <= 1e-9, (e["scene_seed"], su, ang)    # whole degrees: any slip would be >= 0.017
             n += 1
     assert n == 40
+
+
+def test_soft_mask_resize_and_detection_postprocess():
+    """N2, weight-free half (code/masks.py:36-83): the 448 -> 224 bilinear(align_corners=True) resize of soft masks against
+    torch's own F.interpolate on the CPU (the call the reference makes), and the score filter + box halving + NMS chain
+    against a restatement with the oracle's NMS."""
+    import torch.nn.functional as F
+    import smg_b200.synth as synth
+    from smg_b200 import masks as pmasks
+    rs = np.random.RandomState(5)
+    fp, _ = synth._footprints(np.random.RandomState(11), 6, True)
+    soft448 = torch.from_numpy((fp * rs.uniform(0.6, 1.0, size=(6, 1, 1)) + rs.uniform(0, 0.02, size=fp.shape)).astype(np.float32))
+    got = pmasks.resize_soft_masks(soft448[:, None])
+    ref = F.interpolate(soft448[:, None], size=[224, 224], mode="bilinear", align_corners=True)[:, 0].numpy()
+    assert got.shape == (6, 224, 224) and np.abs(got - ref).max() <= 1e-6
+    boxes, _ = synth.make_boxes(2, 6)
+    b4 = np.concatenate([boxes[:, 0], boxes[:, 1]], axis=1) * 2          # detector boxes live on the 448 grid
+    scores = np.array([0.9, 0.8, 0.7, 0.005, 0.3, 0.001], np.float32)     # a failing score in the middle is kept (last passing wins)
+    init, soft, hb, keep, number = pmasks.postprocess_detections(soft448[:, None], b4, scores, 0.01)
+    want_keep = onms.nms((b4.reshape(-1, 2, 2) / 2)[:5], scores[:5], 0.40, 224 * 224 / 60, 224 * 224 / 5)
+    assert keep == want_keep and number == len(want_keep)
+    assert np.array_equal(init, (soft448.numpy() > 0.5)[want_keep]) and np.abs(soft - ref[want_keep]).max() <= 1e-6
+    assert pmasks.postprocess_detections(soft448[:, None], b4, scores * 0, 0.01)[4] == 0
