@@ -44,7 +44,8 @@ typedef enum smg_status {
 
 /* arithmetic mode of the trunk / head convolutions */
 typedef enum smg_precision {
-    SMG_PREC_FP32 = 0, /* CUDA-core FFMA, fp32 operands: parity <= 1e-4 vs the fp32 reference */
+    SMG_PREC_FP32 = 0, /* fp32 accuracy (parity <= 1e-4 vs the fp32 reference): tcgen05 kind::tf32 with hi/lo split operands
+                          ("3xTF32": a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulate); SMG_FP32_TC=0 selects CUDA-core FFMA */
     SMG_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
     SMG_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
 } smg_precision;

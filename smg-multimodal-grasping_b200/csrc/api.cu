@@ -50,7 +50,14 @@ int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     // algorithmic traffic: every input element of the layer read once, every output written once (fp32)
     const double bytes = 4.0 * ((double)a.n * a.hin * a.hin * a.cin + px * a.cout);
     ProfScope ps(h, st, a.taps == 9 ? 2 : 1, 2.0 * px * a.cout * a.cin * a.taps, bytes);
-    if (h->precision == SMG_PREC_FP32) return launch_conv_ffma(h, a, st);
+    if (h->precision == SMG_PREC_FP32) {
+        // fp32 mode: tensor cores with hi/lo split tf32 operands (error ~1e-6, like fp32 FMA chains); CUDA cores on request
+        if (h->fp32_tc) {
+            const int status = launch_conv_umma(h, a, SMG_PREC_FP32, st);
+            if (status != SMG_ERR_UNSUPPORTED) return status;
+        }
+        return launch_conv_ffma(h, a, st);
+    }
     // tf32 dense layers: the persistent TMA-fed kernels (SMG_TMA bits: 64 = conv3_wt.cu, 128 = conv1_t.cu); everything they
     // do not serve (pooled transitions, the head's 1x1, bf16 mode, odd shapes) runs on the register-producer kernel.
     if (h->precision == SMG_PREC_TF32 && !a.pool) {
@@ -115,7 +122,8 @@ int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cudaStrea
                              4.0 * ns * ((double)in_channels * h->H * h->H + 2 * hc * 64 + hc / 4 * 64));
                 double* st_c0 = stats_ptr(h, h->st_conv0) + 2 * (size_t)s0 * 64;
                 int c0_status = SMG_ERR_UNSUPPORTED;
-                if (h->precision == SMG_PREC_TF32 && in_channels == 1 && (h->use_tma & 16))
+                if ((h->precision == SMG_PREC_TF32 || (h->precision == SMG_PREC_FP32 && h->fp32_tc)) && in_channels == 1 &&
+                    (h->use_tma & 16))
                     c0_status = launch_conv0_umma(h, h->input + (size_t)s0 * in_img, ns, T.conv0_umma, h->conv0 + (size_t)s0 * c0_img,
                                                   st_c0, st);
                 if (c0_status == SMG_ERR_UNSUPPORTED)
@@ -280,11 +288,13 @@ static void plan_conv(ArenaPlanner& p, ConvW& cw, int cin, int cout, int taps, u
     const size_t o3 = p.take(conv_packed_bytes_umma(cin, cout, taps, 2));
     const size_t o4 = p.take(conv_packed_bytes_ffma(cin, cout, taps));
     const size_t o5 = p.take(conv_packed_bytes_umma(dgrad_cin_padded(cin, taps), cout, taps, 4));
+    const size_t o6 = p.take(2 * conv_packed_bytes_umma(cin, cout, taps, 4));
     const bool has_t = taps == 9 || (taps == 1 && cout == 128);
     const size_t o7 = has_t ? p.take(conv_packed_bytes_umma(cin, cout, taps, 4)) : 0;
     if (base) {
         if (has_t) cw.w_tf32_t = base + o7;
         cw.w_dgrad_tf32 = base + o5;
+        cw.w_split = base + o6;
         cw.w_ffma = reinterpret_cast<float*>(base + o1);
         cw.w_tf32 = base + o2;
         cw.w_bf16 = base + o3;
@@ -461,6 +471,7 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     if (const char* e = getenv("SMG_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
     if (const char* e = getenv("SMG_ASYNC")) h->force_async = atoi(e);
     if (const char* e = getenv("SMG_TMA")) h->use_tma = atoi(e);
+    if (const char* e = getenv("SMG_FP32_TC")) h->fp32_tc = atoi(e) != 0;
     *out = h;
     return SMG_OK;
 }

@@ -22,13 +22,18 @@
 
 namespace smg {
 
-template <int ELT, int BN, int TAPS>
+// SPLIT = 1 (tf32 elements only): fp32-accurate "3xTF32" mode.  Every operand is kept as hi + lo (hi = the value with its 13
+// low mantissa bits cleared, exactly a tf32 number; lo = value - hi, exact in fp32) and D += a_lo b_hi + a_hi b_lo + a_hi b_hi
+// (the dropped a_lo b_lo term is 2^-22 relative): each A slot / B stage holds the hi image followed by the lo image.
+template <int ELT, int BN, int TAPS, int SPLIT = 0>
 struct SmemPlan {
     using E = EltCfg<ELT>;
     static constexpr int A_LBO = (TAPS == 9 ? E::P_ROWS : E::A_ROWS) * 16;
-    static constexpr int A_SLOT = E::CH * A_LBO;                      // one 32-channel group
+    static constexpr int A_HALF = E::CH * A_LBO;                      // one 32-channel group, one image
+    static constexpr int A_SLOT = (1 + SPLIT) * A_HALF;
     static constexpr int A_SLOTS = TAPS == 9 ? 2 : NA;
-    static constexpr int B_STAGE = E::CH * BN * 16;
+    static constexpr int B_HALF = E::CH * BN * 16;
+    static constexpr int B_STAGE = (1 + SPLIT) * B_HALF;
     static constexpr int B_SLOTS = TAPS == 9 ? NB9 : NB1;
     static constexpr int OFF_BAR = 0;
     static constexpr int OFF_SC = 256;
@@ -40,11 +45,12 @@ struct SmemPlan {
 };
 
 
-template <int ELT, int BN, int TAPS, int POOL>
+template <int ELT, int BN, int TAPS, int POOL, int SPLIT = 0>
 __global__ void __launch_bounds__(448, 2)
 conv_umma_kernel(UmmaDev a) {
+    static_assert(SPLIT == 0 || ELT == 4, "the hi/lo split is a tf32 mode");
     using E = EltCfg<ELT>;
-    using P = SmemPlan<ELT, BN, TAPS>;
+    using P = SmemPlan<ELT, BN, TAPS, SPLIT>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
     uint64_t* a_full = bars;            // [4]
@@ -142,7 +148,7 @@ conv_umma_kernel(UmmaDev a) {
                     roff[i] = -1;
                 }
             }
-            if (ELT == 4 && !POOL && a.async_producer) {
+            if (ELT == 4 && !POOL && !SPLIT && a.async_producer) {
                 // tf32 small-grid path: raw fp32 rows are cp.async'ed straight into their final UMMA slot (NA stages in
                 // flight per thread, no registers held), then normalised IN PLACE by the thread that loaded them.
                 auto issue = [&](int kg) {
@@ -246,6 +252,13 @@ conv_umma_kernel(UmmaDev a) {
                     if (ELT == 4) {
                         pk = make_uint4(__float_as_uint(v[i][0]), __float_as_uint(v[i][1]), __float_as_uint(v[i][2]),
                                         __float_as_uint(v[i][3]));
+                        if (SPLIT) {
+                            const uint4 hi = make_uint4(pk.x & 0xFFFFE000u, pk.y & 0xFFFFE000u, pk.z & 0xFFFFE000u, pk.w & 0xFFFFE000u);
+                            const uint4 lo = make_uint4(__float_as_uint(v[i][0] - __uint_as_float(hi.x)), __float_as_uint(v[i][1] - __uint_as_float(hi.y)),
+                                                        __float_as_uint(v[i][2] - __uint_as_float(hi.z)), __float_as_uint(v[i][3] - __uint_as_float(hi.w)));
+                            *reinterpret_cast<uint4*>(dst + P::A_HALF + (r0 + i * RSTEP) * 16) = lo;
+                            pk = hi;
+                        }
                     } else {
                         pk = make_uint4(pack_bf16x2(v[i][0], v[i][1]), pack_bf16x2(v[i][2], v[i][3]),
                                         pack_bf16x2(v[i][4 % E::EPC], v[i][5 % E::EPC]),
@@ -272,7 +285,7 @@ conv_umma_kernel(UmmaDev a) {
                 const int y = h0 - 1 + py, x = w0 - 1 + px;
                 poff[i] = (q < pfill && y >= 0 && y < hin && x >= 0 && x < hin) ? (y * hin + x) * a.in_cstride : -1;
             }
-            if (ELT == 4 && a.async_producer) {
+            if (ELT == 4 && !SPLIT && a.async_producer) {
                 // tf32 small-grid path: both patch slots are filled with cp.async (raw fp32 lands in its final place,
                 // 2 x 27 KB in flight per CTA) and normalised in place by the loading thread.
                 auto issue = [&](int g) {
@@ -361,6 +374,13 @@ conv_umma_kernel(UmmaDev a) {
                             if (ELT == 4) {
                                 pk = make_uint4(__float_as_uint(t[0]), __float_as_uint(t[1]), __float_as_uint(t[2]),
                                                 __float_as_uint(t[3]));
+                                if (SPLIT) {
+                                    const uint4 hi = make_uint4(pk.x & 0xFFFFE000u, pk.y & 0xFFFFE000u, pk.z & 0xFFFFE000u, pk.w & 0xFFFFE000u);
+                                    const uint4 lo = make_uint4(__float_as_uint(t[0] - __uint_as_float(hi.x)), __float_as_uint(t[1] - __uint_as_float(hi.y)),
+                                                                __float_as_uint(t[2] - __uint_as_float(hi.z)), __float_as_uint(t[3] - __uint_as_float(hi.w)));
+                                    *reinterpret_cast<uint4*>(dst + P::A_HALF + q * 16) = lo;
+                                    pk = hi;
+                                }
                             } else {
                                 pk = make_uint4(pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]),
                                                 pack_bf16x2(t[4 % E::EPC], t[5 % E::EPC]),
@@ -405,6 +425,13 @@ conv_umma_kernel(UmmaDev a) {
                     for (int k = 0; k < MMAS; ++k) {
                         const uint64_t ad = make_desc(sA_u + sa * P::A_SLOT + 2 * k * P::A_LBO, P::A_LBO, 128);
                         const uint64_t bd = make_desc(sB_u + sb * P::B_STAGE + 2 * k * BN * 16, BN * 16, 128);
+                        if (SPLIT) {   // small terms first: a_lo b_hi, a_hi b_lo, then a_hi b_hi
+                            const uint64_t al = make_desc(sA_u + sa * P::A_SLOT + P::A_HALF + 2 * k * P::A_LBO, P::A_LBO, 128);
+                            const uint64_t bl = make_desc(sB_u + sb * P::B_STAGE + P::B_HALF + 2 * k * BN * 16, BN * 16, 128);
+                            umma<ELT>(tmem_base, al, bd, idesc, accum);
+                            umma<ELT>(tmem_base, ad, bl, idesc, 1);
+                            accum = 1;
+                        }
                         umma<ELT>(tmem_base, ad, bd, idesc, accum);
                         accum = 1;
                     }
@@ -426,6 +453,13 @@ conv_umma_kernel(UmmaDev a) {
                             const uint64_t ad =
                                 make_desc(sA_u + sa * P::A_SLOT + 2 * k * P::A_LBO + shift * 16, P::A_LBO, 128);
                             const uint64_t bd = make_desc(sB_u + sb * P::B_STAGE + 2 * k * BN * 16, BN * 16, 128);
+                            if (SPLIT) {
+                                const uint64_t al = make_desc(sA_u + sa * P::A_SLOT + P::A_HALF + 2 * k * P::A_LBO + shift * 16, P::A_LBO, 128);
+                                const uint64_t bl = make_desc(sB_u + sb * P::B_STAGE + P::B_HALF + 2 * k * BN * 16, BN * 16, 128);
+                                umma<ELT>(tmem_base, al, bd, idesc, accum);
+                                umma<ELT>(tmem_base, ad, bl, idesc, 1);
+                                accum = 1;
+                            }
                             umma<ELT>(tmem_base, ad, bd, idesc, accum);
                             accum = 1;
                         }
@@ -621,10 +655,10 @@ void umma_patch_geometry(int hw, int* wp, int* ht) {
     *ht = best_ht;
 }
 
-template <int ELT, int BN, int TAPS, int POOL>
+template <int ELT, int BN, int TAPS, int POOL, int SPLIT = 0>
 static int launch_umma(smg_handle* h, const UmmaDev& d, int n, cudaStream_t st) {
-    using P = SmemPlan<ELT, BN, TAPS>;
-    SMG_TRY(ensure_dyn_smem(h, (const void*)conv_umma_kernel<ELT, BN, TAPS, POOL>, P::TOTAL));
+    using P = SmemPlan<ELT, BN, TAPS, SPLIT>;
+    SMG_TRY(ensure_dyn_smem(h, (const void*)conv_umma_kernel<ELT, BN, TAPS, POOL, SPLIT>, P::TOTAL));
     dim3 grid;
     if (TAPS == 9) {
         const int wt = d.wp - 2;
@@ -635,7 +669,7 @@ static int launch_umma(smg_handle* h, const UmmaDev& d, int n, cudaStream_t st) 
     }
     UmmaDev dd = d;
     dd.async_producer = h->force_async >= 0 ? h->force_async : ((int)(grid.x * grid.y * grid.z) < 2 * h->num_sms ? 1 : 0);
-    conv_umma_kernel<ELT, BN, TAPS, POOL><<<grid, 448, P::TOTAL, st>>>(dd);
+    conv_umma_kernel<ELT, BN, TAPS, POOL, SPLIT><<<grid, 448, P::TOTAL, st>>>(dd);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;
@@ -671,6 +705,28 @@ static int dispatch(smg_handle* h, const ConvArgs& a, UmmaDev& d, cudaStream_t s
     return launch_umma<ELT, 128, 1, 0>(h, d, a.n, st);
 }
 
+// fp32-accurate mode on the tensor cores: tf32 elements, hi/lo split operands (w_split = per stage [hi image][lo image])
+static int dispatch_split(smg_handle* h, const ConvArgs& a, UmmaDev& d, cudaStream_t st) {
+    SMG_CHECK(a.w != nullptr && a.w->w_split != nullptr, SMG_ERR_STATE, "conv_umma: split weights not packed");
+    d.w = a.w->w_split;
+    if (a.taps == 9) {
+        SMG_CHECK(a.cin == 128 && a.cout == 32 && !a.pool, SMG_ERR_UNSUPPORTED, "conv_umma: 3x3 expects 128->32");
+        umma_patch_geometry(d.hout, &d.wp, &d.ht);
+        SMG_CHECK((d.ht + 2) * d.wp <= 5 * MAX_WP && d.ht * d.wp <= UM, SMG_ERR_STATE, "conv_umma: patch %dx%d too large", d.ht, d.wp);
+        const int wt = d.wp - 2;
+        d.tiles_x = (d.hout + wt - 1) / wt;
+        return launch_umma<4, 32, 9, 0, 1>(h, d, a.n, st);
+    }
+    SMG_CHECK(a.cin % KC == 0 && a.cin <= 1024, SMG_ERR_UNSUPPORTED, "conv_umma: cin %d unsupported", a.cin);
+    if (a.cout == 64) {
+        SMG_CHECK(!a.pool, SMG_ERR_UNSUPPORTED, "conv_umma: pooled N=64 not built");
+        return launch_umma<4, 64, 1, 0, 1>(h, d, a.n, st);
+    }
+    SMG_CHECK(a.cout % 128 == 0, SMG_ERR_UNSUPPORTED, "conv_umma: cout %d unsupported", a.cout);
+    if (a.pool) return launch_umma<4, 128, 1, 1, 1>(h, d, a.n, st);
+    return launch_umma<4, 128, 1, 0, 1>(h, d, a.n, st);
+}
+
 int launch_conv_umma(smg_handle* h, const ConvArgs& a, int precision, cudaStream_t st) {
     SMG_CHECK(a.w != nullptr || a.w_umma != nullptr, SMG_ERR_STATE, "conv_umma: no weights");
     UmmaDev d;
@@ -686,6 +742,7 @@ int launch_conv_umma(smg_handle* h, const ConvArgs& a, int precision, cudaStream
     d.async_producer = 0;
     if (precision == SMG_PREC_TF32) return dispatch<4>(h, a, d, st);
     if (precision == SMG_PREC_BF16) return dispatch<2>(h, a, d, st);
+    if (precision == SMG_PREC_FP32) return dispatch_split(h, a, d, st);
     set_error("conv_umma: precision %d is not a tensor-core mode", precision);
     return SMG_ERR_INVALID;
 }

@@ -116,6 +116,17 @@ __global__ void pack_umma_t1_kernel(const float* __restrict__ w, float* __restri
     }
 }
 
+// w_tf32 stage images -> [hi image][lo image] per stage (3xTF32 operands of the fp32 mode)
+__global__ void pack_split_kernel(const float* __restrict__ tf32, float* __restrict__ out, int total, int stage_elems) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int stage = i / stage_elems, within = i - stage * stage_elems;
+        const float v = tf32[i];
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        out[(size_t)(2 * stage) * stage_elems + within] = hi;
+        out[(size_t)(2 * stage + 1) * stage_elems + within] = v - hi;
+    }
+}
+
 // ---- batched variant: one launch packs every convolution of a trunk (blockIdx.y = job) ----
 __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
     const PackJob j = jobs[blockIdx.y];
@@ -157,7 +168,7 @@ __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
         }
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
-            if (!(mask & (pass == 0 ? SMG_PACK_TF32 : SMG_PACK_BF16))) continue;
+            if (!(mask & (pass == 0 ? (SMG_PACK_TF32 | SMG_PACK_FFMA) : SMG_PACK_BF16))) continue;
             const int EPC = pass == 0 ? 4 : 8, CH = 32 / EPC;
             int r = i;
             const int e = r % EPC; r /= EPC;
@@ -170,6 +181,14 @@ __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
             const float v = j.src[((size_t)co * j.k_total + j.k_off + ci) * j.taps + tap];
             if (pass == 0) j.tf32[i] = v;
             else j.bf16[i] = __float2bfloat16_rn(v);
+            if (pass == 0 && (mask & SMG_PACK_FFMA) && j.split != nullptr) {
+                // the same stage sequence with each stage (32 channels x bn rows) stored as [hi image][lo image]
+                const int stage_elems = 32 * j.bn;
+                const int stage = i / stage_elems, within = i - stage * stage_elems;
+                const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                j.split[(size_t)(2 * stage) * stage_elems + within] = hi;
+                j.split[(size_t)(2 * stage + 1) * stage_elems + within] = v - hi;
+            }
         }
     }
 }
@@ -184,6 +203,7 @@ PackJob make_pack_job(const float* w_oihw, const ConvW& cw, int k_offset, int k_
     j.src = w_oihw; j.ffma = cw.w_ffma; j.tf32 = reinterpret_cast<float*>(cw.w_tf32);
     j.tf32_t = reinterpret_cast<float*>(cw.w_tf32_t);
     j.dgrad_tf32 = reinterpret_cast<float*>(cw.w_dgrad_tf32);
+    j.split = reinterpret_cast<float*>(cw.w_split);
     j.bf16 = reinterpret_cast<__nv_bfloat16*>(cw.w_bf16); j.dgrad = cw.w_dgrad;
     j.cin = cw.cin; j.cout = cw.cout; j.taps = cw.taps; j.k_off = k_offset; j.k_total = k_total;
     j.bn = cw.taps == 9 ? 32 : (cw.cout < 128 ? cw.cout : 128);
@@ -229,6 +249,11 @@ int pack_conv_weights(smg_handle* h, const float* w_oihw, ConvW& cw, int k_offse
     if (cw.taps == 9 && cw.w_tf32_t != nullptr) {
         pack_umma_t_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_tf32_t), cw.cout, cw.cin, k_offset,
                                                        k_total);
+        h->launches++;
+    }
+    if (cw.w_split != nullptr) {
+        pack_split_kernel<<<blocks, threads, 0, st>>>(reinterpret_cast<const float*>(cw.w_tf32), reinterpret_cast<float*>(cw.w_split),
+                                                      total, 32 * bn);
         h->launches++;
     }
     if (cw.w_dgrad_tf32 != nullptr) {

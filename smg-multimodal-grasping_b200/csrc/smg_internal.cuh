@@ -78,6 +78,9 @@ struct ConvW {
     // 1x1: [ntile over cin/128][kgroup over cout/32][chunk][n][4], value w[kgroup*32 + ..][ntile*128 + n];
     // 3x3: [kgroup over cout/32][flipped tap][chunk][n = cin][4]
     uint8_t* w_dgrad_tf32 = nullptr;
+    // fp32 mode on the tensor cores ("3xTF32"): the w_tf32 stage sequence with every stage stored as [hi image][lo image]
+    // (hi = weight with its 13 low mantissa bits cleared, lo = weight - hi)
+    uint8_t* w_split = nullptr;
     int cin = 0, cout = 0, taps = 1;
 };
 
@@ -88,6 +91,7 @@ struct PackJob {
     float* tf32;
     float* tf32_t;
     float* dgrad_tf32;
+    float* split;
     __nv_bfloat16* bf16;
     float* dgrad;
     int cin, cout, taps, k_off, k_total, bn;
@@ -171,6 +175,7 @@ struct smg_handle {
                                    // identical input channels (stem_umma.cu), 64 = 3x3 with the weights resident in tensor memory
                                    // (conv3_wt.cu), 128 = persistent 1x1 with swapped operand roles (conv1_t.cu); a cleared bit
                                    // routes the layer to the register-producer kernel of conv_umma.cu
+    bool fp32_tc = true;           // fp32 mode: convolutions on the tensor cores with hi/lo split operands (SMG_FP32_TC=0: CUDA cores)
     int wgrad_cta_cap = 0;         // > 0 while the weight gradients share the GPU with the dgrad chain: max CTAs per wgrad launch
     int force_async = 0;           // tuning: -1 auto by grid size, 0 register producers (default: measured fastest), 1 cp.async producers
     std::vector<const void*> smem_opt_in;   // kernels whose >48 KB dynamic shared memory opt-in was set on this handle's device

@@ -74,6 +74,26 @@ def test_conv_matches_torch(eng, precision, case):
     assert float((q_got - q_ref).abs().max() / q_ref.abs().max()) <= 1e-4
 
 
+@pytest.mark.parametrize("case", [(2, 40, 96, 256, 128, 1, 0), (1, 32, 256, 256, 128, 1, 1), (2, 80, 128, 128, 32, 3, 0)],
+                         ids=lambda c: "n%d_h%d_cin%d_cs%d_cout%d_k%d_pool%d" % c)
+def test_fp32_mode_cuda_core_kernel_still_matches(case, monkeypatch):
+    """fp32 mode runs on the tensor cores with hi/lo split tf32 operands by default (covered by test_conv_matches_torch);
+    SMG_FP32_TC=0 selects the CUDA-core FFMA kernel, which stays as the independent check of the same contract."""
+    from smg_b200 import engine
+    monkeypatch.setenv("SMG_FP32_TC", "0")
+    eng = engine.Engine(0, 4, 640, "fp32")
+    n, hin, cin, cstride, cout, k, pool = case
+    g = torch.Generator(device="cuda").manual_seed(hash(case) % 1000)
+    x = torch.randn((n, hin, hin, cstride), generator=g, device="cuda")
+    scale = torch.rand((n, cin), generator=g, device="cuda") + 0.5
+    shift = torch.randn((n, cin), generator=g, device="cuda") * 0.3
+    w = torch.randn((cout, cin, k, k), generator=g, device="cuda") / (cin * k * k) ** 0.5
+    out, _ = eng.debug_conv("fp32", x, cin, scale, shift, True, pool, w)
+    ref = reference(x, cin, scale, shift, True, pool, w)
+    assert float((out - ref).abs().max() / ref.abs().max()) <= TOL["fp32"]
+    del eng
+
+
 @pytest.mark.parametrize("tma_mask", [0, 64, 128])
 @pytest.mark.parametrize("case", [(5, 80, 224, 256, 128, 1, 0), (2, 40, 96, 256, 128, 1, 0), (4, 80, 128, 128, 32, 3, 0),
                                   (1, 160, 128, 128, 32, 3, 0), (3, 20, 128, 128, 32, 3, 0), (2, 20, 1024, 1024, 128, 1, 0)],
