@@ -52,7 +52,7 @@ int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     ProfScope ps(h, st, a.taps == 9 ? 2 : 1, 2.0 * px * a.cout * a.cin * a.taps, bytes);
     if (h->precision == SMG_PREC_FP32) {
         // fp32 mode: tensor cores with hi/lo split tf32 operands (error ~1e-6, like fp32 FMA chains); CUDA cores on request
-        if (h->fp32_tc) {
+        if (h->fp32_tc && !h->fp32_exact_pass) {
             const int status = launch_conv_umma(h, a, SMG_PREC_FP32, st);
             if (status != SMG_ERR_UNSUPPORTED) return status;
         }
@@ -104,6 +104,10 @@ int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cudaStrea
                   T.packed, h->precision, need);
     }
     SMG_CUDA(cudaMemsetAsync(h->stats, 0, h->stats_bytes, st));
+    // fp32 mode exists for parity: the grad-enabled pass keeps plain fp32 FMA chains (3e-6 of the reference), because the
+    // gradients of this network amplify forward noise through its ReLU kinks (tests/test_gpu_backward.py); the volatile
+    // passes use the tensor cores with split operands (3e-5, inside the 1e-4 bar)
+    h->fp32_exact_pass = save_bott;
     const size_t in_img = (size_t)in_channels * h->H * h->H;
     const size_t c0_img = (size_t)(h->H / 2) * (h->H / 2) * 64;
     int layer_base = 0;
@@ -176,6 +180,7 @@ int trunk_forward(smg_handle* h, int trunk_id, int n, int in_channels, cudaStrea
         layer_base += kBlockLayers[b];
     }
     h->last_n = n;
+    h->fp32_exact_pass = false;
     return SMG_OK;
 }
 

@@ -45,6 +45,9 @@ struct SmemPlan {
 };
 
 
+// fp32 bits rounded to the nearest tf32 value (10 explicit mantissa bits): the hi part of a split operand; |x - hi| <= 2^-12 |x|
+__device__ __forceinline__ uint32_t tf32_rn(uint32_t bits) { return (bits + 0x1000u) & 0xFFFFE000u; }
+
 template <int ELT, int BN, int TAPS, int POOL, int SPLIT = 0>
 __global__ void __launch_bounds__(448, 2)
 conv_umma_kernel(UmmaDev a) {
@@ -253,7 +256,7 @@ conv_umma_kernel(UmmaDev a) {
                         pk = make_uint4(__float_as_uint(v[i][0]), __float_as_uint(v[i][1]), __float_as_uint(v[i][2]),
                                         __float_as_uint(v[i][3]));
                         if (SPLIT) {
-                            const uint4 hi = make_uint4(pk.x & 0xFFFFE000u, pk.y & 0xFFFFE000u, pk.z & 0xFFFFE000u, pk.w & 0xFFFFE000u);
+                            const uint4 hi = make_uint4(tf32_rn(pk.x), tf32_rn(pk.y), tf32_rn(pk.z), tf32_rn(pk.w));
                             const uint4 lo = make_uint4(__float_as_uint(v[i][0] - __uint_as_float(hi.x)), __float_as_uint(v[i][1] - __uint_as_float(hi.y)),
                                                         __float_as_uint(v[i][2] - __uint_as_float(hi.z)), __float_as_uint(v[i][3] - __uint_as_float(hi.w)));
                             *reinterpret_cast<uint4*>(dst + P::A_HALF + (r0 + i * RSTEP) * 16) = lo;
@@ -375,7 +378,7 @@ conv_umma_kernel(UmmaDev a) {
                                 pk = make_uint4(__float_as_uint(t[0]), __float_as_uint(t[1]), __float_as_uint(t[2]),
                                                 __float_as_uint(t[3]));
                                 if (SPLIT) {
-                                    const uint4 hi = make_uint4(pk.x & 0xFFFFE000u, pk.y & 0xFFFFE000u, pk.z & 0xFFFFE000u, pk.w & 0xFFFFE000u);
+                                    const uint4 hi = make_uint4(tf32_rn(pk.x), tf32_rn(pk.y), tf32_rn(pk.z), tf32_rn(pk.w));
                                     const uint4 lo = make_uint4(__float_as_uint(t[0] - __uint_as_float(hi.x)), __float_as_uint(t[1] - __uint_as_float(hi.y)),
                                                                 __float_as_uint(t[2] - __uint_as_float(hi.z)), __float_as_uint(t[3] - __uint_as_float(hi.w)));
                                     *reinterpret_cast<uint4*>(dst + P::A_HALF + q * 16) = lo;

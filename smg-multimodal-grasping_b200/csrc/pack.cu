@@ -121,7 +121,7 @@ __global__ void pack_split_kernel(const float* __restrict__ tf32, float* __restr
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int stage = i / stage_elems, within = i - stage * stage_elems;
         const float v = tf32[i];
-        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);   // nearest tf32
         out[(size_t)(2 * stage) * stage_elems + within] = hi;
         out[(size_t)(2 * stage + 1) * stage_elems + within] = v - hi;
     }
@@ -185,7 +185,7 @@ __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
                 // the same stage sequence with each stage (32 channels x bn rows) stored as [hi image][lo image]
                 const int stage_elems = 32 * j.bn;
                 const int stage = i / stage_elems, within = i - stage * stage_elems;
-                const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);   // nearest tf32
                 j.split[(size_t)(2 * stage) * stage_elems + within] = hi;
                 j.split[(size_t)(2 * stage + 1) * stage_elems + within] = v - hi;
             }
