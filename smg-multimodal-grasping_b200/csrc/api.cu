@@ -225,6 +225,9 @@ int heads_forward(smg_handle* h, int trunk_id, int head_id, int n_rot, int n_mas
     const BlockGeom& g = h->geom[3];
     SMG_CHECK(g.hw == kHeadK, SMG_ERR_INVALID, "heads need H=640 (block-4 spatial %d != %d)", g.hw, kHeadK);
     SMG_TRY(head_partials(h, trunk_id, head_id, n_rot, n_masks, st, groups));
+    const double pairs = (double)groups * n_rot * n_masks;
+    // head tail per (mask, rotation) pair: two [400][64] partial products read three times (mean, variance, dot), 25 600 MACs
+    ProfScope ps(h, st, 3, pairs * 2.0 * 400 * 64 * Hd.n_out, pairs * 2.0 * 400 * 64 * 4);
     return launch_head_tail(h, h->head_p, h->head_p + (size_t)groups * n_rot * g.hw * g.hw * kHeadMid, n_rot, n_masks, Hd, dev_q, st,
                             groups);
 }
@@ -679,12 +682,21 @@ static int qforward_maps_body(smg_handle* h, int trunk_id, int head_id, const do
                               int groups = 1) {
     // Trainer.forward feeds three identical channels (code/trainer.py:178-181): keep ONE plane per sample and use
     // the channel-folded conv0 weights (K = 49 instead of 147)
-    const size_t img = (size_t)h->H * h->H;
-    SMG_TRY(launch_prep(h, dev_scene_hm, groups, hm_size, mean, stddev, h->scene_tmp, 1, st));
-    for (int g = 0; g < groups; ++g)
-        SMG_TRY(launch_rotate(h, h->scene_tmp + (size_t)g * img, host_rot_idx, n_rot, num_rotations,
-                              h->input + (size_t)g * n_rot * img, 1, st));
-    SMG_TRY(launch_prep(h, dev_mask_hms, groups * n_masks, hm_size, mean, stddev, h->input + (size_t)groups * n_rot * img, 1, st));
+    {
+        const double n_px = (double)groups * (n_rot + n_masks) * h->H * h->H;
+        ProfScope ps(h, st, 3, 0.0, 4.0 * n_px);   // K1: one float written per network-input pixel (the heightmaps stay in L2)
+        if (n_rot <= 32) {
+            SMG_TRY(launch_prep_rotate(h, dev_scene_hm, groups, host_rot_idx, n_rot, num_rotations, dev_mask_hms, groups * n_masks,
+                                       hm_size, mean, stddev, h->input, st));
+        } else {
+            const size_t img = (size_t)h->H * h->H;
+            SMG_TRY(launch_prep(h, dev_scene_hm, groups, hm_size, mean, stddev, h->scene_tmp, 1, st));
+            for (int g = 0; g < groups; ++g)
+                SMG_TRY(launch_rotate(h, h->scene_tmp + (size_t)g * img, host_rot_idx, n_rot, num_rotations,
+                                      h->input + (size_t)g * n_rot * img, 1, st));
+            SMG_TRY(launch_prep(h, dev_mask_hms, groups * n_masks, hm_size, mean, stddev, h->input + (size_t)groups * n_rot * img, 1, st));
+        }
+    }
     return qforward_common(h, trunk_id, head_id, n_masks, n_rot, 1, dev_q, dev_bn_mean, dev_bn_var, st, groups);
 }
 
@@ -1188,6 +1200,7 @@ int smg_adam_step(smg_handle* h, float* const* dev_params, const float* const* d
 int smg_argmax(smg_handle* h, const float* dev_q, int n, float* dev_out, int32_t* dev_out_idx, void* stream) {
     SMG_CHECK(h && dev_q && dev_out && dev_out_idx, SMG_ERR_INVALID, "smg_argmax: NULL argument");
     DeviceGuard guard(h->device);
+    ProfScope ps(h, (cudaStream_t)stream, 3, 0.0, 4.0 * n);
     return launch_argmax(h, dev_q, n, dev_out, dev_out_idx, (cudaStream_t)stream);
 }
 

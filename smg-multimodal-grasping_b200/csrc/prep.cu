@@ -67,6 +67,44 @@ __global__ void rotate_kernel(const float* __restrict__ in, int n_rot, RotTheta 
     }
 }
 
+// K1 for the heightmap entry points, ONE launch for a whole pass: sample z < n_scene_samples is scene (z / n_rot) at rotation
+// (z % n_rot), the remaining samples are the masked heightmaps unrotated.  Fuses Trainer.forward's zoom x2 + pad +
+// (x - mean)/std (code/trainer.py:165-185) with the nets' nearest rotation (code/models.py:371-382): the value of rotated pixel
+// (x, y) is the normalised heightmap value at its source pixel, nothing in between is materialised.  One plane per sample
+// (the three channels the reference feeds are identical), four pixels per thread, one 16-byte store each.
+__global__ void __launch_bounds__(256)
+prep_rotate_kernel(const double* __restrict__ scene_hm, const double* __restrict__ mask_hm, int n_rot, int n_scene_samples,
+                   int n_samples, RotTheta th, int hs, double mean, double stddev, float* __restrict__ out, int H) {
+    const int pad = (H - 2 * hs) / 2;
+    const size_t quads = (size_t)H * H / 4;
+    const size_t total = (size_t)n_samples * quads;
+    const float pad_val = (float)((0.0 - mean) / stddev);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int z = (int)(i / quads);
+        const int rem = (int)(i - (size_t)z * quads) * 4;
+        const int y = rem / H, x0 = rem - y * H;
+        const bool is_scene = z < n_scene_samples;
+        const double* hm = is_scene ? scene_hm + (size_t)(z / n_rot) * hs * hs : mask_hm + (size_t)(z - n_scene_samples) * hs * hs;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int sy = y, sx = x0 + j;
+            bool inside = true;
+            if (is_scene) {
+                const int src = rotate_src_index(x0 + j, y, H, th.t[z % n_rot]);
+                inside = src >= 0;
+                sy = src / H;
+                sx = src - sy * H;
+            }
+            const int yy = sy - pad, xx = sx - pad;
+            float f = pad_val;
+            if (yy >= 0 && yy < 2 * hs && xx >= 0 && xx < 2 * hs) f = (float)((__ldg(hm + (size_t)(yy >> 1) * hs + (xx >> 1)) - mean) / stddev);
+            v[j] = inside ? f : 0.f;   // grid_sample pads with zeros OUTSIDE the (already normalised) image
+        }
+        *reinterpret_cast<float4*>(out + (size_t)z * H * H + rem) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 __global__ void rotate_index_kernel(RotTheta th, int32_t* __restrict__ out, int H) {
     const int total = H * H;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -115,6 +153,22 @@ int launch_rotate(smg_handle* h, const float* in, const int* host_rot, int n_rot
         h->launches++;
         SMG_CUDA(cudaGetLastError());
     }
+    return SMG_OK;
+}
+
+int launch_prep_rotate(smg_handle* h, const double* scene_hm, int groups, const int* host_rot, int n_rot, int num_rot,
+                       const double* mask_hm, int n_mask_samples, int hm_size, double mean, double stddev, float* out, cudaStream_t st) {
+    SMG_CHECK(2 * hm_size <= h->H && h->H % 4 == 0 && n_rot >= 1 && n_rot <= 32, SMG_ERR_INVALID,
+              "prep_rotate: hm_size %d / H %d / %d rotations", hm_size, h->H, n_rot);
+    RotTheta th;
+    for (int i = 0; i < n_rot; ++i) rotation_theta(host_rot[i], num_rot, th.t[i]);
+    const int n_samples = groups * n_rot + n_mask_samples;
+    const size_t total = (size_t)n_samples * h->H * h->H / 4;
+    const int blocks = (int)((total + 255) / 256);
+    prep_rotate_kernel<<<blocks < h->num_sms * 16 ? blocks : h->num_sms * 16, 256, 0, st>>>(
+        scene_hm, mask_hm, n_rot, groups * n_rot, n_samples, th, hm_size, mean, stddev, out, h->H);
+    h->launches++;
+    SMG_CUDA(cudaGetLastError());
     return SMG_OK;
 }
 

@@ -318,6 +318,9 @@ int launch_prep(smg_handle* h, const double* hm, int n, int hm_size, double mean
 int launch_rotate(smg_handle* h, const float* in, const int* host_rot, int n_rot, int num_rot, float* out,
                   int channels, cudaStream_t st);
 int launch_rotate_index_map(smg_handle* h, int rot, int num_rot, int32_t* out, cudaStream_t st);
+// the whole input stage of a heightmap pass in one launch: [groups x n_rot] rotated scenes then n_mask_samples masked scenes
+int launch_prep_rotate(smg_handle* h, const double* scene_hm, int groups, const int* host_rot, int n_rot, int num_rot,
+                       const double* mask_hm, int n_mask_samples, int hm_size, double mean, double stddev, float* out, cudaStream_t st);
 int launch_resize_masks(smg_handle* h, const float* in, int n, int hin, int hout, float* out, cudaStream_t st);
 // stem
 int launch_conv0(smg_handle* h, const float* in, int cin, int n, const float* w, float* out, double* stats,

@@ -231,18 +231,25 @@ class Engine:
                                          int(p_mask.shape[0]), q.data_ptr(), self._stream()))
         return q
 
-    def qforward_maps_batch(self, style, scene_hms, mask_hms, mean, std, rot_idx, num_rotations):
+    def qforward_maps_batch(self, style, scene_hms, mask_hms, mean, std, rot_idx, num_rotations, want_bn_stats=False):
         """G independent units in one batch: scene_hms [G,hs,hs], mask_hms [G,M,hs,hs] float64 on the device
-        -> Q [G, M, n_rot, n_out].  Same per-unit results as qforward_maps (BatchNorm is per sample)."""
+        -> Q [G, M, n_rot, n_out].  Same per-unit results as qforward_maps (BatchNorm is per sample).  With want_bn_stats
+        also the per-sample batch statistics [G*(n_rot+M), C] (all rotated scenes first, then all masked scenes)."""
         tid, hid = STYLE_ROUTE[int(style)]
         G, M, hs = mask_hms.shape[0], mask_hms.shape[1], mask_hms.shape[-1]
         n_rot = len(rot_idx)
         rot = (ctypes.c_int * n_rot)(*[int(r) for r in rot_idx])
         q = torch.empty((G, M, n_rot, self.n_out), dtype=torch.float32, device=self.device)
+        mean_t = var_t = None
+        pm = pv = None
+        if want_bn_stats:
+            mean_t = torch.empty((G * (n_rot + M), TRUNK_BN_CHANNELS), dtype=torch.float32, device=self.device)
+            var_t = torch.empty_like(mean_t)
+            pm, pv = mean_t.data_ptr(), var_t.data_ptr()
         _lib.check(self.lib.smg_qforward_maps_batch(self.h, tid, hid, scene_hms.data_ptr(), mask_hms.data_ptr(), G, M, hs,
                                                     float(mean), float(std), rot, n_rot, int(num_rotations), q.data_ptr(),
-                                                    None, None, self._stream()))
-        return q
+                                                    pm, pv, self._stream()))
+        return (q, mean_t, var_t) if want_bn_stats else q
 
     # ------------------------------------------------------------------ training (code/trainer.py:278-384)
     def qforward_train(self, style, scene, mask, rot, num_rotations):

@@ -132,7 +132,9 @@ def decision_local_partials(trainer, ctx, rank):
     max_local = max(hi - lo for _, _, shares in plan.values() for lo, hi in shares)
     eng = model._engine(max(max_local, 18))
     dev = eng.device
+    # the scene and the K object masks cross PCIe once; every masked heightmap (code/main.py:160,186) is formed on the device
     scene_t = torch.from_numpy(np.ascontiguousarray(scene)).to(dev, non_blocking=True)
+    masks_t = torch.from_numpy(np.ascontiguousarray(masks)).to(dev, non_blocking=True)
     send = torch.zeros((cap, 400, 64), dtype=torch.float32, device=dev)
     off = 0
     for style, (n_rot, n_masks, shares) in plan.items():
@@ -142,11 +144,13 @@ def decision_local_partials(trainer, ctx, rank):
             eng.sync_weights(model, style=style)
             rots = [i for i in range(lo, min(hi, n_rot))]
             mids = [i - n_rot for i in range(max(lo, n_rot), hi)]
-            if style == 2:
-                mh = np.stack([scene * (masks[pairs[i][0]] + masks[pairs[i][1]]) for i in mids]) if mids else None
-            else:
-                mh = np.stack([scene * masks[i] for i in mids]) if mids else None
-            mh_t = torch.from_numpy(np.ascontiguousarray(mh)).to(dev, non_blocking=True) if mids else None
+            mh_t = None
+            if mids and style == 2:
+                gi = torch.tensor([pairs[i][0] for i in mids], device=dev)
+                si = torch.tensor([pairs[i][1] for i in mids], device=dev)
+                mh_t = (scene_t[None] * (masks_t[gi] + masks_t[si])).contiguous()
+            elif mids:
+                mh_t = (scene_t[None] * masks_t[mids[0]:mids[-1] + 1]).contiguous()
             nrot_div = model.gnum_rotations if style != 1 else model.snum_rotations
             send[off:off + (hi - lo)] = eng.qpartials(style, scene_t, rots, nrot_div, mh_t, trainer.image_mean, trainer.image_std)
         off += width

@@ -156,7 +156,8 @@ class Trainer(object):
         """G independent (scene, masked scene[s]) units in ONE pass: depth_heightmaps [G,224,224], m_depth_heightmaps
         [G,224,224] or [G,M,224,224] -> numpy Q [G, M, n_rot].  Each unit gets exactly the result `forward` would give
         it (BatchNorm statistics are per sample); batching only makes the late layers of the trunk more efficient.
-        The BatchNorm running-statistics side effect is not reproduced on this path."""
+        With `model.update_running_stats` the BatchNorm running statistics advance as if the G x M units had been evaluated one
+        after the other by `forward` (unit by unit, rotation by rotation: trunk(scene_r) then trunk(mask))."""
         model = self.model_target if (is_target and self.method == 'reinforcement') else self.model
         rots, nrot = self._rotations(model, style, specific_rotation)
         scenes = np.ascontiguousarray(np.asarray(depth_heightmaps, dtype=np.float64))
@@ -167,7 +168,21 @@ class Trainer(object):
         eng = model._engine(G * (len(rots) + M), style)
         s_t = torch.from_numpy(scenes).to(eng.device, non_blocking=True)
         m_t = torch.from_numpy(masks).to(eng.device, non_blocking=True)
-        q = eng.qforward_maps_batch(style, s_t, m_t, self.image_mean, self.image_std, rots, nrot)
+        if model.update_running_stats:
+            q, mean, var = eng.qforward_maps_batch(style, s_t, m_t, self.image_mean, self.image_std, rots, nrot, want_bn_stats=True)
+            nR = len(rots)
+            order, pairs = [], []
+            for g in range(G):
+                for k in range(M):
+                    for i in range(nR):
+                        order += [g * nR + i, G * nR + g * M + k]
+                        pairs.append((g * nR + i, G * nR + g * M + k))
+            trunk = getattr(model, _engine.TRUNK_ATTRS[_engine.STYLE_ROUTE[style][0]])
+            head = getattr(model, _engine.HEAD_ATTRS[_engine.STYLE_ROUTE[style][1]])
+            model._apply_running_stats(trunk, mean, var, order)
+            model._apply_head_running_stats(head, trunk, var, pairs, eng.head_bn_stats(len(pairs)))
+        else:
+            q = eng.qforward_maps_batch(style, s_t, m_t, self.image_mean, self.image_std, rots, nrot)
         if self.method == 'reactive':
             return torch.softmax(q[:, :, :1, :], dim=3)[..., 0].cpu().numpy()
         return q[..., 0].double().cpu().numpy()

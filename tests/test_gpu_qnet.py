@@ -180,6 +180,36 @@ def test_batched_units_equal_single_calls(scene_inputs):
     assert np.abs(batch2 - batch).max() <= 1e-5
 
 
+def test_batched_units_running_stats_equal_serial_calls(scene_inputs):
+    """The BatchNorm running-statistics side effect of Trainer.forward_batch == the same units evaluated one after the other
+    by Trainer.forward (what the reference's step loop does, one train-mode forward per call)."""
+    import smg_b200.synth as synth
+    from smg_b200.trainer import Trainer
+    scenes, masks = [], []
+    for seed in (1, 2):
+        sc = synth.make_scene(seed, num_objects=4, cluttered=False)
+        scenes.append(sc["scene"])
+        masks.append(synth.masked_scene(sc["scene"], sc["masks"], [seed % 4]))
+    states = []
+    for batched in (True, False):
+        torch.manual_seed(0)
+        tr = Trainer("reinforcement", 0.5, False, None, False, precision="tf32")
+        tr.model.gnum_rotations = tr.model.snum_rotations = 4
+        if batched:
+            tr.forward_batch(np.stack(scenes), np.stack(masks), style=0)
+        else:
+            for g in range(2):
+                tr.forward(scenes[g], masks[g], 0, True, False)
+        states.append({k: v.clone() for k, v in tr.model.state_dict().items() if "running" in k or "num_batches" in k})
+    a, b = states
+    for k in ("grasp_depth_trunk.features.norm0.running_mean", "grasp_depth_trunk.features.denseblock4.denselayer16.norm2.running_var",
+              "grasp_depth_trunk.features.norm5.running_var", "graspnet_val.grasp-val-norm0.running_var",
+              "graspnet_val.grasp-val-norm1.running_mean", "grasp_depth_trunk.features.norm0.num_batches_tracked",
+              "graspnet_val.grasp-val-norm1.num_batches_tracked"):
+        assert torch.allclose(a[k].double(), b[k].double(), rtol=1e-4, atol=1e-6), k
+    assert int(a["grasp_depth_trunk.features.norm0.num_batches_tracked"]) == 16      # 2 units x 4 rotations x (scene, mask)
+
+
 def test_reactive_logits_vs_reference(inputs, golden):
     import smg_b200.models as models
     torch.manual_seed(0)
