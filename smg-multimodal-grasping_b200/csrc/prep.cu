@@ -67,38 +67,52 @@ __global__ void rotate_kernel(const float* __restrict__ in, int n_rot, RotTheta 
     }
 }
 
-// K1 for the heightmap entry points, ONE launch for a whole pass: sample z < n_scene_samples is scene (z / n_rot) at rotation
-// (z % n_rot), the remaining samples are the masked heightmaps unrotated.  Fuses Trainer.forward's zoom x2 + pad +
-// (x - mean)/std (code/trainer.py:165-185) with the nets' nearest rotation (code/models.py:371-382): the value of rotated pixel
-// (x, y) is the normalised heightmap value at its source pixel, nothing in between is materialised.  One plane per sample
-// (the three channels the reference feeds are identical), four pixels per thread, one 16-byte store each.
+// K1 for the heightmap entry points: two launches for a whole pass, whatever the number of units.
+//   normalize_hm_kernel  (x - mean)/std of every 224x224 float64 heightmap -> float32, computed ONCE per heightmap pixel
+//                        (code/trainer.py:176-188: float64 arithmetic, then the cast) - 50 k pixels per map, L2-resident;
+//   prep_rotate_kernel   sample z < n_scene_samples is scene (z / n_rot) at rotation (z % n_rot), the remaining samples are
+//                        the masked heightmaps unrotated: the value of network-input pixel (x, y) is the normalised
+//                        heightmap value at the source pixel of the zoom x2 + pad (code/trainer.py:165-173) composed with
+//                        the nearest rotation (code/models.py:371-382); the padded / rotated 640x640 image in between is
+//                        never materialised.  One plane per sample (the three channels the reference feeds are
+//                        identical), four pixels per thread, one 16-byte store each: HBM-write bound.
+__global__ void normalize_hm_kernel(const double* __restrict__ scene_hm, int n_scene, const double* __restrict__ mask_hm,
+                                    int n_mask, int px, double mean, double stddev, float* __restrict__ out) {
+    const size_t total = (size_t)(n_scene + n_mask) * px;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t m = i / px;
+        const double v = m < (size_t)n_scene ? scene_hm[i] : mask_hm[i - (size_t)n_scene * px];
+        out[i] = (float)((v - mean) / stddev);
+    }
+}
+
 __global__ void __launch_bounds__(256)
-prep_rotate_kernel(const double* __restrict__ scene_hm, const double* __restrict__ mask_hm, int n_rot, int n_scene_samples,
-                   int n_samples, RotTheta th, int hs, double mean, double stddev, float* __restrict__ out, int H) {
+prep_rotate_kernel(const float* __restrict__ norm_hm, int groups, int n_rot, int n_scene_samples, int n_samples, RotTheta th,
+                   int hs, float pad_val, float* __restrict__ out, int H) {
     const int pad = (H - 2 * hs) / 2;
     const size_t quads = (size_t)H * H / 4;
     const size_t total = (size_t)n_samples * quads;
-    const float pad_val = (float)((0.0 - mean) / stddev);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int z = (int)(i / quads);
         const int rem = (int)(i - (size_t)z * quads) * 4;
         const int y = rem / H, x0 = rem - y * H;
         const bool is_scene = z < n_scene_samples;
-        const double* hm = is_scene ? scene_hm + (size_t)(z / n_rot) * hs * hs : mask_hm + (size_t)(z - n_scene_samples) * hs * hs;
+        const float* hm = norm_hm + (size_t)(is_scene ? z / n_rot : groups + z - n_scene_samples) * hs * hs;
+        const float* t = th.t[is_scene ? z % n_rot : 0];
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int sy = y, sx = x0 + j;
             bool inside = true;
             if (is_scene) {
-                const int src = rotate_src_index(x0 + j, y, H, th.t[z % n_rot]);
+                const int src = rotate_src_index(x0 + j, y, H, t);
                 inside = src >= 0;
                 sy = src / H;
                 sx = src - sy * H;
             }
             const int yy = sy - pad, xx = sx - pad;
-            float f = pad_val;
-            if (yy >= 0 && yy < 2 * hs && xx >= 0 && xx < 2 * hs) f = (float)((__ldg(hm + (size_t)(yy >> 1) * hs + (xx >> 1)) - mean) / stddev);
+            const bool in_hm = inside && yy >= 0 && yy < 2 * hs && xx >= 0 && xx < 2 * hs;
+            const float f = in_hm ? __ldg(hm + (size_t)(yy >> 1) * hs + (xx >> 1)) : pad_val;
             v[j] = inside ? f : 0.f;   // grid_sample pads with zeros OUTSIDE the (already normalised) image
         }
         *reinterpret_cast<float4*>(out + (size_t)z * H * H + rem) = make_float4(v[0], v[1], v[2], v[3]);
@@ -160,13 +174,24 @@ int launch_prep_rotate(smg_handle* h, const double* scene_hm, int groups, const 
                        const double* mask_hm, int n_mask_samples, int hm_size, double mean, double stddev, float* out, cudaStream_t st) {
     SMG_CHECK(2 * hm_size <= h->H && h->H % 4 == 0 && n_rot >= 1 && n_rot <= 32, SMG_ERR_INVALID,
               "prep_rotate: hm_size %d / H %d / %d rotations", hm_size, h->H, n_rot);
+    SMG_CHECK((size_t)(groups + n_mask_samples) * hm_size * hm_size <= (size_t)(h->max_samples > 3 ? h->max_samples : 3) * h->H * h->H,
+              SMG_ERR_STATE, "prep_rotate: %d heightmaps do not fit the staging buffer", groups + n_mask_samples);
     RotTheta th;
     for (int i = 0; i < n_rot; ++i) rotation_theta(host_rot[i], num_rot, th.t[i]);
+    const int px = hm_size * hm_size;
+    float* norm = h->scene_tmp;   // [groups + n_mask_samples][hm_size^2] normalised heightmaps
+    {
+        const size_t total = (size_t)(groups + n_mask_samples) * px;
+        const int blocks = (int)((total + 255) / 256);
+        normalize_hm_kernel<<<blocks < h->num_sms * 8 ? blocks : h->num_sms * 8, 256, 0, st>>>(scene_hm, groups, mask_hm, n_mask_samples,
+                                                                                            px, mean, stddev, norm);
+        h->launches++;
+    }
     const int n_samples = groups * n_rot + n_mask_samples;
     const size_t total = (size_t)n_samples * h->H * h->H / 4;
     const int blocks = (int)((total + 255) / 256);
     prep_rotate_kernel<<<blocks < h->num_sms * 16 ? blocks : h->num_sms * 16, 256, 0, st>>>(
-        scene_hm, mask_hm, n_rot, groups * n_rot, n_samples, th, hm_size, mean, stddev, out, h->H);
+        norm, groups, n_rot, groups * n_rot, n_samples, th, hm_size, (float)((0.0 - mean) / stddev), out, h->H);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;
