@@ -480,6 +480,7 @@ int smg_create(int device, int max_samples, int H, smg_handle** out) {
     if (const char* e = getenv("SMG_ASYNC")) h->force_async = atoi(e);
     if (const char* e = getenv("SMG_TMA")) h->use_tma = atoi(e);
     if (const char* e = getenv("SMG_FP32_TC")) h->fp32_tc = atoi(e) != 0;
+    if (const char* e = getenv("SMG_PDL")) h->use_pdl = atoi(e) != 0;
     *out = h;
     return SMG_OK;
 }

@@ -90,35 +90,46 @@ bn_bwd_kernel(BnBwd a, int S, float* __restrict__ dgamma, float* __restrict__ db
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     if (active) {
         float* dst_s = APPLY ? a.dst + (size_t)s * npix * a.dst_cstride + 4 * q : nullptr;
-        for (int p = p0 + pl; p < p1; p += PL) {
-            const float4 xv4 = *reinterpret_cast<const float4*>(x_s + (size_t)p * a.x_cstride);
-            float4 dv4;
-            if (a.da_pooled) {
-                const int y = p / a.hw, x = p - y * a.hw;
-                dv4 = *reinterpret_cast<const float4*>(da_s + ((size_t)(y >> 1) * hw_da + (x >> 1)) * a.da_cstride);
-                dv4.x *= 0.25f; dv4.y *= 0.25f; dv4.z *= 0.25f; dv4.w *= 0.25f;
-            } else {
-                dv4 = *reinterpret_cast<const float4*>(da_s + (size_t)p * a.da_cstride);
-            }
-            const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
-            float dz[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
-            float o[4];
+        // four pixels per iteration: their loads are issued together (a loop of dependent 3-load iterations made the small
+        // late-block launches pure latency)
+        for (int pb = p0 + pl; pb < p1; pb += 4 * PL) {
+            float4 xq[4], dq4[4], oq[4];
+            bool ok[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (a.relu && !(fmaf(xv[j], sc[j], sh[j]) > 0.f)) dz[j] = 0.f;
-                const float xh = (xv[j] - mean[j]) * rstd[j];
-                o[j] = gr[j] * (dz[j] - m1[j] - xh * m2[j]);
-                s1[j] += dz[j];
-                s2[j] = fmaf(dz[j], xh, s2[j]);
-            }
-            if (APPLY) {
-                float4* d = reinterpret_cast<float4*>(dst_s + (size_t)p * a.dst_cstride);
-                float4 r = make_float4(o[0], o[1], o[2], o[3]);
-                if (a.accumulate) {
-                    const float4 old = *d;
-                    r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+            for (int u = 0; u < 4; ++u) {
+                const int p = pb + u * PL;
+                ok[u] = p < p1;
+                const int pc = ok[u] ? p : p0;
+                xq[u] = *reinterpret_cast<const float4*>(x_s + (size_t)pc * a.x_cstride);
+                if (a.da_pooled) {
+                    const int y = pc / a.hw, x = pc - y * a.hw;
+                    dq4[u] = *reinterpret_cast<const float4*>(da_s + ((size_t)(y >> 1) * hw_da + (x >> 1)) * a.da_cstride);
+                } else {
+                    dq4[u] = *reinterpret_cast<const float4*>(da_s + (size_t)pc * a.da_cstride);
                 }
-                *d = r;
+                if (APPLY && a.accumulate) oq[u] = *reinterpret_cast<const float4*>(dst_s + (size_t)pc * a.dst_cstride);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!ok[u]) continue;
+                const int p = pb + u * PL;
+                const float sc_d = a.da_pooled ? 0.25f : 1.f;
+                const float xv[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
+                float dz[4] = {dq4[u].x * sc_d, dq4[u].y * sc_d, dq4[u].z * sc_d, dq4[u].w * sc_d};
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (a.relu && !(fmaf(xv[j], sc[j], sh[j]) > 0.f)) dz[j] = 0.f;
+                    const float xh = (xv[j] - mean[j]) * rstd[j];
+                    o[j] = gr[j] * (dz[j] - m1[j] - xh * m2[j]);
+                    s1[j] += dz[j];
+                    s2[j] = fmaf(dz[j], xh, s2[j]);
+                }
+                if (APPLY) {
+                    float4 r = make_float4(o[0], o[1], o[2], o[3]);
+                    if (a.accumulate) { r.x += oq[u].x; r.y += oq[u].y; r.z += oq[u].z; r.w += oq[u].w; }
+                    *reinterpret_cast<float4*>(dst_s + (size_t)p * a.dst_cstride) = r;
+                }
             }
         }
     }
@@ -516,9 +527,9 @@ int launch_bn_bwd(smg_handle* h, BnBwd a, int S, bool apply, float* dgamma, floa
               SMG_ERR_INVALID, "bn_bwd: C %d / strides must be multiples of 4 (C <= 1024)", a.C);
     const int npix = a.hw * a.hw;
     const int Q = a.C / 4, PL = 256 / Q;
-    // pixels per CTA: at least 8 per pixel lane, and enough CTAs to fill the GPU twice
+    // pixels per CTA: at least 4 per pixel lane (one batch of loads), and enough CTAs to fill the GPU twice
     int ppc = 2048;
-    while (ppc > 8 * PL && (npix + ppc - 1) / ppc * S < 2 * h->num_sms) ppc >>= 1;
+    while (ppc > 4 * PL && (npix + ppc - 1) / ppc * S < 2 * h->num_sms) ppc >>= 1;
     a.pix_per_cta = ppc;
     dim3 grid((npix + ppc - 1) / ppc, S);
     if (apply) bn_bwd_kernel<1><<<grid, 256, 0, st>>>(a, S, dgamma, dbeta);

@@ -96,10 +96,15 @@ conv1_t_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, const float* 
     const uint32_t tmem_base = *tmem_ptr;          // columns [0,256) accumulators, [256, 256 + cin) weights
     const uint32_t tmem_w = tmem_base + 256;
     const int total_stages = ntiles * KG;
+    // Programmatic dependent launch: barriers, tensor memory and (below) the weight fill touch nothing an earlier kernel of
+    // the pass writes, so this CTA may be resident while the previous layer drains.  Everything that reads the previous
+    // kernel's output (statistics, activations) sits behind pdl_wait(); the epilogue's stores follow from the loads.
+    pdl_launch_dependents();
 
     if (warp == 17) {
         // =============================== loader ===============================
         if (lane == 0) {
+            pdl_wait();
             int qa = 0, ta = 0, ka = 0;      // next activation stage: global index, tile, channel group
             int qb = RES ? total_stages : 0, kb = 0;
             Tile1 ca = coord(tile_begin);
@@ -135,6 +140,7 @@ conv1_t_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, const float* 
         const int chunk = j ^ (rbase & 7);                    // logical 4-channel chunk held by that piece
         int cur_s = -1;
         int q0 = 0;                                           // global index of the tile's first stage
+        pdl_wait();                                           // the tables below read the producers' statistics
         for (int it = 0; it < ntiles; ++it, q0 += KG) {
             const Tile1 c = coord(tile_begin + it);
             if (c.s != cur_s) {
@@ -336,8 +342,22 @@ int launch_conv1_t(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     SMG_TRY(ensure_dyn_smem(h, (const void*)conv1_t_kernel<false>, T1<false>::TOTAL));
     const int grid = total < h->num_sms ? total : h->num_sms;
     const float* w_t = reinterpret_cast<const float*>(a.w->w_tf32_t);
-    if (a.cin <= T_RES_MAXK) conv1_t_kernel<true><<<grid, T_THREADS, T1<true>::TOTAL, st>>>(tm, d, w_t, total);
-    else conv1_t_kernel<false><<<grid, T_THREADS, T1<false>::TOTAL, st>>>(tm, d, w_t, total);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(T_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->use_pdl ? 1 : 0;
+    if (a.cin <= T_RES_MAXK) {
+        cfg.dynamicSmemBytes = T1<true>::TOTAL;
+        SMG_CUDA(cudaLaunchKernelEx(&cfg, conv1_t_kernel<true>, tm, d, w_t, total));
+    } else {
+        cfg.dynamicSmemBytes = T1<false>::TOTAL;
+        SMG_CUDA(cudaLaunchKernelEx(&cfg, conv1_t_kernel<false>, tm, d, w_t, total));
+    }
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;

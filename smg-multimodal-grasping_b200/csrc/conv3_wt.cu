@@ -100,10 +100,12 @@ conv3_wt_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int total_ti
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tmem_d = tmem_base + W_KCOLS;
+    pdl_launch_dependents();   // see conv1_t.cu: set-up and weight fill may overlap the previous kernel's tail
 
     if (warp == 15) {
         // =============================== loader ===============================
         if (lane == 0) {
+            pdl_wait();
             for (int n = 0; n < 4 * ntiles; ++n) {
                 const int slot = n % W_NSLOT;
                 const TileCoord c = coord(tile_begin + (n >> 2));
@@ -122,6 +124,7 @@ conv3_wt_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, int total_ti
         constexpr int NI = 7;                                 // 7 x 32 = 224 >= patch rows
         int cur_s = -1;
         uint32_t inside = 0, filled = 0;
+        pdl_wait();                                           // the scale/shift tables read the producer's statistics
         for (int n = 0; n < 4 * ntiles; ++n) {
             const int g = n & 3;
             const int slot = n % W_NSLOT;
@@ -347,7 +350,17 @@ int launch_conv3_wt(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
     static long long* trace_dev = nullptr;
     if (trace_path != nullptr && trace_dev == nullptr) SMG_CUDA(cudaMalloc(&trace_dev, 7 * 64 * sizeof(long long)));
     if (trace_dev != nullptr) SMG_CUDA(cudaMemsetAsync(trace_dev, 0, 7 * 64 * sizeof(long long), st));
-    conv3_wt_kernel<<<grid, W_THREADS, W_TOTAL, st>>>(tm, d, total, trace_dev);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(W_THREADS);
+    cfg.dynamicSmemBytes = W_TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->use_pdl ? 1 : 0;
+    SMG_CUDA(cudaLaunchKernelEx(&cfg, conv3_wt_kernel, tm, d, total, trace_dev));
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     if (trace_dev != nullptr) {

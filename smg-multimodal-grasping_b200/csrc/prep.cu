@@ -49,6 +49,18 @@ __device__ __forceinline__ int rotate_src_index(int x, int y, int H, const float
     return -1;
 }
 
+// the same index arithmetic with the per-launch constants (step = 2/(H-1), half = (H-1)/2, both rounded to float exactly
+// like the divisions above) and the row coordinate hoisted: what the fused input kernel runs per pixel
+__device__ __forceinline__ bool rotate_src_xy(float bx, float by, int H, float half, const float* t, int& sx, int& sy) {
+    const float gx = __fmaf_rn(1.0f, t[2], __fmaf_rn(by, t[1], __fmul_rn(bx, t[0])));
+    const float gy = __fmaf_rn(1.0f, t[5], __fmaf_rn(by, t[4], __fmul_rn(bx, t[3])));
+    const float ix = rintf(__fmul_rn(__fadd_rn(gx, 1.0f), half));
+    const float iy = rintf(__fmul_rn(__fadd_rn(gy, 1.0f), half));
+    sx = (int)ix;
+    sy = (int)iy;
+    return ix >= 0.0f && ix < (float)H && iy >= 0.0f && iy < (float)H;
+}
+
 struct RotTheta {
     float t[32][6];
 };
@@ -88,7 +100,7 @@ __global__ void normalize_hm_kernel(const double* __restrict__ scene_hm, int n_s
 
 __global__ void __launch_bounds__(256)
 prep_rotate_kernel(const float* __restrict__ norm_hm, int groups, int n_rot, int n_scene_samples, int n_samples, RotTheta th,
-                   int hs, float pad_val, float* __restrict__ out, int H) {
+                   int hs, float pad_val, float* __restrict__ out, int H, float step, float half) {
     const int pad = (H - 2 * hs) / 2;
     const size_t quads = (size_t)H * H / 4;
     const size_t total = (size_t)n_samples * quads;
@@ -99,17 +111,13 @@ prep_rotate_kernel(const float* __restrict__ norm_hm, int groups, int n_rot, int
         const bool is_scene = z < n_scene_samples;
         const float* hm = norm_hm + (size_t)(is_scene ? z / n_rot : groups + z - n_scene_samples) * hs * hs;
         const float* t = th.t[is_scene ? z % n_rot : 0];
+        const float by = base_coord(y, H, step);
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int sy = y, sx = x0 + j;
             bool inside = true;
-            if (is_scene) {
-                const int src = rotate_src_index(x0 + j, y, H, t);
-                inside = src >= 0;
-                sy = src / H;
-                sx = src - sy * H;
-            }
+            if (is_scene) inside = rotate_src_xy(base_coord(x0 + j, H, step), by, H, half, t, sx, sy);
             const int yy = sy - pad, xx = sx - pad;
             const bool in_hm = inside && yy >= 0 && yy < 2 * hs && xx >= 0 && xx < 2 * hs;
             const float f = in_hm ? __ldg(hm + (size_t)(yy >> 1) * hs + (xx >> 1)) : pad_val;
@@ -191,7 +199,8 @@ int launch_prep_rotate(smg_handle* h, const double* scene_hm, int groups, const 
     const size_t total = (size_t)n_samples * h->H * h->H / 4;
     const int blocks = (int)((total + 255) / 256);
     prep_rotate_kernel<<<blocks < h->num_sms * 16 ? blocks : h->num_sms * 16, 256, 0, st>>>(
-        norm, groups, n_rot, groups * n_rot, n_samples, th, hm_size, (float)((0.0 - mean) / stddev), out, h->H);
+        norm, groups, n_rot, groups * n_rot, n_samples, th, hm_size, (float)((0.0 - mean) / stddev), out, h->H,
+        2.0f / (float)(h->H - 1), (float)(h->H - 1) / 2.0f);
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;

@@ -175,6 +175,7 @@ struct smg_handle {
                                    // identical input channels (stem_umma.cu), 64 = 3x3 with the weights resident in tensor memory
                                    // (conv3_wt.cu), 128 = persistent 1x1 with swapped operand roles (conv1_t.cu); a cleared bit
                                    // routes the layer to the register-producer kernel of conv_umma.cu
+    bool use_pdl = true;           // programmatic dependent launch between the persistent dense-layer kernels (SMG_PDL=0: off)
     bool fp32_exact_pass = false;  // set while a grad-enabled fp32 pass runs: CUDA-core FFMA convolutions (see trunk_forward)
     bool fp32_tc = true;           // fp32 mode: convolutions on the tensor cores with hi/lo split operands (SMG_FP32_TC=0: CUDA cores)
     int wgrad_cta_cap = 0;         // > 0 while the weight gradients share the GPU with the dgrad chain: max CTAs per wgrad launch
