@@ -63,15 +63,22 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+__device__ __forceinline__ float group_sum(const float (*r)[64], int c) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += r[i][c];
+    return t;
+}
+
 // one CTA per (mask k, rotation r) pair.  p: [n_rot + n_masks][400][64]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 head_tail_kernel(const float* __restrict__ p, const float* __restrict__ p_mask, int n_rot, int n_masks, int npix,
                  const float* __restrict__ g1,
                  const float* __restrict__ b1, const float* __restrict__ w1, int n_out, float* __restrict__ q,
                  float* __restrict__ bn1_stats) {
-    __shared__ float red[2][4][64];
+    __shared__ float red[2][16][64];   // 64 channels x 16 pixel groups: 25 pixels per thread and pass
     __shared__ float s_sc[64], s_sh[64];
-    __shared__ float s_part[8][4];
+    __shared__ float s_part[32][4];
     // samples: [groups x n_rot] rotated scenes, then [groups x n_masks] masked scenes; blockIdx.z = group (unit)
     const int r = blockIdx.x, k0 = blockIdx.y, grp = blockIdx.z, groups = gridDim.z;
     const int k = grp * n_masks + k0;   // mask index over all groups == row of q / bn1_stats
@@ -80,20 +87,20 @@ head_tail_kernel(const float* __restrict__ p, const float* __restrict__ p_mask, 
     const float* pm = p_mask + (size_t)k * npix * 64;   // masked-scene partials: [groups x n_masks], mask index k over all groups
     // pass 1: mean
     float su = 0.f;
-    for (int px = g; px < npix; px += 4) su += ps[px * 64 + c] + pm[px * 64 + c];
+    for (int px = g; px < npix; px += 16) su += ps[px * 64 + c] + pm[px * 64 + c];
     red[0][g][c] = su;
     __syncthreads();
-    const float mean = (red[0][0][c] + red[0][1][c] + red[0][2][c] + red[0][3][c]) / (float)npix;
+    const float mean = group_sum(red[0], c) / (float)npix;
     // pass 2: biased variance around the mean
     float sq = 0.f;
-    for (int px = g; px < npix; px += 4) {
+    for (int px = g; px < npix; px += 16) {
         const float d = ps[px * 64 + c] + pm[px * 64 + c] - mean;
         sq = fmaf(d, d, sq);
     }
     red[1][g][c] = sq;
     __syncthreads();
     if (tid < 64) {
-        const float var = (red[1][0][c] + red[1][1][c] + red[1][2][c] + red[1][3][c]) / (float)npix;
+        const float var = group_sum(red[1], c) / (float)npix;
         const float sc = g1[c] * rsqrtf(var + kBnEps);
         s_sc[c] = sc;
         s_sh[c] = b1[c] - mean * sc;
@@ -106,7 +113,7 @@ head_tail_kernel(const float* __restrict__ p, const float* __restrict__ p_mask, 
     __syncthreads();
     const float sc = s_sc[c], sh = s_sh[c];
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int px = g; px < npix; px += 4) {
+    for (int px = g; px < npix; px += 16) {
         const float y = fmaxf(fmaf(ps[px * 64 + c] + pm[px * 64 + c], sc, sh), 0.f);
 #pragma unroll
         for (int o = 0; o < 4; ++o)
@@ -121,7 +128,7 @@ head_tail_kernel(const float* __restrict__ p, const float* __restrict__ p_mask, 
     __syncthreads();
     if (tid < n_out) {
         float v = 0.f;
-        for (int w = 0; w < 8; ++w) v += s_part[w][tid];
+        for (int w = 0; w < 32; ++w) v += s_part[w][tid];
         q[((size_t)k * n_rot + r) * n_out + tid] = v;
     }
 }
@@ -212,7 +219,7 @@ int launch_head_tail(smg_handle* h, const float* p, const float* p_mask, int n_r
     SMG_CHECK(hw.n_out >= 1 && hw.n_out <= 4, SMG_ERR_INVALID, "head_tail: n_out %d", hw.n_out);
     dim3 grid(n_rot, n_masks, groups);
     const bool fits = (size_t)groups * n_rot * n_masks * 128 <= h->head_bn1_floats;
-    head_tail_kernel<<<grid, 256, 0, st>>>(p, p_mask, n_rot, n_masks, npix, hw.norm1.gamma, hw.norm1.beta, hw.conv1, hw.n_out, q,
+    head_tail_kernel<<<grid, 1024, 0, st>>>(p, p_mask, n_rot, n_masks, npix, hw.norm1.gamma, hw.norm1.beta, hw.conv1, hw.n_out, q,
                                            fits ? h->head_bn1 : nullptr);
     h->head_bn1_pairs = fits ? groups * n_rot * n_masks : 0;
     h->launches++;
