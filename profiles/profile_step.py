@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--precision", default="tf32")
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--mode", default="infer", choices=["infer", "train"])
+    ap.add_argument("--units", type=int, default=1, help="units per step (bench.py's default step has 4)")
     args = ap.parse_args()
     if args.mode == "train":
         return train(args)
@@ -30,6 +31,8 @@ def main():
     tr = Trainer("reinforcement", 0.5, False, None, False, precision=args.precision)
     tr.model.gnum_rotations = tr.model.snum_rotations = bench.R
     tr.model.update_running_stats = False
+    if args.units > 1:
+        return infer_batch(args, tr)
     eng = tr.model._engine(bench.R + 1)
     scenes, masks = bench.make_units(2, 100)
     sd, md = torch.from_numpy(scenes).cuda(), torch.from_numpy(masks).cuda()
@@ -40,6 +43,24 @@ def main():
     torch.cuda.cudart().cudaProfilerStart()
     for i in range(args.steps):
         q = eng.qforward_maps(0, sd[i % 2], md[i % 2:i % 2 + 1], bench.MEAN, bench.STD, rots, bench.R)
+        eng.argmax(q)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+
+
+def infer_batch(args, tr):
+    """bench.py's step: G units in one smg_qforward_maps_batch call (set SMG_NO_GRAPHS=1 to list every launch)."""
+    G = args.units
+    eng = tr.model._engine(G * (bench.R + 1))
+    scenes, masks = bench.make_units(G, 100)
+    sd, md = torch.from_numpy(scenes).cuda(), torch.from_numpy(masks).cuda()
+    rots = list(range(bench.R))
+    for i in range(3):
+        eng.qforward_maps_batch(0, sd, md[:, None], bench.MEAN, bench.STD, rots, bench.R)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    for i in range(args.steps):
+        q = eng.qforward_maps_batch(0, sd, md[:, None], bench.MEAN, bench.STD, rots, bench.R)
         eng.argmax(q)
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()

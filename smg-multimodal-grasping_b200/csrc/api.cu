@@ -58,8 +58,12 @@ int conv_dispatch(smg_handle* h, const ConvArgs& a, cudaStream_t st) {
         }
         return launch_conv_ffma(h, a, st);
     }
-    // tf32 dense layers: the persistent TMA-fed kernels (SMG_TMA bits: 64 = conv3_wt.cu, 128 = conv1_t.cu); everything they
-    // do not serve (pooled transitions, the head's 1x1, bf16 mode, odd shapes) runs on the register-producer kernel.
+    // tf32: the persistent TMA-fed kernels (SMG_TMA bits: 32 = trans_t.cu, 64 = conv3_wt.cu, 128 = conv1_t.cu); everything they
+    // do not serve (the head's 1x1, bf16 mode, odd shapes) runs on the register-producer kernel.
+    if (h->precision == SMG_PREC_TF32 && a.pool && a.taps == 1 && (h->use_tma & 32)) {
+        const int status = launch_trans_t(h, a, st);
+        if (status != SMG_ERR_UNSUPPORTED) return status;
+    }
     if (h->precision == SMG_PREC_TF32 && !a.pool) {
         if (a.taps == 1 && (h->use_tma & 128)) {
             const int status = launch_conv1_t(h, a, st);

@@ -125,6 +125,37 @@ def test_tma_kernel_variants_match_torch(case, tma_mask, monkeypatch):
     del eng
 
 
+@pytest.mark.parametrize("tma_mask", [0, 32])
+@pytest.mark.parametrize("case", [(3, 160, 256, 256, 128, 1, 1), (2, 80, 512, 512, 256, 1, 1), (3, 40, 1024, 1024, 512, 1, 1),
+                                  (2, 24, 64, 96, 128, 1, 1), (5, 6, 512, 512, 256, 1, 1)],
+                         ids=lambda c: "n%d_h%d_cin%d_cs%d_cout%d_k%d_pool%d" % c)
+def test_transition_kernel_variants_match_torch(case, tma_mask, monkeypatch):
+    """The pooled transition (BN-ReLU -> avg-pool 2x2 -> 1x1 conv) on both tf32 kernels: SMG_TMA bit 32 = the persistent
+    TMA-fed trans_t.cu (the three densenet transitions at their real sizes: 128-column tiles, 80-column tiles, two
+    output-channel parts; plus a map smaller than one tile and a channel slice of a wider buffer), 0 = conv_umma.cu."""
+    from smg_b200 import engine
+    monkeypatch.setenv("SMG_TMA", str(tma_mask))
+    eng = engine.Engine(0, 5, 640, "fp32")
+    n, hin, cin, cstride, cout, k, pool = case
+    g = torch.Generator(device="cuda").manual_seed(hash(case) % 1000 + tma_mask)
+    x = torch.randn((n, hin, hin, cstride), generator=g, device="cuda")
+    scale = torch.rand((n, cin), generator=g, device="cuda") + 0.5
+    shift = torch.randn((n, cin), generator=g, device="cuda") * 0.3
+    w = torch.randn((cout, cin, k, k), generator=g, device="cuda") / (cin * k * k) ** 0.5
+    out_cstride, out_coff = cout + 64, 32
+    out, stats = eng.debug_conv("tf32", x, cin, scale, shift, True, pool, w, out_cstride, out_coff)
+    ref = reference(x, cin, scale, shift, True, pool, w)
+    got = out[..., out_coff:out_coff + cout]
+    err = float((got - ref).abs().max() / ref.abs().max())
+    print("mask %d %s: rel-max err %.2e" % (tma_mask, case, err))
+    assert err <= TOL["tf32"]
+    assert float(out[..., :out_coff].abs().max()) == 0 and float(out[..., out_coff + cout:].abs().max()) == 0
+    s_ref, q_ref = got.double().sum((1, 2)), (got.double() ** 2).sum((1, 2))
+    assert float((stats[:, out_coff:out_coff + cout, 0] - s_ref).abs().max() / s_ref.abs().max()) <= 1e-4
+    assert float((stats[:, out_coff:out_coff + cout, 1] - q_ref).abs().max() / q_ref.abs().max()) <= 1e-4
+    del eng
+
+
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
 def test_conv_no_relu_identity_prologue(eng, precision):
     x = torch.randn((1, 20, 20, 128), device="cuda")
