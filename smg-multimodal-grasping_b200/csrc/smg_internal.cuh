@@ -171,7 +171,7 @@ struct smg_handle {
     int64_t workspace_bytes = 0;
     double l2_chunk_bytes = 0.0;   // >0: run each dense block over sample chunks of about this footprint (L2 residency)
     int pack_mask = 15;            // weight layouts written by smg_set_*_weights (SMG_PACK_*)
-    int use_tma = 208;             // A/B bit mask of the persistent TMA-fed tf32 kernels (SMG_TMA): 16 = tensor-core 7x7 stem for
+    int use_tma = 240;             // A/B bit mask of the persistent TMA-fed tf32 kernels (SMG_TMA): 16 = tensor-core 7x7 stem for
                                    // identical input channels (stem_umma.cu), 64 = 3x3 with the weights resident in tensor memory
                                    // (conv3_wt.cu), 128 = persistent 1x1 with swapped operand roles (conv1_t.cu); a cleared bit
                                    // routes the layer to the register-producer kernel of conv_umma.cu

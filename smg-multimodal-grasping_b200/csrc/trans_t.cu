@@ -17,7 +17,7 @@
 // Layers with more than MB x 128 output channels are split into output-channel parts walked concurrently by the two halves
 // of the grid.  Epilogue as in conv1_t.cu: a warp owns 32 channels, every store instruction
 // writes one pixel's 128 contiguous bytes, statistics are per-thread sums.
-// Warps (576 threads): 0-3 / 8-11 pool-transform (two groups, tied to the operand-stage parity), 4-7 epilogue of even
+// Warps (576 threads): 0-3 / 8-11 pool-transform (256 threads, every raw box in order), 4-7 epilogue of even
 // tiles, 12-15 epilogue of odd tiles (quadrant = warp mod 4), 16 MMA issuer, 17 TMA loader.
 #include "tma_common.cuh"
 
@@ -31,7 +31,7 @@ constexpr int X_THREADS = 576;
 template <int MB>
 struct XP {
     static constexpr int NR = MB == 1 ? 7 : 6;            // raw stages
-    static constexpr int NO = MB == 1 ? 4 : 2;            // operand stages (even: see the transform groups)
+    static constexpr int NO = MB == 1 ? 4 : 2;            // operand stages
     static constexpr int NW = 2;                          // weight stages of MB x 16 KB
     static constexpr int OFF_R = 0;
     static constexpr int OFF_O = OFF_R + NR * X_STAGE;
@@ -53,6 +53,24 @@ struct XTile {
     int s, oy0, ox0, part;
 };
 
+#ifdef SMG_DEBUG_HANG
+// debugging aid: a wait that does not complete within ~1 s reports where it is stuck and traps
+__device__ __noinline__ void dbg_wait(uint64_t* bar, uint32_t parity, int what, int idx) {
+    const long long t0 = clock64();
+    while (!mbar_test(bar, parity)) {
+        if (clock64() - t0 > 2000000000ll) {
+            printf("trans_t stuck: block %d thread %d wait %d idx %d parity %u\n", blockIdx.x, threadIdx.x, what, idx, parity);
+            __trap();
+        }
+    }
+}
+#define XWAIT(bar, parity, what, idx) dbg_wait(bar, parity, what, idx)
+#define XWAIT_SLEEP(bar, parity, ns, what, idx) dbg_wait(bar, parity, what, idx)
+#else
+#define XWAIT(bar, parity, what, idx) mbar_wait(bar, parity)
+#define XWAIT_SLEEP(bar, parity, ns, what, idx) mbar_wait_sleep(bar, parity, ns)
+#endif
+
 template <int MB>
 __global__ void __launch_bounds__(X_THREADS, 1)
 trans_t_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, XGeom g, int total_tiles) {
@@ -61,8 +79,8 @@ trans_t_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, XGeom g, int 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q::OFF_BAR);
     uint64_t* raw_full = bars;          // [8] raw box landed
-    uint64_t* raw_empty = bars + 8;     // [8] read by the 128 pool threads that own it
-    uint64_t* op_ready = bars + 16;     // [4] pooled operand written (128 threads)
+    uint64_t* raw_empty = bars + 8;     // [8] read by the 256 pool threads
+    uint64_t* op_ready = bars + 16;     // [4] pooled operand written (256 threads)
     uint64_t* op_empty = bars + 20;     // [4] MMAs retired
     uint64_t* b_full = bars + 24;       // [2] weight stage landed
     uint64_t* b_empty = bars + 26;      // [2]
@@ -106,8 +124,8 @@ trans_t_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, XGeom g, int 
 
     if (warp == 16 && lane == 0) {
         if (smem_u32(smem) & 1023u) __trap();   // the swizzled stages rely on a 1024-byte aligned window
-        for (int i = 0; i < NR; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 128); }
-        for (int i = 0; i < NO; ++i) { mbar_init(&op_ready[i], 128); mbar_init(&op_empty[i], 1); }
+        for (int i = 0; i < NR; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 256); }
+        for (int i = 0; i < NO; ++i) { mbar_init(&op_ready[i], 256); mbar_init(&op_empty[i], 1); }
         for (int i = 0; i < NW; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
         fence_barrier_init();
@@ -129,12 +147,24 @@ trans_t_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, XGeom g, int 
             int qb = 0, tb = 0, kb = 0;              // next weight stage
             XTile ca = coord(tile_begin), cb = ca;
             const int total_raw = total_ops * 4;
+#ifdef SMG_DEBUG_HANG
+            long long t_last = clock64();
+#endif
             while (qa < total_raw || qb < total_ops) {
+#ifdef SMG_DEBUG_HANG
+                if (clock64() - t_last > 2000000000ll) {
+                    printf("trans_t stuck: block %d loader qa %d / %d qb %d / %d ntiles %d KG %d\n", blockIdx.x, qa, total_raw, qb, total_ops, ntiles, KG);
+                    __trap();
+                }
+#endif
                 if (qa < total_raw && mbar_test(&raw_empty[qa % NR], ((qa / NR) & 1) ^ 1)) {
                     const int slot = qa % NR;
                     mbar_arrive_expect_tx(&raw_full[slot], raw_bytes);
                     tma_tile_4d(sR + slot * X_STAGE, &tmA, ka * KC, 2 * ca.ox0, 2 * (ca.oy0 + sa * g.sr), ca.s, &raw_full[slot]);
                     ++qa;
+#ifdef SMG_DEBUG_HANG
+                    t_last = clock64();
+#endif
                     if (++sa == 4) {
                         sa = 0;
                         if (++ka == KG) {
@@ -160,29 +190,26 @@ trans_t_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, XGeom g, int 
         }
     } else if (is_transform) {
         // =============================== pool + transform ===============================
-        // two groups of four warps; group g owns the operand stages with global index = g (mod 2).  NO is even: a slot is
-        // always served by the same group.  A thread owns one 16-byte channel chunk j of the pooled pixels pl + 16 i.
+        // All 256 threads consume EVERY raw box, in order: thread = (pooled pixel pp of the box, 16-byte channel chunk j).
+        // (The first version split the operand stages between two 128-thread groups that shared the raw ring: a group
+        // could then wait on a raw slot two uses ahead of the other group's pending use of the same slot, and the one-bit
+        // barrier parity aliased - rare wrong pooled values and hangs inside the network, never in isolation.)
         const int ptid = warp < 4 ? tid : tid - 128;          // 0..255
-        const int grp = ptid >> 7;
-        const int gt = ptid & 127;
-        const int j = gt & 7;                                 // logical 4-channel chunk
-        const int pl = gt >> 3;                               // pooled pixels pl, pl + 16 of every raw box
-        // byte offsets inside a raw stage of the top-left raw row of the thread's two pooled pixels (-1: no such pixel)
-        int r00[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int pp = pl + 16 * i;
-            const int ppy = pp / g.tw, ppx = pp - ppy * g.tw;
-            r00[i] = pp < npp ? (2 * ppy) * (2 * g.tw) + 2 * ppx : -1;
-        }
+        const int j = ptid & 7;                               // logical 4-channel chunk
+        const int pp = ptid >> 3;                             // pooled pixel of the raw box (32 per box at most)
+        const int ppy = pp / g.tw, ppx = pp - ppy * g.tw;
+        const bool has_px = pp < npp;
+        const int r00 = (2 * ppy) * (2 * g.tw) + 2 * ppx;     // top-left raw row of the pooled pixel
         const int rw = 2 * g.tw;                              // raw rows per raw image row of the box
-        auto raw_ptr = [&](const uint8_t* stage, int r) {     // chunk j of raw row r under the 128-byte swizzle
-            return reinterpret_cast<const float4*>(stage + r * 128 + ((j ^ (r & 7)) << 4));
-        };
+        // chunk j of raw rows r00, r00 + 1, r00 + rw, r00 + rw + 1 under the 128-byte swizzle
+        const int o0 = r00 * 128 + ((j ^ (r00 & 7)) << 4);
+        const int o1 = (r00 + 1) * 128 + ((j ^ ((r00 + 1) & 7)) << 4);
+        const int o2 = (r00 + rw) * 128 + ((j ^ ((r00 + rw) & 7)) << 4);
+        const int o3 = (r00 + rw + 1) * 128 + ((j ^ ((r00 + rw + 1) & 7)) << 4);
         int cur_s = -1;
-        int q0 = 0;                                           // global index of the tile's first operand stage
+        int q = 0;                                            // operand stage (global index inside this CTA)
         pdl_wait();                                           // the tables below read the producers' statistics
-        for (int it = 0; it < ntiles; ++it, q0 += KG) {
+        for (int it = 0; it < ntiles; ++it) {
             const XTile c = coord(tile_begin + it);
             if (c.s != cur_s) {
                 asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -209,46 +236,40 @@ trans_t_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, XGeom g, int 
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 cur_s = c.s;
             }
-            for (int kg = (grp - q0) & 1; kg < KG; kg += 2) {
-                const int q = q0 + kg;
+            for (int kg = 0; kg < KG; ++kg, ++q) {
                 const int oslot = q % NO;
                 const float4 sc = *reinterpret_cast<const float4*>(s_sc + kg * KC + j * 4);
                 const float4 sh = *reinterpret_cast<const float4*>(s_sh + kg * KC + j * 4);
-                mbar_wait_sleep(&op_empty[oslot], ((q / NO) & 1) ^ 1, 32);
+                XWAIT_SLEEP(&op_empty[oslot], ((q / NO) & 1) ^ 1, 32, 1, q);
                 uint8_t* op = sO + oslot * X_STAGE;
-#pragma unroll 1
+#pragma unroll
                 for (int sub = 0; sub < 4; ++sub) {
                     const int qr = q * 4 + sub;
                     const int rslot = qr % NR;
                     const uint8_t* stage = sR + rslot * X_STAGE;
-                    mbar_wait_sleep(&raw_full[rslot], (qr / NR) & 1, 64);
-                    float4 x[2][4];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        if (r00[i] >= 0) {
-                            x[i][0] = *raw_ptr(stage, r00[i]);
-                            x[i][1] = *raw_ptr(stage, r00[i] + 1);
-                            x[i][2] = *raw_ptr(stage, r00[i] + rw);
-                            x[i][3] = *raw_ptr(stage, r00[i] + rw + 1);
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        if (r00[i] < 0) continue;
+                    XWAIT_SLEEP(&raw_full[rslot], (qr / NR) & 1, 64, 2, qr);
+                    if (has_px) {
+                        float4 x[4];
+                        x[0] = *reinterpret_cast<const float4*>(stage + o0);
+                        x[1] = *reinterpret_cast<const float4*>(stage + o1);
+                        x[2] = *reinterpret_cast<const float4*>(stage + o2);
+                        x[3] = *reinterpret_cast<const float4*>(stage + o3);
                         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
                             float4 y;
-                            y.x = fmaf(x[i][t].x, sc.x, sh.x); y.y = fmaf(x[i][t].y, sc.y, sh.y);
-                            y.z = fmaf(x[i][t].z, sc.z, sh.z); y.w = fmaf(x[i][t].w, sc.w, sh.w);
+                            y.x = fmaf(x[t].x, sc.x, sh.x); y.y = fmaf(x[t].y, sc.y, sh.y);
+                            y.z = fmaf(x[t].z, sc.z, sh.z); y.w = fmaf(x[t].w, sc.w, sh.w);
                             if (a.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
                             acc.x += y.x; acc.y += y.y; acc.z += y.z; acc.w += y.w;
                         }
                         acc.x *= 0.25f; acc.y *= 0.25f; acc.z *= 0.25f; acc.w *= 0.25f;
-                        const int p = sub * npp + pl + 16 * i;
+                        const int p = sub * npp + pp;
                         *reinterpret_cast<float4*>(op + p * 128 + ((j ^ (p & 7)) << 4)) = acc;
                     }
-                    mbar_arrive(&raw_empty[rslot]);           // the raw values are in registers: the box may be refilled
+                    // the raw values are in registers: order the generic-proxy reads before the copy engine's refill
+                    fence_proxy_async();
+                    mbar_arrive(&raw_empty[rslot]);
                 }
                 fence_proxy_async();
                 mbar_arrive(&op_ready[oslot]);
@@ -263,13 +284,13 @@ trans_t_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, XGeom g, int 
             int q = 0;
             for (int it = 0; it < ntiles; ++it) {
                 const int buf = it & 1;
-                mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+                XWAIT(&t_empty[buf], ((it >> 1) & 1) ^ 1, 3, it);   // the epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * MB * 128);
                 for (int kg = 0; kg < KG; ++kg, ++q) {
                     const int so = q % NO, sb = q % NW;
-                    mbar_wait(&op_ready[so], (q / NO) & 1);
-                    mbar_wait(&b_full[sb], (q / NW) & 1);
+                    XWAIT(&op_ready[so], (q / NO) & 1, 4, q);
+                    XWAIT(&b_full[sb], (q / NW) & 1, 5, q);
                     tc_fence_after();
 #pragma unroll
                     for (int mb = 0; mb < MB; ++mb) {
@@ -315,7 +336,7 @@ trans_t_kernel(const __grid_constant__ CUtensorMap tmA, UmmaDev a, XGeom g, int 
                 cur_s = c.s;
                 cur_part = c.part;
             }
-            mbar_wait_sleep(&t_full[eg], (it >> 1) & 1, 64);
+            XWAIT_SLEEP(&t_full[eg], (it >> 1) & 1, 64, 6, it);
             tc_fence_after();
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {

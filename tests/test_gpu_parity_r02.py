@@ -76,6 +76,29 @@ def test_benched_config_tf32_batch4_graph_replay_vs_reference(scene_inputs, gold
     assert np.abs(q_single - q3[1, 0]).max() / scale <= 1e-5
 
 
+def test_repeated_passes_are_stable(scene_inputs):
+    """The Q pass has no data-dependent schedule: repeating it must give the same Q every time (the only run-to-run freedom
+    is the order of the double-precision statistics atomics, ~1e-7).  Regression test for a barrier-parity aliasing fault of
+    the first transition kernel that produced ~1e-2 deviations in about one pass of a hundred, and only inside the network
+    (L2-hot inputs), never in the isolated kernel tests."""
+    import smg_b200.synth as synth
+    scene, mask0, _, sc = scene_inputs
+    tr = _trainer(precision="tf32", rotations=16)
+    tr.model.update_running_stats = False
+    scenes = np.stack([scene] * 4)
+    masks = np.stack([synth.masked_scene(scene, sc["masks"], [k]) for k in range(4)])
+    q_single = tr.forward(scene, masks[0], 0, True, False)
+    q_batch = tr.forward_batch(scenes, masks, 0)
+    scale = np.abs(q_batch).max()
+    worst = 0.0
+    for rep in range(60):
+        for k in range(2):
+            worst = max(worst, np.abs(tr.forward(scene, masks[0], 0, True, False) - q_single).max() / scale)
+        worst = max(worst, np.abs(tr.forward_batch(scenes, masks, 0) - q_batch).max() / scale)
+    print("180 repeated passes: worst deviation %.2e of scale" % worst)
+    assert worst <= 1e-5
+
+
 # --------------------------------------------------------------------------------------------------
 # (b) highly-cluttered K = 10 scene through forward_all / decide, all three primitives
 # --------------------------------------------------------------------------------------------------
