@@ -14,8 +14,8 @@ latency configuration) on seeded synthetic 224x224 heightmaps with random-init w
   e2e     U/s through the reference-facing call Trainer.forward: float64 heightmaps in pinned host
           memory, H2D copy and D2H read of the 16 Q values inside the timed region
   roofline      dominant kernel class timed with CUDA events inside the library (smg_profile_*)
-  cpu_baseline  the oracle port of the reference path (recomputing the mask pass per rotation, as the
-                reference does) timed on this box's host cores on a bounded sample
+  cpu_baseline  the unmodified reference (baseline/_ref/code; the oracle port if that copy is absent) timed on this box's
+                host cores on a bounded sample
 
   gpu_reference the unmodified reference on torch.cuda (stock PyTorch + cuDNN, TF32 off and on) on the same GPU, same
                 unit and same Trainer.backprop call: the bar BASELINE.md section 4 names (N = 1, rank 0)
@@ -64,7 +64,8 @@ def measured_peaks():
 def ncu_traffic(cls):
     """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one representative launch of a kernel class, read from
     the newest committed `ncu --set full` summary of that kernel under profiles/ (never a literal in this file), next to
-    the algorithmic bytes of the same launch (block-1 layer, 17 samples: the launch profiles/profile_step.py captures)."""
+    the algorithmic bytes of the same launch (block-1 layer of profiles/profile_step.py; the summary's `samples` row says how
+    many samples that launch processed: 68 = the benched 4-unit step)."""
     import csv
     import glob
     stem = {"conv1x1": "conv1_t", "conv3x3": "conv3_wt"}.get(cls)
@@ -76,16 +77,19 @@ def ncu_traffic(cls):
     vals = {}
     with open(files[-1]) as f:
         for row in csv.reader(f):
+            if len(row) >= 2 and row[0] == "samples":
+                vals["samples"] = float(row[1])
             if len(row) >= 3 and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"):
                 scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0, "us": 1.0, "ms": 1e3}.get(row[2], 1.0)
                 vals[row[0]] = float(row[1]) * scale
     if "dram__bytes_read.sum" not in vals or "dram__bytes_write.sum" not in vals:
         return None
-    px = 17 * 160 * 160
+    samples = int(vals.get("samples", 17))      # the r01 / first r02 captures are one-unit steps (17 samples)
+    px = samples * 160 * 160
     algo = {"conv1x1": px * (192 + 128) * 4.0, "conv3x3": px * (128 + 32) * 4.0}[cls]
     return {"source": os.path.relpath(files[-1], ROOT), "dram_bytes": vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"],
             "algorithmic_bytes": algo, "launch_us_under_ncu": vals.get("gpu__time_duration.sum"),
-            "launch": "block-1 %s layer, 17 samples" % ("1x1 K=192" if cls == "conv1x1" else "3x3")}
+            "launch": "block-1 %s layer, %d samples" % ("1x1 K=192" if cls == "conv1x1" else "3x3", samples)}
 
 
 class ClockSampler:

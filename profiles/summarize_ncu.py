@@ -1,7 +1,10 @@
 """Turn `ncu -i X.ncu-rep --page raw --csv` into the small `metric,value,unit` summaries kept under profiles/.
 
     ncu -i gpurun_out/prof.ncu-rep --page raw --csv > /tmp/raw.csv
-    python profiles/summarize_ncu.py /tmp/raw.csv <kernel-name-substring> [launch-index] > profiles/rNN_<kernel>_ncu_summary.csv
+    python profiles/summarize_ncu.py /tmp/raw.csv <kernel-name-substring> [launch-index] [samples] > profiles/rNN_<kernel>_ncu_summary.csv
+
+`samples` (how many samples the captured launch processed) is written as a `samples` row; bench.py uses it for the
+algorithmic bytes of the same launch.
 """
 import csv
 import sys
@@ -24,6 +27,8 @@ def main():
         sys.exit("no launch of a kernel matching %r" % pat)
     r = hits[min(which, len(hits) - 1)]
     print("metric,value,unit")
+    if len(sys.argv) > 4:
+        print("samples,%d," % int(sys.argv[4]))
     for k in ("Kernel Name", "Block Size", "Grid Size"):
         if k in hdr:
             print('%s,"%s",' % (k, r[hdr.index(k)]))
