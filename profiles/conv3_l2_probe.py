@@ -12,7 +12,7 @@ from smg_b200 import engine  # noqa: E402
 eng = engine.Engine(0, 70, 640, "fp32")
 hin = int(sys.argv[1]) if len(sys.argv) > 1 else 160
 prev = None
-for n in (1, 2, 3, 4, 6, 8, 17, 34, 68):
+for n in ([int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else (1, 2, 3, 4, 6, 8, 17, 34, 68)):
     g = torch.Generator(device="cuda").manual_seed(n)
     x = torch.randn((n, hin, hin, 128), generator=g, device="cuda")
     scale = torch.rand((n, 128), generator=g, device="cuda") + 0.5
