@@ -654,6 +654,45 @@ def run_gpu_arm(args):
                 line_extra[key] = {"error": repr(exc)[:300]}
         tr.model.precision = precision
 
+    # ---- BASELINE config 3: the reactive E+S policy (classification heads, weighted cross-entropy), forward + backward
+    # through the same public calls (rank 0 only; no collective inside)
+    if rank == 0 and not args.no_extras and not args.no_backprop:
+        try:
+            import smg_b200.synth as synth
+            from smg_b200.trainer import Trainer
+            sc = synth.make_scene(100, num_objects=4, cluttered=False)
+            obj_masks = sc["masks"].astype(np.float64)
+            trr = Trainer("reactive", 0.5, False, None, False, precision=precision)
+            trr.image_mean, trr.image_std = MEAN, STD
+            mk = synth.masked_scene(sc["scene"], sc["masks"], [0])
+
+            def rfwd(i):
+                return trr.forward(sc["scene"], mk, i % 2, True, False)
+
+            def rbp(i):
+                return trr.backprop(sc["scene"], "grasp" if i % 2 == 0 else "suction", [i % 4, 0], [i % 4, 0], [], [],
+                                    float(i % 2), obj_masks.copy(), [0] * 4, [0] * 4, [])
+
+            out = {}
+            for key, fn, n_it in (("forward_calls_per_s", rfwd, 20), ("backprop_steps_per_s", rbp, 20)):
+                for i in range(6):
+                    fn(i)
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(n_it):
+                    fn(i)
+                e1.record()
+                torch.cuda.synchronize()
+                out[key] = n_it / (e0.elapsed_time(e1) / 1e3)
+            out["precision"] = precision
+            out["what"] = ("reactive_net (3-class heads): Trainer.forward (rotation 0, softmax P(class 0), host heightmaps in, "
+                           "probability out) and Trainer.backprop (weighted cross-entropy, fused captured step) alternating the "
+                           "enveloping and sucking primitives")
+            line_extra["reactive"] = out
+            del trr
+        except Exception as exc:
+            line_extra["reactive"] = {"error": repr(exc)[:300]}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",

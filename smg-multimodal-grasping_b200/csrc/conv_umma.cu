@@ -25,16 +25,19 @@ namespace smg {
 // SPLIT = 1 (tf32 elements only): fp32-accurate "3xTF32" mode.  Every operand is kept as hi + lo (hi = the value with its 13
 // low mantissa bits cleared, exactly a tf32 number; lo = value - hi, exact in fp32) and D += a_lo b_hi + a_hi b_lo + a_hi b_hi
 // (the dropped a_lo b_lo term is 2^-22 relative): each A slot / B stage holds the hi image followed by the lo image.
+// TAPS = 1: 1x1; 9: 3x3 as nine shifted taps of N = BN output channels; 3: 3x3 with the three dx taps MERGED into N (BN = 3 x cout
+// columns = (dx, co)): three row-shifted taps (dy) of wider MMAs, the dx shift is applied when the staged accumulator is read back
+// (out[m][co] = E[m][co] + E[m+1][cout+co] + E[m+2][2 cout+co]).  Used by the fp32 (split) mode, whose N = 32 MMAs are issue-bound.
 template <int ELT, int BN, int TAPS, int SPLIT = 0>
 struct SmemPlan {
     using E = EltCfg<ELT>;
-    static constexpr int A_LBO = (TAPS == 9 ? E::P_ROWS : E::A_ROWS) * 16;
+    static constexpr int A_LBO = (TAPS != 1 ? E::P_ROWS : E::A_ROWS) * 16;
     static constexpr int A_HALF = E::CH * A_LBO;                      // one 32-channel group, one image
     static constexpr int A_SLOT = (1 + SPLIT) * A_HALF;
-    static constexpr int A_SLOTS = TAPS == 9 ? 2 : NA;
+    static constexpr int A_SLOTS = TAPS != 1 ? 2 : NA;
     static constexpr int B_HALF = E::CH * BN * 16;
     static constexpr int B_STAGE = (1 + SPLIT) * B_HALF;
-    static constexpr int B_SLOTS = TAPS == 9 ? NB9 : NB1;
+    static constexpr int B_SLOTS = TAPS == 9 ? NB9 : (TAPS == 3 ? 3 : NB1);   // TAPS == 3: 24 KB stages (96 rows, hi + lo)
     static constexpr int OFF_BAR = 0;
     static constexpr int OFF_SC = 256;
     static constexpr int OFF_A = OFF_SC + 2 * 1024 * 4;
@@ -76,9 +79,11 @@ conv_umma_kernel(UmmaDev a) {
     const int hw_out = hout * hout;
     const int KG = a.cin / KC;
 
+    constexpr int NOUT = TAPS == 3 ? BN / 3 : BN;      // output channels of the tile
+    constexpr int TMC = BN == 96 ? 128 : BN;           // tensor-memory columns (a power of two)
     // tile origin
     int m0 = 0, h0 = 0, w0 = 0;
-    if (TAPS == 9) {
+    if (TAPS != 1) {
         const int ty = blockIdx.x / a.tiles_x, tx = blockIdx.x - ty * a.tiles_x;
         h0 = ty * a.ht;
         w0 = tx * (a.wp - 2);
@@ -93,7 +98,7 @@ conv_umma_kernel(UmmaDev a) {
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(tmem_ptr, BN);
+    if (warp == 4) tmem_alloc(tmem_ptr, TMC);
     // BN prologue parameters of this sample
     if (a.prologue_mode == 0) {
         const double cnt = (double)hin * hin;
@@ -400,7 +405,7 @@ conv_umma_kernel(UmmaDev a) {
     } else if (warp == 9) {
         // =============================== weight loader ===============================
         if (lane == 0) {
-            const int nstages = TAPS == 9 ? 9 * KG : KG;
+            const int nstages = TAPS * KG;
             const uint8_t* wsrc = a.w + (size_t)ntile * nstages * P::B_STAGE;
             for (int j = 0; j < nstages; ++j) {
                 const int slot = j % P::B_SLOTS;
@@ -445,12 +450,12 @@ conv_umma_kernel(UmmaDev a) {
                 for (int g = 0; g < KG; ++g) {
                     const int sa = g & 1;
                     mbar_wait(&a_full[sa], (g >> 1) & 1);
-                    for (int t = 0; t < 9; ++t) {
-                        const int j = g * 9 + t;
-                        const int sb = j % NB9;
-                        mbar_wait(&b_full[sb], (j / NB9) & 1);
+                    for (int t = 0; t < TAPS; ++t) {
+                        const int j = g * TAPS + t;
+                        const int sb = j % P::B_SLOTS;
+                        mbar_wait(&b_full[sb], (j / P::B_SLOTS) & 1);
                         tc_fence_after();
-                        const int shift = (t / 3) * a.wp + (t % 3);
+                        const int shift = TAPS == 3 ? t * a.wp : (t / 3) * a.wp + (t % 3);
 #pragma unroll
                         for (int k = 0; k < MMAS; ++k) {
                             const uint64_t ad =
@@ -480,7 +485,9 @@ conv_umma_kernel(UmmaDev a) {
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         bool valid;
-        if (TAPS == 9) {
+        if (TAPS == 3) {
+            valid = true;                    // partial sums of every patch row are needed by the rows before it
+        } else if (TAPS == 9) {
             const int i = row / a.wp, j = row - i * a.wp;
             valid = i < a.ht && j < a.wp - 2 && h0 + i < hout && w0 + j < hout;
         } else {
@@ -503,7 +510,7 @@ conv_umma_kernel(UmmaDev a) {
         for (int r = warp; r < UM; r += NW) {
             int pix;
             bool ok;
-            if (TAPS == 9) {
+            if (TAPS != 1) {
                 const int i = r / a.wp, j = r - i * a.wp;
                 ok = i < a.ht && j < a.wp - 2 && h0 + i < hout && w0 + j < hout;
                 pix = (h0 + i) * hout + w0 + j;
@@ -511,23 +518,31 @@ conv_umma_kernel(UmmaDev a) {
                 ok = m0 + r < hw_out;
                 pix = m0 + r;
             }
+            if (TAPS == 3) {
+                // dx-merged accumulator: combine the three column blocks of rows r, r + 1, r + 2 and keep the result in the
+                // first block of row r (nobody else reads E_0[r]), where the statistics below expect the tile's output
+                float v = 0.f;
+                if (ok) v = (s_out[r * (BN + 1) + lane] + s_out[(r + 1) * (BN + 1) + NOUT + lane]) + s_out[(r + 2) * (BN + 1) + 2 * NOUT + lane];
+                s_out[r * (BN + 1) + lane] = v;
+            }
             if (!ok) continue;
-            float* o = a.out + ((size_t)s * hw_out + pix) * a.out_cstride + a.out_coff + ntile * BN;
-            const int nvalid = a.cout - ntile * BN;   // < BN only on the zero-padded last tile of a data-gradient convolution
+            float* o = a.out + ((size_t)s * hw_out + pix) * a.out_cstride + a.out_coff + ntile * NOUT;
+            const int nvalid = a.cout - ntile * NOUT;   // < NOUT only on the zero-padded last tile of a data-gradient convolution
 #pragma unroll
-            for (int cb = 0; cb < BN; cb += 32)
+            for (int cb = 0; cb < NOUT; cb += 32)
                 if (cb + lane < nvalid) o[cb + lane] = s_out[r * (BN + 1) + cb + lane];
         }
+        if (TAPS == 3) __syncthreads();   // the combined rows were written by different warps than the ones that sum them
         // per-channel statistics of this tile (invalid rows were staged as zeros): partial column sums by all
         // threads, combined in shared memory (the scale/shift tables are dead by now), ONE double atomic pair per
         // channel and tile
         if (a.bnr_sums != nullptr) {
             // BatchNorm(+ReLU) backward reduction over this tile: channel = column, rows split over the row groups
-            constexpr int GROUPS = 448 / BN;
+            constexpr int GROUPS = 448 / NOUT;
             constexpr int RPG = (UM + GROUPS - 1) / GROUPS;
             float* red = s_sc;
-            const int cidx = tid % BN, g = tid / BN;
-            const int ch = ntile * BN + cidx;
+            const int cidx = tid % NOUT, g = tid / NOUT;
+            const int ch = ntile * NOUT + cidx;
             if (g < GROUPS) {
                 float s1 = 0.f, s2 = 0.f;
                 if (ch < a.cout) {
@@ -549,7 +564,7 @@ conv_umma_kernel(UmmaDev a) {
                             const int r = rb + u;
                             int pix;
                             bool ok;
-                            if (TAPS == 9) {
+                            if (TAPS != 1) {
                                 const int i = r / a.wp, j = r - i * a.wp;
                                 ok = r < rend && i < a.ht && j < a.wp - 2 && h0 + i < hout && w0 + j < hout;
                                 pix = (h0 + i) * hout + w0 + j;
@@ -569,28 +584,28 @@ conv_umma_kernel(UmmaDev a) {
                         }
                     }
                 }
-                red[g * BN + cidx] = s1;
-                red[(GROUPS + g) * BN + cidx] = s2;
+                red[g * NOUT + cidx] = s1;
+                red[(GROUPS + g) * NOUT + cidx] = s2;
             }
             __syncthreads();
-            if (tid < BN && ntile * BN + tid < a.cout) {
+            if (tid < NOUT && ntile * NOUT + tid < a.cout) {
                 double t1 = 0.0, t2 = 0.0;
 #pragma unroll
                 for (int g2 = 0; g2 < GROUPS; ++g2) {
-                    t1 += (double)red[g2 * BN + tid];
-                    t2 += (double)red[(GROUPS + g2) * BN + tid];
+                    t1 += (double)red[g2 * NOUT + tid];
+                    t2 += (double)red[(GROUPS + g2) * NOUT + tid];
                 }
-                double* sm = a.bnr_sums + 2 * ((size_t)s * a.cout + ntile * BN + tid);
+                double* sm = a.bnr_sums + 2 * ((size_t)s * a.cout + ntile * NOUT + tid);
                 atomicAdd(sm, t1);
                 atomicAdd(sm + 1, t2);
             }
             __syncthreads();
         }
         if (a.out_stats != nullptr) {
-            constexpr int GROUPS = 448 / BN;                        // row groups: 3 (N=128), 7 (N=64), 14 (N=32)
+            constexpr int GROUPS = 448 / NOUT;                        // row groups: 3 (N=128), 7 (N=64), 14 (N=32)
             constexpr int RPG = (UM + GROUPS - 1) / GROUPS;          // rows per group
             float* red = s_sc;                                       // [2][GROUPS][BN] floats <= 3.5 KB
-            const int cidx = tid % BN, g = tid / BN;
+            const int cidx = tid % NOUT, g = tid / NOUT;
             if (g < GROUPS) {
                 float su = 0.f, sq = 0.f;
                 const int r1 = (g + 1) * RPG < UM ? (g + 1) * RPG : UM;
@@ -599,18 +614,18 @@ conv_umma_kernel(UmmaDev a) {
                     su += x;
                     sq = fmaf(x, x, sq);
                 }
-                red[g * BN + cidx] = su;
-                red[(GROUPS + g) * BN + cidx] = sq;
+                red[g * NOUT + cidx] = su;
+                red[(GROUPS + g) * NOUT + cidx] = sq;
             }
             __syncthreads();
-            if (tid < BN && ntile * BN + tid < a.cout) {
+            if (tid < NOUT && ntile * NOUT + tid < a.cout) {
                 double su = 0.0, sq = 0.0;
 #pragma unroll
                 for (int g2 = 0; g2 < GROUPS; ++g2) {
-                    su += (double)red[g2 * BN + tid];
-                    sq += (double)red[(GROUPS + g2) * BN + tid];
+                    su += (double)red[g2 * NOUT + tid];
+                    sq += (double)red[(GROUPS + g2) * NOUT + tid];
                 }
-                double* st = a.out_stats + 2 * ((size_t)s * a.out_stats_stride + a.out_coff + ntile * BN + tid);
+                double* st = a.out_stats + 2 * ((size_t)s * a.out_stats_stride + a.out_coff + ntile * NOUT + tid);
                 atomicAdd(st, su);
                 atomicAdd(st + 1, sq);
             }
@@ -619,7 +634,7 @@ conv_umma_kernel(UmmaDev a) {
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, TMC);
     }
 }
 
@@ -663,7 +678,7 @@ static int launch_umma(smg_handle* h, const UmmaDev& d, int n, cudaStream_t st) 
     using P = SmemPlan<ELT, BN, TAPS, SPLIT>;
     SMG_TRY(ensure_dyn_smem(h, (const void*)conv_umma_kernel<ELT, BN, TAPS, POOL, SPLIT>, P::TOTAL));
     dim3 grid;
-    if (TAPS == 9) {
+    if (TAPS != 1) {
         const int wt = d.wp - 2;
         const int tx = (d.hout + wt - 1) / wt, ty = (d.hout + d.ht - 1) / d.ht;
         grid = dim3(tx * ty, 1, n);
@@ -718,7 +733,7 @@ static int dispatch_split(smg_handle* h, const ConvArgs& a, UmmaDev& d, cudaStre
         SMG_CHECK((d.ht + 2) * d.wp <= 5 * MAX_WP && d.ht * d.wp <= UM, SMG_ERR_STATE, "conv_umma: patch %dx%d too large", d.ht, d.wp);
         const int wt = d.wp - 2;
         d.tiles_x = (d.hout + wt - 1) / wt;
-        return launch_umma<4, 32, 9, 0, 1>(h, d, a.n, st);
+        return launch_umma<4, 96, 3, 0, 1>(h, d, a.n, st);   // dx merged into N: a third of the MMAs of the nine-tap form
     }
     SMG_CHECK(a.cin % KC == 0 && a.cin <= 1024, SMG_ERR_UNSUPPORTED, "conv_umma: cin %d unsupported", a.cin);
     if (a.cout == 64) {

@@ -127,6 +127,30 @@ __global__ void pack_split_kernel(const float* __restrict__ tf32, float* __restr
     }
 }
 
+// 3x3 split weights for the dx-merged tensor-core form (conv_umma.cu, TAPS == 3): stage (kgroup, dy) = [hi | lo] images of
+// [chunk (8)][n = dx*cout + co][4 floats]; element i of the hi/lo pair
+__device__ __forceinline__ void split3_store(const float* __restrict__ w, float* __restrict__ out, int i, int cout, int k_off,
+                                             int k_total) {
+    int r = i;
+    const int e = r % 4; r /= 4;
+    const int n = r % (3 * cout); r /= 3 * cout;
+    const int c = r % 8; r /= 8;
+    const int dy = r % 3, kg = r / 3;
+    const int dx = n / cout, co = n - dx * cout, ci = kg * 32 + c * 4 + e;
+    const float v = w[((size_t)co * k_total + k_off + ci) * 9 + dy * 3 + dx];
+    const int stage_elems = 32 * 3 * cout;
+    const int stage = i / stage_elems, within = i - stage * stage_elems;
+    const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);   // nearest tf32
+    out[(size_t)(2 * stage) * stage_elems + within] = hi;
+    out[(size_t)(2 * stage + 1) * stage_elems + within] = v - hi;
+}
+
+__global__ void pack_split3_kernel(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int k_off, int k_total) {
+    const int total = 9 * cin * cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+        split3_store(w, out, i, cout, k_off, k_total);
+}
+
 // ---- batched variant: one launch packs every convolution of a trunk (blockIdx.y = job) ----
 __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
     const PackJob j = jobs[blockIdx.y];
@@ -181,7 +205,9 @@ __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int mask) {
             const float v = j.src[((size_t)co * j.k_total + j.k_off + ci) * j.taps + tap];
             if (pass == 0) j.tf32[i] = v;
             else j.bf16[i] = __float2bfloat16_rn(v);
-            if (pass == 0 && (mask & SMG_PACK_FFMA) && j.split != nullptr) {
+            if (pass == 0 && (mask & SMG_PACK_FFMA) && j.split != nullptr && j.taps == 9) {
+                split3_store(j.src, j.split, i, j.cout, j.k_off, j.k_total);
+            } else if (pass == 0 && (mask & SMG_PACK_FFMA) && j.split != nullptr) {
                 // the same stage sequence with each stage (32 channels x bn rows) stored as [hi image][lo image]
                 const int stage_elems = 32 * j.bn;
                 const int stage = i / stage_elems, within = i - stage * stage_elems;
@@ -252,8 +278,11 @@ int pack_conv_weights(smg_handle* h, const float* w_oihw, ConvW& cw, int k_offse
         h->launches++;
     }
     if (cw.w_split != nullptr) {
-        pack_split_kernel<<<blocks, threads, 0, st>>>(reinterpret_cast<const float*>(cw.w_tf32), reinterpret_cast<float*>(cw.w_split),
-                                                      total, 32 * bn);
+        if (cw.taps == 9)
+            pack_split3_kernel<<<blocks, threads, 0, st>>>(w_oihw, reinterpret_cast<float*>(cw.w_split), cw.cout, cw.cin, k_offset, k_total);
+        else
+            pack_split_kernel<<<blocks, threads, 0, st>>>(reinterpret_cast<const float*>(cw.w_tf32), reinterpret_cast<float*>(cw.w_split),
+                                                          total, 32 * bn);
         h->launches++;
     }
     if (cw.w_dgrad_tf32 != nullptr) {

@@ -78,8 +78,9 @@ struct ConvW {
     // 1x1: [ntile over cin/128][kgroup over cout/32][chunk][n][4], value w[kgroup*32 + ..][ntile*128 + n];
     // 3x3: [kgroup over cout/32][flipped tap][chunk][n = cin][4]
     uint8_t* w_dgrad_tf32 = nullptr;
-    // fp32 mode on the tensor cores ("3xTF32"): the w_tf32 stage sequence with every stage stored as [hi image][lo image]
-    // (hi = weight with its 13 low mantissa bits cleared, lo = weight - hi)
+    // fp32 mode on the tensor cores ("3xTF32"): 1x1: the w_tf32 stage sequence with every stage stored as [hi image][lo image]
+    // (hi = nearest tf32 value, lo = weight - hi); 3x3: stages (kgroup, dy) of [hi | lo] x [chunk][dx*cout + co][4] for the
+    // dx-merged form of conv_umma.cu (TAPS == 3)
     uint8_t* w_split = nullptr;
     int cin = 0, cout = 0, taps = 1;
 };
