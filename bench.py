@@ -564,8 +564,8 @@ def run_gpu_arm(args):
             rep = {"batch": B, "samples_per_gpu": hi - lo, "n_gpus": world, "scaling": "strong",
                    "ms_per_batch_step": float(t.item()) / nrep, "samples_per_s": B * nrep / (float(t.item()) / 1e3),
                    "allreduce_bytes": grad_bytes, "precision": precision,
-                   "what": "Trainer.backprop_batch: per-sample grad-enabled pass + backward (graph replay), local sum, NCCL all-reduce of the "
-                           "flat 368-tensor gradient (first n-1 samples' sum overlapped with the last sample), mean, one multi-tensor Adam, re-pack"}
+                   "what": "Trainer.backprop_batch: per-sample grad-enabled pass + backward (graph replay, two interleaved pipelines per GPU), local sum, NCCL all-reduce of the "
+                           "flat 368-tensor gradient, mean, one multi-tensor Adam, re-pack"}
             if world > 1:
                 # the all-reduce alone on the same buffer (device time)
                 Gf = tr._fused[0]["flat"]["grad"]

@@ -337,12 +337,14 @@ class Trainer(object):
         """Data-parallel replay step (BASELINE config 4): `samples` is THIS rank's share of a batch
         of `total` independent transitions, each a dict(depth_heightmap, m_depth_heightmap, style, rotation, label_value)
         with global position first_index + i.  Every sample runs the grad-enabled pass and the backward at the SAME weights
-        (`smg_train_step` with SMG_STEP_GRADS_ONLY); the per-sample gradients are summed locally, all-reduced over the ranks
-        (one flat 28.5 MB buffer; the reduction of the first n-1 samples' sum overlaps the last sample's backward), averaged
-        (`reduction="mean"`) and applied by ONE multi-tensor Adam launch on every rank.  The result equals the serial
+        (`smg_train_step` with SMG_STEP_GRADS_ONLY), consecutive samples alternating between two handles whose kernel chains
+        interleave on the GPU; the per-sample gradients are summed locally, all-reduced over the ranks (one flat 28.5 MB
+        buffer), averaged (`reduction="mean"`) and applied by ONE multi-tensor Adam launch on every rank.  The result equals the serial
         single-GPU step over the same batch; BatchNorm running statistics follow the weighted-sum rule of the serial order.
         All samples of a batch must use the same primitive (one trunk + head).  Returns (mean loss, seconds spent waiting
         for the all-reduce)."""
+        import ctypes
+        import os
         import time
         from . import parallel as _parallel
         rank, world = (0, 1) if local_only else _parallel._world(group)
@@ -356,55 +358,81 @@ class Trainer(object):
             for p, g in zip(st["params"], st["views"]["grad"]):
                 p.grad = g
             self._fused_last_style = style
-        eng._mean_std = (self.image_mean, self.image_std)
         kind = 1 if self.method == 'reactive' else 0
         cw = [1.0, 1.0, 0.0] if kind else [1.0, 1.0, 1.0]
         group_ = self.optimizer.param_groups[0]
         G = st["flat"]["grad"]
-        acc = st.setdefault("acc", torch.zeros_like(G))
-        acc.zero_()
+        n = len(samples)
+        # Two pipelines: the captured per-sample step is a chain of ~500 kernels, most of them far too small to fill 148 SMs
+        # with two samples (blocks 3-4 run on 7-25 CTAs), so consecutive samples alternate between two handles (own
+        # workspace, own streams, own gradient buffer, same weights) and their chains interleave on the GPU.
+        # SMG_REPLAY_STREAMS=1 keeps the single pipeline.
+        lanes = 2 if (n >= 4 and os.environ.get("SMG_REPLAY_STREAMS", "2") != "1") else 1
+        pipes = [{"eng": eng, "G": G, "ptrs": st["ptrs"], "stream": torch.cuda.current_stream(eng.device)}]
+        if lanes == 2:
+            rp = st.get("replay2")
+            if rp is None:
+                G2 = torch.zeros_like(G)
+                base = G.storage_offset()
+                views2 = [G2[v.storage_offset() - base:v.storage_offset() - base + v.numel()].view_as(v) for v in st["views"]["grad"]]
+                arr2 = (ctypes.c_void_p * len(views2))(*[v.data_ptr() for v in views2])
+                import weakref
+                weakref.finalize(model, _engine.drop_engine, ("replay2", id(model)))
+                rp = st["replay2"] = {"G": G2, "views": views2, "ptrs": (st["ptrs"][0], arr2, st["ptrs"][2], st["ptrs"][3]),
+                                      "stream": torch.cuda.Stream(device=eng.device), "acc": torch.zeros_like(G)}
+            eng2 = _engine.get_engine(model._device_index(), 18, 640, model.precision, owner=("replay2", id(model)))
+            eng2.sync_weights(model, force=True, style=style)   # the fused steps update the parameters in place: always re-pack
+            pipes.append({"eng": eng2, "G": rp["G"], "ptrs": rp["ptrs"], "stream": rp["stream"], "acc": rp["acc"]})
+        pipes[0]["acc"] = st.setdefault("acc", torch.zeros_like(G))
         tid, hid = _engine.STYLE_ROUTE[style]
         trunk, head = getattr(model, _engine.TRUNK_ATTRS[tid]), getattr(model, _engine.HEAD_ATTRS[hid])
-        n = len(samples)
-        loss_sum = torch.zeros(1, dtype=torch.float32, device=eng.device)
-        bn_sum = None
-        work_acc = None
+        main = pipes[0]["stream"]
+        for pp in pipes:
+            pp["eng"]._mean_std = (self.image_mean, self.image_std)
+            pp["stream"].wait_stream(main)
+            with torch.cuda.stream(pp["stream"]):
+                pp["acc"].zero_()
+                pp["loss"] = torch.zeros(1, dtype=torch.float32, device=eng.device)
+                pp["bn"] = None
         for i, smp in enumerate(samples):
-            hm = torch.from_numpy(np.stack([np.asarray(smp["depth_heightmap"], np.float64),
-                                            np.asarray(smp["m_depth_heightmap"], np.float64)])).to(eng.device, non_blocking=True)
-            rot = 0 if style == 2 else int(smp["rotation"])
-            loss, q, mean, var = eng.train_step(style, hm[0], hm[1], rot, model.gnum_rotations, kind, float(smp["label_value"]),
-                                                cw, st["ptrs"], len(st["params"]), 1, want_bn_stats=model.update_running_stats,
-                                                grads_only=True)
-            loss_sum += loss
-            if model.update_running_stats:
-                j = 2 * (first_index + i)
-                w0 = _parallel.ema_pass_weights(j, 2 * total)
-                w1 = _parallel.ema_pass_weights(j + 1, 2 * total)
-                contrib = torch.cat([w0 * mean[0].double() + w1 * mean[1].double(), w0 * var[0].double() + w1 * var[1].double()])
-                # the head's two BatchNorms see one call per sample (see models._apply_head_running_stats)
-                wh = _parallel.ema_pass_weights(first_index + i, total)
-                norm5 = trunk.features.norm5
-                v5 = var[:, -1024:].double()
-                var_z = norm5.weight.double() ** 2 * v5 / (v5 + 1e-5)
-                h1 = eng.head_bn_stats(1).double()[0]
-                unb = 400.0 / 399.0
-                contrib = torch.cat([contrib, wh * norm5.bias.double(), wh * norm5.bias.double(), wh * unb * var_z[0],
-                                     wh * unb * var_z[1], wh * h1[0], wh * unb * h1[1]])
-                bn_sum = contrib if bn_sum is None else bn_sum + contrib
-            if i < n - 1:
-                acc += G
-                if i == n - 2 and world > 1:
-                    work_acc = _parallel.allreduce_flat(acc, group, async_op=True)   # overlaps the last sample's passes
+            pp = pipes[i % lanes]
+            e = pp["eng"]
+            with torch.cuda.stream(pp["stream"]):
+                hm = torch.from_numpy(np.stack([np.asarray(smp["depth_heightmap"], np.float64),
+                                                np.asarray(smp["m_depth_heightmap"], np.float64)])).to(eng.device, non_blocking=True)
+                rot = 0 if style == 2 else int(smp["rotation"])
+                loss, q, mean, var = e.train_step(style, hm[0], hm[1], rot, model.gnum_rotations, kind, float(smp["label_value"]),
+                                                  cw, pp["ptrs"], len(st["params"]), 1, want_bn_stats=model.update_running_stats,
+                                                  grads_only=True)
+                pp["loss"] += loss
+                pp["acc"] += pp["G"]
+                if model.update_running_stats:
+                    j = 2 * (first_index + i)
+                    w0 = _parallel.ema_pass_weights(j, 2 * total)
+                    w1 = _parallel.ema_pass_weights(j + 1, 2 * total)
+                    contrib = torch.cat([w0 * mean[0].double() + w1 * mean[1].double(), w0 * var[0].double() + w1 * var[1].double()])
+                    # the head's two BatchNorms see one call per sample (see models._apply_head_running_stats)
+                    wh = _parallel.ema_pass_weights(first_index + i, total)
+                    norm5 = trunk.features.norm5
+                    v5 = var[:, -1024:].double()
+                    var_z = norm5.weight.double() ** 2 * v5 / (v5 + 1e-5)
+                    h1 = e.head_bn_stats(1).double()[0]
+                    unb = 400.0 / 399.0
+                    contrib = torch.cat([contrib, wh * norm5.bias.double(), wh * norm5.bias.double(), wh * unb * var_z[0],
+                                         wh * unb * var_z[1], wh * h1[0], wh * unb * h1[1]])
+                    pp["bn"] = contrib if pp["bn"] is None else pp["bn"] + contrib
+        for pp in pipes[1:]:
+            main.wait_stream(pp["stream"])
+        torch.add(pipes[0]["acc"], pipes[1]["acc"], out=G) if lanes == 2 else G.copy_(pipes[0]["acc"])
+        loss_sum = pipes[0]["loss"] + pipes[1]["loss"] if lanes == 2 else pipes[0]["loss"]
+        bn_sum = pipes[0]["bn"]
+        if lanes == 2 and pipes[1]["bn"] is not None:
+            bn_sum = pipes[1]["bn"] if bn_sum is None else bn_sum + pipes[1]["bn"]
         t0 = time.perf_counter()
-        work_last = _parallel.allreduce_flat(G, group, async_op=True) if world > 1 else None
-        for w in (work_acc, work_last):
-            if w is not None:
-                w.wait()
         if world > 1:
+            _parallel.allreduce_flat(G, group, async_op=False)      # one flat 28.5 MB all-reduce (0.1 ms over NVLink)
             torch.cuda.current_stream(eng.device).synchronize()
         wait_s = time.perf_counter() - t0
-        G += acc
         if reduction == "mean":
             G /= float(total)
         if world > 1:

@@ -88,3 +88,41 @@ def test_replay_batch_step_equals_serial_accumulation(scene_inputs):
     for k in ("grasp_depth_trunk.features.denseblock3.denselayer9.norm2.running_var", "grasp_depth_trunk.features.norm0.running_mean",
               "graspnet_val.grasp-val-norm1.running_mean", "graspnet_val.grasp-val-norm0.running_var"):
         assert torch.allclose(ba[k], bb[k], rtol=2e-4, atol=1e-6), k
+
+
+def test_replay_two_pipelines_equal_one_pipeline(scene_inputs, monkeypatch):
+    """backprop_batch alternates consecutive samples between two handles (own workspace, streams and gradient buffer); the
+    result must equal the single-pipeline run of the same batch: same mean loss, same averaged gradient (up to the order of
+    the float sums), same weights after the Adam step, same BatchNorm running statistics."""
+    import smg_b200.synth as synth
+    scene, _, _, sc = scene_inputs
+    samples = []
+    for obj, rot, label in [(0, 3, 1.0), (1, 7, 0.0), (2, 12, 2.5), (3, 0, 0.3), (0, 9, 1.7), (1, 15, 0.8), (2, 5, 0.1)]:
+        samples.append({"depth_heightmap": scene, "m_depth_heightmap": synth.masked_scene(scene, sc["masks"], [obj]), "style": 0,
+                        "rotation": rot, "label_value": label})
+    a, b = _trainer("tf32", 16), _trainer("tf32", 16)
+    monkeypatch.setenv("SMG_REPLAY_STREAMS", "1")
+    loss_b, _ = b.backprop_batch(samples)
+    monkeypatch.setenv("SMG_REPLAY_STREAMS", "2")
+    loss_a, _ = a.backprop_batch(samples)
+    assert "replay2" in a._fused[0] and "replay2" not in b._fused[0]
+    assert abs(loss_a - loss_b) <= 1e-5 * max(1.0, abs(loss_b))
+    pa, pb = dict(a.model.named_parameters()), dict(b.model.named_parameters())
+    worst = 0.0
+    for k, p in pb.items():
+        if p.grad is not None:
+            worst = max(worst, float((pa[k].grad - p.grad).abs().max()) / max(float(p.grad.abs().max()), 1e-12))
+    print("two pipelines vs one: worst per-tensor deviation of the averaged gradient %.2e" % worst)
+    assert worst <= 2e-4      # same per-sample gradients (atomics noise ~4e-5), summed in a different order
+    k = "grasp_depth_trunk.features.denseblock2.denselayer5.conv1.weight"
+    assert float((pa[k].detach() - pb[k].detach()).abs().max()) <= 2.1e-4          # one Adam step of lr = 1e-4 each way at most
+    ba, bb = dict(a.model.named_buffers()), dict(b.model.named_buffers())
+    for k in ("grasp_depth_trunk.features.denseblock3.denselayer9.norm2.running_var", "grasp_depth_trunk.features.norm0.running_mean",
+              "graspnet_val.grasp-val-norm1.running_mean"):
+        assert torch.allclose(ba[k], bb[k], rtol=2e-4, atol=1e-6), k
+    # second batch: the second handle must have picked up the updated weights (a stale copy would reproduce the first loss)
+    loss_a2, _ = a.backprop_batch(samples)
+    monkeypatch.setenv("SMG_REPLAY_STREAMS", "1")
+    loss_b2, _ = b.backprop_batch(samples)
+    print("losses: first batch %.6f / %.6f, second batch %.6f / %.6f" % (loss_a, loss_b, loss_a2, loss_b2))
+    assert abs(loss_a2 - loss_b2) <= 2e-2 * max(1.0, abs(loss_b2)) and abs(loss_a2 - loss_a) > 1e-6
