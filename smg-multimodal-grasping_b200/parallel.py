@@ -128,33 +128,66 @@ def decision_context(trainer, depth_heightmap, masks, world, is_ets=True, is_tar
 def decision_local_partials(trainer, ctx, rank):
     """This rank's share of every primitive's samples through the trunk + head half: the all-gather's send buffer
     [cap, 400, 64] (zero-padded where the shares are uneven)."""
+    import os
+    from . import engine as _engine
     model, plan, cap, scene, masks, pairs = ctx["model"], ctx["plan"], ctx["cap"], ctx["scene"], ctx["masks"], ctx["pairs"]
     max_local = max(hi - lo for _, _, shares in plan.values() for lo, hi in shares)
     eng = model._engine(max(max_local, 18))
     dev = eng.device
+    # The three primitives use three different trunks, and a rank's share of one primitive is a handful of samples whose
+    # kernel chain cannot fill the GPU: each primitive gets its own handle and stream, so the three chains interleave
+    # (SMG_DECISION_STREAMS=1 runs them one after the other on the model's own handle).
+    lanes = os.environ.get("SMG_DECISION_STREAMS", "3") != "1"
+    main = torch.cuda.current_stream(dev)
     # the scene and the K object masks cross PCIe once; every masked heightmap (code/main.py:160,186) is formed on the device
     scene_t = torch.from_numpy(np.ascontiguousarray(scene)).to(dev, non_blocking=True)
     masks_t = torch.from_numpy(np.ascontiguousarray(masks)).to(dev, non_blocking=True)
     send = torch.zeros((cap, 400, 64), dtype=torch.float32, device=dev)
     off = 0
+    used = []
     for style, (n_rot, n_masks, shares) in plan.items():
         lo, hi = shares[rank]
         width = max(h_ - l_ for l_, h_ in shares)
         if hi > lo:
-            eng.sync_weights(model, style=style)
-            rots = [i for i in range(lo, min(hi, n_rot))]
-            mids = [i - n_rot for i in range(max(lo, n_rot), hi)]
-            mh_t = None
-            if mids and style == 2:
-                gi = torch.tensor([pairs[i][0] for i in mids], device=dev)
-                si = torch.tensor([pairs[i][1] for i in mids], device=dev)
-                mh_t = (scene_t[None] * (masks_t[gi] + masks_t[si])).contiguous()
-            elif mids:
-                mh_t = (scene_t[None] * masks_t[mids[0]:mids[-1] + 1]).contiguous()
-            nrot_div = model.gnum_rotations if style != 1 else model.snum_rotations
-            send[off:off + (hi - lo)] = eng.qpartials(style, scene_t, rots, nrot_div, mh_t, trainer.image_mean, trainer.image_std)
+            if lanes:
+                e = _engine.get_engine(dev, max(max_local, 18), 640, model.precision, owner=("decision", int(style), id(model)))
+                stream = _decision_stream(dev, int(style))
+                if not getattr(model, "_smg_decision_finalizer", False):
+                    import weakref
+                    for s_ in (0, 1, 2):
+                        weakref.finalize(model, _engine.drop_engine, ("decision", s_, id(model)))
+                    object.__setattr__(model, "_smg_decision_finalizer", True)
+            else:
+                e, stream = eng, main
+            stream.wait_stream(main)
+            used.append(stream)
+            with torch.cuda.stream(stream):
+                e.sync_weights(model, style=style)
+                rots = [i for i in range(lo, min(hi, n_rot))]
+                mids = [i - n_rot for i in range(max(lo, n_rot), hi)]
+                mh_t = None
+                if mids and style == 2:
+                    gi = torch.tensor([pairs[i][0] for i in mids], device=dev)
+                    si = torch.tensor([pairs[i][1] for i in mids], device=dev)
+                    mh_t = (scene_t[None] * (masks_t[gi] + masks_t[si])).contiguous()
+                elif mids:
+                    mh_t = (scene_t[None] * masks_t[mids[0]:mids[-1] + 1]).contiguous()
+                nrot_div = model.gnum_rotations if style != 1 else model.snum_rotations
+                send[off:off + (hi - lo)] = e.qpartials(style, scene_t, rots, nrot_div, mh_t, trainer.image_mean, trainer.image_std)
         off += width
+    for stream in used:
+        main.wait_stream(stream)
     return send
+
+
+_DECISION_STREAMS = {}
+
+
+def _decision_stream(dev, style):
+    key = (str(dev), int(style))
+    if key not in _DECISION_STREAMS:
+        _DECISION_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _DECISION_STREAMS[key]
 
 
 def decision_from_partials(trainer, ctx, recv, rank=0, group=None):
