@@ -10,7 +10,7 @@
 //   -> 1x1 dgrad -> BN1 reduce -> BN1 apply (accumulates into the block gradient buffer).
 // The activations a = relu(bn(x)) are never stored: every kernel recomputes them from the raw buffers and
 // the (sum, sumsq) statistics saved by the forward pass.
-#include "smg_internal.cuh"
+#include "umma_common.cuh"
 
 namespace smg {
 
@@ -51,6 +51,8 @@ template <int APPLY>
 __global__ void __launch_bounds__(256)
 bn_bwd_kernel(BnBwd a, int S, float* __restrict__ dgamma, float* __restrict__ dbeta) {
     extern __shared__ __align__(16) float4 red[];   // APPLY = 0: [2][PL][Q]
+    pdl_launch_dependents();                        // see conv_umma.cu: the backward chain is launch-latency bound
+    pdl_wait();
     const int s = blockIdx.y;
     const int Q = a.C >> 2;
     const int PL = 256 / Q;
@@ -532,8 +534,22 @@ int launch_bn_bwd(smg_handle* h, BnBwd a, int S, bool apply, float* dgamma, floa
     while (ppc > 4 * PL && (npix + ppc - 1) / ppc * S < 2 * h->num_sms) ppc >>= 1;
     a.pix_per_cta = ppc;
     dim3 grid((npix + ppc - 1) / ppc, S);
-    if (apply) bn_bwd_kernel<1><<<grid, 256, 0, st>>>(a, S, dgamma, dbeta);
-    else bn_bwd_kernel<0><<<grid, 256, 2 * PL * Q * sizeof(float4), st>>>(a, S, nullptr, nullptr);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->use_pdl ? 1 : 0;
+    float* nullp = nullptr;
+    if (apply) {
+        SMG_CUDA(cudaLaunchKernelEx(&cfg, bn_bwd_kernel<1>, a, S, dgamma, dbeta));
+    } else {
+        cfg.dynamicSmemBytes = 2 * PL * Q * sizeof(float4);
+        SMG_CUDA(cudaLaunchKernelEx(&cfg, bn_bwd_kernel<0>, a, S, nullp, nullp));
+    }
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;

@@ -99,6 +99,10 @@ conv_umma_kernel(UmmaDev a) {
         fence_barrier_init();
     }
     if (warp == 4) tmem_alloc(tmem_ptr, TMC);
+    // Programmatic dependent launch (the training step chains ~240 of these kernels with the BatchNorm-backward kernels,
+    // many of them on 7-50 CTAs): the successor may become resident now; everything below reads what the predecessor wrote
+    pdl_launch_dependents();
+    pdl_wait();
     // BN prologue parameters of this sample
     if (a.prologue_mode == 0) {
         const double cnt = (double)hin * hin;
@@ -687,7 +691,17 @@ static int launch_umma(smg_handle* h, const UmmaDev& d, int n, cudaStream_t st) 
     }
     UmmaDev dd = d;
     dd.async_producer = h->force_async >= 0 ? h->force_async : ((int)(grid.x * grid.y * grid.z) < 2 * h->num_sms ? 1 : 0);
-    conv_umma_kernel<ELT, BN, TAPS, POOL, SPLIT><<<grid, 448, P::TOTAL, st>>>(dd);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(448);
+    cfg.dynamicSmemBytes = P::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->use_pdl ? 1 : 0;
+    SMG_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<ELT, BN, TAPS, POOL, SPLIT>, dd));
     h->launches++;
     SMG_CUDA(cudaGetLastError());
     return SMG_OK;
