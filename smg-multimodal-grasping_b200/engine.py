@@ -105,9 +105,9 @@ class Engine:
         path: 368 (data_ptr, version) pairs instead of 1104).  The Parameter lists are cached per (model, submodule):
         torch keeps Parameter identity across .cuda() / load_state_dict / optimizer steps.  The fused training step updates
         the parameters in place from a library kernel (no version bump): the trainer counts those updates in
-        `model._smg_epoch`, which is part of the signature, so that OTHER handles of the same model re-pack too."""
+        `model._smg_epoch` (per trunk / head), which is part of the signature, so that OTHER handles of the same model re-pack too."""
         n_out = 3 if model.__class__.__name__ == "reactive_net" else 1
-        epoch = getattr(model, "_smg_epoch", 0)
+        epochs = getattr(model, "_smg_epoch", None) or {}
         tids, hids = range(len(TRUNK_ATTRS)), range(len(HEAD_ATTRS))
         if style is not None:
             t_only, h_only = STYLE_ROUTE[int(style)]
@@ -118,7 +118,7 @@ class Engine:
             params = self._param_lists.get((id(model), key, id(sub)))
             if params is None or force:
                 params = self._param_lists[(id(model), key, id(sub))] = trunk_param_list(sub)
-            sig = (id(model), epoch, tuple([(p.data_ptr(), p._version) for p in params]))
+            sig = (id(model), epochs.get(key, 0), tuple([(p.data_ptr(), p._version) for p in params]))
             if force or self._sig.get(key) != sig:
                 dev = self._device_params(key, params)
                 _lib.check(self.lib.smg_set_trunk_weights(self.h, tid, _ptr_array(dev), len(dev), self._stream()))
@@ -129,7 +129,7 @@ class Engine:
             params = self._param_lists.get((id(model), key, id(sub)))
             if params is None or force:
                 params = self._param_lists[(id(model), key, id(sub))] = head_param_list(sub)
-            sig = (id(model), epoch, tuple([(p.data_ptr(), p._version) for p in params]))
+            sig = (id(model), epochs.get(key, 0), tuple([(p.data_ptr(), p._version) for p in params]))
             if force or self._sig.get(key) != sig:
                 dev = self._device_params(key, params)
                 _lib.check(self.lib.smg_set_head_weights(self.h, hid, _ptr_array(dev), n_out, self._stream()))
@@ -139,12 +139,13 @@ class Engine:
     def mark_synced(self, model, style):
         """The packed weights of `style`'s trunk and head on THIS handle are current (the fused training step re-packs them
         itself): record the signature without packing again."""
-        epoch = getattr(model, "_smg_epoch", 0)
+        epochs = getattr(model, "_smg_epoch", None) or {}
         tid, hid = STYLE_ROUTE[int(style)]
         for key, attr in ((("t", tid), TRUNK_ATTRS[tid]), (("h", hid), HEAD_ATTRS[hid])):
             params = self._param_lists.get((id(model), key, id(getattr(model, attr))))
             if params is not None:
-                self._sig[key] = (id(model), epoch, tuple([(p.data_ptr(), p._version) for p in params]))
+                self._sig[key] = (id(model), epochs.get(key, 0), tuple([(p.data_ptr(), p._version) for p in params]))
+
 
     # ------------------------------------------------------------------ K1
     def prep(self, heightmaps, mean, std):
@@ -439,6 +440,18 @@ class Engine:
         _lib.check(self.lib.smg_nms(self.h, b.data_ptr() if n else None, n, float(co_thresh), float(min_area),
                                     float(max_area), keep.data_ptr(), cnt.data_ptr(), self._stream()))
         return keep, cnt
+
+
+def bump_weight_epoch(model, style):
+    """The fused training step changed the parameters of `style`'s trunk and head in place (no torch version bump): make every
+    handle of this model see it at its next sync_weights."""
+    tid, hid = STYLE_ROUTE[int(style)]
+    epochs = getattr(model, "_smg_epoch", None)
+    if epochs is None:
+        epochs = {}
+        object.__setattr__(model, "_smg_epoch", epochs)
+    for key in (("t", tid), ("h", hid)):
+        epochs[key] = epochs.get(key, 0) + 1
 
 
 def drop_engine(owner):

@@ -324,7 +324,7 @@ class Trainer(object):
                                             st["ptrs"], len(st["params"]), step, group["lr"], group["betas"][0],
                                             group["betas"][1], group["eps"], want_bn_stats=model.update_running_stats)
         torch._foreach_add_(st["steps"], 1)
-        model._smg_epoch = getattr(model, "_smg_epoch", 0) + 1      # parameters changed in place: other handles must re-pack
+        _engine.bump_weight_epoch(model, style)                      # parameters changed in place: other handles must re-pack
         eng.mark_synced(model, style)                                # this one re-packed inside the step
         if model.update_running_stats:
             tid, hid = _engine.STYLE_ROUTE[int(style)]
@@ -449,7 +449,7 @@ class Trainer(object):
         eng.adam_step_ptrs(st["ptrs"], numel, len(st["params"]), step, group_["lr"], group_["betas"][0], group_["betas"][1],
                            group_["eps"])
         torch._foreach_add_(st["steps"], 1)
-        model._smg_epoch = getattr(model, "_smg_epoch", 0) + 1
+        _engine.bump_weight_epoch(model, style)
         eng.sync_weights(model, force=True, style=style)        # re-pack the updated weights
         if model.update_running_stats and bn_sum is not None:
             if world > 1:

@@ -126,3 +126,24 @@ def test_replay_two_pipelines_equal_one_pipeline(scene_inputs, monkeypatch):
     loss_b2, _ = b.backprop_batch(samples)
     print("losses: first batch %.6f / %.6f, second batch %.6f / %.6f" % (loss_a, loss_b, loss_a2, loss_b2))
     assert abs(loss_a2 - loss_b2) <= 2e-2 * max(1.0, abs(loss_b2)) and abs(loss_a2 - loss_a) > 1e-6
+
+
+def test_secondary_handles_follow_in_place_training_steps(scene_inputs):
+    """The fused training step updates the parameters in place from a library kernel (torch's version counters do not move);
+    the per-primitive handles of the sharded decision and the second replay pipeline must still re-pack: after a training
+    step the sharded decision (secondary handles) and `decision.decide` (the model's own handle) give the same tables."""
+    import smg_b200.synth as synth
+    from smg_b200 import decision, parallel
+    sc = synth.make_scene(5, num_objects=3, cluttered=False)
+    masks = sc["masks"].astype(np.float64)
+    tr = _trainer("tf32", 4)
+    tr.model.update_running_stats = False
+    before = parallel.decide_sharded(tr, sc["depth"], masks, is_ets=True)            # secondary handles pack the initial weights
+    for i in range(2):                                                                # two in-place updates of the grasp trunk + head
+        tr.backprop(sc["depth"] * masks.sum(0), "grasp", [i, 1], [0, 0], [], [], 1.0, masks.copy(), [0] * 3, [0] * 3, [])
+    ref = decision.decide(tr, sc["depth"], masks, is_ets=True)
+    out = parallel.decide_sharded(tr, sc["depth"], masks, is_ets=True)
+    scale = np.abs(ref["gra_conf"]).max()
+    assert np.abs(ref["gra_conf"] - before["gra_conf"]).max() > 1e-3 * scale, "the training steps must have changed the table"
+    for k in ("gra_conf", "suc_conf", "gs_conf"):
+        assert np.abs(out[k] - ref[k]).max() <= 1e-5 * scale, k
