@@ -501,6 +501,7 @@ int smg_destroy(smg_handle* h) {
     if (h->step.adam_tables) cudaFree(h->step.adam_tables);
     if (h->bn_regions_dev) cudaFree(h->bn_regions_dev);
     if (h->geo_out) cudaFree(h->geo_out);
+    if (h->bn_stage) cudaFree(h->bn_stage);
     if (h->train.arena) cudaFree(h->train.arena);
     if (h->train.wstream) cudaStreamDestroy(h->train.wstream);
     for (auto& e : h->train.ev)
@@ -760,9 +761,17 @@ int smg_qforward_maps_batch(smg_handle* h, int trunk_id, int head_id, const doub
     const size_t hm_elems = (size_t)hm_size * hm_size;
     SMG_CHECK(2 * hm_size <= h->H, SMG_ERR_INVALID, "smg_qforward_maps: hm_size %d too large for H %d", hm_size, h->H);
     h->train.valid = false;   // also on the graph-replay path, which does not go through trunk_forward
-    const bool graphable = h->use_graphs && !h->profile && !dev_bn_mean && !dev_bn_var;
+    const bool want_stats = dev_bn_mean != nullptr && dev_bn_var != nullptr;
+    const bool graphable = h->use_graphs && !h->profile && (want_stats || (!dev_bn_mean && !dev_bn_var));
     if (!graphable) return qforward_maps_body(h, trunk_id, head_id, dev_scene_hm, dev_mask_hms, n_masks, hm_size, mean, stddev,
                                               host_rot_idx, n_rot, num_rotations, dev_q, dev_bn_mean, dev_bn_var, st, groups);
+    // the BatchNorm running-statistics side effect needs the per-sample batch statistics of the pass: exported inside the
+    // captured graph into a staging buffer of the handle (allocated on first use, outside any capture), copied out below
+    const size_t bn_floats = (size_t)h->max_samples * SMG_TRUNK_BN_CHANNELS;
+    if (want_stats && h->bn_stage == nullptr) SMG_CUDA(cudaMalloc(&h->bn_stage, 2 * bn_floats * sizeof(float)));
+    float* st_mean = want_stats ? h->bn_stage : nullptr;
+    float* st_var = want_stats ? h->bn_stage + bn_floats : nullptr;
+    const size_t bn_bytes = (size_t)groups * (n_rot + n_masks) * SMG_TRUNK_BN_CHANNELS * sizeof(float);
     // stage the inputs at fixed addresses: [groups] scenes, then [groups x n_masks] masks
     double* stage_masks = h->hm_stage + (size_t)groups * hm_elems;
     SMG_CUDA(cudaMemcpyAsync(h->hm_stage, dev_scene_hm, (size_t)groups * hm_elems * 8, cudaMemcpyDeviceToDevice, st));
@@ -771,14 +780,14 @@ int smg_qforward_maps_batch(smg_handle* h, int trunk_id, int head_id, const doub
     for (auto& g : h->graphs)
         if (g.trunk_id == trunk_id && g.head_id == head_id && g.n_masks == n_masks && g.n_rot == n_rot && g.groups == groups &&
             g.num_rot == num_rotations && g.hm_size == hm_size && g.precision == h->precision && g.mean == mean &&
-            g.stddev == stddev && g.rots == std::vector<int>(host_rot_idx, host_rot_idx + n_rot)) {
+            g.stddev == stddev && g.stats == (want_stats ? 1 : 0) && g.rots == std::vector<int>(host_rot_idx, host_rot_idx + n_rot)) {
             G = &g;
             break;
         }
     if (!G) {
         smg_handle::QGraph g;
         g.trunk_id = trunk_id; g.head_id = head_id; g.n_masks = n_masks; g.n_rot = n_rot; g.num_rot = num_rotations; g.groups = groups;
-        g.hm_size = hm_size; g.precision = h->precision; g.mean = mean; g.stddev = stddev;
+        g.hm_size = hm_size; g.precision = h->precision; g.mean = mean; g.stddev = stddev; g.stats = want_stats ? 1 : 0;
         g.rots.assign(host_rot_idx, host_rot_idx + n_rot);
         h->graphs.push_back(g);
         G = &h->graphs.back();
@@ -788,8 +797,12 @@ int smg_qforward_maps_batch(smg_handle* h, int trunk_id, int head_id, const doub
         // first sighting: run eagerly (also performs the one-time cudaFuncSetAttribute calls)
         G->seen = 1;
         SMG_TRY(qforward_maps_body(h, trunk_id, head_id, h->hm_stage, stage_masks, n_masks, hm_size, mean, stddev,
-                                   host_rot_idx, n_rot, num_rotations, h->q_stage, nullptr, nullptr, st, groups));
+                                   host_rot_idx, n_rot, num_rotations, h->q_stage, st_mean, st_var, st, groups));
         SMG_CUDA(cudaMemcpyAsync(dev_q, h->q_stage, q_bytes, cudaMemcpyDeviceToDevice, st));
+        if (want_stats) {
+            SMG_CUDA(cudaMemcpyAsync(dev_bn_mean, st_mean, bn_bytes, cudaMemcpyDeviceToDevice, st));
+            SMG_CUDA(cudaMemcpyAsync(dev_bn_var, st_var, bn_bytes, cudaMemcpyDeviceToDevice, st));
+        }
         return SMG_OK;
     }
     SMG_CUDA(cudaEventRecord(h->g_in, st));
@@ -799,7 +812,7 @@ int smg_qforward_maps_batch(smg_handle* h, int trunk_id, int head_id, const doub
         const int64_t launches_before = h->launches;
         SMG_CUDA(cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeRelaxed));
         const int status = qforward_maps_body(h, trunk_id, head_id, h->hm_stage, stage_masks, n_masks, hm_size, mean,
-                                              stddev, host_rot_idx, n_rot, num_rotations, h->q_stage, nullptr, nullptr, h->gstream,
+                                              stddev, host_rot_idx, n_rot, num_rotations, h->q_stage, st_mean, st_var, h->gstream,
                                               groups);
         cudaError_t e = cudaStreamEndCapture(h->gstream, &graph);
         const int64_t captured = h->launches - launches_before;
@@ -816,13 +829,19 @@ int smg_qforward_maps_batch(smg_handle* h, int trunk_id, int head_id, const doub
             return SMG_ERR_CUDA;
         }
         G->n_launches = captured;
+        G->head_pairs = h->head_bn1_pairs;
         G->seen = 2;
     }
+    h->head_bn1_pairs = G->head_pairs;   // launch_head_tail's host-side bookkeeping does not run on a replay
     SMG_CUDA(cudaGraphLaunch(G->exec, h->gstream));
     h->launches += G->n_launches;
     SMG_CUDA(cudaEventRecord(h->g_out, h->gstream));
     SMG_CUDA(cudaStreamWaitEvent(st, h->g_out, 0));
     SMG_CUDA(cudaMemcpyAsync(dev_q, h->q_stage, q_bytes, cudaMemcpyDeviceToDevice, st));
+    if (want_stats) {
+        SMG_CUDA(cudaMemcpyAsync(dev_bn_mean, st_mean, bn_bytes, cudaMemcpyDeviceToDevice, st));
+        SMG_CUDA(cudaMemcpyAsync(dev_bn_var, st_var, bn_bytes, cudaMemcpyDeviceToDevice, st));
+    }
     return SMG_OK;
 }
 

@@ -211,6 +211,7 @@ struct smg_handle {
     // addresses, so it is captured once per (trunk, head, shapes, rotations, precision) and replayed
     double* hm_stage = nullptr;   // [1 + S][(H/2)^2] heightmap staging (scene, then masks)
     float* q_stage = nullptr;     // [S*S*4] result staging
+    float* bn_stage = nullptr;    // [2][max_samples][SMG_TRUNK_BN_CHANNELS] statistics staging of the captured passes (lazy)
     cudaStream_t gstream = nullptr;
     cudaEvent_t g_in = nullptr, g_out = nullptr;
     bool use_graphs = true;
@@ -218,6 +219,8 @@ struct smg_handle {
         int trunk_id, head_id, n_masks, n_rot, num_rot, hm_size, precision, groups;
         double mean, stddev;
         std::vector<int> rots;
+        int stats = 0;            // 1: the captured pass also exports the per-sample BatchNorm statistics (bn_stage)
+        int head_pairs = 0;       // head_bn1_pairs of the captured pass (host-side state the replay must restore)
         int seen = 0;
         int64_t n_launches = 0;   // kernels inside the captured graph (for smg_launch_count)
         cudaGraphExec_t exec = nullptr;

@@ -91,10 +91,18 @@ class _SmgNet(nn.Module):
         """BatchNorm2d train-mode side effect: running = (1-m)*running + m*batch for each trunk call in
         `order` (sample indices; the reference calls trunk(scene_r) then trunk(mask) per rotation)."""
         k = len(order)
-        wl = [0.0] * mean.shape[0]
-        for i, s in enumerate(order):
-            wl[s] += _BN_MOMENTUM * (1 - _BN_MOMENTUM) ** (k - 1 - i)
-        w = torch.tensor(wl, dtype=torch.float64, device=mean.device)
+        # the per-sample weights depend on the call pattern only: built once per pattern and kept on the device (a fresh
+        # torch.tensor(..., device=cuda) is a synchronous pageable copy that waits for the whole pass in front of it)
+        cache = self.__dict__.setdefault("_bn_weight_cache", {})
+        key = ("trunk", mean.shape[0], tuple(order), str(mean.device))
+        w = cache.get(key)
+        if w is None:
+            wl = [0.0] * mean.shape[0]
+            for i, s in enumerate(order):
+                wl[s] += _BN_MOMENTUM * (1 - _BN_MOMENTUM) ** (k - 1 - i)
+            if len(cache) > 64:
+                cache.clear()
+            w = cache[key] = torch.tensor(wl, dtype=torch.float64, device=mean.device)
         self._apply_running_sums(trunk, (w[:, None] * mean.double()).sum(0), (w[:, None] * var.double()).sum(0), k)
 
     @torch.no_grad()
@@ -130,14 +138,21 @@ class _SmgNet(nn.Module):
         norm0, norm1 = bns[0], bns[1]
         norm5 = trunk.features.norm5
         k = len(pairs)
-        w = torch.tensor([_BN_MOMENTUM * (1 - _BN_MOMENTUM) ** (k - 1 - i) for i in range(k)], dtype=torch.float64,
-                         device=var.device)
+        cache = self.__dict__.setdefault("_bn_weight_cache", {})
+        key = ("head", tuple(pairs), str(var.device))
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) > 64:
+                cache.clear()
+            ent = cache[key] = (torch.tensor([_BN_MOMENTUM * (1 - _BN_MOMENTUM) ** (k - 1 - i) for i in range(k)],
+                                             dtype=torch.float64, device=var.device),
+                                torch.tensor([p[0] for p in pairs], device=var.device),
+                                torch.tensor([p[1] for p in pairs], device=var.device))
+        w, si, mi = ent
         decay = (1 - _BN_MOMENTUM) ** k
         n = 400.0
         v5 = var[:, -1024:].double()
         var_z = norm5.weight.double() ** 2 * v5 / (v5 + 1e-5)                       # [samples, 1024]
-        si = torch.tensor([p[0] for p in pairs], device=var.device)
-        mi = torch.tensor([p[1] for p in pairs], device=var.device)
         bv = torch.cat([(w[:, None] * var_z[si]).sum(0), (w[:, None] * var_z[mi]).sum(0)]) * (n / (n - 1.0))
         bm = torch.cat([norm5.bias.double(), norm5.bias.double()]) * w.sum()
         norm0.running_mean.mul_(decay).add_(bm.to(norm0.running_mean))
