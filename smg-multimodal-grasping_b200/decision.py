@@ -22,22 +22,37 @@ def decide(trainer, depth_heightmap, masks, is_ets=True, is_target=False):
     masks = np.asarray(masks, np.float64)
     K = masks.shape[0]
     scene = scene_from_masks(depth_heightmap, masks)
-    single = scene[None] * masks                                     # code/main.py:160
     model = trainer.model_target if (is_target and trainer.method == "reinforcement") else trainer.model
     eng = model._engine(max(model.gnum_rotations, model.snum_rotations) + max(K, K * (K - 1) // 2))
+    # the scene and the K object masks cross PCIe once; the masked heightmaps are formed on the device
+    scene_t = torch.from_numpy(np.ascontiguousarray(scene)).to(eng.device)
+    masks_t = torch.from_numpy(np.ascontiguousarray(masks)).to(eng.device)
+    single = scene_t[None] * masks_t                                 # code/main.py:160
 
     def table(style, m):
-        q = trainer.forward_all(scene, m, style=style, is_target=is_target)       # [n, R, n_out] on the device
+        q = trainer.forward_all(scene_t, m, style=style, is_target=is_target)     # [n, R, n_out] on the device
         if trainer.method == "reactive":
             # the reference's reactive forward only looks at rotation 0 -> softmax P(class 0) (code/trainer.py:195-199)
             return torch.softmax(q[:, :1, :], dim=2)[:, :, 0]
         return q[:, :, 0]
 
+    # all three passes are enqueued before the first device-to-host read, so the GPU never waits for the host in between
     gra = table(0, single)
     suc = table(1, single)
-    out = {"gra_conf": gra.double().cpu().numpy(), "suc_conf": suc.double().cpu().numpy()}
     vg, ig = eng.argmax(gra)
     vs, isx = eng.argmax(suc)
+    pairs, flat, v, i = [], None, None, None
+    if is_ets and K > 1:
+        pairs = [(g, s) for g in range(K) for s in range(g + 1, K)]
+        gi = torch.from_numpy(np.asarray([g for g, _ in pairs], np.int64)).to(eng.device)
+        si = torch.from_numpy(np.asarray([s_ for _, s_ in pairs], np.int64)).to(eng.device)
+        pm = scene_t[None] * (masks_t[gi] + masks_t[si])                            # code/main.py:186
+        gs = table(2, pm)[:, 0]
+        flat = torch.full((K * K,), -100.0, device=gs.device)
+        idx = torch.from_numpy(np.asarray([g * K + s for g, s in pairs], np.int64)).to(gs.device, non_blocking=True)
+        flat[idx] = gs.float()
+        v, i = eng.argmax(flat)
+    out = {"gra_conf": gra.double().cpu().numpy(), "suc_conf": suc.double().cpu().numpy()}
     bestg_conf, bests_conf = float(vg.item()), float(vs.item())
     Rg, Rs = gra.shape[1], suc.shape[1]
     out["bestg_id"] = (int(ig.item()) // Rg, int(ig.item()) % Rg)      # np.unravel_index(np.argmax(...)) (main.py:172-173)
@@ -45,14 +60,6 @@ def decide(trainer, depth_heightmap, masks, is_ets=True, is_target=False):
     bestgs_conf, bestgs_num, bestgs_g_id, bestgs_s_id = 0.0, (), [], []
     gs_conf = np.zeros((K, K))
     if is_ets and K > 1:
-        pairs = [(g, s) for g in range(K) for s in range(g + 1, K)]
-        pm = np.stack([scene * (masks[g] + masks[s]) for g, s in pairs])           # code/main.py:186
-        gs = table(2, pm)[:, 0]
-        gs_conf[:, :] = -100.0
-        flat = torch.full((K * K,), -100.0, device=gs.device)
-        idx = torch.tensor([g * K + s for g, s in pairs], device=gs.device)
-        flat[idx] = gs.float()
-        v, i = eng.argmax(flat)
         bestgs_conf = float(v.item())
         bestgs_num = (int(i.item()) // K, int(i.item()) % K)
         gs_conf = flat.view(K, K).double().cpu().numpy()

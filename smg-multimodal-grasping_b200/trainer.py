@@ -130,12 +130,20 @@ class Trainer(object):
         """Q table [n_masks, n_rot(, 3)] for one scene and MANY masked heightmaps in one de-duplicated pass."""
         model = self.model_target if (is_target and self.method == 'reinforcement') else self.model
         rots, nrot = self._rotations(model, style, specific_rotation)
-        masks = np.ascontiguousarray(np.asarray(m_depth_heightmaps, dtype=np.float64))
-        if masks.ndim == 2:
-            masks = masks[None]
-        eng = model._engine(len(rots) + masks.shape[0], style)
-        scene = torch.from_numpy(np.ascontiguousarray(depth_heightmap, dtype=np.float64)).to(eng.device, non_blocking=True)
-        masks_t = torch.from_numpy(masks).to(eng.device, non_blocking=True)
+        if torch.is_tensor(m_depth_heightmaps):
+            # heightmaps already on the device (decision.decide forms the masked scenes there): no host round trip
+            masks = m_depth_heightmaps if m_depth_heightmaps.dim() == 3 else m_depth_heightmaps[None]
+            eng = model._engine(len(rots) + masks.shape[0], style)
+            masks_t = masks.to(eng.device, torch.float64).contiguous()
+            scene = (depth_heightmap if torch.is_tensor(depth_heightmap) else
+                     torch.from_numpy(np.ascontiguousarray(depth_heightmap, dtype=np.float64))).to(eng.device, torch.float64).contiguous()
+        else:
+            masks = np.ascontiguousarray(np.asarray(m_depth_heightmaps, dtype=np.float64))
+            if masks.ndim == 2:
+                masks = masks[None]
+            eng = model._engine(len(rots) + masks.shape[0], style)
+            scene = torch.from_numpy(np.ascontiguousarray(depth_heightmap, dtype=np.float64)).to(eng.device, non_blocking=True)
+            masks_t = torch.from_numpy(masks).to(eng.device, non_blocking=True)
         if model.update_running_stats:
             q, mean, var = eng.qforward_maps(style, scene, masks_t, self.image_mean, self.image_std, rots, nrot,
                                              want_bn_stats=True)
