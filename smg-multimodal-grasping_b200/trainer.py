@@ -267,10 +267,14 @@ class Trainer(object):
         tid, hid = _engine.STYLE_ROUTE[int(style)]
         params = _engine.trunk_param_list(getattr(model, _engine.TRUNK_ATTRS[tid])) + \
             _engine.head_param_list(getattr(model, _engine.HEAD_ATTRS[hid]))
-        key = (int(style), tuple(p.data_ptr() for p in params))
         st = self._fused.get(int(style))
-        if st is not None and st["key"] == key:
-            return st
+        if st is not None and len(st["params"]) == len(params):
+            # cheap validation on the per-step path (368 data_ptr() calls cost ~60 us): parameters move together (.cuda(),
+            # .to()), so three probes decide; engine.sync_weights compares every pointer before the weights are used anyway
+            probe = (0, len(params) // 2, len(params) - 1)
+            if all(st["params"][i] is params[i] and st["key"][1][i] == params[i].data_ptr() for i in probe):
+                return st
+        key = (int(style), tuple(p.data_ptr() for p in params))
         for p in params:
             if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError("smg_b200: training needs contiguous float32 parameters on the GPU")
@@ -283,15 +287,17 @@ class Trainer(object):
             for k in flat:
                 views[k].append(flat[k][off:off + p.numel()].view_as(p))
             off += p.numel()
+        # torch.optim.Adam keeps one scalar `step` tensor per parameter; here they are views of ONE flat CPU tensor, so the
+        # per-step increment is a single add (torch._foreach_add_ over 368 CPU scalars costs ~1.5 ms of host time per step)
+        steps_flat = torch.zeros(len(params), dtype=torch.float32)
         steps = []
         for i, p in enumerate(params):
             s = self.optimizer.state[p]
             if len(s) != 0:                       # already stepped by torch: adopt its moments
                 views["exp_avg"][i].copy_(s["exp_avg"])
                 views["exp_avg_sq"][i].copy_(s["exp_avg_sq"])
-                step = s["step"] if torch.is_tensor(s["step"]) else torch.tensor(float(s["step"]))
-            else:
-                step = torch.tensor(0.0, dtype=torch.float32)
+                steps_flat[i] = float(s["step"])
+            step = steps_flat[i]                  # 0-dim view
             s["step"], s["exp_avg"], s["exp_avg_sq"] = step, views["exp_avg"][i], views["exp_avg_sq"][i]
             steps.append(step)
 
@@ -301,7 +307,7 @@ class Trainer(object):
                 a[i] = t.data_ptr()
             return a
 
-        st = {"key": key, "params": params, "flat": flat, "views": views, "steps": steps,
+        st = {"key": key, "params": params, "flat": flat, "views": views, "steps": steps, "steps_flat": steps_flat,
               "ptrs": (arr(params), arr(views["grad"]), arr(views["exp_avg"]), arr(views["exp_avg_sq"]))}
         self._fused[int(style)] = st
         return st
@@ -317,8 +323,16 @@ class Trainer(object):
             for p, g in zip(st["params"], st["views"]["grad"]):
                 p.grad = g
             self._fused_last_style = style
-        hm = torch.from_numpy(np.stack([np.asarray(depth_heightmap, np.float64), np.asarray(m_depth_heightmap, np.float64)]))
-        hm = hm.to(eng.device, non_blocking=True)
+        # the two heightmaps go through a pinned staging buffer (a pageable source makes the copy synchronous); the step ends
+        # with a host read of the loss, so the buffer is free again when the next call fills it
+        pin = st.get("hm_pin")
+        d_np, m_np = np.asarray(depth_heightmap, np.float64), np.asarray(m_depth_heightmap, np.float64)
+        if pin is None or pin.shape[1:] != d_np.shape:
+            pin = st["hm_pin"] = torch.empty((2,) + d_np.shape, dtype=torch.float64).pin_memory()
+            st["hm_pin_np"] = pin.numpy()
+        np.copyto(st["hm_pin_np"][0], d_np)
+        np.copyto(st["hm_pin_np"][1], m_np)
+        hm = pin.to(eng.device, non_blocking=True)
         rot = 0 if style == 2 else int(rot)                 # ES is pinned to rotation 0 (code/models.py:567)
         group = self.optimizer.param_groups[0]
         step = int(st["steps"][0]) + 1
@@ -331,7 +345,7 @@ class Trainer(object):
         loss, q, mean, var = eng.train_step(style, hm[0], hm[1], rot, model.gnum_rotations, kind, float(label_value), cw,
                                             st["ptrs"], len(st["params"]), step, group["lr"], group["betas"][0],
                                             group["betas"][1], group["eps"], want_bn_stats=model.update_running_stats)
-        torch._foreach_add_(st["steps"], 1)
+        st["steps_flat"] += 1
         _engine.bump_weight_epoch(model, style)                      # parameters changed in place: other handles must re-pack
         eng.mark_synced(model, style)                                # this one re-packed inside the step
         if model.update_running_stats:
@@ -456,7 +470,7 @@ class Trainer(object):
             numel = st["numel"] = (ctypes.c_int64 * len(st["params"]))(*[p.numel() for p in st["params"]])
         eng.adam_step_ptrs(st["ptrs"], numel, len(st["params"]), step, group_["lr"], group_["betas"][0], group_["betas"][1],
                            group_["eps"])
-        torch._foreach_add_(st["steps"], 1)
+        st["steps_flat"] += 1
         _engine.bump_weight_epoch(model, style)
         eng.sync_weights(model, force=True, style=style)        # re-pack the updated weights
         if model.update_running_stats and bn_sum is not None:
