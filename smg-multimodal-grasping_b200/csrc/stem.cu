@@ -128,7 +128,7 @@ pool0_kernel(const float* __restrict__ conv0, const double* __restrict__ stats_i
              int out_cstride, double* __restrict__ stats_out, int stats_out_stride, int Hc, int pix_per_cta) {
     __shared__ __align__(16) float s_sc[64];
     __shared__ __align__(16) float s_sh[64];
-    __shared__ float s_sum[16][64], s_sq[16][64];
+    __shared__ double s_sum[16][64], s_sq[16][64];
     const int s = blockIdx.y;
     const int tid = threadIdx.x;
     const int Hp = Hc / 2;
@@ -148,11 +148,17 @@ pool0_kernel(const float* __restrict__ conv0, const double* __restrict__ stats_i
     const float4 sh = *reinterpret_cast<const float4*>(&s_sh[cg * 4]);
     const float* cin = conv0 + (size_t)s * Hc * Hc * 64;
     float* o = out + (size_t)s * Hp * Hp * out_cstride;
-    float4 su = make_float4(0, 0, 0, 0), sq = make_float4(0, 0, 0, 0);
-    const int p0 = blockIdx.x * pix_per_cta;
-    const int p1 = min(p0 + pix_per_cta, Hp * Hp);
-    for (int p = p0 + pl; p < p1; p += 16) {
-        const int py = p / Hp, px = p - py * Hp;
+    // statistics in double from the first addition: the consumers form var = E[x^2] - mean^2, and a channel whose spread is
+    // small against its mean (a large BatchNorm bias) loses (mean/std)^2 of the precision of these sums
+    double su[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
+    // a CTA owns a 16 x 16 block of pooled pixels (pix_per_cta = 256): its 3x3/2 windows cover 33 x 33 conv0 pixels, 1.06
+    // reads per unique input (256 consecutive pixels of a row needed 5 full conv0 rows: 1.4x, ncu: 2.53 GB read for 1.78 GB)
+    const int tiles_x = (Hp + 15) >> 4;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    for (int q = pl; q < pix_per_cta; q += 16) {
+        const int py = ty * 16 + (q >> 4), px = tx * 16 + (q & 15);
+        if (py >= Hp || px >= Hp) continue;
+        const int p = py * Hp + px;
         float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
@@ -170,19 +176,25 @@ pool0_kernel(const float* __restrict__ conv0, const double* __restrict__ stats_i
             }
         }
         *reinterpret_cast<float4*>(o + (size_t)p * out_cstride + cg * 4) = m;
-        su.x += m.x; su.y += m.y; su.z += m.z; su.w += m.w;
-        sq.x = fmaf(m.x, m.x, sq.x); sq.y = fmaf(m.y, m.y, sq.y);
-        sq.z = fmaf(m.z, m.z, sq.z); sq.w = fmaf(m.w, m.w, sq.w);
+        const float mv[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            su[j] += (double)mv[j];
+            sq[j] = fma((double)mv[j], (double)mv[j], sq[j]);
+        }
     }
-    s_sum[pl][cg * 4 + 0] = su.x; s_sum[pl][cg * 4 + 1] = su.y; s_sum[pl][cg * 4 + 2] = su.z; s_sum[pl][cg * 4 + 3] = su.w;
-    s_sq[pl][cg * 4 + 0] = sq.x; s_sq[pl][cg * 4 + 1] = sq.y; s_sq[pl][cg * 4 + 2] = sq.z; s_sq[pl][cg * 4 + 3] = sq.w;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s_sum[pl][cg * 4 + j] = su[j];
+        s_sq[pl][cg * 4 + j] = sq[j];
+    }
     __syncthreads();
     if (tid < 64) {
         double a = 0, b = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            a += (double)s_sum[i][tid];
-            b += (double)s_sq[i][tid];
+            a += s_sum[i][tid];
+            b += s_sq[i][tid];
         }
         double* st = stats_out + 2 * ((size_t)s * stats_out_stride + tid);
         atomicAdd(st, a);
@@ -215,8 +227,9 @@ int launch_conv0(smg_handle* h, const float* in, int cin, int n, const float* w,
 int launch_pool0(smg_handle* h, int n, const float* conv0, const double* stats_in, const float* gamma,
                  const float* beta, float* out, int out_cstride, double* stats_out, cudaStream_t st) {
     const int Hc = h->H / 2, Hp = Hc / 2;
-    const int pix_per_cta = 256;
-    dim3 grid((Hp * Hp + pix_per_cta - 1) / pix_per_cta, n);
+    const int pix_per_cta = 256;                 // one 16 x 16 block of pooled pixels
+    const int tiles = (Hp + 15) / 16;
+    dim3 grid(tiles * tiles, n);
     pool0_kernel<<<grid, 256, 0, st>>>(conv0, stats_in, 64, gamma, beta, out, out_cstride, stats_out, out_cstride, Hc,
                                        pix_per_cta);
     h->launches++;

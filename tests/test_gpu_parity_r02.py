@@ -159,12 +159,18 @@ def test_get_label_value_all_branches_vs_reference(gold2, scene_inputs):
 # --------------------------------------------------------------------------------------------------
 # (d) kink-free end-to-end gradients
 # --------------------------------------------------------------------------------------------------
-def _kink_free_state(sd, beta=10.0):
-    """Every BatchNorm bias = +10: the ReLU kinks move 10 sigma away from the batch mean, so no pre-activation sits within
-    rounding of a kink (the masks are still computed and applied).  With the kinks out of the way the same PyTorch code in
-    fp32 and fp64 agrees to 2.3e-4 on every tensor (conv0: 5e-4, its max-pool is a kink of its own), instead of 6e-2 at the
-    reference's own initialisation - measured with oracle/qnet.py.  (At +6 ONE element of block-2 channel 177 still sits
-    on the kink of every later norm1 and moves everything upstream by 2e-3: profiles/debug_kinkfree.py.)"""
+def _kink_free_state(sd, beta=None):
+    """Every BatchNorm bias = +12: the ReLU kinks move 12 sigma away from the batch mean, so (almost) no pre-activation sits
+    within rounding of a kink (the masks are still computed and applied).  With the kinks out of the way the same PyTorch
+    code in fp32 and fp64 agrees to 2.3e-4 on every tensor (conv0: 5e-4, its max-pool is a kink of its own), instead of 6e-2
+    at the reference's own initialisation - measured with oracle/qnet.py.  "Almost": the heightmap features are heavy-tailed
+    (a flat background and a few object pixels many sigma away), so for a given bias a single element can still land on a
+    kink and move its layer's gradients by a fixed amount whichever way the last bit of the statistics falls: at +6 one
+    element of block-2 channel 177 (2e-3, profiles/debug_kinkfree.py); at +10 one element of the first dense layer (7.5e-3
+    on three tensors once pool0 accumulated its statistics in double; with the earlier fp32 partial sums it fell on the
+    oracle's side).  +8, +9, +11 and +12 are clean (every tensor <= 3e-4); SMG_TEST_BETA overrides the value."""
+    if beta is None:
+        beta = float(os.environ.get("SMG_TEST_BETA", "12"))
     out = {k: v.clone() for k, v in sd.items()}
     for k in out:
         if "norm" in k and k.endswith(".bias"):
