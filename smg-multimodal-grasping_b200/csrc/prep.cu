@@ -101,30 +101,43 @@ __global__ void normalize_hm_kernel(const double* __restrict__ scene_hm, int n_s
 __global__ void __launch_bounds__(256)
 prep_rotate_kernel(const float* __restrict__ norm_hm, int groups, int n_rot, int n_scene_samples, int n_samples, RotTheta th,
                    int hs, float pad_val, float* __restrict__ out, int H, float step, float half) {
-    const int pad = (H - 2 * hs) / 2;
-    const size_t quads = (size_t)H * H / 4;
-    const size_t total = (size_t)n_samples * quads;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int z = (int)(i / quads);
-        const int rem = (int)(i - (size_t)z * quads) * 4;
-        const int y = rem / H, x0 = rem - y * H;
-        const bool is_scene = z < n_scene_samples;
-        const float* hm = norm_hm + (size_t)(is_scene ? z / n_rot : groups + z - n_scene_samples) * hs * hs;
-        const float* t = th.t[is_scene ? z % n_rot : 0];
-        const float by = base_coord(y, H, step);
-        float v[4];
+    // blockIdx.y = sample: no 64-bit index arithmetic per pixel, and the sample's affine matrix is read ONCE into shared memory
+    // (indexing the by-value parameter array dynamically makes every thread copy it to local memory)
+    __shared__ float s_t[6];
+    const int z = blockIdx.y;
+    const bool is_scene = z < n_scene_samples;
+    if (threadIdx.x < 6) {
+        const int r = is_scene ? z % n_rot : 0;
+        float v = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int sy = y, sx = x0 + j;
-            bool inside = true;
-            if (is_scene) inside = rotate_src_xy(base_coord(x0 + j, H, step), by, H, half, t, sx, sy);
-            const int yy = sy - pad, xx = sx - pad;
-            const bool in_hm = inside && yy >= 0 && yy < 2 * hs && xx >= 0 && xx < 2 * hs;
-            const float f = in_hm ? __ldg(hm + (size_t)(yy >> 1) * hs + (xx >> 1)) : pad_val;
-            v[j] = inside ? f : 0.f;   // grid_sample pads with zeros OUTSIDE the (already normalised) image
-        }
-        *reinterpret_cast<float4*>(out + (size_t)z * H * H + rem) = make_float4(v[0], v[1], v[2], v[3]);
+        for (int k = 0; k < 32; ++k)
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+                if (k == r && c == (int)threadIdx.x) v = th.t[k][c];   // static indices: plain constant-bank reads
+        s_t[threadIdx.x] = v;
     }
+    __syncthreads();
+    const int pad = (H - 2 * hs) / 2;
+    const int quads = H * H / 4;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= quads) return;
+    const int rem = i * 4;
+    const int y = rem / H, x0 = rem - y * H;
+    const float* hm = norm_hm + (size_t)(is_scene ? z / n_rot : groups + z - n_scene_samples) * hs * hs;
+    const float t[6] = {s_t[0], s_t[1], s_t[2], s_t[3], s_t[4], s_t[5]};
+    const float by = base_coord(y, H, step);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int sy = y, sx = x0 + j;
+        bool inside = true;
+        if (is_scene) inside = rotate_src_xy(base_coord(x0 + j, H, step), by, H, half, t, sx, sy);
+        const int yy = sy - pad, xx = sx - pad;
+        const bool in_hm = inside && yy >= 0 && yy < 2 * hs && xx >= 0 && xx < 2 * hs;
+        const float f = in_hm ? __ldg(hm + (size_t)(yy >> 1) * hs + (xx >> 1)) : pad_val;
+        v[j] = inside ? f : 0.f;   // grid_sample pads with zeros OUTSIDE the (already normalised) image
+    }
+    *reinterpret_cast<float4*>(out + (size_t)z * H * H + rem) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 __global__ void rotate_index_kernel(RotTheta th, int32_t* __restrict__ out, int H) {
@@ -196,9 +209,8 @@ int launch_prep_rotate(smg_handle* h, const double* scene_hm, int groups, const 
         h->launches++;
     }
     const int n_samples = groups * n_rot + n_mask_samples;
-    const size_t total = (size_t)n_samples * h->H * h->H / 4;
-    const int blocks = (int)((total + 255) / 256);
-    prep_rotate_kernel<<<blocks < h->num_sms * 16 ? blocks : h->num_sms * 16, 256, 0, st>>>(
+    const int quads = h->H * h->H / 4;
+    prep_rotate_kernel<<<dim3((quads + 255) / 256, n_samples), 256, 0, st>>>(
         norm, groups, n_rot, groups * n_rot, n_samples, th, hm_size, (float)((0.0 - mean) / stddev), out, h->H,
         2.0f / (float)(h->H - 1), (float)(h->H - 1) / 2.0f);
     h->launches++;
