@@ -99,24 +99,13 @@ __global__ void normalize_hm_kernel(const double* __restrict__ scene_hm, int n_s
 }
 
 __global__ void __launch_bounds__(256)
-prep_rotate_kernel(const float* __restrict__ norm_hm, int groups, int n_rot, int n_scene_samples, int n_samples, RotTheta th,
-                   int hs, float pad_val, float* __restrict__ out, int H, float step, float half) {
-    // blockIdx.y = sample: no 64-bit index arithmetic per pixel, and the sample's affine matrix is read ONCE into shared memory
-    // (indexing the by-value parameter array dynamically makes every thread copy it to local memory)
-    __shared__ float s_t[6];
+prep_rotate_kernel(const float* __restrict__ norm_hm, int groups, int n_rot, int n_scene_samples, int n_samples,
+                   const __grid_constant__ RotTheta th, int hs, float pad_val, float* __restrict__ out, int H, float step, float half) {
+    // blockIdx.y = sample: no 64-bit index arithmetic per pixel; the matrix table is a __grid_constant__ parameter, so the
+    // sample's row is read in place (a plain by-value array indexed dynamically is first copied to every thread's local memory)
     const int z = blockIdx.y;
     const bool is_scene = z < n_scene_samples;
-    if (threadIdx.x < 6) {
-        const int r = is_scene ? z % n_rot : 0;
-        float v = 0.f;
-#pragma unroll
-        for (int k = 0; k < 32; ++k)
-#pragma unroll
-            for (int c = 0; c < 6; ++c)
-                if (k == r && c == (int)threadIdx.x) v = th.t[k][c];   // static indices: plain constant-bank reads
-        s_t[threadIdx.x] = v;
-    }
-    __syncthreads();
+    const float* t = th.t[is_scene ? z % n_rot : 0];
     const int pad = (H - 2 * hs) / 2;
     const int quads = H * H / 4;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,7 +113,6 @@ prep_rotate_kernel(const float* __restrict__ norm_hm, int groups, int n_rot, int
     const int rem = i * 4;
     const int y = rem / H, x0 = rem - y * H;
     const float* hm = norm_hm + (size_t)(is_scene ? z / n_rot : groups + z - n_scene_samples) * hs * hs;
-    const float t[6] = {s_t[0], s_t[1], s_t[2], s_t[3], s_t[4], s_t[5]};
     const float by = base_coord(y, H, step);
     float v[4];
 #pragma unroll
